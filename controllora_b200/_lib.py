@@ -1,0 +1,73 @@
+"""ctypes binding of libcontrollora_b200.so (C ABI: include/controllora_b200.h).
+
+The product path has no CPU or library fallback: if the shared library is missing, or a call fails, this module
+raises.  PyTorch is used only as the owner of device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libcontrollora_b200.so"
+
+
+class CLError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise CLError(
+                f"{LIB_PATH} is missing: run `python -m controllora_b200.build` (or __graft_entry__.build()). "
+                "controllora_b200 has no CPU / PyTorch fallback for its CUDA kernels."
+            )
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.cl_last_error.restype = C.c_char_p
+        _lib.cl_launch_count.restype = C.c_int64
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().cl_last_error().decode("utf-8", "replace")
+        raise CLError(f"{what} failed with status {status}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().cl_launch_count())
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("a_mode", C.c_int32),
+        ("a", C.c_void_p),
+        ("lda", C.c_int64),
+        ("n_img", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("pad_lo", C.c_int32),
+        ("b", C.c_void_p),
+        ("ldb", C.c_int64),
+        ("ext", C.c_void_p),
+        ("ldb_ext", C.c_int64),
+        ("bias", C.c_void_p),
+        ("row_bias", C.c_void_p),
+        ("rows_per_group", C.c_int32),
+        ("residual", C.c_void_p),
+        ("ldr", C.c_int64),
+        ("lora_up", C.c_void_p),
+        ("lora_rp", C.c_int32),
+        ("lora_scale", C.c_float),
+        ("t_add", C.c_void_p),
+        ("t_out", C.c_void_p),
+        ("out", C.c_void_p),
+        ("ldd", C.c_int64),
+        ("out_fp32", C.c_int32),
+        ("block_n", C.c_int32),
+    ]

@@ -1,0 +1,488 @@
+// K1/K4 — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] = epilogue( A[M,K] * B[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM.
+//
+// One CTA per SM, 12 warps:
+//   warp 0      TMA producer   (A tile 128x64, B tile BNx64 [+16 LoRA-down rows], 128B swizzle, mbarrier ring)
+//   warp 1      MMA issuer     (one elected thread, tcgen05.mma cta_group::1, M=128, N=BN[+16], K=16)
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue       (tcgen05.ld -> LoRA rank-r update in fp32 -> smem transpose -> bias/residual ->
+//                               coalesced global stores); two TMEM accumulator buffers so the epilogue of tile i
+//                               overlaps the main loop of tile i+1.
+// The A operand is either a plain row-major matrix or an NHWC image read as 3x3 windows (implicit GEMM: the
+// "im2col" is done by TMA box loads with shifted coordinates, out-of-bounds zero fill == conv zero padding).
+//
+// Replaces the cuBLAS/cuDNN calls behind models.py:124-147,231-282,373-423 (attention projections + LoRA side
+// path) and diffusers' FeedForward / ResnetBlock2D / Transformer2DModel projections.
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/controllora_b200.h"
+
+namespace clb {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;                       // 64 bf16 = 128 B = one swizzle row
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+static constexpr int NUM_EPI_WARPS = 8;
+static constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
+static constexpr int STAGE_ROW_BYTES = 128;              // epilogue staging: 32 fp32 columns per row
+static constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 32 * STAGE_ROW_BYTES;
+
+struct GemmParams {
+    int M, N, K;
+    int num_k_blocks;
+    int a_mode;
+    // conv geometry (output space)
+    int n_img, Ho, Wo, C, cblocks, pad_lo;
+    int bw, bh, bn, tiles_w, tiles_h, tiles_n;
+    int num_m_blocks, num_n_blocks;
+    // epilogue
+    const float* bias;
+    const float* row_bias;
+    int rows_per_group;
+    const __nv_bfloat16* residual;
+    long long ldr;
+    const float* lora_up;
+    int lora_rp;
+    float lora_scale;
+    const float* t_add;
+    float* t_out;
+    void* out;
+    long long ldd;
+    int out_fp32;
+};
+
+template <int BN, int EXT>
+struct GemmCfg {
+    static constexpr int UMMA_N = BN + EXT;
+    static constexpr int B_STAGE_BYTES = UMMA_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int BUF_COLS = (UMMA_N + 31) / 32 * 32;
+    static constexpr int TMEM_COLS = (2 * BUF_COLS <= 32) ? 32 : (2 * BUF_COLS <= 64) ? 64 : (2 * BUF_COLS <= 128) ? 128
+                                   : (2 * BUF_COLS <= 256) ? 256 : 512;
+    static_assert(2 * BUF_COLS <= 512, "TMEM overflow");
+    static_assert(UMMA_N % 16 == 0 && UMMA_N >= 16 && UMMA_N <= 256, "invalid UMMA N");
+    static_assert(BN % 32 == 0, "BN must be a multiple of the 32-column epilogue granule");
+};
+
+// Decode tile-local row r (0..127) into the global output row (or -1 if masked) and its row_bias group.
+__device__ __forceinline__ void decode_row(const GemmParams& p, int m_blk, int r, int& m, int& grp) {
+    if (p.a_mode == 0) {
+        m = m_blk * BLOCK_M + r;
+        if (m >= p.M) m = -1;
+        grp = (m >= 0 && p.rows_per_group > 0) ? m / p.rows_per_group : 0;
+    } else {
+        int tw = m_blk % p.tiles_w;
+        int th = (m_blk / p.tiles_w) % p.tiles_h;
+        int tn = m_blk / (p.tiles_w * p.tiles_h);
+        int dw = r % p.bw, dh = (r / p.bw) % p.bh, dn = r / (p.bw * p.bh);
+        int n = tn * p.bn + dn, h = th * p.bh + dh, w = tw * p.bw + dw;
+        if (n < p.n_img && h < p.Ho && w < p.Wo) {
+            m = (n * p.Ho + h) * p.Wo + w;
+            grp = (p.rows_per_group > 0) ? m / p.rows_per_group : 0;
+        } else {
+            m = -1;
+            grp = 0;
+        }
+    }
+}
+
+template <int BN, int EXT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmE, const GemmParams p, const int num_stages) {
+    using Cfg = GemmCfg<BN, EXT>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve (base is 1024-aligned by the runtime for dynamic smem declared __align__(1024); re-align anyway)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem_a + num_stages * A_STAGE_BYTES;
+    uint8_t* smem_stage = smem_b + num_stages * Cfg::B_STAGE_BYTES;          // epilogue staging
+    float* smem_up = reinterpret_cast<float*>(smem_stage + EPI_STAGING_BYTES);  // [N][rp] when LoRA is on
+    const int up_floats = (p.lora_up != nullptr) ? p.N * p.lora_rp : 0;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_up) + ((up_floats * 4 + 15) & ~15));
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + num_stages;
+    uint64_t* tmem_full = bars + 2 * num_stages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (EXT) tma_prefetch_desc(&tmE);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (int i = 0; i < num_stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) {
+        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    // LoRA-up table -> smem (persistent for the CTA lifetime)
+    for (int i = threadIdx.x; i < up_floats; i += NUM_THREADS) smem_up[i] = p.lora_up[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp_idx == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / p.num_n_blocks;
+                const int n_blk = tile % p.num_n_blocks;
+                int tw = 0, th = 0, tn = 0;
+                if (p.a_mode != 0) {
+                    tw = m_blk % p.tiles_w;
+                    th = (m_blk / p.tiles_w) % p.tiles_h;
+                    tn = m_blk / (p.tiles_w * p.tiles_h);
+                }
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+                    uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+                    if (p.a_mode == 0) {
+                        tma_load_2d(&tmA, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
+                    } else {
+                        const int tap = kb / p.cblocks, cb = kb % p.cblocks;
+                        const int ky = tap / 3, kx = tap % 3;
+                        if (p.a_mode == 1) {
+                            tma_load_4d(&tmA, &full_bar[stage], sa, cb * BLOCK_K, tw * p.bw + kx - 1,
+                                        th * p.bh + ky - 1, tn * p.bn);
+                        } else {
+                            const int iy = ky - p.pad_lo, ix = kx - p.pad_lo;
+                            tma_load_5d(&tmA, &full_bar[stage], sa, (ix & 1) * p.C + cb * BLOCK_K,
+                                        tw * p.bw + (ix >> 1), iy & 1, th * p.bh + (iy >> 1), tn * p.bn);
+                        }
+                    }
+                    tma_load_2d(&tmB, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BN);
+                    if (EXT) tma_load_2d(&tmE, &full_bar[stage], sb + BN * 128, kb * BLOCK_K, 0);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, Cfg::UMMA_N, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t buf_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * Cfg::BUF_COLS;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024, 2);
+                        const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, 1024, 2);
+                        tc_mma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tmem_full[buf]);        // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // ===================================================== epilogue
+        const int ew = warp_idx - 4;              // 0..7
+        const int quad = warp_idx & 3;            // TMEM lane quadrant this warp may access
+        const int half = ew >> 2;                 // the two warps of a quadrant split the column granules
+        uint8_t* stg = smem_stage + ew * 32 * STAGE_ROW_BYTES;
+        const int rp = p.lora_rp;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile / p.num_n_blocks;
+            const int n_blk = tile % p.num_n_blocks;
+            const int buf = it & 1;
+            const uint32_t buf_phase = (it >> 1) & 1;
+            // rows: phase-1 thread owns row (quad*32 + lane); phase-2 lane handles rows (lane>>3) + 4*i
+            int my_m, my_grp;
+            decode_row(p, m_blk, quad * 32 + lane, my_m, my_grp);
+
+            mbar_wait(&tmem_full[buf], buf_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + (uint32_t(quad * 32) << 16) + buf * Cfg::BUF_COLS;
+
+            float tl[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tl[j] = 0.f;
+            if (EXT) {
+                uint32_t e[16];
+                tmem_ld_32x16(t_base + BN, e);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tl[j] = __uint_as_float(e[j]) + __uint_as_float(e[j + 8]);
+                if (my_m >= 0) {
+                    if (p.t_add != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < rp) tl[j] += p.t_add[(long long)my_m * rp + j];
+                    }
+                    if (p.t_out != nullptr && n_blk == 0 && half == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < rp) p.t_out[(long long)my_m * rp + j] = tl[j];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tl[j] *= p.lora_scale;
+            }
+
+            for (int g = half; g < BN / 32; g += 2) {
+                const int col0 = n_blk * BN + g * 32;   // first global column of this granule
+                if (col0 >= p.N) break;                   // (warp-uniform) nothing to store
+                uint32_t v[32];
+                tmem_ld_32x32(t_base + g * 32, v);
+                tc_wait_ld();
+                float f[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]);
+                if (EXT) {
+                    if (rp == 4) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int n = min(col0 + c, p.N - 1);
+                            const float4 u = *reinterpret_cast<const float4*>(smem_up + n * 4);
+                            f[c] += tl[0] * u.x + tl[1] * u.y + tl[2] * u.z + tl[3] * u.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int n = min(col0 + c, p.N - 1);
+                            const float4 u0 = *reinterpret_cast<const float4*>(smem_up + n * 8);
+                            const float4 u1 = *reinterpret_cast<const float4*>(smem_up + n * 8 + 4);
+                            f[c] += tl[0] * u0.x + tl[1] * u0.y + tl[2] * u0.z + tl[3] * u0.w + tl[4] * u1.x +
+                                    tl[5] * u1.y + tl[6] * u1.z + tl[7] * u1.w;
+                        }
+                    }
+                }
+                // ---- phase 1 -> smem (row = lane, 8 chunks of 16 B, XOR swizzle keeps both phases conflict-free)
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 q = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    *reinterpret_cast<float4*>(stg + lane * STAGE_ROW_BYTES + ((j ^ (lane & 7)) << 4)) = q;
+                }
+                __syncwarp();
+                // ---- phase 2: lane -> (row = (lane>>3) + 4*i, chunk = lane&7): coalesced bias/residual/store
+                const int ch = lane & 7;
+                const int n0 = col0 + ch * 4;
+                float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool col_ok = n0 < p.N;  // N % 4 == 0 is enforced on the host
+                if (col_ok && p.bias != nullptr) bz = *reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = (lane >> 3) + 4 * i;
+                    const int m = __shfl_sync(0xffffffffu, my_m, r);
+                    const int grp = __shfl_sync(0xffffffffu, my_grp, r);
+                    if (m < 0 || !col_ok) continue;
+                    float4 q = *reinterpret_cast<const float4*>(stg + r * STAGE_ROW_BYTES + ((ch ^ (r & 7)) << 4));
+                    q.x += bz.x; q.y += bz.y; q.z += bz.z; q.w += bz.w;
+                    if (p.row_bias != nullptr) {
+                        const float4 rb = *reinterpret_cast<const float4*>(p.row_bias + (long long)grp * p.N + n0);
+                        q.x += rb.x; q.y += rb.y; q.z += rb.z; q.w += rb.w;
+                    }
+                    if (p.residual != nullptr) {
+                        const uint2 rr = *reinterpret_cast<const uint2*>(p.residual + (long long)m * p.ldr + n0);
+                        const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y);
+                        q.x += a.x; q.y += a.y; q.z += b.x; q.w += b.y;
+                    }
+                    if (p.out_fp32) {
+                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)m * p.ldd + n0) = q;
+                    } else {
+                        uint2 o;
+                        o.x = pack_bf16x2(q.x, q.y);
+                        o.y = pack_bf16x2(q.z, q.w);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldd + n0) = o;
+                    }
+                }
+            }
+            // all TMEM reads of this buffer are complete (tc_wait_ld above) -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+
+template <int BN, int EXT>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tE, const GemmParams& p,
+                       cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, EXT>;
+    const int up_bytes = (p.lora_up != nullptr) ? ((p.N * p.lora_rp * 4 + 15) & ~15) : 0;
+    const int fixed = 1024 /*align slack*/ + EPI_STAGING_BYTES + up_bytes + 256 /*barriers*/;
+    int stages = (232448 - fixed) / Cfg::STAGE_BYTES;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: not enough shared memory for 2 stages");
+    const int smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_done = true;
+    }
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    int grid = num_sms();
+    if (grid > num_tiles) grid = num_tiles;
+    gemm_tc_kernel<BN, EXT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tA, tB, tE, p, stages);
+    count_launch();
+    CL_CUDA_CHECK(cudaGetLastError());
+    return CL_OK;
+}
+
+}  // namespace clb
+
+using namespace clb;
+
+extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (a == nullptr || a->a == nullptr || a->b == nullptr || a->out == nullptr)
+        return set_error(CL_ERR_INVALID, "cl_gemm: null pointer");
+    if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(CL_ERR_INVALID, "cl_gemm: non-positive dims");
+    if (a->N % 4 != 0) return set_error(CL_ERR_INVALID, "cl_gemm: N must be a multiple of 4");
+    if (a->K % 8 != 0 || a->ldb % 8 != 0) return set_error(CL_ERR_INVALID, "cl_gemm: K/ldb must be multiples of 8");
+    const bool lora = a->lora_up != nullptr;
+    if (lora && (a->ext == nullptr || (a->lora_rp != 4 && a->lora_rp != 8)))
+        return set_error(CL_ERR_INVALID, "cl_gemm: LoRA epilogue needs ext and lora_rp in {4,8}");
+    if (lora && a->N * a->lora_rp * 4 > 49152) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: LoRA N too large");
+    if ((a->t_add || a->t_out) && !lora) return set_error(CL_ERR_INVALID, "cl_gemm: t_add/t_out need the LoRA epilogue");
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.a_mode = a->a_mode;
+    p.num_k_blocks = (a->K + BLOCK_K - 1) / BLOCK_K;
+    CUtensorMap tA, tB, tE;
+    memset(&tE, 0, sizeof(tE));
+
+    if (a->a_mode == 0) {
+        if (a->lda % 8 != 0) return set_error(CL_ERR_INVALID, "cl_gemm: lda must be a multiple of 8");
+        p.num_m_blocks = (a->M + BLOCK_M - 1) / BLOCK_M;
+        uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
+        uint64_t strides[1] = {(uint64_t)a->lda * 2};
+        uint32_t box[2] = {BLOCK_K, BLOCK_M};
+        CL_CHECK(get_tensor_map(&tA, a->a, 2, dims, strides, box, /*swizzle128=*/true));
+    } else if (a->a_mode == 1 || a->a_mode == 2) {
+        if (a->C % 64 != 0) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: conv C must be a multiple of 64");
+        if (a->K != 9 * a->C) return set_error(CL_ERR_INVALID, "cl_gemm: conv K must be 9*C");
+        const int s = (a->a_mode == 2) ? 2 : 1;
+        if (a->H % s || a->W % s) return set_error(CL_ERR_INVALID, "cl_gemm: stride-2 conv needs even H, W");
+        p.n_img = a->n_img; p.Ho = a->H / s; p.Wo = a->W / s; p.C = a->C; p.cblocks = a->C / 64;
+        p.pad_lo = a->pad_lo;
+        if (a->M != p.n_img * p.Ho * p.Wo) return set_error(CL_ERR_INVALID, "cl_gemm: conv M != n*Ho*Wo");
+        int bw = 128;
+        while (bw > 1 && (p.Wo % bw) != 0) bw >>= 1;
+        int bh = 128 / bw;
+        while (bh > 1 && (p.Ho % bh) != 0) bh >>= 1;
+        int bn = 128 / (bw * bh);
+        if (bw > 256 || bh > 256 || bn > 256) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: conv tile");
+        p.bw = bw; p.bh = bh; p.bn = bn;
+        p.tiles_w = p.Wo / bw; p.tiles_h = p.Ho / bh; p.tiles_n = (p.n_img + bn - 1) / bn;
+        p.num_m_blocks = p.tiles_w * p.tiles_h * p.tiles_n;
+        const uint64_t C = a->C, W = a->W, H = a->H, NI = a->n_img;
+        if (a->a_mode == 1) {
+            uint64_t dims[4] = {C, W, H, NI};
+            uint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+            uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+            CL_CHECK(get_tensor_map(&tA, a->a, 4, dims, strides, box, true));
+        } else {
+            uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, NI};
+            uint64_t strides[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
+            uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bn};
+            CL_CHECK(get_tensor_map(&tA, a->a, 5, dims, strides, box, true));
+        }
+    } else {
+        return set_error(CL_ERR_INVALID, "cl_gemm: bad a_mode");
+    }
+
+    // block_n choice: LoRA needs UMMA_N = BN + 16 <= 256.
+    int bn_sel = a->block_n;
+    if (bn_sel == 0) {
+        if (lora) bn_sel = (a->N % 160 == 0) ? 160 : (a->N % 128 == 0 ? 128 : 160);
+        else if (a->N % 256 == 0) bn_sel = 256;
+        else if (a->N % 160 == 0) bn_sel = 160;
+        else if (a->N % 128 == 0) bn_sel = 128;
+        else if (a->N <= 64) bn_sel = 64;
+        else if (a->N <= 128) bn_sel = 128;
+        else bn_sel = 160;
+    }
+    p.num_n_blocks = (a->N + bn_sel - 1) / bn_sel;
+    {
+        uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+        uint64_t strides[1] = {(uint64_t)a->ldb * 2};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)bn_sel};
+        CL_CHECK(get_tensor_map(&tB, a->b, 2, dims, strides, box, true));
+    }
+    if (lora) {
+        if (a->ldb_ext % 8 != 0) return set_error(CL_ERR_INVALID, "cl_gemm: ldb_ext must be a multiple of 8");
+        uint64_t dims[2] = {(uint64_t)a->K, 16};
+        uint64_t strides[1] = {(uint64_t)a->ldb_ext * 2};
+        uint32_t box[2] = {BLOCK_K, 16};
+        CL_CHECK(get_tensor_map(&tE, a->ext, 2, dims, strides, box, true));
+    }
+
+    p.bias = a->bias; p.row_bias = a->row_bias; p.rows_per_group = a->rows_per_group;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.ldr = a->ldr;
+    p.lora_up = a->lora_up; p.lora_rp = lora ? a->lora_rp : 4; p.lora_scale = a->lora_scale;
+    p.t_add = a->t_add; p.t_out = a->t_out;
+    p.out = a->out; p.ldd = a->ldd; p.out_fp32 = a->out_fp32;
+    if (p.row_bias && p.rows_per_group <= 0) return set_error(CL_ERR_INVALID, "cl_gemm: rows_per_group");
+    if ((p.ldd % 4) || (p.residual && (p.ldr % 4))) return set_error(CL_ERR_INVALID, "cl_gemm: ldd/ldr % 4");
+
+    if (lora) {
+        switch (bn_sel) {
+            case 64: return launch_gemm<64, 16>(tA, tB, tE, p, stream);
+            case 128: return launch_gemm<128, 16>(tA, tB, tE, p, stream);
+            case 160: return launch_gemm<160, 16>(tA, tB, tE, p, stream);
+            default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n for LoRA must be 64/128/160");
+        }
+    }
+    switch (bn_sel) {
+        case 64: return launch_gemm<64, 0>(tA, tB, tE, p, stream);
+        case 128: return launch_gemm<128, 0>(tA, tB, tE, p, stream);
+        case 160: return launch_gemm<160, 0>(tA, tB, tE, p, stream);
+        case 256: return launch_gemm<256, 0>(tA, tB, tE, p, stream);
+        default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n must be 64/128/160/256");
+    }
+}
