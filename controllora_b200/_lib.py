@@ -71,3 +71,15 @@ class GemmArgs(C.Structure):
         ("out_fp32", C.c_int32),
         ("block_n", C.c_int32),
     ]
+
+
+class AttnFwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32), ("d", C.c_int32),
+        ("q", C.c_void_p), ("ldq", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64),
+        ("o", C.c_void_p), ("ldo", C.c_int64),
+        ("lse", C.c_void_p),
+        ("scale", C.c_float),
+    ]

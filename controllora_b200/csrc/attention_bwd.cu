@@ -1,0 +1,519 @@
+// K2 (backward) — attention gradients on tcgen05 / TMEM, recomputing the probabilities from Q, K and the saved
+// log-sum-exp (the reference's autograd instead keeps the materialised N x N probabilities of every layer).
+//
+//   P = exp2(S*scale*log2e - LSE),  dP = dO V^T,  dS = P o (dP - delta) * scale,  delta = rowsum(dO o O)
+//   dV = P^T dO,   dK = dS^T Q,   dQ = dS K
+//
+// Two kernels, no atomics:
+//   attn_bwd_dkv: CTA = (batch, head, 128-key block), loops over query blocks.  Works on the transposed problem so
+//       that TMEM lane == key row:   S^T = K Q^T,  dP^T = V dO^T  (both operands K-major smem tiles);  the softmax
+//       warps turn them into bf16 P^T and dS^T tiles in smem (K-major over queries);  dV += P^T dO and
+//       dK += dS^T Q then consume the *same* dO / Q smem tiles again, this time as MN-major B operands.
+//   attn_bwd_dq:  CTA = (batch, head, 128-query block), loops over key blocks:  S = Q K^T, dP = dO V^T,
+//       dS -> smem,  dQ += dS K (K tile as MN-major B operand).
+// Warp roles as in the forward kernel: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 4-7 softmax/epilogue.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/controllora_b200.h"
+
+namespace clb {
+
+int make_head_map(CUtensorMap* tm, const void* ptr, int B, int H, int N, int d, long long ld, int box_rows);
+
+struct AttnBwdParams {
+    int B, H, Nq, Nk, d;
+    const float* lse;     // [B, H, Nq] log2-domain
+    const float* delta;   // [B, H, Nq]
+    __nv_bfloat16* dq; long long lddq;
+    __nv_bfloat16* dk; long long lddk;
+    __nv_bfloat16* dv; long long lddv;
+    float scale, scale_log2;
+    int num_blocks;       // key blocks (dkv) or query blocks (dq) per (b, h)
+};
+
+// write 32 consecutive bf16 values (columns [c32*32, c32*32+32) of row r) into a K-major 128B-swizzled tile whose
+// 64-column chunks are `chunk_stride` bytes apart
+__device__ __forceinline__ void store_row32_swz(uint8_t* tile, int chunk_stride, int r, int c32, const uint32_t (&pk)[16]) {
+    uint8_t* rowp = tile + (c32 >> 1) * chunk_stride + r * 128;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int chunk = (c32 & 1) * 4 + q;
+        *reinterpret_cast<uint4*>(rowp + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+}
+
+// TMEM accumulator rows -> bf16 global rows (thread = row), columns [0, d)
+template <int DP>
+__device__ __forceinline__ void store_acc_rows(uint32_t taddr, __nv_bfloat16* rowptr, bool row_ok, int d, float mul) {
+#pragma unroll
+    for (int c = 0; c < DP / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tc_wait_ld();
+        if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const int col = c * 32 + j;
+                if (col < d) {
+                    uint4 o4;
+                    o4.x = pack_bf16x2(__uint_as_float(v[j]) * mul, __uint_as_float(v[j + 1]) * mul);
+                    o4.y = pack_bf16x2(__uint_as_float(v[j + 2]) * mul, __uint_as_float(v[j + 3]) * mul);
+                    o4.z = pack_bf16x2(__uint_as_float(v[j + 4]) * mul, __uint_as_float(v[j + 5]) * mul);
+                    o4.w = pack_bf16x2(__uint_as_float(v[j + 6]) * mul, __uint_as_float(v[j + 7]) * mul);
+                    *reinterpret_cast<uint4*>(rowptr + col) = o4;
+                }
+            }
+        }
+    }
+}
+
+// ===================================================================================================== dK, dV
+template <int DP, int BQ, int STAGES>
+struct DkvCfg {
+    static constexpr int BK = 128;                              // keys per CTA == TMEM lanes
+    static constexpr int DCH = DP / 64;
+    static constexpr int KV_BYTES = DCH * BK * 128;             // K tile (and V tile)
+    static constexpr int QD_TILE = DCH * BQ * 128;              // Q_j tile (and dO_j tile)
+    static constexpr int STAGE_BYTES = 2 * QD_TILE;
+    static constexpr int PT_BYTES = (BQ / 64) * BK * 128;       // P^T tile (and dS^T tile)
+    static constexpr int SMEM_BYTES = 1024 + 2 * KV_BYTES + STAGES * STAGE_BYTES + 2 * PT_BYTES + 2 * 2 * BQ * 4 + 256;
+    static constexpr int TM_ST = 0, TM_DPT = BQ, TM_DK = 2 * BQ, TM_DV = 2 * BQ + DP;
+    static_assert(2 * BQ + 2 * DP <= 512, "TMEM");
+    static_assert(BQ % 64 == 0, "BQ");
+};
+
+template <int DP, int BQ, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                    const AttnBwdParams p) {
+    using Cfg = DkvCfg<DP, BQ, STAGES>;
+    constexpr int BK = Cfg::BK;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_k = smem;
+    uint8_t* smem_v = smem_k + Cfg::KV_BYTES;
+    uint8_t* smem_st = smem_v + Cfg::KV_BYTES;                       // stages: [Q_j | dO_j]
+    uint8_t* smem_pt = smem_st + STAGES * Cfg::STAGE_BYTES;
+    uint8_t* smem_dst = smem_pt + Cfg::PT_BYTES;
+    float* smem_lse = reinterpret_cast<float*>(smem_dst + Cfg::PT_BYTES);   // [2][BQ]
+    float* smem_delta = smem_lse + 2 * BQ;                                  // [2][BQ]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_delta + 2 * BQ);
+    uint64_t* kv_full = bars;
+    uint64_t* st_full = bars + 1;             // STAGES
+    uint64_t* st_empty = st_full + STAGES;    // STAGES
+    uint64_t* s_full = st_empty + STAGES;
+    uint64_t* p_full = s_full + 1;
+    uint64_t* acc_full = p_full + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb = blockIdx.x % p.num_blocks;
+    const int bh = blockIdx.x / p.num_blocks;
+    const int h = bh % p.H, b = bh / p.H;
+    const int k0 = kb * BK;
+    const int num_q = (p.Nq + BQ - 1) / BQ;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 4);
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(kv_full, 2 * Cfg::KV_BYTES);
+            for (int c = 0; c < Cfg::DCH; ++c) {
+                tma_load_4d(&tmK, kv_full, smem_k + c * BK * 128, c * 64, h, k0, b);
+                tma_load_4d(&tmV, kv_full, smem_v + c * BK * 128, c * 64, h, k0, b);
+            }
+            int stage = 0; uint32_t phase = 0;
+            for (int j = 0; j < num_q; ++j) {
+                mbar_wait(&st_empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&st_full[stage], Cfg::STAGE_BYTES);
+                uint8_t* sq = smem_st + stage * Cfg::STAGE_BYTES;
+                uint8_t* sdo = sq + Cfg::QD_TILE;
+                for (int c = 0; c < Cfg::DCH; ++c) {
+                    tma_load_4d(&tmQ, &st_full[stage], sq + c * BQ * 128, c * 64, h, j * BQ, b);
+                    tma_load_4d(&tmDO, &st_full[stage], sdo + c * BQ * 128, c * 64, h, j * BQ, b);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, BQ, 0, 0);    // [keys x queries], both K-major
+            constexpr uint32_t idesc_g = make_idesc_bf16(128, DP, 0, 1);    // [keys x d], B MN-major
+            mbar_wait(kv_full, 0);
+            const uint32_t sk = smem_u32(smem_k), sv = smem_u32(smem_v);
+            const uint32_t spt = smem_u32(smem_pt), sdst = smem_u32(smem_dst);
+            int stage = 0; uint32_t phase = 0;
+            for (int j = 0; j < num_q; ++j) {
+                mbar_wait(&st_full[stage], phase);
+                tc_fence_after();
+                const uint32_t sq = smem_u32(smem_st + stage * Cfg::STAGE_BYTES);
+                const uint32_t sdo = sq + Cfg::QD_TILE;
+#pragma unroll
+                for (int kk = 0; kk < DP / 16; ++kk) {
+                    const uint32_t offa = (kk / 4) * (BK * 128) + (kk % 4) * 32;
+                    const uint32_t offb = (kk / 4) * (BQ * 128) + (kk % 4) * 32;
+                    tc_mma_ss(tmem_base + Cfg::TM_ST, make_smem_desc(sk + offa, 16, 1024, 2),
+                              make_smem_desc(sq + offb, 16, 1024, 2), idesc_s, kk != 0);
+                }
+#pragma unroll
+                for (int kk = 0; kk < DP / 16; ++kk) {
+                    const uint32_t offa = (kk / 4) * (BK * 128) + (kk % 4) * 32;
+                    const uint32_t offb = (kk / 4) * (BQ * 128) + (kk % 4) * 32;
+                    tc_mma_ss(tmem_base + Cfg::TM_DPT, make_smem_desc(sv + offa, 16, 1024, 2),
+                              make_smem_desc(sdo + offb, 16, 1024, 2), idesc_s, kk != 0);
+                }
+                tc_commit(s_full);
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < BQ / 16; ++kk) {
+                    const uint32_t offa = (kk / 4) * (BK * 128) + (kk % 4) * 32;
+                    // dV += P^T dO_j ;  dK += dS^T Q_j   (B tiles [queries][64 d]: MN-major, LBO = chunk stride)
+                    tc_mma_ss(tmem_base + Cfg::TM_DV, make_smem_desc(spt + offa, 16, 1024, 2),
+                              make_smem_desc(sdo + kk * 2048, BQ * 128, 1024, 2), idesc_g, (j | kk) != 0);
+                    tc_mma_ss(tmem_base + Cfg::TM_DK, make_smem_desc(sdst + offa, 16, 1024, 2),
+                              make_smem_desc(sq + kk * 2048, BQ * 128, 1024, 2), idesc_g, (j | kk) != 0);
+                }
+                tc_commit(&st_empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(acc_full);
+        }
+    } else if (warp_idx >= 4) {
+        const int quad = warp_idx & 3;
+        const int r = quad * 32 + lane;                // key row within the block
+        const int st = threadIdx.x - 128;              // 0..127
+        const uint32_t lane_off = uint32_t(quad * 32) << 16;
+        const bool key_ok = (k0 + r) < p.Nk;
+        const long long stat_base = ((long long)b * p.H + h) * p.Nq;
+        for (int j = 0; j < num_q; ++j) {
+            // stage this query block's LSE / delta (double-buffered; the named barrier orders it w.r.t. the reads)
+            float* ls = smem_lse + (j & 1) * BQ;
+            float* de = smem_delta + (j & 1) * BQ;
+            if (st < BQ) {
+                const int q = j * BQ + st;
+                ls[st] = (q < p.Nq) ? p.lse[stat_base + q] : INFINITY;   // +inf -> P = 0 for padded queries
+                de[st] = (q < p.Nq) ? p.delta[stat_base + q] : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < BQ / 32; ++c) {
+                uint32_t s[32], g[32];
+                tmem_ld_32x32(tmem_base + Cfg::TM_ST + lane_off + c * 32, s);
+                tmem_ld_32x32(tmem_base + Cfg::TM_DPT + lane_off + c * 32, g);
+                tc_wait_ld();
+                uint32_t pk[16], dk_[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -ls[c * 32 + i]));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -ls[c * 32 + i + 1]));
+                    if (!key_ok) { p0 = 0.f; p1 = 0.f; }
+                    const float d0 = p0 * (__uint_as_float(g[i]) - de[c * 32 + i]) * p.scale;
+                    const float d1 = p1 * (__uint_as_float(g[i + 1]) - de[c * 32 + i + 1]) * p.scale;
+                    pk[i >> 1] = pack_bf16x2(p0, p1);
+                    dk_[i >> 1] = pack_bf16x2(d0, d1);
+                }
+                store_row32_swz(smem_pt, BK * 128, r, c, pk);
+                store_row32_swz(smem_dst, BK * 128, r, c, dk_);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const long long row = (long long)b * p.Nk + k0 + r;
+        store_acc_rows<DP>(tmem_base + Cfg::TM_DK + lane_off, p.dk + row * p.lddk + h * p.d, key_ok, p.d, 1.f);
+        store_acc_rows<DP>(tmem_base + Cfg::TM_DV + lane_off, p.dv + row * p.lddv + h * p.d, key_ok, p.d, 1.f);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ===================================================================================================== dQ
+template <int DP, int BKB, int STAGES>
+struct DqCfg {
+    static constexpr int BM = 128;
+    static constexpr int DCH = DP / 64;
+    static constexpr int QD_BYTES = DCH * BM * 128;             // Q tile (and dO tile)
+    static constexpr int KV_TILE = DCH * BKB * 128;
+    static constexpr int STAGE_BYTES = 2 * KV_TILE;
+    static constexpr int DS_BYTES = (BKB / 64) * BM * 128;
+    static constexpr int SMEM_BYTES = 1024 + 2 * QD_BYTES + STAGES * STAGE_BYTES + DS_BYTES + 256;
+    static constexpr int TM_S = 0, TM_DP = BKB, TM_DQ = 2 * BKB;
+    static_assert(2 * BKB + DP <= 512, "TMEM");
+};
+
+template <int DP, int BKB, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                   const AttnBwdParams p) {
+    using Cfg = DqCfg<DP, BKB, STAGES>;
+    constexpr int BM = Cfg::BM;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_q = smem;
+    uint8_t* smem_do = smem_q + Cfg::QD_BYTES;
+    uint8_t* smem_kv = smem_do + Cfg::QD_BYTES;
+    uint8_t* smem_ds = smem_kv + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ds + Cfg::DS_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + STAGES;
+    uint64_t* s_full = kv_empty + STAGES;
+    uint64_t* p_full = s_full + 1;
+    uint64_t* acc_full = p_full + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = blockIdx.x % p.num_blocks;
+    const int bh = blockIdx.x / p.num_blocks;
+    const int h = bh % p.H, b = bh / p.H;
+    const int q0 = qb * BM;
+    const int num_kv = (p.Nk + BKB - 1) / BKB;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 4);
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, 2 * Cfg::QD_BYTES);
+            for (int c = 0; c < Cfg::DCH; ++c) {
+                tma_load_4d(&tmQ, q_full, smem_q + c * BM * 128, c * 64, h, q0, b);
+                tma_load_4d(&tmDO, q_full, smem_do + c * BM * 128, c * 64, h, q0, b);
+            }
+            int stage = 0; uint32_t phase = 0;
+            for (int i = 0; i < num_kv; ++i) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&kv_full[stage], Cfg::STAGE_BYTES);
+                uint8_t* sk = smem_kv + stage * Cfg::STAGE_BYTES;
+                uint8_t* sv = sk + Cfg::KV_TILE;
+                for (int c = 0; c < Cfg::DCH; ++c) {
+                    tma_load_4d(&tmK, &kv_full[stage], sk + c * BKB * 128, c * 64, h, i * BKB, b);
+                    tma_load_4d(&tmV, &kv_full[stage], sv + c * BKB * 128, c * 64, h, i * BKB, b);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, BKB, 0, 0);
+            constexpr uint32_t idesc_g = make_idesc_bf16(128, DP, 0, 1);
+            mbar_wait(q_full, 0);
+            const uint32_t sq = smem_u32(smem_q), sdo = smem_u32(smem_do), sds = smem_u32(smem_ds);
+            int stage = 0; uint32_t phase = 0;
+            for (int i = 0; i < num_kv; ++i) {
+                mbar_wait(&kv_full[stage], phase);
+                tc_fence_after();
+                const uint32_t sk = smem_u32(smem_kv + stage * Cfg::STAGE_BYTES);
+                const uint32_t sv = sk + Cfg::KV_TILE;
+#pragma unroll
+                for (int kk = 0; kk < DP / 16; ++kk) {
+                    const uint32_t offa = (kk / 4) * (BM * 128) + (kk % 4) * 32;
+                    const uint32_t offb = (kk / 4) * (BKB * 128) + (kk % 4) * 32;
+                    tc_mma_ss(tmem_base + Cfg::TM_S, make_smem_desc(sq + offa, 16, 1024, 2),
+                              make_smem_desc(sk + offb, 16, 1024, 2), idesc_s, kk != 0);
+                }
+#pragma unroll
+                for (int kk = 0; kk < DP / 16; ++kk) {
+                    const uint32_t offa = (kk / 4) * (BM * 128) + (kk % 4) * 32;
+                    const uint32_t offb = (kk / 4) * (BKB * 128) + (kk % 4) * 32;
+                    tc_mma_ss(tmem_base + Cfg::TM_DP, make_smem_desc(sdo + offa, 16, 1024, 2),
+                              make_smem_desc(sv + offb, 16, 1024, 2), idesc_s, kk != 0);
+                }
+                tc_commit(s_full);
+                mbar_wait(p_full, i & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < BKB / 16; ++kk) {
+                    const uint32_t offa = (kk / 4) * (BM * 128) + (kk % 4) * 32;
+                    tc_mma_ss(tmem_base + Cfg::TM_DQ, make_smem_desc(sds + offa, 16, 1024, 2),
+                              make_smem_desc(sk + kk * 2048, BKB * 128, 1024, 2), idesc_g, (i | kk) != 0);
+                }
+                tc_commit(&kv_empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(acc_full);
+        }
+    } else if (warp_idx >= 4) {
+        const int quad = warp_idx & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_off = uint32_t(quad * 32) << 16;
+        const int q = q0 + r;
+        const bool q_ok = q < p.Nq;
+        const long long stat = ((long long)b * p.H + h) * p.Nq + q;
+        const float lse = q_ok ? p.lse[stat] : INFINITY;
+        const float delta = q_ok ? p.delta[stat] : 0.f;
+        for (int i = 0; i < num_kv; ++i) {
+            mbar_wait(s_full, i & 1);
+            tc_fence_after();
+            const int kbase = i * BKB;
+#pragma unroll
+            for (int c = 0; c < BKB / 32; ++c) {
+                uint32_t s[32], g[32];
+                tmem_ld_32x32(tmem_base + Cfg::TM_S + lane_off + c * 32, s);
+                tmem_ld_32x32(tmem_base + Cfg::TM_DP + lane_off + c * 32, g);
+                tc_wait_ld();
+                uint32_t dk_[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(s[j]), p.scale_log2, -lse));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -lse));
+                    if (kbase + c * 32 + j >= p.Nk) p0 = 0.f;
+                    if (kbase + c * 32 + j + 1 >= p.Nk) p1 = 0.f;
+                    const float d0 = p0 * (__uint_as_float(g[j]) - delta) * p.scale;
+                    const float d1 = p1 * (__uint_as_float(g[j + 1]) - delta) * p.scale;
+                    dk_[j >> 1] = pack_bf16x2(d0, d1);
+                }
+                store_row32_swz(smem_ds, BM * 128, r, c, dk_);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const long long row = (long long)b * p.Nq + q;
+        store_acc_rows<DP>(tmem_base + Cfg::TM_DQ + lane_off, p.dq + row * p.lddq + h * p.d, q_ok, p.d, 1.f);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ===================================================================================================== delta
+// delta[b, h, q] = sum_d dO[b, q, h*d + :] * O[b, q, h*d + :]
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ d_o,
+                                  long long lddo, float* __restrict__ delta, int B, int H, int Nq, int d) {
+    const long long total = (long long)B * Nq * H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int h = (int)(i % H);
+        const long long bq = i / H;
+        const int q = (int)(bq % Nq);
+        const int b = (int)(bq / Nq);
+        const __nv_bfloat16* po = o + bq * ldo + h * d;
+        const __nv_bfloat16* pd = d_o + bq * lddo + h * d;
+        float s = 0.f;
+        for (int c = 0; c < d; c += 8) {
+            const uint4 a = *reinterpret_cast<const uint4*>(po + c);
+            const uint4 g = *reinterpret_cast<const uint4*>(pd + c);
+            const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+            const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
+            s += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+        }
+        delta[((long long)b * H + h) * Nq + q] = s;
+    }
+}
+
+template <int DP, int BQ, int STAGES_KV, int BKB, int STAGES_Q>
+static int launch_attn_bwd(const cl_attn_bwd_args* a, cudaStream_t stream) {
+    CUtensorMap tq, tk, tv, tdo;
+    AttnBwdParams p;
+    p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.d = a->d;
+    p.lse = a->lse; p.delta = a->delta;
+    p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.lddq = a->lddq;
+    p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
+    p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.lddv = a->lddv;
+    p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+    {
+        const long long total = (long long)a->B * a->Nq * a->H;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+        attn_delta_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->o), a->ldo,
+                                                      reinterpret_cast<const __nv_bfloat16*>(a->d_o), a->lddo, a->delta,
+                                                      a->B, a->H, a->Nq, a->d);
+        count_launch();
+    }
+    if (a->dk != nullptr) {
+        using Cfg = DkvCfg<DP, BQ, STAGES_KV>;
+        CL_CHECK(make_head_map(&tq, a->q, a->B, a->H, a->Nq, a->d, a->ldq, BQ));
+        CL_CHECK(make_head_map(&tdo, a->d_o, a->B, a->H, a->Nq, a->d, a->lddo, BQ));
+        CL_CHECK(make_head_map(&tk, a->k, a->B, a->H, a->Nk, a->d, a->ldk, 128));
+        CL_CHECK(make_head_map(&tv, a->v, a->B, a->H, a->Nk, a->d, a->ldv, 128));
+        static bool done = false;
+        if (!done) {
+            CL_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<DP, BQ, STAGES_KV>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+            done = true;
+        }
+        p.num_blocks = (a->Nk + 127) / 128;
+        attn_bwd_dkv_kernel<DP, BQ, STAGES_KV><<<a->B * a->H * p.num_blocks, 256, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+        count_launch();
+    }
+    if (a->dq != nullptr) {
+        using Cfg = DqCfg<DP, BKB, STAGES_Q>;
+        CL_CHECK(make_head_map(&tq, a->q, a->B, a->H, a->Nq, a->d, a->ldq, 128));
+        CL_CHECK(make_head_map(&tdo, a->d_o, a->B, a->H, a->Nq, a->d, a->lddo, 128));
+        CL_CHECK(make_head_map(&tk, a->k, a->B, a->H, a->Nk, a->d, a->ldk, BKB));
+        CL_CHECK(make_head_map(&tv, a->v, a->B, a->H, a->Nk, a->d, a->ldv, BKB));
+        static bool done = false;
+        if (!done) {
+            CL_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel<DP, BKB, STAGES_Q>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+            done = true;
+        }
+        p.num_blocks = (a->Nq + 127) / 128;
+        attn_bwd_dq_kernel<DP, BKB, STAGES_Q><<<a->B * a->H * p.num_blocks, 256, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+        count_launch();
+    }
+    CL_CUDA_CHECK(cudaGetLastError());
+    return CL_OK;
+}
+
+}  // namespace clb
+
+using namespace clb;
+
+extern "C" int cl_attn_bwd(const cl_attn_bwd_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a || !a->q || !a->k || !a->v || !a->o || !a->d_o || !a->lse || !a->delta)
+        return set_error(CL_ERR_INVALID, "cl_attn_bwd: null pointer");
+    if ((a->dk == nullptr) != (a->dv == nullptr)) return set_error(CL_ERR_INVALID, "cl_attn_bwd: dk and dv go together");
+    if (a->d % 8 != 0 || a->d <= 0 || a->d > 192) return set_error(CL_ERR_UNSUPPORTED, "cl_attn_bwd: head dim must be a multiple of 8, <= 192");
+    if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8) || (a->lddo % 8) || (a->dq && a->lddq % 8) ||
+        (a->dk && ((a->lddk % 8) || (a->lddv % 8))))
+        return set_error(CL_ERR_INVALID, "cl_attn_bwd: row strides must be multiples of 8");
+    if (a->d <= 64) return launch_attn_bwd<64, 128, 2, 128, 2>(a, stream);
+    if (a->d <= 128) return launch_attn_bwd<128, 128, 1, 128, 1>(a, stream);
+    return launch_attn_bwd<192, 64, 1, 64, 2>(a, stream);
+}

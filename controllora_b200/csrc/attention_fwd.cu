@@ -1,0 +1,342 @@
+// K2 (forward) — fused scaled-dot-product attention on tcgen05 / TMEM for sm_100a.
+//
+//   O = softmax(Q K^T * scale) V,   per (batch, head);  Q/K/V/O are bf16 token matrices [B, N, H*d] (row stride ld*),
+//   head h = columns [h*d, (h+1)*d).  The N x N probability matrix is never written to HBM (the reference
+//   materialises it: attn.get_attention_scores + torch.bmm, models.py:140-141, 270-271, 407-408).
+//
+// One CTA = one (batch, head, 128-query block); 8 warps:
+//   warp 0     TMA producer: Q once, then a ring of K/V tiles (4-D tensor maps {d, H, N, B}; the head dim is padded
+//              to a multiple of 64 purely by TMA out-of-bounds zero fill — nothing is padded in HBM)
+//   warp 1     MMA issuer:   S = Q K^T      (A, B K-major from smem, D in TMEM columns [0, BLOCK_N))
+//                            O += P V       (A = P K-major from smem, B = V *MN-major* from smem, D in TMEM)
+//   warp 2     TMEM allocator
+//   warps 4-7  softmax: thread r owns query row r == TMEM lane r (no cross-thread reductions): online max / sum in
+//              the exp2 domain, rescales O in TMEM, writes P (bf16) into the 128B-swizzled K-major smem tile.
+// Per-CTA work is serialised S -> softmax -> PV; the kernel is sized so that two CTAs are resident per SM and one
+// CTA's softmax (MUFU-bound) overlaps the other's tensor-core work.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/controllora_b200.h"
+
+namespace clb {
+
+struct AttnFwdParams {
+    int B, H, Nq, Nk, d;
+    __nv_bfloat16* o;
+    long long ldo;
+    float* lse;
+    float scale_log2;
+    int num_q_blocks;
+};
+
+template <int DP, int BLOCK_N, int STAGES>
+struct AttnFwdCfg {
+    static constexpr int BLOCK_M = 128;
+    static constexpr int DCH = DP / 64;                       // 64-column chunks of the (padded) head dim
+    static constexpr int NCH = BLOCK_N / 64;                  // 64-key chunks of the P tile
+    static constexpr int Q_BYTES = DCH * BLOCK_M * 128;
+    static constexpr int KV_TILE_BYTES = DCH * BLOCK_N * 128; // one K (or V) tile
+    static constexpr int STAGE_BYTES = 2 * KV_TILE_BYTES;
+    static constexpr int P_BYTES = NCH * BLOCK_M * 128;
+    static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + P_BYTES + 128;
+    static constexpr int TMEM_NEED = BLOCK_N + DP;
+    static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+    static_assert(DP % 64 == 0 && BLOCK_N % 64 == 0, "tile dims");
+    static_assert(DP <= 256 && BLOCK_N <= 256, "UMMA N limit");
+};
+
+template <int DP, int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(256, (DP <= 64) ? 2 : 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+    using Cfg = AttnFwdCfg<DP, BLOCK_N, STAGES>;
+    constexpr int BLOCK_M = Cfg::BLOCK_M;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // no static shared memory in this kernel: the dynamic segment starts 1024-byte aligned (checked below)
+    uint8_t* smem = smem_raw;
+    uint8_t* smem_q = smem;
+    uint8_t* smem_kv = smem_q + Cfg::Q_BYTES;
+    uint8_t* smem_p = smem_kv + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + Cfg::P_BYTES);
+    uint64_t* q_full = bars;                 // 1
+    uint64_t* kv_full = bars + 1;            // STAGES
+    uint64_t* kv_empty = kv_full + STAGES;   // STAGES
+    uint64_t* s_full = kv_empty + STAGES;    // 1
+    uint64_t* p_full = s_full + 1;           // 1
+    uint64_t* o_full = p_full + 1;           // 1
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 1);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int qb = blockIdx.x % p.num_q_blocks;
+    const int bh = blockIdx.x / p.num_q_blocks;
+    const int h = bh % p.H;
+    const int b = bh / p.H;
+    const int q0 = qb * BLOCK_M;
+    const int num_kv = (p.Nk + BLOCK_N - 1) / BLOCK_N;
+
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+        printf("attn_fwd: dynamic smem base not 1024-aligned\n");
+        __trap();
+    }
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 4);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp_idx == 2) {
+        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_s = tmem_base;
+    const uint32_t tmem_o = tmem_base + BLOCK_N;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+            for (int c = 0; c < Cfg::DCH; ++c)
+                tma_load_4d(&tmQ, q_full, smem_q + c * BLOCK_M * 128, c * 64, h, q0, b);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < num_kv; ++i) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&kv_full[stage], Cfg::STAGE_BYTES);
+                uint8_t* sk = smem_kv + stage * Cfg::STAGE_BYTES;
+                uint8_t* sv = sk + Cfg::KV_TILE_BYTES;
+                for (int c = 0; c < Cfg::DCH; ++c) {
+                    tma_load_4d(&tmK, &kv_full[stage], sk + c * BLOCK_N * 128, c * 64, h, i * BLOCK_N, b);
+                    tma_load_4d(&tmV, &kv_full[stage], sv + c * BLOCK_N * 128, c * 64, h, i * BLOCK_N, b);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(BLOCK_M, DP, 0, 1);  // B = V is MN-major
+            mbar_wait(q_full, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t sq = smem_u32(smem_q);
+            const uint32_t sp = smem_u32(smem_p);
+            for (int i = 0; i < num_kv; ++i) {
+                mbar_wait(&kv_full[stage], phase);
+                tc_fence_after();
+                const uint32_t sk = smem_u32(smem_kv + stage * Cfg::STAGE_BYTES);
+                const uint32_t sv = sk + Cfg::KV_TILE_BYTES;
+                // S = Q K^T  (K loop over the padded head dim)
+#pragma unroll
+                for (int kk = 0; kk < DP / 16; ++kk) {
+                    const uint32_t off = (kk / 4) * (BLOCK_M * 128) + (kk % 4) * 32;
+                    const uint32_t offk = (kk / 4) * (BLOCK_N * 128) + (kk % 4) * 32;
+                    tc_mma_ss(tmem_s, make_smem_desc(sq + off, 16, 1024, 2), make_smem_desc(sk + offk, 16, 1024, 2),
+                              idesc_s, kk != 0 ? 1u : 0u);
+                }
+                tc_commit(s_full);
+                // O += P V  (K loop over the keys of this block)
+                mbar_wait(p_full, i & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < BLOCK_N / 16; ++kk) {
+                    const uint32_t offp = (kk / 4) * (BLOCK_M * 128) + (kk % 4) * 32;
+                    const uint64_t adesc = make_smem_desc(sp + offp, 16, 1024, 2);
+                    // V tile: [keys][64 d] rows of 128 B; MN-major: LBO = next 64-d chunk, SBO = next 8 keys
+                    const uint64_t bdesc = make_smem_desc(sv + kk * 2048, BLOCK_N * 128, 1024, 2);
+                    tc_mma_ss(tmem_o, adesc, bdesc, idesc_o, (i | kk) != 0 ? 1u : 0u);
+                }
+                tc_commit(&kv_empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(o_full);
+        }
+    } else if (warp_idx >= 4) {
+        const int quad = warp_idx & 3;
+        const int r = quad * 32 + lane;                 // query row within the block == TMEM lane
+        const uint32_t lane_off = uint32_t(quad * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int i = 0; i < num_kv; ++i) {
+            mbar_wait(s_full, i & 1);
+            tc_fence_after();
+            const int kbase = i * BLOCK_N;
+            // ---- pass 1: row max
+            float mloc = -INFINITY;
+            const bool tail = kbase + BLOCK_N > p.Nk;   // only the last key block needs column masking
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_s + lane_off + c * 32, v);
+                tc_wait_ld();
+                if (!tail) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, __uint_as_float(v[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = (kbase + c * 32 + j < p.Nk) ? __uint_as_float(v[j]) : -INFINITY;
+                        mloc = fmaxf(mloc, s);
+                    }
+                }
+            }
+            const float m_new = fmaxf(m_run, mloc * p.scale_log2);
+            const float alpha = fast_exp2(m_run - m_new);   // first block: exp2(-inf) = 0
+            l_run *= alpha;
+            m_run = m_new;
+            // ---- rescale the O accumulator (S_i was issued after PV_{i-1}: s_full implies PV_{i-1} retired);
+            //      skipped when no row of this warp raised its max (warp-uniform: tcgen05.ld/st are .aligned)
+            if (i > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+                for (int c = 0; c < DP / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_o + lane_off + c * 32, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                    asm volatile(
+                        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(
+                            tmem_o + lane_off + c * 32),
+                        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+                        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+                        "r"(v[30]), "r"(v[31])
+                        : "memory");
+                }
+                tc_wait_st();
+            }
+            // ---- pass 2: P = exp2(S*scale - m), row sum, bf16 -> swizzled K-major smem tile
+            float lsum = 0.f;
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_s + lane_off + c * 32, v);
+                tc_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -m_new));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -m_new));
+                    if (tail) {
+                        if (kbase + c * 32 + j >= p.Nk) p0 = 0.f;
+                        if (kbase + c * 32 + j + 1 >= p.Nk) p1 = 0.f;
+                    }
+                    lsum += p0 + p1;
+                    pk[j >> 1] = pack_bf16x2(p0, p1);
+                }
+                // 32 keys = 64 B = four 16-byte chunks of this row
+                uint8_t* rowp = smem_p + (c / 2) * (BLOCK_M * 128) + r * 128;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int chunk = (c & 1) * 4 + q;
+                    *reinterpret_cast<uint4*>(rowp + ((chunk ^ (r & 7)) << 4)) =
+                        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
+            }
+            l_run += lsum;
+            tc_fence_before();
+            fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l -> bf16 -> global; LSE (log2 domain) for the backward pass
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        const int q = q0 + r;
+        const float inv_l = 1.f / l_run;
+        __nv_bfloat16* orow = p.o + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
+#pragma unroll
+        for (int c = 0; c < DP / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_o + lane_off + c * 32, v);
+            tc_wait_ld();
+            if (q < p.Nq) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const int col = c * 32 + j;
+                    if (col < p.d) {   // d % 8 == 0
+                        uint4 o4;
+                        o4.x = pack_bf16x2(__uint_as_float(v[j]) * inv_l, __uint_as_float(v[j + 1]) * inv_l);
+                        o4.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv_l, __uint_as_float(v[j + 3]) * inv_l);
+                        o4.z = pack_bf16x2(__uint_as_float(v[j + 4]) * inv_l, __uint_as_float(v[j + 5]) * inv_l);
+                        o4.w = pack_bf16x2(__uint_as_float(v[j + 6]) * inv_l, __uint_as_float(v[j + 7]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + col) = o4;
+                    }
+                }
+            }
+        }
+        if (q < p.Nq && p.lse != nullptr) p.lse[((long long)b * p.H + h) * p.Nq + q] = m_run + log2f(l_run);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+int make_head_map(CUtensorMap* tm, const void* ptr, int B, int H, int N, int d, long long ld, int box_rows) {
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)N, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)N * ld * 2};
+    uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
+    return get_tensor_map(tm, ptr, 4, dims, strides, box, true);
+}
+
+template <int DP, int BLOCK_N, int STAGES>
+static int launch_attn_fwd(const cl_attn_fwd_args* a, cudaStream_t stream) {
+    using Cfg = AttnFwdCfg<DP, BLOCK_N, STAGES>;
+    CUtensorMap tq, tk, tv;
+    CL_CHECK(make_head_map(&tq, a->q, a->B, a->H, a->Nq, a->d, a->ldq, 128));
+    CL_CHECK(make_head_map(&tk, a->k, a->B, a->H, a->Nk, a->d, a->ldk, BLOCK_N));
+    CL_CHECK(make_head_map(&tv, a->v, a->B, a->H, a->Nk, a->d, a->ldv, BLOCK_N));
+    AttnFwdParams p;
+    p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.d = a->d;
+    p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.ldo = a->ldo; p.lse = a->lse;
+    p.scale_log2 = a->scale * 1.4426950408889634f;
+    p.num_q_blocks = (a->Nq + 127) / 128;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CL_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<DP, BLOCK_N, STAGES>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int grid = a->B * a->H * p.num_q_blocks;
+    attn_fwd_kernel<DP, BLOCK_N, STAGES><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    count_launch();
+    CL_CUDA_CHECK(cudaGetLastError());
+    return CL_OK;
+}
+
+}  // namespace clb
+
+using namespace clb;
+
+extern "C" int cl_attn_fwd(const cl_attn_fwd_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a || !a->q || !a->k || !a->v || !a->o) return set_error(CL_ERR_INVALID, "cl_attn_fwd: null pointer");
+    if (a->d % 8 != 0 || a->d <= 0 || a->d > 192) return set_error(CL_ERR_UNSUPPORTED, "cl_attn_fwd: head dim must be a multiple of 8, <= 192");
+    if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8)) return set_error(CL_ERR_INVALID, "cl_attn_fwd: row strides must be multiples of 8");
+    if (a->B <= 0 || a->H <= 0 || a->Nq <= 0 || a->Nk <= 0) return set_error(CL_ERR_INVALID, "cl_attn_fwd: dims");
+    if (a->d <= 64) return launch_attn_fwd<64, 128, 2>(a, stream);
+    if (a->d <= 128) return launch_attn_fwd<128, 128, 2>(a, stream);
+    return launch_attn_fwd<192, 64, 2>(a, stream);
+}

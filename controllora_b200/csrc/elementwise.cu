@@ -1,0 +1,309 @@
+// HBM-bound glue kernels of the UNet path (all 16-byte vectorised, grid-stride, channels-last bf16):
+// GEGLU, residual adds, nearest-2x upsample (+ its adjoint), channel concat / split, zero insertion for the
+// stride-2 conv adjoint, bf16<->fp32 layout changes at the UNet boundary.
+#include <stdio.h>
+
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/controllora_b200.h"
+
+namespace clb {
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+static inline int ew_blocks(long long work, int threads = 256) {
+    long long b = (work + threads - 1) / threads;
+    const long long cap = (long long)num_sms() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+#define GRID_STRIDE(i, n) \
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+// ---------------------------------------------------------------- GEGLU: out = a * gelu_erf(g), p = [a | g]
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ out, long long T, int F) {
+    const int ch = F / 8;
+    GRID_STRIDE(i, T * ch) {
+        const long long t = i / ch;
+        const int c = (int)(i % ch) * 8;
+        float a[8], g[8], o[8];
+        ld8(p + t * 2 * F + c, a);
+        ld8(p + t * 2 * F + F + c, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = a[j] * gelu_f(g[j]);
+        st8(out + t * F + c, o);
+    }
+}
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ p, const __nv_bfloat16* __restrict__ dout,
+                                 __nv_bfloat16* __restrict__ dp, long long T, int F) {
+    const int ch = F / 8;
+    GRID_STRIDE(i, T * ch) {
+        const long long t = i / ch;
+        const int c = (int)(i % ch) * 8;
+        float a[8], g[8], d[8], da[8], dg[8];
+        ld8(p + t * 2 * F + c, a);
+        ld8(p + t * 2 * F + F + c, g);
+        ld8(dout + t * F + c, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            da[j] = d[j] * gelu_f(g[j]);
+            dg[j] = d[j] * a[j] * gelu_grad_f(g[j]);
+        }
+        st8(dp + t * 2 * F + c, da);
+        st8(dp + t * 2 * F + F + c, dg);
+    }
+}
+
+// ---------------------------------------------------------------- out = a + b
+__global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                           __nv_bfloat16* __restrict__ out, long long n8) {
+    GRID_STRIDE(i, n8) {
+        float x[8], y[8];
+        ld8(a + i * 8, x);
+        ld8(b + i * 8, y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += y[j];
+        st8(out + i * 8, x);
+    }
+}
+
+// ---------------------------------------------------------------- nearest 2x upsample and its adjoint
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int H, int W, int C) {
+    const int ch = C / 8;
+    const long long total = (long long)n * 2 * H * 2 * W * ch;
+    GRID_STRIDE(i, total) {
+        const int c = (int)(i % ch);
+        long long r = i / ch;
+        const int wo = (int)(r % (2 * W)); r /= 2 * W;
+        const int ho = (int)(r % (2 * H));
+        const int b = (int)(r / (2 * H));
+        const uint4 v = *reinterpret_cast<const uint4*>(x + (((long long)b * H + ho / 2) * W + wo / 2) * C + c * 8);
+        *reinterpret_cast<uint4*>(y + i * 8) = v;
+    }
+}
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int n, int H, int W,
+                                      int C, int accumulate) {
+    const int ch = C / 8;
+    const long long total = (long long)n * H * W * ch;
+    GRID_STRIDE(i, total) {
+        const int c = (int)(i % ch);
+        long long r = i / ch;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        float acc[8];
+        if (accumulate) ld8(dx + i * 8, acc);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        }
+#pragma unroll
+        for (int dyy = 0; dyy < 2; ++dyy)
+#pragma unroll
+            for (int dxx = 0; dxx < 2; ++dxx) {
+                float v[8];
+                ld8(dy + (((long long)b * 2 * H + 2 * h + dyy) * 2 * W + 2 * w + dxx) * C + c * 8, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[j];
+            }
+        st8(dx + i * 8, acc);
+    }
+}
+
+// ---------------------------------------------------------------- zero insertion (adjoint of stride-2 sampling)
+// out [n, 2H, 2W, C] = 0 except out[b, 2h+off, 2w+off, :] = x[b, h, w, :]
+__global__ void zero_insert2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int H, int W,
+                                     int C, int off) {
+    const int ch = C / 8;
+    const long long total = (long long)n * 2 * H * 2 * W * ch;
+    GRID_STRIDE(i, total) {
+        const int c = (int)(i % ch);
+        long long r = i / ch;
+        const int wo = (int)(r % (2 * W)); r /= 2 * W;
+        const int ho = (int)(r % (2 * H));
+        const int b = (int)(r / (2 * H));
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if ((ho & 1) == off && (wo & 1) == off)
+            v = *reinterpret_cast<const uint4*>(x + (((long long)b * H + ho / 2) * W + wo / 2) * C + c * 8);
+        *reinterpret_cast<uint4*>(y + i * 8) = v;
+    }
+}
+
+// ---------------------------------------------------------------- channel concat / split on [M, C] matrices
+__global__ void concat_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                              __nv_bfloat16* __restrict__ out, long long M, int Ca, int Cb) {
+    const int ch = (Ca + Cb) / 8, cha = Ca / 8;
+    GRID_STRIDE(i, M * ch) {
+        const long long m = i / ch;
+        const int c = (int)(i % ch);
+        const uint4 v = (c < cha) ? *reinterpret_cast<const uint4*>(a + m * Ca + c * 8)
+                                  : *reinterpret_cast<const uint4*>(b + m * Cb + (c - cha) * 8);
+        *reinterpret_cast<uint4*>(out + i * 8) = v;
+    }
+}
+// dst[m, :] (+)= src[m, c_off : c_off + Cd]
+__global__ void slice_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long M, int Cs,
+                             int c_off, int Cd, int accumulate) {
+    const int ch = Cd / 8;
+    GRID_STRIDE(i, M * ch) {
+        const long long m = i / ch;
+        const int c = (int)(i % ch);
+        float v[8];
+        ld8(src + m * Cs + c_off + c * 8, v);
+        if (accumulate) {
+            float o[8];
+            ld8(dst + i * 8, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += o[j];
+        }
+        st8(dst + i * 8, v);
+    }
+}
+
+// ---------------------------------------------------------------- layout / dtype changes at the boundary
+// NCHW (fp32 or bf16) -> NHWC bf16, and NHWC bf16 -> NCHW fp32 (used for control states / their gradients)
+template <typename TIn>
+__global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? (float)x[((long long)b * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < C) y[((long long)b * HW + p) * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+}
+__global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n, int C, int HW,
+                                        int accumulate) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(x[((long long)b * HW + p) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        if (c < C && p < HW) {
+            const long long o = ((long long)b * C + c) * HW + p;
+            y[o] = accumulate ? y[o] + tile[threadIdx.x][i] : tile[threadIdx.x][i];
+        }
+    }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+    GRID_STRIDE(i, n) y[i] = __float2bfloat16(x[i]);
+}
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+    GRID_STRIDE(i, n) y[i] = __bfloat162float(x[i]);
+}
+
+}  // namespace clb
+
+using namespace clb;
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BFW(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define STREAM cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_)
+#define DONE()                           \
+    count_launch();                      \
+    CL_CUDA_CHECK(cudaGetLastError());   \
+    return CL_OK
+
+extern "C" int cl_geglu_fwd(const void* p, void* out, int64_t T, int F, void* stream_) {
+    STREAM;
+    if (!p || !out || F % 8) return set_error(CL_ERR_INVALID, "cl_geglu_fwd: bad args");
+    geglu_fwd_kernel<<<ew_blocks(T * (F / 8)), 256, 0, stream>>>(BF(p), BFW(out), T, F);
+    DONE();
+}
+extern "C" int cl_geglu_bwd(const void* p, const void* dout, void* dp, int64_t T, int F, void* stream_) {
+    STREAM;
+    if (!p || !dout || !dp || F % 8) return set_error(CL_ERR_INVALID, "cl_geglu_bwd: bad args");
+    geglu_bwd_kernel<<<ew_blocks(T * (F / 8)), 256, 0, stream>>>(BF(p), BF(dout), BFW(dp), T, F);
+    DONE();
+}
+extern "C" int cl_add(const void* a, const void* b, void* out, int64_t n, void* stream_) {
+    STREAM;
+    if (!a || !b || !out || n % 8) return set_error(CL_ERR_INVALID, "cl_add: bad args (n %% 8)");
+    add_kernel<<<ew_blocks(n / 8), 256, 0, stream>>>(BF(a), BF(b), BFW(out), n / 8);
+    DONE();
+}
+extern "C" int cl_upsample2x_fwd(const void* x, void* y, int n, int H, int W, int C, void* stream_) {
+    STREAM;
+    if (!x || !y || C % 8) return set_error(CL_ERR_INVALID, "cl_upsample2x_fwd: bad args");
+    upsample2x_kernel<<<ew_blocks((long long)n * 4 * H * W * (C / 8)), 256, 0, stream>>>(BF(x), BFW(y), n, H, W, C);
+    DONE();
+}
+extern "C" int cl_upsample2x_bwd(const void* dy, void* dx, int n, int H, int W, int C, int accumulate, void* stream_) {
+    STREAM;
+    if (!dy || !dx || C % 8) return set_error(CL_ERR_INVALID, "cl_upsample2x_bwd: bad args");
+    upsample2x_bwd_kernel<<<ew_blocks((long long)n * H * W * (C / 8)), 256, 0, stream>>>(BF(dy), BFW(dx), n, H, W, C, accumulate);
+    DONE();
+}
+extern "C" int cl_zero_insert2x(const void* x, void* y, int n, int H, int W, int C, int off, void* stream_) {
+    STREAM;
+    if (!x || !y || C % 8 || (off != 0 && off != 1)) return set_error(CL_ERR_INVALID, "cl_zero_insert2x: bad args");
+    zero_insert2x_kernel<<<ew_blocks((long long)n * 4 * H * W * (C / 8)), 256, 0, stream>>>(BF(x), BFW(y), n, H, W, C, off);
+    DONE();
+}
+extern "C" int cl_concat_channels(const void* a, const void* b, void* out, int64_t M, int Ca, int Cb, void* stream_) {
+    STREAM;
+    if (!a || !b || !out || Ca % 8 || Cb % 8) return set_error(CL_ERR_INVALID, "cl_concat_channels: bad args");
+    concat_kernel<<<ew_blocks(M * ((Ca + Cb) / 8)), 256, 0, stream>>>(BF(a), BF(b), BFW(out), M, Ca, Cb);
+    DONE();
+}
+extern "C" int cl_slice_channels(const void* src, void* dst, int64_t M, int Cs, int c_off, int Cd, int accumulate,
+                                 void* stream_) {
+    STREAM;
+    if (!src || !dst || Cs % 8 || Cd % 8 || c_off % 8 || c_off + Cd > Cs) return set_error(CL_ERR_INVALID, "cl_slice_channels: bad args");
+    slice_kernel<<<ew_blocks(M * (Cd / 8)), 256, 0, stream>>>(BF(src), BFW(dst), M, Cs, c_off, Cd, accumulate);
+    DONE();
+}
+extern "C" int cl_nchw_to_nhwc(const void* x, int x_is_fp32, void* y, int n, int C, int HW, void* stream_) {
+    STREAM;
+    if (!x || !y) return set_error(CL_ERR_INVALID, "cl_nchw_to_nhwc: null");
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, n), block(32, 8);
+    if (x_is_fp32) nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(x), BFW(y), n, C, HW);
+    else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(BF(x), BFW(y), n, C, HW);
+    DONE();
+}
+extern "C" int cl_nhwc_to_nchw_f32(const void* x, float* y, int n, int C, int HW, int accumulate, void* stream_) {
+    STREAM;
+    if (!x || !y) return set_error(CL_ERR_INVALID, "cl_nhwc_to_nchw_f32: null");
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, n), block(32, 8);
+    nhwc_to_nchw_f32_kernel<<<grid, block, 0, stream>>>(BF(x), y, n, C, HW, accumulate);
+    DONE();
+}
+extern "C" int cl_f32_to_bf16(const float* x, void* y, int64_t n, void* stream_) {
+    STREAM;
+    if (!x || !y) return set_error(CL_ERR_INVALID, "cl_f32_to_bf16: null");
+    f32_to_bf16_kernel<<<ew_blocks(n), 256, 0, stream>>>(x, BFW(y), n);
+    DONE();
+}
+extern "C" int cl_bf16_to_f32(const void* x, float* y, int64_t n, void* stream_) {
+    STREAM;
+    if (!x || !y) return set_error(CL_ERR_INVALID, "cl_bf16_to_f32: null");
+    bf16_to_f32_kernel<<<ew_blocks(n), 256, 0, stream>>>(BF(x), y, n);
+    DONE();
+}

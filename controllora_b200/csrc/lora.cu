@@ -1,0 +1,295 @@
+// LoRA side-path kernels: operand packing for the fused GEMM epilogue and the skinny rank-r reductions of the
+// backward pass (dA, dB) — everything that models.py:89-97,185 (LoRALinearLayer instances) adds to autograd, minus
+// the parts already folded into the tcgen05 GEMM.  All HBM-bound: each activation matrix is read exactly once.
+#include <stdio.h>
+
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/controllora_b200.h"
+
+namespace clb {
+
+// ------------------------------------------------------------------------------------------ batched packing
+// One launch prepares every LoRA operand of a step from the fp32 master weights (descriptor table in device memory):
+//   kind 0: ext[16, K] bf16   rows row_off+j <- hi(src(j, k)), rows 8+row_off+j <- lo(src(j, k)), j < r
+//   kind 1: table[N, rp] fp32  table[n*rp + row_off + j] <- src(j, n), j < r
+// with src(j, k) = src[j*s_j + k*s_k].  Rows / columns not covered by any descriptor must be pre-zeroed once.
+__global__ void __launch_bounds__(256)
+lora_pack_kernel(const cl_pack_desc* __restrict__ descs, int n_desc) {
+    const int di = blockIdx.y;
+    if (di >= n_desc) return;
+    const cl_pack_desc d = descs[di];
+    const float* src = reinterpret_cast<const float*>(d.src);
+    const long long total = (long long)d.r * d.K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i / d.K);
+        const int k = (int)(i % d.K);
+        const float v = src[(long long)j * d.s_j + (long long)k * d.s_k];
+        if (d.kind == 0) {
+            __nv_bfloat16* ext = reinterpret_cast<__nv_bfloat16*>(d.dst);
+            const __nv_bfloat16 hi = __float2bfloat16(v);
+            const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+            ext[(long long)(d.row_off + j) * d.ld + k] = hi;
+            ext[(long long)(8 + d.row_off + j) * d.ld + k] = lo;
+        } else {
+            float* tab = reinterpret_cast<float*>(d.dst);
+            tab[(long long)k * d.ld + d.row_off + j] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ out[j, c] += alpha * sum_m a[m, j] * b[m, c]
+// a: fp32 [M, lda] (first r columns used), b: bf16 [M, ldb] (C columns), out fp32 with strides (so_j, so_c).
+// Thread layout as in the GroupNorm reduction: a thread owns one 8-column chunk for all rows of its slab.
+template <int R>
+__global__ void __launch_bounds__(512)
+skinny_atb_kernel(const float* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b, long long ldb,
+                  float* __restrict__ out, long long so_j, long long so_c, float alpha, int M, int C, int rows_per_cta) {
+    const int chunks = C / 8;
+    const int rows_par = blockDim.x / chunks;
+    const int chunk = threadIdx.x % chunks;
+    const int rsub = threadIdx.x / chunks;
+    const bool active = rsub < rows_par;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int row1 = min(M, row0 + rows_per_cta);
+    float acc[R][8];
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+    if (active) {
+        for (int m = row0 + rsub; m < row1; m += rows_par) {
+            const uint4 u = *reinterpret_cast<const uint4*>(b + (long long)m * ldb + chunk * 8);
+            const float2 b0 = unpack_bf16x2(u.x), b1 = unpack_bf16x2(u.y), b2 = unpack_bf16x2(u.z), b3 = unpack_bf16x2(u.w);
+            const float bv[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+            float av[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) av[j] = a[(long long)m * lda + j];
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[j][i] += av[j] * bv[i];
+        }
+    }
+    // combine the row-parallel partials of this CTA in shared memory, then one global atomic per output element
+    extern __shared__ float sh[];   // [R][C]
+    for (int i = threadIdx.x; i < R * C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(&sh[j * C + chunk * 8 + i], acc[j][i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
+        const int j = i / C, c = i % C;
+        atomicAdd(&out[j * so_j + c * so_c], alpha * sh[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ e[m, j] = sum_n a[m, n] * u[n*rp + j]
+// a bf16 [M, lda], u fp32 [N, rp]; one warp per row.
+template <int RP>
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const float* __restrict__ u, float* __restrict__ e, int M, int N) {
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= M) return;
+    float acc[RP];
+#pragma unroll
+    for (int j = 0; j < RP; ++j) acc[j] = 0.f;
+    for (int n = lane * 8; n < N; n += 256) {
+        const uint4 v = *reinterpret_cast<const uint4*>(a + (long long)m * lda + n);
+        const float2 a0 = unpack_bf16x2(v.x), a1 = unpack_bf16x2(v.y), a2 = unpack_bf16x2(v.z), a3 = unpack_bf16x2(v.w);
+        const float av[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < RP; ++j) acc[j] += av[i] * u[(long long)(n + i) * RP + j];
+    }
+#pragma unroll
+    for (int j = 0; j < RP; ++j) {
+        const float s = warp_sum(acc[j]);
+        if (lane == 0) e[(long long)m * RP + j] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ per-row tiny matmul
+// out[m, i] (+)= alpha * sum_j a[m*lda + j] * w[i*sw_i + j*sw_j],  i < I, j < J   (I, J <= 8)
+// out_mode 0: fp32 out[m*ldo + i] ; out_mode 1: bf16 hi/lo pair -> out_bf[m*ldo + col_off + i], [.. + lo_off + i]
+__global__ void __launch_bounds__(256)
+rowmat_kernel(const float* __restrict__ a, int lda, const float* __restrict__ w, int sw_i, int sw_j, int I, int J,
+              float alpha, void* __restrict__ out, int ldo, int out_mode, int col_off, int lo_off, int accumulate, int M) {
+    __shared__ float sw[64];
+    if (threadIdx.x < I * J) sw[threadIdx.x] = w[(threadIdx.x / J) * sw_i + (threadIdx.x % J) * sw_j];
+    __syncthreads();
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
+        float av[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) av[j] = (j < J) ? a[(long long)m * lda + j] : 0.f;
+        for (int i = 0; i < I; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < J) s += av[j] * sw[i * J + j];
+            s *= alpha;
+            if (out_mode == 0) {
+                float* o = reinterpret_cast<float*>(out) + (long long)m * ldo + i;
+                *o = accumulate ? *o + s : s;
+            } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + (long long)m * ldo + col_off + i;
+                const __nv_bfloat16 hi = __float2bfloat16(s);
+                o[0] = hi;
+                o[lo_off] = __float2bfloat16(s - __bfloat162float(hi));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ out[i, j] += alpha * sum_m a[m, i] * b[m, j]
+__global__ void __launch_bounds__(256)
+skinny_small_kernel(const float* __restrict__ a, int lda, int I, const float* __restrict__ b, int ldb, int J,
+                    float* __restrict__ out, float alpha, int M) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
+        float av[8], bv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) av[i] = (i < I) ? a[(long long)m * lda + i] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bv[j] = (j < J) ? b[(long long)m * ldb + j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] += av[i] * bv[j];
+    }
+    __shared__ float sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float s = warp_sum(acc[i][j]);
+            if ((threadIdx.x & 31) == 0 && i < I && j < J) atomicAdd(&sh[i * 8 + j], s);
+        }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int i = threadIdx.x / 8, j = threadIdx.x % 8;
+        if (i < I && j < J) atomicAdd(&out[i * J + j], alpha * sh[threadIdx.x]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ weight-space tiny matmul (fp32)
+// out[i*so_i + k*so_k] (+)= alpha * sum_j a[i*sa_i + j*sa_j] * b[j*sb_j + k*sb_k]
+__global__ void __launch_bounds__(256)
+small_matmul_kernel(const float* __restrict__ a, long long sa_i, long long sa_j, const float* __restrict__ b, long long sb_j,
+                    long long sb_k, float* __restrict__ out, long long so_i, long long so_k, int I, int J, int K, float alpha,
+                    int accumulate) {
+    const long long total = (long long)I * K;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / K), k = (int)(t % K);
+        float s = 0.f;
+        for (int j = 0; j < J; ++j) s += a[i * sa_i + j * sa_j] * b[j * sb_j + k * sb_k];
+        float* o = out + i * so_i + k * so_k;
+        *o = accumulate ? *o + alpha * s : alpha * s;
+    }
+}
+
+}  // namespace clb
+
+using namespace clb;
+#define STREAM cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_)
+#define DONE()                         \
+    count_launch();                    \
+    CL_CUDA_CHECK(cudaGetLastError()); \
+    return CL_OK
+
+extern "C" int cl_lora_pack_batch(const cl_pack_desc* descs_dev, int n_desc, int max_elems, void* stream_) {
+    STREAM;
+    if (!descs_dev || n_desc <= 0) return set_error(CL_ERR_INVALID, "cl_lora_pack_batch: bad args");
+    int bx = (max_elems + 255) / 256;
+    if (bx > 16) bx = 16;
+    if (bx < 1) bx = 1;
+    lora_pack_kernel<<<dim3(bx, n_desc), 256, 0, stream>>>(descs_dev, n_desc);
+    DONE();
+}
+
+extern "C" int cl_skinny_atb(const float* a, int lda, int r, const void* b, int64_t ldb, float* out, int64_t so_j,
+                             int64_t so_c, float alpha, int M, int Ccols, void* stream_) {
+    STREAM;
+    if (!a || !b || !out || Ccols % 8) return set_error(CL_ERR_INVALID, "cl_skinny_atb: bad args");
+    const int chunks = Ccols / 8;
+    if (chunks > 512) return set_error(CL_ERR_UNSUPPORTED, "cl_skinny_atb: C too large");
+    int rows_par = 512 / chunks;
+    if (rows_par < 1) rows_par = 1;
+    int threads = ((rows_par * chunks + 31) / 32) * 32;
+    if (threads > 512) { rows_par = 1; threads = ((chunks + 31) / 32) * 32; }
+    int ctas = num_sms() * 2;
+    int rows_per_cta = (M + ctas - 1) / ctas;
+    if (rows_per_cta < rows_par * 4) rows_per_cta = rows_par * 4;
+    const int grid = (M + rows_per_cta - 1) / rows_per_cta;
+    const __nv_bfloat16* bb = reinterpret_cast<const __nv_bfloat16*>(b);
+#define SK_CASE(R)                                                                                                      \
+    case R: {                                                                                                           \
+        const size_t smem = (size_t)R * Ccols * sizeof(float);                                                          \
+        static bool done = false;                                                                                       \
+        if (!done) {                                                                                                    \
+            CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+            done = true;                                                                                                \
+        }                                                                                                               \
+        skinny_atb_kernel<R><<<grid, threads, smem, stream>>>(a, lda, bb, ldb, out, so_j, so_c, alpha, M, Ccols, rows_per_cta); \
+        break;                                                                                                          \
+    }
+    switch (r) {
+        SK_CASE(1) SK_CASE(2) SK_CASE(3) SK_CASE(4) SK_CASE(8)
+        default: return set_error(CL_ERR_UNSUPPORTED, "cl_skinny_atb: r must be 1..4 or 8");
+    }
+#undef SK_CASE
+    DONE();
+}
+
+extern "C" int cl_rowdot(const void* a, int64_t lda, const float* u, int rp, float* e, int M, int N, void* stream_) {
+    STREAM;
+    if (!a || !u || !e || N % 8) return set_error(CL_ERR_INVALID, "cl_rowdot: bad args");
+    const __nv_bfloat16* aa = reinterpret_cast<const __nv_bfloat16*>(a);
+    if (rp == 4) rowdot_kernel<4><<<(M + 7) / 8, 256, 0, stream>>>(aa, lda, u, e, M, N);
+    else if (rp == 8) rowdot_kernel<8><<<(M + 7) / 8, 256, 0, stream>>>(aa, lda, u, e, M, N);
+    else return set_error(CL_ERR_UNSUPPORTED, "cl_rowdot: rp must be 4 or 8");
+    DONE();
+}
+
+extern "C" int cl_rowmat(const float* a, int lda, const float* w, int sw_i, int sw_j, int I, int J, float alpha, void* out,
+                         int ldo, int out_mode, int col_off, int lo_off, int accumulate, int M, void* stream_) {
+    STREAM;
+    if (!a || !w || !out || I > 8 || J > 8 || I < 1 || J < 1) return set_error(CL_ERR_INVALID, "cl_rowmat: bad args");
+    int blocks = (M + 255) / 256;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    rowmat_kernel<<<blocks, 256, 0, stream>>>(a, lda, w, sw_i, sw_j, I, J, alpha, out, ldo, out_mode, col_off, lo_off, accumulate, M);
+    DONE();
+}
+
+extern "C" int cl_skinny_small(const float* a, int lda, int I, const float* b, int ldb, int J, float* out, float alpha, int M,
+                               void* stream_) {
+    STREAM;
+    if (!a || !b || !out || I > 8 || J > 8) return set_error(CL_ERR_INVALID, "cl_skinny_small: bad args");
+    int blocks = (M + 255) / 256;
+    if (blocks > num_sms()) blocks = num_sms();
+    skinny_small_kernel<<<blocks, 256, 0, stream>>>(a, lda, I, b, ldb, J, out, alpha, M);
+    DONE();
+}
+
+extern "C" int cl_small_matmul(const float* a, int64_t sa_i, int64_t sa_j, const float* b, int64_t sb_j, int64_t sb_k, float* out,
+                               int64_t so_i, int64_t so_k, int I, int J, int K, float alpha, int accumulate, void* stream_) {
+    STREAM;
+    if (!a || !b || !out) return set_error(CL_ERR_INVALID, "cl_small_matmul: null");
+    const long long total = (long long)I * K;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+    small_matmul_kernel<<<blocks, 256, 0, stream>>>(a, sa_i, sa_j, b, sb_j, sb_k, out, so_i, so_k, I, J, K, alpha, accumulate);
+    DONE();
+}

@@ -1,0 +1,378 @@
+// K5 — GroupNorm(+SiLU) and LayerNorm, forward and input-gradient, on channels-last bf16 tensors.  HBM-bound:
+// every pass reads/writes 16-byte vectors, fully coalesced along C; statistics in fp32 (fp64 for the cross-CTA
+// GroupNorm combine).  Replaces ATen native_group_norm / layer_norm (+ F.silu) called by diffusers' ResnetBlock2D,
+// Transformer2DModel, BasicTransformerBlock and by models.py:515-543 (ConvBlock2D).
+#include <stdio.h>
+
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/controllora_b200.h"
+
+namespace clb {
+
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+__device__ __forceinline__ float silu_grad_f(float z) {
+    const float s = 1.f / (1.f + __expf(-z));
+    return s * (1.f + z * (1.f - s));
+}
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm
+// Layout: x [n, HW, C]; group g = channels [g*cpg, (g+1)*cpg).  A CTA owns a slab of rows of one image; thread t
+// always handles the same 8-channel chunk (blockDim.x is a multiple of C/8), so per-channel partial sums stay in
+// registers; the per-group combine goes through shared memory and one fp64 atomic per (group, CTA).
+
+static constexpr int GN_MAX_CHUNKS = 512;  // C <= 4096
+
+// mode 0: forward statistics      -> ws[(n*G+g)*2 + {0,1}] += {sum x, sum x^2}
+// mode 1: backward reductions     -> ws[(n*G+g)*2 + {0,1}] += {sum dz*gamma, sum dz*gamma*xhat},
+//                                    dgamma[c] += sum dz*xhat, dbeta[c] += sum dz   (when dgamma != nullptr)
+template <int MODE>
+__global__ void __launch_bounds__(512)
+gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
+                 double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int HW, int C, int G,
+                 int rows_per_cta, int silu) {
+    const int n = blockIdx.y;
+    const int chunks = C / 8;
+    const int cpg = C / G;
+    const int rows_par = blockDim.x / chunks;      // rows processed per iteration
+    const int chunk = threadIdx.x % chunks;
+    const int rsub = threadIdx.x / chunks;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int row1 = min(HW, row0 + rows_per_cta);
+    const bool active = rsub < rows_par;
+    const int c0 = chunk * 8;
+
+    float a0[8], a1[8];  // MODE 0: sum, sumsq.  MODE 1: dz*gamma, dz*gamma*xhat
+    float g0[8], g1[8];  // MODE 1: dgamma / dbeta partials
+    float gam[8], bet[8], mean[8], rstd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a0[j] = a1[j] = g0[j] = g1[j] = 0.f; }
+    if (MODE == 1 && active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            gam[j] = gamma[c0 + j];
+            bet[j] = beta[c0 + j];
+            const int g = (c0 + j) / cpg;
+            mean[j] = stats[(n * G + g) * 2];
+            rstd[j] = stats[(n * G + g) * 2 + 1];
+        }
+    }
+    if (active) {
+        for (int r = row0 + rsub; r < row1; r += rows_par) {
+            const long long off = ((long long)n * HW + r) * C + c0;
+            float xv[8];
+            load8(x + off, xv);
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] += xv[j] * xv[j]; }
+            } else {
+                float dv[8];
+                load8(dy + off, dv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (xv[j] - mean[j]) * rstd[j];
+                    float dz = dv[j];
+                    if (silu) dz *= silu_grad_f(xh * gam[j] + bet[j]);
+                    a0[j] += dz * gam[j];
+                    a1[j] += dz * gam[j] * xh;
+                    g0[j] += dz * xh;
+                    g1[j] += dz;
+                }
+            }
+        }
+    }
+    // combine: shared per-channel arrays (fp32 atomics within the CTA), then per-group fp64 atomics to global
+    __shared__ float sh0[GN_MAX_CHUNKS * 8];
+    __shared__ float sh1[GN_MAX_CHUNKS * 8];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { sh0[i] = 0.f; sh1[i] = 0.f; }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&sh0[c0 + j], a0[j]); atomicAdd(&sh1[c0 + j], a1[j]); }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s0 += sh0[c]; s1 += sh1[c]; }
+        atomicAdd(&ws[(n * G + g) * 2], s0);
+        atomicAdd(&ws[(n * G + g) * 2 + 1], s1);
+    }
+    if (MODE == 1 && dgamma != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) { sh0[i] = 0.f; sh1[i] = 0.f; }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { atomicAdd(&sh0[c0 + j], g0[j]); atomicAdd(&sh1[c0 + j], g1[j]); }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            atomicAdd(&dgamma[i], sh0[i]);
+            atomicAdd(&dbeta[i], sh1[i]);
+        }
+    }
+}
+
+// forward apply: y = act((x - mean) * rstd * gamma + beta); writes float stats {mean, rstd} for the backward pass.
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const double* __restrict__ ws, float* __restrict__ stats, __nv_bfloat16* __restrict__ y, int HW, int C,
+                int G, float eps, int silu, long long total_chunks) {
+    const int chunks = C / 8;
+    const int cpg = C / G;
+    const double inv_m = 1.0 / ((double)HW * cpg);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int chunk = (int)(i % chunks);
+        const long long row = i / chunks;
+        const int n = (int)(row / HW);
+        const int c0 = chunk * 8;
+        float xv[8], o[8];
+        load8(x + row * C + c0, xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c0 + j) / cpg;
+            const double s0 = ws[(n * G + g) * 2], s1 = ws[(n * G + g) * 2 + 1];
+            const double mu = s0 * inv_m;
+            double var = s1 * inv_m - mu * mu;
+            if (var < 0.0) var = 0.0;
+            const float rs = (float)(1.0 / sqrt(var + (double)eps));
+            const float z = (xv[j] - (float)mu) * rs * gamma[c0 + j] + beta[c0 + j];
+            o[j] = silu ? silu_f(z) : z;
+            if (stats != nullptr && (row % HW) == 0 && ((c0 + j) % cpg) == 0) {
+                stats[(n * G + g) * 2] = (float)mu;
+                stats[(n * G + g) * 2 + 1] = rs;
+            }
+        }
+        store8(y + row * C + c0, o);
+    }
+}
+
+// backward apply: dx (+)= rstd * (dz*gamma - s1/m - xhat * s2/m)
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
+                    const double* __restrict__ ws, __nv_bfloat16* __restrict__ dx, int HW, int C, int G, int silu,
+                    int accumulate, long long total_chunks) {
+    const int chunks = C / 8;
+    const int cpg = C / G;
+    const float inv_m = 1.f / ((float)HW * cpg);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int chunk = (int)(i % chunks);
+        const long long row = i / chunks;
+        const int n = (int)(row / HW);
+        const int c0 = chunk * 8;
+        float xv[8], dv[8], o[8];
+        load8(x + row * C + c0, xv);
+        load8(dy + row * C + c0, dv);
+        if (accumulate) load8(dx + row * C + c0, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c0 + j) / cpg;
+            const float mu = stats[(n * G + g) * 2], rs = stats[(n * G + g) * 2 + 1];
+            const float s1 = (float)ws[(n * G + g) * 2] * inv_m, s2 = (float)ws[(n * G + g) * 2 + 1] * inv_m;
+            const float xh = (xv[j] - mu) * rs;
+            float dz = dv[j];
+            if (silu) dz *= silu_grad_f(xh * gamma[c0 + j] + beta[c0 + j]);
+            const float d = rs * (dz * gamma[c0 + j] - s1 - xh * s2);
+            o[j] = accumulate ? o[j] + d : d;
+        }
+        store8(dx + row * C + c0, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// One warp per row; the row (C <= 2560) lives in registers.
+static constexpr int LN_MAX_IT = 10;  // 10 * 32 lanes * 8 = 2560 channels
+
+template <int LN_IT>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              __nv_bfloat16* __restrict__ y, float* __restrict__ stats, int T, int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= T) return;
+    const int chunks = C / 8;
+    float v[LN_IT][8];
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < LN_IT; ++it) {
+        const int ch = it * 32 + lane;
+        if (ch < chunks) {
+            load8(x + (long long)row * C + ch * 8, v[it]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[it][j];
+        }
+    }
+    const float mu = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < LN_IT; ++it) {
+        const int ch = it * 32 + lane;
+        if (ch < chunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[it][j] - mu; q += d * d; }
+        }
+    }
+    const float rs = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+    for (int it = 0; it < LN_IT; ++it) {
+        const int ch = it * 32 + lane;
+        if (ch < chunks) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (v[it][j] - mu) * rs * gamma[ch * 8 + j] + beta[ch * 8 + j];
+            store8(y + (long long)row * C + ch * 8, o);
+        }
+    }
+    if (lane == 0 && stats != nullptr) { stats[row * 2] = mu; stats[row * 2 + 1] = rs; }
+}
+
+template <int LN_IT>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+              const float* __restrict__ gamma, const float* __restrict__ stats, __nv_bfloat16* __restrict__ dx, int T,
+              int C, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= T) return;
+    const int chunks = C / 8;
+    const float mu = stats[row * 2], rs = stats[row * 2 + 1];
+    float xh[LN_IT][8], dg[LN_IT][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < LN_IT; ++it) {
+        const int ch = it * 32 + lane;
+        if (ch < chunks) {
+            float xv[8], dv[8];
+            load8(x + (long long)row * C + ch * 8, xv);
+            load8(dy + (long long)row * C + ch * 8, dv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                xh[it][j] = (xv[j] - mu) * rs;
+                dg[it][j] = dv[j] * gamma[ch * 8 + j];
+                s1 += dg[it][j];
+                s2 += dg[it][j] * xh[it][j];
+            }
+        }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+#pragma unroll
+    for (int it = 0; it < LN_IT; ++it) {
+        const int ch = it * 32 + lane;
+        if (ch < chunks) {
+            float o[8];
+            if (accumulate) load8(dx + (long long)row * C + ch * 8, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = rs * (dg[it][j] - s1 - xh[it][j] * s2);
+                o[j] = accumulate ? o[j] + d : d;
+            }
+            store8(dx + (long long)row * C + ch * 8, o);
+        }
+    }
+}
+
+}  // namespace clb
+
+using namespace clb;
+
+static int gn_launch_geometry(int HW, int C, int n, int& threads, int& rows_per_cta, int& grid_x) {
+    const int chunks = C / 8;
+    if (C % 8 != 0 || chunks > GN_MAX_CHUNKS) return set_error(CL_ERR_UNSUPPORTED, "groupnorm: C must be a multiple of 8 and <= 4096");
+    int rows_par = 512 / chunks;
+    if (rows_par < 1) rows_par = 1;
+    threads = ((rows_par * chunks + 31) / 32) * 32;
+    if (threads > 512) { rows_par = 1; threads = ((chunks + 31) / 32) * 32; }
+    // aim for ~4 CTAs per SM across the batch
+    int target_ctas = (num_sms() * 4 + n - 1) / n;
+    rows_per_cta = (HW + target_ctas - 1) / target_ctas;
+    if (rows_per_cta < rows_par) rows_per_cta = rows_par;
+    grid_x = (HW + rows_per_cta - 1) / rows_per_cta;
+    return CL_OK;
+}
+
+extern "C" int cl_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
+                                double* ws, int n, int HW, int C, int G, float eps, int silu, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!x || !gamma || !beta || !y || !ws) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: null pointer");
+    if (G <= 0 || C % G != 0) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: C %% G != 0");
+    int threads, rows_per_cta, grid_x;
+    CL_CHECK(gn_launch_geometry(HW, C, n, threads, rows_per_cta, grid_x));
+    CL_CUDA_CHECK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * n * G, stream));
+    gn_reduce_kernel<0><<<dim3(grid_x, n), threads, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, ws, nullptr, nullptr, HW, C, G,
+        rows_per_cta, 0);
+    const long long total = (long long)n * HW * (C / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    gn_apply_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, ws, stats,
+                                                reinterpret_cast<__nv_bfloat16*>(y), HW, C, G, eps, silu, total);
+    count_launch(2);
+    CL_CUDA_CHECK(cudaGetLastError());
+    return CL_OK;
+}
+
+extern "C" int cl_groupnorm_bwd(const void* x, const void* dy, const float* gamma, const float* beta,
+                                const float* stats, void* dx, float* dgamma, float* dbeta, double* ws, int n, int HW,
+                                int C, int G, int silu, int accumulate, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!x || !dy || !gamma || !beta || !stats || !dx || !ws) return set_error(CL_ERR_INVALID, "cl_groupnorm_bwd: null pointer");
+    if (G <= 0 || C % G != 0) return set_error(CL_ERR_INVALID, "cl_groupnorm_bwd: C %% G != 0");
+    int threads, rows_per_cta, grid_x;
+    CL_CHECK(gn_launch_geometry(HW, C, n, threads, rows_per_cta, grid_x));
+    CL_CUDA_CHECK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * n * G, stream));
+    gn_reduce_kernel<1><<<dim3(grid_x, n), threads, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, beta, stats, ws,
+        dgamma, dbeta, HW, C, G, rows_per_cta, silu);
+    const long long total = (long long)n * HW * (C / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    gn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, beta, stats, ws,
+        reinterpret_cast<__nv_bfloat16*>(dx), HW, C, G, silu, accumulate, total);
+    count_launch(2);
+    CL_CUDA_CHECK(cudaGetLastError());
+    return CL_OK;
+}
+
+extern "C" int cl_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, int T,
+                                int C, float eps, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!x || !gamma || !beta || !y) return set_error(CL_ERR_INVALID, "cl_layernorm_fwd: null pointer");
+    if (C % 8 != 0 || C > LN_MAX_IT * 256) return set_error(CL_ERR_UNSUPPORTED, "cl_layernorm_fwd: C must be a multiple of 8, <= 2560");
+#define LN_FWD(IT) ln_fwd_kernel<IT><<<(T + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), stats, T, C, eps)
+    if (C <= 512) LN_FWD(2); else if (C <= 768) LN_FWD(3); else if (C <= 1280) LN_FWD(5); else LN_FWD(10);
+#undef LN_FWD
+    count_launch();
+    CL_CUDA_CHECK(cudaGetLastError());
+    return CL_OK;
+}
+
+extern "C" int cl_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* stats, void* dx, int T,
+                                int C, int accumulate, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!x || !dy || !gamma || !stats || !dx) return set_error(CL_ERR_INVALID, "cl_layernorm_bwd: null pointer");
+    if (C % 8 != 0 || C > LN_MAX_IT * 256) return set_error(CL_ERR_UNSUPPORTED, "cl_layernorm_bwd: C must be a multiple of 8, <= 2560");
+#define LN_BWD(IT) ln_bwd_kernel<IT><<<(T + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, stats, reinterpret_cast<__nv_bfloat16*>(dx), T, C, accumulate)
+    if (C <= 512) LN_BWD(2); else if (C <= 768) LN_BWD(3); else if (C <= 1280) LN_BWD(5); else LN_BWD(10);
+#undef LN_BWD
+    count_launch();
+    CL_CUDA_CHECK(cudaGetLastError());
+    return CL_OK;
+}

@@ -1,0 +1,320 @@
+// Small SIMT kernels at the edges of the UNet: conv_in (4 -> C0), conv_out (C0 -> 4) and its input gradient, the
+// timestep embedding + tiny-M linears (time MLP, all time_emb_proj layers at once), and the fused MSE loss.
+// None of them is GEMM-shaped enough for tensor cores (K = 36, N = 4, or M = batch), all are weight/HBM-bound.
+//
+// Replaces: diffusers UNet2DConditionModel.conv_in / time_proj / time_embedding / ResnetBlock2D.time_emb_proj /
+// conv_out as reached from train_text_to_image_control_lora.py:782, and F.mse_loss at :783.
+#include <stdio.h>
+
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/controllora_b200.h"
+
+namespace clb {
+
+__device__ __forceinline__ float siluf(float z) { return z / (1.f + __expf(-z)); }
+
+// ------------------------------------------------------------------------------------------ conv_in (3x3, Cin small)
+// x: NCHW fp32 [n, Cin, H, W] (rounded to bf16 on load == the reference's cast to weight_dtype), w: bf16 [Cout][3][3][Cin],
+// y: NHWC bf16 [n, H, W, Cout].  CTA = 32 consecutive pixels of one image row-major; thread = (pixel, co) pairs.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+               __nv_bfloat16* __restrict__ y, int n, int H, int W, int Cout) {
+    constexpr int KK = 9 * CIN;
+    extern __shared__ float sm[];
+    float* sw = sm;                 // [Cout][KK]
+    float* sx = sm + Cout * KK;     // [32][KK]
+    for (int i = threadIdx.x; i < Cout * KK; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
+    const long long pix0 = (long long)blockIdx.x * 32;
+    const long long npix = (long long)n * H * W;
+    for (int i = threadIdx.x; i < 32 * KK; i += blockDim.x) {
+        const int pl = i / KK, k = i % KK;
+        const long long pix = pix0 + pl;
+        float v = 0.f;
+        if (pix < npix) {
+            const int tap = k / CIN, ci = k % CIN;
+            const int b = (int)(pix / (H * W));
+            const int hw = (int)(pix % (H * W));
+            const int h = hw / W + tap / 3 - 1, ww = hw % W + tap % 3 - 1;
+            if (h >= 0 && h < H && ww >= 0 && ww < W)
+                v = __bfloat162float(__float2bfloat16(x[(((long long)b * CIN + ci) * H + h) * W + ww]));
+        }
+        sx[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * Cout; i += blockDim.x) {
+        const int pl = i / Cout, co = i % Cout;
+        const long long pix = pix0 + pl;
+        if (pix >= npix) continue;
+        float acc = bias ? bias[co] : 0.f;
+#pragma unroll
+        for (int k = 0; k < KK; ++k) acc += sx[pl * KK + k] * sw[co * KK + k];
+        y[pix * Cout + co] = __float2bfloat16(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ conv_out (3x3, Cout small)
+// x: NHWC bf16 [n, H, W, C], w: bf16 [COUT][3][3][C], y: NCHW fp32 [n, COUT, H, W].  One warp per output pixel.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_out_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                float* __restrict__ y, int n, int H, int W, int C) {
+    extern __shared__ __nv_bfloat16 swb[];   // [COUT][9][C]
+    for (int i = threadIdx.x; i < COUT * 9 * C / 8; i += blockDim.x)
+        reinterpret_cast<uint4*>(swb)[i] = reinterpret_cast<const uint4*>(w)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int chunks = C / 8;
+    const long long npix = (long long)n * H * W;
+    for (long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix;
+         pix += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const int b = (int)(pix / (H * W));
+        const int hw = (int)(pix % (H * W));
+        const int h0 = hw / W, w0 = hw % W;
+        float acc[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int h = h0 + tap / 3 - 1, ww = w0 + tap % 3 - 1;
+            if (h < 0 || h >= H || ww < 0 || ww >= W) continue;
+            const __nv_bfloat16* xp = x + (((long long)b * H + h) * W + ww) * C;
+            for (int ch = lane; ch < chunks; ch += 32) {
+                const uint4 xv = *reinterpret_cast<const uint4*>(xp + ch * 8);
+                const float2 x0 = unpack_bf16x2(xv.x), x1 = unpack_bf16x2(xv.y), x2 = unpack_bf16x2(xv.z), x3 = unpack_bf16x2(xv.w);
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const uint4 wv = *reinterpret_cast<const uint4*>(swb + ((long long)co * 9 + tap) * C + ch * 8);
+                    const float2 w0f = unpack_bf16x2(wv.x), w1f = unpack_bf16x2(wv.y), w2f = unpack_bf16x2(wv.z), w3f = unpack_bf16x2(wv.w);
+                    acc[co] += x0.x * w0f.x + x0.y * w0f.y + x1.x * w1f.x + x1.y * w1f.y + x2.x * w2f.x + x2.y * w2f.y +
+                               x3.x * w3f.x + x3.y * w3f.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            const float s = warp_sum(acc[co]);
+            if (lane == 0) y[(((long long)b * COUT + co) * H + h0) * W + w0] = s + (bias ? bias[co] : 0.f);
+        }
+    }
+}
+
+// input gradient of conv_out: dy NCHW fp32 [n, COUT, H, W] -> dx NHWC bf16 [n, H, W, C]; thread = (pixel, 8 channels)
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_out_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dx, int n,
+                    int H, int W, int C) {
+    extern __shared__ __nv_bfloat16 swb[];   // [COUT][9][C]
+    for (int i = threadIdx.x; i < COUT * 9 * C / 8; i += blockDim.x)
+        reinterpret_cast<uint4*>(swb)[i] = reinterpret_cast<const uint4*>(w)[i];
+    __syncthreads();
+    const int chunks = C / 8;
+    const long long total = (long long)n * H * W * chunks;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const long long pix = i / chunks;
+        const int b = (int)(pix / (H * W));
+        const int hw = (int)(pix % (H * W));
+        const int h0 = hw / W, w0 = hw % W;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            // y[h0 - ky + 1, w0 - kx + 1] used x[h0, w0] through tap (ky, kx)
+            const int h = h0 - (tap / 3) + 1, ww = w0 - (tap % 3) + 1;
+            if (h < 0 || h >= H || ww < 0 || ww >= W) continue;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const float g = dy[(((long long)b * COUT + co) * H + h) * W + ww];
+                const uint4 wv = *reinterpret_cast<const uint4*>(swb + ((long long)co * 9 + tap) * C + ch * 8);
+                const float2 a = unpack_bf16x2(wv.x), bq = unpack_bf16x2(wv.y), c = unpack_bf16x2(wv.z), d = unpack_bf16x2(wv.w);
+                acc[0] += g * a.x; acc[1] += g * a.y; acc[2] += g * bq.x; acc[3] += g * bq.y;
+                acc[4] += g * c.x; acc[5] += g * c.y; acc[6] += g * d.x; acc[7] += g * d.y;
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(dx + pix * C + ch * 8) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ timestep embedding
+// out[b, :] = [cos(t * f_i) | sin(t * f_i)], f_i = exp(-ln(10000) * i / half)   (flip_sin_to_cos, freq_shift 0)
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    const int half = dim / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
+        const int b = i / half, j = i % half;
+        const float f = expf(-9.210340371976184f * (float)j / (float)half);
+        const float a = t[b] * f;
+        out[b * dim + j] = cosf(a);
+        out[b * dim + half + j] = sinf(a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ tiny-M linear
+// out[b, n] = act_out( sum_k act_in(x[b, k]) * W[n, k] + bias[n] );  x fp32 [Bt, K], W bf16 [N, K]; warp per n.
+static constexpr int SL_MAXB = 8;
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                    float* __restrict__ out, int Bt, int N, int K, int silu_in, int silu_out) {
+    extern __shared__ float sxs[];  // [nb][K]
+    const int b0 = blockIdx.y * SL_MAXB;
+    const int nb = min(SL_MAXB, Bt - b0);
+    for (int i = threadIdx.x; i < nb * K; i += blockDim.x) {
+        float v = x[(long long)(b0 + i / K) * K + i % K];
+        sxs[i] = silu_in ? siluf(v) : v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int nrow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (nrow >= N) return;
+    float acc[SL_MAXB];
+#pragma unroll
+    for (int b = 0; b < SL_MAXB; ++b) acc[b] = 0.f;
+    for (int k = lane * 8; k < K; k += 256) {
+        const uint4 wv = *reinterpret_cast<const uint4*>(w + (long long)nrow * K + k);
+        const float2 w0 = unpack_bf16x2(wv.x), w1 = unpack_bf16x2(wv.y), w2 = unpack_bf16x2(wv.z), w3 = unpack_bf16x2(wv.w);
+#pragma unroll
+        for (int b = 0; b < SL_MAXB; ++b) {
+            if (b < nb) {
+                const float* xp = sxs + b * K + k;
+                acc[b] += xp[0] * w0.x + xp[1] * w0.y + xp[2] * w1.x + xp[3] * w1.y + xp[4] * w2.x + xp[5] * w2.y +
+                          xp[6] * w3.x + xp[7] * w3.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < SL_MAXB; ++b) {
+        if (b < nb) {
+            float s = warp_sum(acc[b]);
+            if (lane == 0) {
+                s += bias ? bias[nrow] : 0.f;
+                out[(long long)(b0 + b) * N + nrow] = silu_out ? siluf(s) : s;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ MSE (mean) + gradient
+// loss += sum((pred - target)^2) / n ; dpred = 2 (pred - target) / n * gscale
+__global__ void __launch_bounds__(256)
+mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ loss,
+           float* __restrict__ dpred, long long n, float gscale) {
+    float s = 0.f;
+    const float inv = 1.f / (float)n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float d = pred[i] - target[i];
+        s += d * d;
+        if (dpred) dpred[i] = 2.f * d * inv * gscale;
+    }
+    s = warp_sum(s);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+        atomicAdd(loss, t * inv);
+    }
+}
+
+}  // namespace clb
+
+using namespace clb;
+#define STREAM cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_)
+#define DONE()                         \
+    count_launch();                    \
+    CL_CUDA_CHECK(cudaGetLastError()); \
+    return CL_OK
+
+extern "C" int cl_conv_in(const float* x, const void* w, const float* bias, void* y, int n, int Cin, int H, int W, int Cout,
+                          void* stream_) {
+    STREAM;
+    if (!x || !w || !y) return set_error(CL_ERR_INVALID, "cl_conv_in: null");
+    const long long npix = (long long)n * H * W;
+    const int grid = (int)((npix + 31) / 32);
+    const size_t smem = (size_t)(Cout + 32) * 9 * Cin * sizeof(float);
+    if (smem > 200 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_in: weights do not fit shared memory");
+#define CONV_IN_CASE(CI)                                                                                         \
+    case CI: {                                                                                                   \
+        static bool done = false;                                                                                \
+        if (!done) {                                                                                             \
+            CL_CUDA_CHECK(cudaFuncSetAttribute(conv_in_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            done = true;                                                                                         \
+        }                                                                                                        \
+        conv_in_kernel<CI><<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(w), bias,      \
+                                                        reinterpret_cast<__nv_bfloat16*>(y), n, H, W, Cout);     \
+        break;                                                                                                   \
+    }
+    switch (Cin) {
+        CONV_IN_CASE(3)
+        CONV_IN_CASE(4)
+        default: return set_error(CL_ERR_UNSUPPORTED, "cl_conv_in: Cin must be 3 or 4");
+    }
+#undef CONV_IN_CASE
+    DONE();
+}
+
+extern "C" int cl_conv_out(const void* x, const void* w, const float* bias, float* y, int n, int H, int W, int C, int Cout,
+                           void* stream_) {
+    STREAM;
+    if (!x || !w || !y) return set_error(CL_ERR_INVALID, "cl_conv_out: null");
+    if (Cout != 4 || C % 8) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_out: Cout must be 4, C %% 8 == 0");
+    const size_t smem = (size_t)4 * 9 * C * 2;
+    static bool done = false;
+    if (!done) {
+        CL_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        done = true;
+    }
+    if (smem > 200 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_out: C too large");
+    conv_out_kernel<4><<<num_sms() * 4, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                            reinterpret_cast<const __nv_bfloat16*>(w), bias, y, n, H, W, C);
+    DONE();
+}
+
+extern "C" int cl_conv_out_bwd(const float* dy, const void* w, void* dx, int n, int H, int W, int C, int Cout, void* stream_) {
+    STREAM;
+    if (!dy || !w || !dx) return set_error(CL_ERR_INVALID, "cl_conv_out_bwd: null");
+    if (Cout != 4 || C % 8) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_out_bwd: Cout must be 4, C %% 8 == 0");
+    const size_t smem = (size_t)4 * 9 * C * 2;
+    static bool done = false;
+    if (!done) {
+        CL_CUDA_CHECK(cudaFuncSetAttribute(conv_out_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        done = true;
+    }
+    if (smem > 200 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_out_bwd: C too large");
+    conv_out_bwd_kernel<4><<<num_sms() * 4, 256, smem, stream>>>(dy, reinterpret_cast<const __nv_bfloat16*>(w),
+                                                                reinterpret_cast<__nv_bfloat16*>(dx), n, H, W, C);
+    DONE();
+}
+
+extern "C" int cl_timestep_embedding(const float* t, float* out, int B, int dim, void* stream_) {
+    STREAM;
+    if (!t || !out || dim % 2) return set_error(CL_ERR_INVALID, "cl_timestep_embedding: bad args");
+    timestep_embedding_kernel<<<(B * dim / 2 + 255) / 256, 256, 0, stream>>>(t, out, B, dim);
+    DONE();
+}
+
+extern "C" int cl_small_linear(const float* x, const void* w, const float* bias, float* out, int Bt, int N, int K,
+                               int silu_in, int silu_out, void* stream_) {
+    STREAM;
+    if (!x || !w || !out || K % 8) return set_error(CL_ERR_INVALID, "cl_small_linear: bad args");
+    const size_t smem = (size_t)SL_MAXB * K * sizeof(float);
+    if (smem > 48 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_small_linear: K too large");
+    dim3 grid((N + 7) / 8, (Bt + SL_MAXB - 1) / SL_MAXB);
+    small_linear_kernel<<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, Bt, N, K,
+                                                     silu_in, silu_out);
+    DONE();
+}
+
+extern "C" int cl_mse_loss(const float* pred, const float* target, float* loss, float* dpred, int64_t n, float gscale,
+                           void* stream_) {
+    STREAM;
+    if (!pred || !target || !loss) return set_error(CL_ERR_INVALID, "cl_mse_loss: null");
+    CL_CUDA_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+    mse_kernel<<<blocks, 256, 0, stream>>>(pred, target, loss, dpred, n, gscale);
+    DONE();
+}

@@ -128,3 +128,231 @@ def split_bf16_ext(down: torch.Tensor, k: int) -> torch.Tensor:
     ext[:r] = hi
     ext[8 : 8 + r] = lo
     return ext
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# generic helpers for the flat (non-struct) entry points
+# ----------------------------------------------------------------------------------------------------------------
+def _call(name: str, *args):
+    fn = getattr(_lib.lib(), name)
+    check(fn(*args, _stream()), name)
+
+
+def _p(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+_ws_cache = {}
+
+
+def _gn_ws(device, n, G):
+    key = (device, n * G)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = torch.empty(2 * n * G, device=device, dtype=torch.float64)
+        _ws_cache[key] = ws
+    return ws
+
+
+def attention_fwd(q, k, v, heads: int, scale: float, out=None, need_lse=True):
+    """q [B, Nq, H*d], k/v [B, Nk, H*d] bf16 (last dim contiguous, arbitrary row stride) -> o [B, Nq, H*d], lse [B,H,Nq]."""
+    from ._lib import AttnFwdArgs
+
+    _req(q, BF16, "q"); _req(k, BF16, "k"); _req(v, BF16, "v")
+    B, Nq, HD = q.shape
+    Nk = k.shape[1]
+    d = HD // heads
+    for t in (q, k, v):
+        assert t.stride(2) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
+    if out is None:
+        out = torch.empty(B, Nq, HD, device=q.device, dtype=BF16)
+    lse = torch.empty(B, heads, Nq, device=q.device, dtype=torch.float32) if need_lse else None
+    a = AttnFwdArgs()
+    a.B, a.H, a.Nq, a.Nk, a.d = B, heads, Nq, Nk, d
+    a.q, a.ldq = _ptr(q), q.stride(1)
+    a.k, a.ldk = _ptr(k), k.stride(1)
+    a.v, a.ldv = _ptr(v), v.stride(1)
+    a.o, a.ldo = _ptr(out), out.stride(1)
+    a.lse = _ptr(lse)
+    a.scale = float(scale)
+    check(_lib.lib().cl_attn_fwd(C.byref(a), _stream()), "cl_attn_fwd")
+    return out, lse
+
+
+def groupnorm_fwd(x, gamma, beta, G: int, eps: float, silu: bool, out=None):
+    """x NHWC [n, H, W, C] (or [n, HW, C]) bf16 -> (y, stats[n, G, 2])"""
+    _req(x, BF16, "x")
+    n, C_ = x.shape[0], x.shape[-1]
+    HW = x.numel() // (n * C_)
+    assert x.is_contiguous()
+    y = torch.empty_like(x) if out is None else out
+    stats = torch.empty(n, G, 2, device=x.device, dtype=torch.float32)
+    _call("cl_groupnorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(stats), _p(_gn_ws(x.device, n, G)),
+          n, HW, C_, G, C.c_float(eps), int(silu))
+    return y, stats
+
+
+def groupnorm_bwd(x, dy, gamma, beta, stats, G: int, silu: bool, dx=None, accumulate=False, dgamma=None, dbeta=None):
+    n, C_ = x.shape[0], x.shape[-1]
+    HW = x.numel() // (n * C_)
+    assert x.is_contiguous() and dy.is_contiguous()
+    if dx is None:
+        dx = torch.empty_like(x)
+        accumulate = False
+    _call("cl_groupnorm_bwd", _p(x), _p(dy), _p(gamma), _p(beta), _p(stats), _p(dx), _p(dgamma), _p(dbeta),
+          _p(_gn_ws(x.device, n, G)), n, HW, C_, G, int(silu), int(accumulate))
+    return dx
+
+
+def layernorm_fwd(x, gamma, beta, eps: float = 1e-5):
+    _req(x, BF16, "x")
+    assert x.is_contiguous()
+    C_ = x.shape[-1]
+    T = x.numel() // C_
+    y = torch.empty_like(x)
+    stats = torch.empty(T, 2, device=x.device, dtype=torch.float32)
+    _call("cl_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(stats), T, C_, C.c_float(eps))
+    return y, stats
+
+
+def layernorm_bwd(x, dy, gamma, stats, dx=None, accumulate=False):
+    C_ = x.shape[-1]
+    T = x.numel() // C_
+    assert x.is_contiguous() and dy.is_contiguous()
+    if dx is None:
+        dx = torch.empty_like(x)
+        accumulate = False
+    _call("cl_layernorm_bwd", _p(x), _p(dy), _p(gamma), _p(stats), _p(dx), T, C_, int(accumulate))
+    return dx
+
+
+def geglu_fwd(p):
+    F2 = p.shape[-1]
+    T = p.numel() // F2
+    out = torch.empty(*p.shape[:-1], F2 // 2, device=p.device, dtype=BF16)
+    _call("cl_geglu_fwd", _p(p), _p(out), C.c_int64(T), F2 // 2)
+    return out
+
+
+def geglu_bwd(p, dout):
+    F2 = p.shape[-1]
+    T = p.numel() // F2
+    dp = torch.empty_like(p)
+    _call("cl_geglu_bwd", _p(p), _p(dout), _p(dp), C.c_int64(T), F2 // 2)
+    return dp
+
+
+def add(a, b, out=None):
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    out = torch.empty_like(a) if out is None else out
+    _call("cl_add", _p(a), _p(b), _p(out), C.c_int64(a.numel()))
+    return out
+
+
+def upsample2x_fwd(x):
+    n, H, W, C_ = x.shape
+    y = torch.empty(n, 2 * H, 2 * W, C_, device=x.device, dtype=BF16)
+    _call("cl_upsample2x_fwd", _p(x), _p(y), n, H, W, C_)
+    return y
+
+
+def upsample2x_bwd(dy, dx=None, accumulate=False):
+    n, H2, W2, C_ = dy.shape
+    if dx is None:
+        dx = torch.empty(n, H2 // 2, W2 // 2, C_, device=dy.device, dtype=BF16)
+        accumulate = False
+    _call("cl_upsample2x_bwd", _p(dy), _p(dx), n, H2 // 2, W2 // 2, C_, int(accumulate))
+    return dx
+
+
+def zero_insert2x(x, off: int):
+    n, H, W, C_ = x.shape
+    y = torch.empty(n, 2 * H, 2 * W, C_, device=x.device, dtype=BF16)
+    _call("cl_zero_insert2x", _p(x), _p(y), n, H, W, C_, off)
+    return y
+
+
+def concat_channels(a, b):
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    M = a.numel() // Ca
+    out = torch.empty(*a.shape[:-1], Ca + Cb, device=a.device, dtype=BF16)
+    _call("cl_concat_channels", _p(a), _p(b), _p(out), C.c_int64(M), Ca, Cb)
+    return out
+
+
+def slice_channels(src, c_off: int, Cd: int, dst=None, accumulate=False):
+    Cs = src.shape[-1]
+    M = src.numel() // Cs
+    if dst is None:
+        dst = torch.empty(*src.shape[:-1], Cd, device=src.device, dtype=BF16)
+        accumulate = False
+    _call("cl_slice_channels", _p(src), _p(dst), C.c_int64(M), Cs, c_off, Cd, int(accumulate))
+    return dst
+
+
+def nchw_to_nhwc(x):
+    n, C_, H, W = x.shape
+    assert x.is_contiguous() and x.dtype in (torch.float32, BF16)
+    y = torch.empty(n, H, W, C_, device=x.device, dtype=BF16)
+    _call("cl_nchw_to_nhwc", _p(x), int(x.dtype == torch.float32), _p(y), n, C_, H * W)
+    return y
+
+
+def nhwc_to_nchw_f32(x, out=None, accumulate=False):
+    n, H, W, C_ = x.shape
+    if out is None:
+        out = torch.empty(n, C_, H, W, device=x.device, dtype=torch.float32)
+        accumulate = False
+    _call("cl_nhwc_to_nchw_f32", _p(x), _p(out), n, C_, H * W, int(accumulate))
+    return out
+
+
+def f32_to_bf16(x):
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _call("cl_f32_to_bf16", _p(x), _p(y), C.c_int64(x.numel()))
+    return y
+
+
+def conv_in(x, w, bias, cout: int):
+    """x NCHW fp32 [n, Cin, H, W]; w bf16 [Cout, 3, 3, Cin] -> NHWC bf16"""
+    n, Cin, H, W = x.shape
+    _req(x, torch.float32, "x")
+    y = torch.empty(n, H, W, cout, device=x.device, dtype=BF16)
+    _call("cl_conv_in", _p(x.contiguous()), _p(w), _p(bias), _p(y), n, Cin, H, W, cout)
+    return y
+
+
+def conv_out(x, w, bias):
+    n, H, W, C_ = x.shape
+    y = torch.empty(n, 4, H, W, device=x.device, dtype=torch.float32)
+    _call("cl_conv_out", _p(x), _p(w), _p(bias), _p(y), n, H, W, C_, 4)
+    return y
+
+
+def conv_out_bwd(dy, w, C_: int):
+    n, _, H, W = dy.shape
+    dx = torch.empty(n, H, W, C_, device=dy.device, dtype=BF16)
+    _call("cl_conv_out_bwd", _p(dy.contiguous()), _p(w), _p(dx), n, H, W, C_, 4)
+    return dx
+
+
+def timestep_embedding(t, dim: int):
+    t = t.to(torch.float32).contiguous()
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
+    _call("cl_timestep_embedding", _p(t), _p(out), t.shape[0], dim)
+    return out
+
+
+def small_linear(x, w, bias, silu_in=False, silu_out=False):
+    Bt, K = x.shape
+    N = w.shape[0]
+    out = torch.empty(Bt, N, device=x.device, dtype=torch.float32)
+    _call("cl_small_linear", _p(x), _p(w), _p(bias), _p(out), Bt, N, K, int(silu_in), int(silu_out))
+    return out
+
+
+def mse_loss(pred, target, gscale: float = 1.0, need_grad=True):
+    loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred) if need_grad else None
+    _call("cl_mse_loss", _p(pred), _p(target), _p(loss), _p(dpred), C.c_int64(pred.numel()), C.c_float(gscale))
+    return loss, dpred

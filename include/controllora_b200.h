@@ -85,6 +85,136 @@ typedef struct {
 
 int cl_gemm(const cl_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K2: fused attention  O = softmax(Q K^T * scale) V  per (batch, head), probabilities never leave the SM.
+ *
+ * Replaces: attn.head_to_batch_dim + attn.get_attention_scores (baddbmm + softmax) + torch.bmm +
+ *           attn.batch_to_head_dim   (models.py:126,137-142 / 244,267-272 / 381,404-409).
+ * q/k/v/o: bf16 [B, N, H*d] token matrices with row strides ld* (elements); head h = columns [h*d, (h+1)*d).
+ * lse (optional, fp32 [B, H, Nq]) receives log2-domain log-sum-exp of the scaled scores for the backward pass.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t B, H, Nq, Nk, d;
+    const void* q; int64_t ldq;
+    const void* k; int64_t ldk;
+    const void* v; int64_t ldv;
+    void* o; int64_t ldo;
+    float* lse;
+    float scale;
+} cl_attn_fwd_args;
+
+int cl_attn_fwd(const cl_attn_fwd_args* args, void* stream);
+
+/* Backward of cl_attn_fwd (what torch autograd derives for baddbmm/softmax/bmm in the reference): recomputes the
+ * probabilities from q, k and `lse`.  `delta` is fp32 scratch [B, H, Nq].  dq and/or (dk, dv) may be NULL to skip
+ * them (e.g. cross-attention to the frozen text encoder needs no dk/dv when its k/v projections carry no LoRA). */
+typedef struct {
+    int32_t B, H, Nq, Nk, d;
+    const void* q; int64_t ldq;
+    const void* k; int64_t ldk;
+    const void* v; int64_t ldv;
+    const void* o; int64_t ldo;
+    const void* d_o; int64_t lddo;
+    const float* lse;
+    float* delta;
+    void* dq; int64_t lddq;
+    void* dk; int64_t lddk;
+    void* dv; int64_t lddv;
+    float scale;
+} cl_attn_bwd_args;
+
+int cl_attn_bwd(const cl_attn_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K5: normalisation.  GroupNorm(+SiLU) on NHWC [n, HW, C] and LayerNorm on [T, C], forward and dX backward.
+ * Replaces torch.nn.GroupNorm / F.silu / LayerNorm inside diffusers ResnetBlock2D, Transformer2DModel,
+ * BasicTransformerBlock, UNet conv_norm_out, and models.py:515-543 (ConvBlock2D, where dgamma/dbeta are needed).
+ * `ws` is caller-provided scratch of 2*n*G doubles; `stats` (fp32 [n, G, 2] = mean, rstd) feeds the backward.
+ * ---------------------------------------------------------------------------------------------------------- */
+int cl_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, double* ws,
+                     int n, int HW, int C, int G, float eps, int silu, void* stream);
+int cl_groupnorm_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* stats,
+                     void* dx, float* dgamma /* nullable, accumulated */, float* dbeta, double* ws, int n, int HW,
+                     int C, int G, int silu, int accumulate_dx, void* stream);
+int cl_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats /* [T,2] */,
+                     int T, int C, float eps, void* stream);
+int cl_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* stats, void* dx, int T, int C,
+                     int accumulate_dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Elementwise glue (bf16, channels-last).  GEGLU = diffusers FeedForward's `a * gelu(g)` on p = [a | g].
+ * ---------------------------------------------------------------------------------------------------------- */
+int cl_geglu_fwd(const void* p, void* out, int64_t T, int F, void* stream);
+int cl_geglu_bwd(const void* p, const void* dout, void* dp, int64_t T, int F, void* stream);
+int cl_add(const void* a, const void* b, void* out, int64_t n, void* stream);
+int cl_upsample2x_fwd(const void* x, void* y, int n, int H, int W, int C, void* stream);      /* F.interpolate nearest */
+int cl_upsample2x_bwd(const void* dy, void* dx, int n, int H, int W, int C, int accumulate, void* stream);
+int cl_zero_insert2x(const void* x, void* y, int n, int H, int W, int C, int off, void* stream); /* stride-2 adjoint */
+int cl_concat_channels(const void* a, const void* b, void* out, int64_t M, int Ca, int Cb, void* stream); /* torch.cat(dim=1) */
+int cl_slice_channels(const void* src, void* dst, int64_t M, int Cs, int c_off, int Cd, int accumulate, void* stream);
+int cl_nchw_to_nhwc(const void* x, int x_is_fp32, void* y, int n, int C, int HW, void* stream);
+int cl_nhwc_to_nchw_f32(const void* x, float* y, int n, int C, int HW, int accumulate, void* stream);
+int cl_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+int cl_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * UNet edges: conv_in (NCHW fp32 -> NHWC bf16), conv_out (NHWC bf16 -> NCHW fp32) + its dX, sinusoidal timestep
+ * embedding, tiny-M linear (time MLP and all ResnetBlock2D.time_emb_proj at once), fused MSE loss + gradient
+ * (train_text_to_image_control_lora.py:782-783).
+ * ---------------------------------------------------------------------------------------------------------- */
+int cl_conv_in(const float* x, const void* w /* bf16 [Cout][3][3][Cin] */, const float* bias, void* y, int n, int Cin,
+               int H, int W, int Cout, void* stream);
+int cl_conv_out(const void* x, const void* w /* bf16 [4][3][3][C] */, const float* bias, float* y, int n, int H, int W,
+                int C, int Cout, void* stream);
+int cl_conv_out_bwd(const float* dy, const void* w, void* dx, int n, int H, int W, int C, int Cout, void* stream);
+int cl_timestep_embedding(const float* t, float* out, int B, int dim, void* stream);
+int cl_small_linear(const float* x, const void* w, const float* bias, float* out, int Bt, int N, int K, int silu_in,
+                    int silu_out, void* stream);
+int cl_mse_loss(const float* pred, const float* target, float* loss, float* dpred, int64_t n, float gscale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * LoRA side path (diffusers LoRALinearLayer instances created at models.py:89-97,185,316-323).
+ *
+ * cl_lora_pack_batch: one launch converts every fp32 LoRA master weight of a step into the operands the fused GEMM
+ *   consumes (kind 0: bf16 hi/lo `ext` rows; kind 1: fp32 [N, rp] `lora_up` table).  `descs` lives in device memory.
+ * cl_skinny_atb:   out[j*so_j + c*so_c] += alpha * sum_m a[m*lda + j] * b[m*ldb + c]      (dA / dB reductions)
+ * cl_rowdot:       e[m*rp + j] = sum_n a[m*lda + n] * u[n*rp + j]                         (dY * B_up when no dX GEMM runs)
+ * cl_rowmat:       out[m, i] (+)= alpha * sum_j a[m*lda + j] * w[i*sw_i + j*sw_j]         (rank-r x rank-r per-row maps)
+ * cl_skinny_small: out[i*J + j] += alpha * sum_m a[m*lda + i] * b[m*ldb + j]
+ * cl_small_matmul: weight-space fp32 product with arbitrary strides.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* src;   /* fp32 */
+    void* dst;
+    int32_t kind;      /* 0: ext (bf16 [16, ld]), 1: table (fp32 [K, ld]) */
+    int32_t r, K;      /* src(j, k), j < r, k < K */
+    int64_t s_j, s_k;  /* element strides of src */
+    int32_t ld;        /* dst leading dimension (elements) */
+    int32_t row_off;   /* first ext row / table column written */
+} cl_pack_desc;
+
+int cl_lora_pack_batch(const cl_pack_desc* descs_dev, int n_desc, int max_elems, void* stream);
+int cl_skinny_atb(const float* a, int lda, int r, const void* b, int64_t ldb, float* out, int64_t so_j, int64_t so_c,
+                  float alpha, int M, int C, void* stream);
+int cl_rowdot(const void* a, int64_t lda, const float* u, int rp, float* e, int M, int N, void* stream);
+int cl_rowmat(const float* a, int lda, const float* w, int sw_i, int sw_j, int I, int J, float alpha, void* out, int ldo,
+              int out_mode, int col_off, int lo_off, int accumulate, int M, void* stream);
+int cl_skinny_small(const float* a, int lda, int I, const float* b, int ldb, int J, float* out, float alpha, int M,
+                    void* stream);
+int cl_small_matmul(const float* a, int64_t sa_i, int64_t sa_j, const float* b, int64_t sb_j, int64_t sb_k, float* out,
+                    int64_t so_i, int64_t so_k, int I, int J, int K, float alpha, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K8: optimizer on the flat fp32 parameter / gradient arenas (train_text_to_image_control_lora.py:791-796:
+ * clip_grad_norm_(max_norm) + torch.optim.AdamW step + zero_grad), no host synchronisation.
+ *   cl_sumsq:  *out += sum x^2   (call once per arena after zeroing *out; the total grad norm)
+ *   cl_adamw:  g' = g * grad_scale * min(1, max_norm / (sqrt(*gnorm_sq) * grad_scale + 1e-6));  AdamW(p, g', m, v);  g = 0
+ * ---------------------------------------------------------------------------------------------------------- */
+int cl_sumsq(const float* x, int64_t n, float* out, void* stream);
+int cl_adamw(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+             float weight_decay, int step, const float* gnorm_sq, float max_norm, float grad_scale, int zero_grad,
+             void* stream);
+
 #ifdef __cplusplus
 }
 #endif
