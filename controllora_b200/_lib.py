@@ -83,3 +83,32 @@ class AttnFwdArgs(C.Structure):
         ("lse", C.c_void_p),
         ("scale", C.c_float),
     ]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("Nq", C.c_int32), ("Nk", C.c_int32), ("d", C.c_int32),
+        ("q", C.c_void_p), ("ldq", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64),
+        ("o", C.c_void_p), ("ldo", C.c_int64),
+        ("d_o", C.c_void_p), ("lddo", C.c_int64),
+        ("lse", C.c_void_p),
+        ("delta", C.c_void_p),
+        ("dq", C.c_void_p), ("lddq", C.c_int64),
+        ("dk", C.c_void_p), ("lddk", C.c_int64),
+        ("dv", C.c_void_p), ("lddv", C.c_int64),
+        ("scale", C.c_float),
+    ]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p),
+        ("dst", C.c_void_p),
+        ("kind", C.c_int32),
+        ("r", C.c_int32), ("K", C.c_int32),
+        ("s_j", C.c_int64), ("s_k", C.c_int64),
+        ("ld", C.c_int32),
+        ("row_off", C.c_int32),
+    ]

@@ -31,9 +31,15 @@ lora_pack_kernel(const cl_pack_desc* __restrict__ descs, int n_desc) {
             const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
             ext[(long long)(d.row_off + j) * d.ld + k] = hi;
             ext[(long long)(8 + d.row_off + j) * d.ld + k] = lo;
-        } else {
+        } else if (d.kind == 1) {
             float* tab = reinterpret_cast<float*>(d.dst);
             tab[(long long)k * d.ld + d.row_off + j] = v;
+        } else {
+            // kind 2: bf16 transposed table, value duplicated in the hi and lo column slots
+            __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(d.dst);
+            const __nv_bfloat16 hi = __float2bfloat16(v);
+            tb[(long long)k * d.ld + d.row_off + j] = hi;
+            tb[(long long)k * d.ld + 8 + d.row_off + j] = hi;
         }
     }
 }
@@ -144,6 +150,47 @@ rowmat_kernel(const float* __restrict__ a, int lda, const float* __restrict__ w,
                 o[lo_off] = __float2bfloat16(s - __bfloat162float(hi));
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ hi/lo combine
+// src fp32 [M, 16*nb] laid out in 16-column blocks [hi0..3 | hi4..7 | lo0..3 | lo4..7] -> dst fp32 [M, 8*nb] = hi + lo
+__global__ void __launch_bounds__(256)
+hilo_combine_kernel(const float* __restrict__ src, float* __restrict__ dst, long long M, int nb) {
+    const long long total = M * nb * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / (nb * 8);
+        const int c = (int)(i % (nb * 8));
+        const int blk = c / 8, j = c % 8;
+        const float* sp = src + m * nb * 16 + blk * 16;
+        dst[i] = sp[j] + sp[8 + j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ rank-r update of a bf16 matrix
+// out[m, c] = x[m, c] + alpha * sum_j t[m*ldt + j] * tab[c*rp + j]
+template <int RP>
+__global__ void __launch_bounds__(256)
+rank_update_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ t, int ldt, const float* __restrict__ tab,
+                   float alpha, __nv_bfloat16* __restrict__ out, long long M, int C) {
+    const int chunks = C / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M * chunks; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / chunks;
+        const int c0 = (int)(i % chunks) * 8;
+        float tv[RP];
+#pragma unroll
+        for (int j = 0; j < RP; ++j) tv[j] = alpha * t[m * ldt + j];
+        const uint4 u = *reinterpret_cast<const uint4*>(x + m * C + c0);
+        const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
+        float xv[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+#pragma unroll
+            for (int j = 0; j < RP; ++j) xv[e] += tv[j] * tab[(long long)(c0 + e) * RP + j];
+        uint4 o;
+        o.x = pack_bf16x2(xv[0], xv[1]); o.y = pack_bf16x2(xv[2], xv[3]);
+        o.z = pack_bf16x2(xv[4], xv[5]); o.w = pack_bf16x2(xv[6], xv[7]);
+        *reinterpret_cast<uint4*>(out + m * C + c0) = o;
     }
 }
 
@@ -270,6 +317,31 @@ extern "C" int cl_rowmat(const float* a, int lda, const float* w, int sw_i, int 
     int blocks = (M + 255) / 256;
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     rowmat_kernel<<<blocks, 256, 0, stream>>>(a, lda, w, sw_i, sw_j, I, J, alpha, out, ldo, out_mode, col_off, lo_off, accumulate, M);
+    DONE();
+}
+
+extern "C" int cl_hilo_combine(const float* src, float* dst, int64_t M, int nb, void* stream_) {
+    STREAM;
+    if (!src || !dst || nb < 1) return set_error(CL_ERR_INVALID, "cl_hilo_combine: bad args");
+    long long total = M * nb * 8;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    hilo_combine_kernel<<<blocks, 256, 0, stream>>>(src, dst, M, nb);
+    DONE();
+}
+
+extern "C" int cl_rank_update(const void* x, const float* t, int ldt, const float* tab, int rp, float alpha, void* out,
+                              int64_t M, int Ccols, void* stream_) {
+    STREAM;
+    if (!x || !t || !tab || !out || Ccols % 8) return set_error(CL_ERR_INVALID, "cl_rank_update: bad args");
+    long long total = M * (Ccols / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+    __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
+    if (rp == 4) rank_update_kernel<4><<<blocks, 256, 0, stream>>>(xx, t, ldt, tab, alpha, oo, M, Ccols);
+    else if (rp == 8) rank_update_kernel<8><<<blocks, 256, 0, stream>>>(xx, t, ldt, tab, alpha, oo, M, Ccols);
+    else return set_error(CL_ERR_UNSUPPORTED, "cl_rank_update: rp must be 4 or 8");
     DONE();
 }
 

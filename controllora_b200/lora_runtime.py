@@ -1,0 +1,332 @@
+"""Maps the reference's attention-processor objects (LoRACrossAttnProcessor / ControlLoRACrossAttnProcessor[V2],
+/root/reference/models.py:72-431) onto fused kernel launches.
+
+For every attention layer the adapter chain [pre_loras..., processor, post_loras...] (models.py:232-243 etc.) is packed
+into one rank<=8 `LoraSlot` per projection, so a projection and all of its LoRA deltas are ONE tcgen05 GEMM launch.
+
+v1 control (models.py:237-238):  q = Wq h + s Bq Aq (h + s Bc Ac c)
+        = Wq h + s Bq ( Aq h  +  s (Aq Bc) (Ac c) )               -> `t_add` of the fused GEMM epilogue,
+  with u = Ac c computed for all processors of a UNet level by one GEMM over the level's control state.
+V2 control (models.py:369, 415):  h' = h + s Bc Ac [h ; c]  is a rank-r update of the hidden states (before q/k/v and
+  again before to_out), done by one skinny GEMM + one rank-update kernel.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import engine as E
+from . import ops
+from .engine import Ctx, LoraSlot, Var
+
+BF16 = torch.bfloat16
+
+
+def _is_v1(p) -> bool:
+    return type(p).__name__ == "ControlLoRACrossAttnProcessor"
+
+
+def _is_v2(p) -> bool:
+    return type(p).__name__ == "ControlLoRACrossAttnProcessorV2"
+
+
+class _LevelCtx:
+    """Per control-state tensor (== per UNet resolution level): the stacked `to_control.down` operands of every
+    processor fed by that tensor, and the per-forward products."""
+
+    def __init__(self):
+        self.procs: List = []           # (processor, LayerPlan)
+        self.cc = 0                     # control channels
+        self.stack = None               # bf16 [16*nb, Cc]   (hi/lo rows of the control-down matrices)
+        self.stack_t = None             # bf16 [Cc, 16*nb]   (transposed, hi duplicated) for the d-control GEMM
+        self.nb = 0
+        # per forward
+        self.c: Optional[Var] = None    # [B, HW, Cc] bf16
+        self.u = None                   # fp32 [T, 8*nb]
+        self.du = None                  # bf16 [T, 16*nb]
+
+
+class LayerPlan:
+    def __init__(self):
+        self.kind = "none"
+        self.proc = None
+        self.chain: List = []
+        self.q = self.k = self.v = self.out = None   # LoraSlot
+        self.level: Optional[_LevelCtx] = None
+        self.col = 0           # first column of this processor's block inside level.u
+        self.ctrl_adapter = None        # engine.Adapter of the processor's own to_q_lora (v1)
+        # V2 helper tables (fp32): Bc [C, rp] etc. are read directly from the parameters
+
+
+class LoraRuntime:
+    """Built once per (UNet, processor wiring); `begin()` runs at the start of every UNet forward."""
+
+    def __init__(self, weights, device, grad_of: Callable[[torch.nn.Parameter], torch.Tensor]):
+        self.W = weights
+        self.device = device
+        self.grad_of = grad_of
+        self.plan = ops.PackPlan(device)        # slot operands (ext / tables of every projection)
+        self.v2_plan = ops.PackPlan(device)     # V2 hidden-state-update operands
+        self.level_plan = ops.PackPlan(device)  # stacked control-down operands per level (rebuilt when levels change)
+        self.layers: Dict[str, LayerPlan] = {}
+        self.levels: Dict[int, _LevelCtx] = {}
+        self.signature = None
+        self._build()
+
+    # ------------------------------------------------------------------------------------------------ build
+    @staticmethod
+    def make_signature(weights) -> tuple:
+        sig = []
+        for name, L in weights.attn_layers.items():
+            p = L.processor
+            if p is None or not hasattr(p, "to_q_lora"):
+                sig.append(None)
+                continue
+            chain = [*getattr(p, "pre_loras", []), p, *getattr(p, "post_loras", [])]
+            sig.append(tuple((id(a), a.key_states_skipped, a.value_states_skipped, a.output_states_skipped) for a in chain))
+        return tuple(sig)
+
+    def _adapter(self, slot: LoraSlot, layer) -> E.Adapter:
+        a = slot.add(layer.down.weight, layer.up.weight)
+        a.down_grad = self.grad_of(layer.down.weight)
+        a.up_grad = self.grad_of(layer.up.weight)
+        return a
+
+    def _build(self):
+        dev = self.device
+        for name, L in self.W.attn_layers.items():
+            lp = LayerPlan()
+            self.layers[name] = lp
+            p = L.processor
+            if p is None or not hasattr(p, "to_q_lora"):
+                continue
+            lp.proc = p
+            chain = [*getattr(p, "pre_loras", []), p, *getattr(p, "post_loras", [])]
+            lp.chain = chain
+            for a in chain:
+                if getattr(a, "post_add", False):
+                    raise NotImplementedError("lora_post_add=True (configs/post-add.json) is not on the CUDA path yet")
+                if a is not p and (_is_v1(a) or _is_v2(a)):
+                    raise NotImplementedError("stacking a second *Control*LoRA processor as pre/post LoRA is not supported")
+            if _is_v1(p) and getattr(p, "concat_hidden", False):
+                raise NotImplementedError("lora_concat_hidden=True for v1 processors (configs/danbooru-sketch.json) is not on the CUDA path yet")
+            lp.kind = "v1" if _is_v1(p) else ("v2" if _is_v2(p) else "plain")
+            C = L.to_q.w.shape[0]
+            kv_in = L.to_k.w.shape[1]
+            lp.q = LoraSlot(C, C, dev)
+            lp.k = LoraSlot(C, kv_in, dev)
+            lp.v = LoraSlot(C, kv_in, dev)
+            lp.out = LoraSlot(C, C, dev)
+            for a in chain:
+                ad = self._adapter(lp.q, a.to_q_lora)
+                if a is p:
+                    lp.ctrl_adapter = ad
+                if not a.key_states_skipped:
+                    self._adapter(lp.k, a.to_k_lora)
+                if not a.value_states_skipped:
+                    self._adapter(lp.v, a.to_v_lora)
+                if a is p or not a.output_states_skipped:
+                    self._adapter(lp.out, a.to_out_lora)
+            lp.q.finalize(self.plan, need_dx=True)
+            lp.k.finalize(self.plan, need_dx=not L.is_cross)
+            lp.v.finalize(self.plan, need_dx=not L.is_cross)
+            lp.out.finalize(self.plan, need_dx=True)
+            if lp.kind == "v2":
+                self._v2_tables(lp)
+        self.signature = self.make_signature(self.W)
+
+    # ------------------------------------------------------------------------------------------------ per forward
+    def begin(self, ctx: Ctx, control_vars: Dict[int, Var]):
+        """control_vars: data_ptr of each processor's control-state tensor -> Var [B, HW, Cc] (NHWC bf16)."""
+        # (re)group control processors by the tensor that was injected into them
+        groups: Dict[int, List[LayerPlan]] = {}
+        for lp in self.layers.values():
+            if lp.kind in ("v1", "v2"):
+                cs = lp.proc.control_states
+                assert cs is not None, "inject_control_states() must run before the UNet forward (models.py:227)"
+                groups.setdefault(cs.data_ptr(), []).append(lp)
+        key = tuple((k, tuple(id(lp) for lp in v)) for k, v in groups.items())
+        if getattr(self, "_level_key", None) != key:
+            self._build_levels(groups, control_vars)
+            self._level_key = key
+        self.plan.run()
+        self.v2_plan.run()
+        self.level_plan.run()
+        s = ctx.scale
+        for k, lv in self.levels.items():
+            c = control_vars[k]
+            lv.c = c
+            T = c.data.shape[0] * c.data.shape[1]
+            c2 = c.data.view(T, lv.cc)
+            u16 = ops.gemm(c2, lv.stack, out_fp32=True)
+            lv.u = ops.hilo_combine(u16, lv.nb)
+            lv.du = None
+            if ctx.tape is not None and c.rg:
+                lv.du = torch.zeros(T, 16 * lv.nb, device=self.device, dtype=BF16)
+        for lp in self.layers.values():
+            lp.t_add = None
+            if lp.kind == "v1":
+                self._v1_prepare(ctx, lp)
+
+    def _build_levels(self, groups, control_vars):
+        self.levels = {}
+        plan = ops.PackPlan(self.device)
+        for key, lps in groups.items():
+            lv = _LevelCtx()
+            cvar = control_vars[key]
+            lv.cc = cvar.data.shape[-1]
+            v2 = lps[0].kind == "v2"
+            lv.nb = len(lps) if v2 else (len(lps) + 1) // 2
+            lv.stack = torch.zeros(16 * lv.nb, lv.cc, device=self.device, dtype=BF16)
+            lv.stack_t = torch.zeros(lv.cc, 16 * lv.nb, device=self.device, dtype=BF16)
+            for i, lp in enumerate(lps):
+                lp.level = lv
+                p = lp.proc
+                C = p.hidden_size
+                if v2:
+                    lp.col = 8 * i
+                    downs = [(p.to_control.down.weight[:, C:], 0), (p.to_control_out.down.weight[:, C:], 4)]
+                    blk = i
+                else:
+                    lp.col = 4 * i
+                    downs = [(p.to_control.down.weight, 4 * (i % 2))]
+                    blk = i // 2
+                for dn, off in downs:
+                    assert dn.shape[1] == lv.cc, "control-state channels do not match to_control.down"
+                    plan.add_ext(dn, lv.stack[16 * blk:16 * blk + 16], row_off=off)
+                    r = dn.shape[0]
+                    # kind 2: stack_t[k, 16*blk + off + j] and [.. + 8 ..] <- bf16(dn[j, k])
+                    plan.add(dn, lv.stack_t[:, 16 * blk:], 2, r, lv.cc, dn.stride(0), dn.stride(1), lv.stack_t.stride(0), off)
+            self.levels[key] = lv
+        self.level_plan = plan
+
+    # ------------------------------------------------------------------------------------------------ v1
+    def _v1_prepare(self, ctx: Ctx, lp: LayerPlan):
+        p, lv, ad = lp.proc, lp.level, lp.ctrl_adapter
+        s = ctx.scale
+        r = ad.down.shape[0]
+        Aq = ad.down                      # [r, C]
+        Bc = p.to_control.up.weight       # [C, rc]
+        rc = Bc.shape[1]
+        C = Aq.shape[1]
+        M = torch.empty(r, rc, device=self.device, dtype=torch.float32)
+        ops.small_matmul(Aq, C, 1, Bc, rc, 1, M, rc, 1, r, C, rc)                  # M = Aq Bc
+        T = lv.u.shape[0]
+        rp = lp.q.rp
+        t_add = torch.zeros(T, rp, device=self.device, dtype=torch.float32) if lp.q.rank != r else \
+            torch.empty(T, rp, device=self.device, dtype=torch.float32)
+        u = lv.u[:, lp.col:]
+        # t_add[:, col_a + i] = s * sum_j u[:, j] * M[i, j]
+        ops.rowmat(u, M, rc, 1, r, rc, s, t_add[:, ad.col:], rp)
+        lp.t_add, lp.M = t_add, M
+
+    def _v1_q_bwd(self, ctx: Ctx, lp: LayerPlan, e, t_out, dy2):
+        """Gradients of the control branch of a v1 q-projection (see module docstring)."""
+        p, lv, ad = lp.proc, lp.level, lp.ctrl_adapter
+        s = ctx.scale
+        r = ad.down.shape[0]
+        Aq, Bc, Ac = ad.down, p.to_control.up.weight, p.to_control.down.weight
+        rc = Bc.shape[1]
+        C = Aq.shape[1]
+        u = lv.u[:, lp.col:]
+        ea = e[:, ad.col:]
+        G = torch.zeros(r, rc, device=self.device, dtype=torch.float32)
+        ops.skinny_small(ea, r, u, rc, G, 1.0)                                     # G = e^T u
+        ops.small_matmul(G, rc, 1, Bc, 1, rc, ad.down_grad, C, 1, r, rc, C, alpha=s * s, accumulate=True)   # dAq += s^2 G Bc^T
+        ops.small_matmul(Aq, 1, C, G, rc, 1, self.grad_of(Bc), rc, 1, C, r, rc, alpha=s * s, accumulate=True)  # dBc += s^2 Aq^T G
+        T = u.shape[0]
+        du = torch.empty(T, rc, device=self.device, dtype=torch.float32)
+        ops.rowmat(ea, lp.M, 1, rc, rc, r, s * s, du, rc)                           # du = s^2 e M
+        ops.skinny_atb(du, rc, lv.c.data.view(T, lv.cc), self.grad_of(Ac), lv.cc, 1, 1.0)   # dAc += du^T c
+        if lv.du is not None:
+            i = lp.col // 4
+            ops.rowmat(ea, lp.M, 1, rc, rc, r, s * s, lv.du, 16 * lv.nb, out_mode=1, col_off=16 * (i // 2) + 4 * (i % 2), lo_off=8)
+
+    # ------------------------------------------------------------------------------------------------ V2
+    def _v2_inject(self, ctx: Ctx, lp: LayerPlan, h: Var, which: int) -> Var:
+        """h' = h + s * Bc ( Ac_h h + Ac_c c )   (which = 0: to_control before q/k/v, 1: to_control_out before to_out)."""
+        p, lv = lp.proc, lp.level
+        layer = p.to_control if which == 0 else p.to_control_out
+        s = ctx.scale
+        C = p.hidden_size
+        down, up = layer.down.weight, layer.up.weight      # [rc, C + Cc], [C, rc]
+        rc = down.shape[0]
+        T = h.data.shape[0] * h.data.shape[1]
+        h2 = h.data.view(T, C)
+        ext = lp.v2_ext[which]
+        # t = h Ac_h^T (tensor core, N = 16 hi/lo columns) + u_c
+        th16 = ops.gemm(h2, ext, out_fp32=True)
+        t = ops.hilo_combine(th16, 1)                      # [T, 8], cols 0..rc-1 valid
+        uc = lv.u[:, lp.col + 4 * which:]
+        ops.rowmat(uc, lp.v2_eye, 4, 1, rc, rc, 1.0, t, 8, accumulate=True)        # t[:, :rc] += u_c
+        out = Var(ops.rank_update(h.data, t, lp.v2_up[which], s), rg=True)
+        if ctx.tape is not None:
+            def bwd():
+                dy = out.grad
+                out.grad = None
+                if dy is None:
+                    return
+                dy2 = dy.view(T, C)
+                dt = ops.rowdot(dy2, lp.v2_up[which])                           # [T, 4] = dy Bc   (unscaled)
+                # dBc[c, j] += s * sum_m dy[m, c] t[m, j]
+                ops.skinny_atb(t, rc, dy2, self.grad_of(up), 1, rc, s)
+                # dAc_h[j, k] += s * sum_m dt[m, j] h[m, k] ; dAc_c likewise with c
+                gdown = self.grad_of(down)
+                ops.skinny_atb(dt, rc, h2, gdown, C + lv.cc, 1, s)
+                ops.skinny_atb(dt, rc, lv.c.data.view(T, lv.cc), gdown[:, C:], C + lv.cc, 1, s)
+                # dh = dy + s * dt Ac_h
+                if h.rg:
+                    E.give_tensor(h, ops.rank_update(dy, dt, lp.v2_down_tab[which], s))
+                if lv.du is not None:
+                    i = lp.col // 8
+                    ops.rowmat(dt, lp.v2_eye, 4, 1, rc, rc, s, lv.du, 16 * lv.nb, out_mode=1, col_off=16 * i + 4 * which, lo_off=8)
+
+            ctx.tape.record(bwd)
+        return out
+
+    def _v2_tables(self, lp: LayerPlan):
+        """Per-processor packed operands for the V2 hidden-state update (built lazily, packed every step)."""
+        if getattr(lp, "v2_ext", None) is not None:
+            return
+        p = lp.proc
+        C = p.hidden_size
+        dev = self.device
+        lp.v2_ext, lp.v2_up, lp.v2_down_tab = [], [], []
+        for layer in (p.to_control, p.to_control_out):
+            down, up = layer.down.weight, layer.up.weight
+            ext = torch.zeros(16, C, device=dev, dtype=BF16)
+            upt = torch.zeros(C, 4, device=dev, dtype=torch.float32)
+            dnt = torch.zeros(C, 4, device=dev, dtype=torch.float32)
+            self.v2_plan.add_ext(down[:, :C], ext)
+            self.v2_plan.add_table(up, upt)
+            self.v2_plan.add_table(down[:, :C], dnt, transposed=True)
+            lp.v2_ext.append(ext); lp.v2_up.append(upt); lp.v2_down_tab.append(dnt)
+        lp.v2_eye = torch.eye(4, device=dev, dtype=torch.float32)
+
+    # ------------------------------------------------------------------------------------------------ attention layer
+    def attn_fn(self, ctx: Ctx, L, hs: Var, ehs: Optional[Var], residual: Var) -> Var:
+        lp = self.layers[L.name]
+        if lp.kind == "v2":
+            hs = self._v2_inject(ctx, lp, hs, 0)
+        kv_in = hs if ehs is None else ehs
+        on_q = None
+        if lp.kind == "v1":
+            on_q = lambda e, t_out, dy2: self._v1_q_bwd(ctx, lp, e, t_out, dy2)
+        q = E.linear(ctx, hs, L.to_q, slot=lp.q, t_add=getattr(lp, "t_add", None), on_slot_bwd=on_q)
+        k = E.linear(ctx, kv_in, L.to_k, slot=lp.k)
+        v = E.linear(ctx, kv_in, L.to_v, slot=lp.v)
+        o = E.attention(ctx, q, k, v, L.heads)
+        if lp.kind == "v2":
+            o = self._v2_inject(ctx, lp, o, 1)
+        return E.linear(ctx, o, L.to_out, slot=lp.out, residual=residual)
+
+    def finish_backward(self, ctx: Ctx):
+        """After the tape ran: one GEMM per level turns the collected du blocks into d(control state)."""
+        for lv in self.levels.values():
+            if lv.du is None or lv.c is None or not lv.c.rg:
+                continue
+            T = lv.du.shape[0]
+            E.give_produce(lv.c, lambda buf, acc, lv=lv, T=T: ops.gemm(lv.du, lv.stack_t, out=buf.view(T, lv.cc),
+                                                                     residual=buf.view(T, lv.cc) if acc else None))
+            lv.du = None

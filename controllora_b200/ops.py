@@ -356,3 +356,146 @@ def mse_loss(pred, target, gscale: float = 1.0, need_grad=True):
     dpred = torch.empty_like(pred) if need_grad else None
     _call("cl_mse_loss", _p(pred), _p(target), _p(loss), _p(dpred), C.c_int64(pred.numel()), C.c_float(gscale))
     return loss, dpred
+
+
+def attention_bwd(q, k, v, o, d_o, lse, heads: int, scale: float, need_dq=True, need_dkv=True, dq=None, dk=None, dv=None):
+    from ._lib import AttnBwdArgs
+
+    B, Nq, HD = q.shape
+    Nk = k.shape[1]
+    d = HD // heads
+    for t in (q, k, v, o, d_o):
+        assert t.stride(2) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
+    delta = torch.empty(B, heads, Nq, device=q.device, dtype=torch.float32)
+    if need_dq and dq is None:
+        dq = torch.empty(B, Nq, HD, device=q.device, dtype=BF16)
+    if need_dkv and dk is None:
+        dk = torch.empty(B, Nk, HD, device=q.device, dtype=BF16)
+        dv = torch.empty(B, Nk, HD, device=q.device, dtype=BF16)
+    a = AttnBwdArgs()
+    a.B, a.H, a.Nq, a.Nk, a.d = B, heads, Nq, Nk, d
+    a.q, a.ldq = _ptr(q), q.stride(1)
+    a.k, a.ldk = _ptr(k), k.stride(1)
+    a.v, a.ldv = _ptr(v), v.stride(1)
+    a.o, a.ldo = _ptr(o), o.stride(1)
+    a.d_o, a.lddo = _ptr(d_o), d_o.stride(1)
+    a.lse, a.delta = _ptr(lse), _ptr(delta)
+    if need_dq:
+        a.dq, a.lddq = _ptr(dq), dq.stride(1)
+    if need_dkv:
+        a.dk, a.lddk = _ptr(dk), dk.stride(1)
+        a.dv, a.lddv = _ptr(dv), dv.stride(1)
+    a.scale = float(scale)
+    check(_lib.lib().cl_attn_bwd(C.byref(a), _stream()), "cl_attn_bwd")
+    return dq, dk, dv
+
+
+class PackPlan:
+    """Device-resident descriptor table for cl_lora_pack_batch (built once; re-run every step)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.descs = []
+        self.max_elems = 1
+        self._dev = None
+        self._keep = []
+
+    def add(self, src: torch.Tensor, dst: torch.Tensor, kind: int, r: int, K: int, s_j: int, s_k: int, ld: int, row_off: int):
+        from ._lib import PackDesc
+
+        d = PackDesc()
+        d.src, d.dst = src.data_ptr(), dst.data_ptr()
+        d.kind, d.r, d.K, d.s_j, d.s_k, d.ld, d.row_off = kind, r, K, s_j, s_k, ld, row_off
+        self.descs.append(d)
+        self._keep.append((src, dst))
+        self.max_elems = max(self.max_elems, r * K)
+        self._dev = None
+
+    def add_ext(self, down_like: torch.Tensor, ext: torch.Tensor, row_off: int = 0, transposed: bool = False):
+        """ext rows <- rows of `down_like` ([r, K]); transposed=True reads a [K, r] matrix (e.g. up.weight) instead."""
+        if transposed:
+            K, r = down_like.shape
+            self.add(down_like, ext, 0, r, K, down_like.stride(1), down_like.stride(0), ext.stride(0), row_off)
+        else:
+            r, K = down_like.shape
+            self.add(down_like, ext, 0, r, K, down_like.stride(0), down_like.stride(1), ext.stride(0), row_off)
+
+    def add_table(self, up_like: torch.Tensor, table: torch.Tensor, col_off: int = 0, transposed: bool = False):
+        """table[n, col_off + j] <- up_like[n, j] ([N, r]); transposed=True reads a [r, N] matrix (down.weight)."""
+        if transposed:
+            r, N = up_like.shape
+            self.add(up_like, table, 1, r, N, up_like.stride(0), up_like.stride(1), table.stride(0), col_off)
+        else:
+            N, r = up_like.shape
+            self.add(up_like, table, 1, r, N, up_like.stride(1), up_like.stride(0), table.stride(0), col_off)
+
+    def run(self):
+        from ._lib import PackDesc
+
+        if not self.descs:
+            return
+        if self._dev is None:
+            arr = (PackDesc * len(self.descs))(*self.descs)
+            raw = bytes(arr)
+            host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+            self._dev = host.to(self.device)
+        _call("cl_lora_pack_batch", C.c_void_p(self._dev.data_ptr()), len(self.descs), self.max_elems)
+
+
+def skinny_atb(a, r: int, b, out, so_j: int, so_c: int, alpha: float):
+    """out[j*so_j + c*so_c] += alpha * sum_m a[m, j] * b[m, c];  a fp32 [M, lda], b bf16 [M, C]"""
+    M = a.shape[0]
+    b2 = b.view(-1, b.shape[-1]) if b.is_contiguous() else b
+    assert b2.shape[0] == M and b2.stride(1) == 1
+    _call("cl_skinny_atb", _p(a), a.stride(0), r, _p(b2), C.c_int64(b2.stride(0)), _p(out), C.c_int64(so_j), C.c_int64(so_c),
+          C.c_float(alpha), M, b2.shape[1])
+
+
+def rowdot(a, u):
+    """e[m, j] = sum_n a[m, n] * u[n, j];  a bf16 [M, N], u fp32 [N, rp]"""
+    a2 = a.view(-1, a.shape[-1]) if a.is_contiguous() else a
+    M, N = a2.shape
+    rp = u.shape[1]
+    e = torch.empty(M, rp, device=a.device, dtype=torch.float32)
+    _call("cl_rowdot", _p(a2), C.c_int64(a2.stride(0)), _p(u), rp, _p(e), M, N)
+    return e
+
+
+def rowmat(a, w, sw_i: int, sw_j: int, I: int, J: int, alpha: float, out, ldo: int, out_mode=0, col_off=0, lo_off=0, accumulate=False):
+    M = a.shape[0]
+    _call("cl_rowmat", _p(a), a.stride(0), _p(w), sw_i, sw_j, I, J, C.c_float(alpha), _p(out), ldo, out_mode, col_off, lo_off,
+          int(accumulate), M)
+
+
+def skinny_small(a, I: int, b, J: int, out, alpha: float):
+    _call("cl_skinny_small", _p(a), a.stride(0), I, _p(b), b.stride(0), J, _p(out), C.c_float(alpha), a.shape[0])
+
+
+def small_matmul(a, sa_i, sa_j, b, sb_j, sb_k, out, so_i, so_k, I, J, K, alpha=1.0, accumulate=False):
+    _call("cl_small_matmul", _p(a), C.c_int64(sa_i), C.c_int64(sa_j), _p(b), C.c_int64(sb_j), C.c_int64(sb_k), _p(out),
+          C.c_int64(so_i), C.c_int64(so_k), I, J, K, C.c_float(alpha), int(accumulate))
+
+
+def sumsq(x, out):
+    _call("cl_sumsq", _p(x), C.c_int64(x.numel()), _p(out))
+
+
+def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0, zero_grad=True):
+    _call("cl_adamw", _p(p), _p(g), _p(m), _p(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(beta1), C.c_float(beta2),
+          C.c_float(eps), C.c_float(wd), int(step), _p(gnorm_sq), C.c_float(max_norm), C.c_float(grad_scale), int(zero_grad))
+
+
+def hilo_combine(src, nb: int):
+    M = src.shape[0]
+    dst = torch.empty(M, 8 * nb, device=src.device, dtype=torch.float32)
+    _call("cl_hilo_combine", _p(src), _p(dst), C.c_int64(M), nb)
+    return dst
+
+
+def rank_update(x, t, tab, alpha: float, out=None):
+    """out = x + alpha * t[:, :rp] @ tab^T ; x bf16 [M, C], t fp32 [M, ldt], tab fp32 [C, rp]"""
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    out = torch.empty_like(x) if out is None else out
+    _call("cl_rank_update", _p(x), _p(t), t.stride(0), _p(tab), tab.shape[1], C.c_float(alpha), _p(out), C.c_int64(M), Cc)
+    return out

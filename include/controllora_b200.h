@@ -186,7 +186,7 @@ int cl_mse_loss(const float* pred, const float* target, float* loss, float* dpre
 typedef struct {
     const void* src;   /* fp32 */
     void* dst;
-    int32_t kind;      /* 0: ext (bf16 [16, ld]), 1: table (fp32 [K, ld]) */
+    int32_t kind;      /* 0: ext (bf16 [16, ld] hi/lo rows), 1: table (fp32 [K, ld]), 2: bf16 [K, ld] table, value in hi and lo slots */
     int32_t r, K;      /* src(j, k), j < r, k < K */
     int64_t s_j, s_k;  /* element strides of src */
     int32_t ld;        /* dst leading dimension (elements) */
@@ -199,6 +199,9 @@ int cl_skinny_atb(const float* a, int lda, int r, const void* b, int64_t ldb, fl
 int cl_rowdot(const void* a, int64_t lda, const float* u, int rp, float* e, int M, int N, void* stream);
 int cl_rowmat(const float* a, int lda, const float* w, int sw_i, int sw_j, int I, int J, float alpha, void* out, int ldo,
               int out_mode, int col_off, int lo_off, int accumulate, int M, void* stream);
+int cl_hilo_combine(const float* src, float* dst, int64_t M, int nb, void* stream);  /* [M,16nb] hi|lo blocks -> [M,8nb] */
+int cl_rank_update(const void* x, const float* t, int ldt, const float* tab, int rp, float alpha, void* out, int64_t M,
+                   int C, void* stream);                                            /* out = x + alpha * t * tab^T */
 int cl_skinny_small(const float* a, int lda, int I, const float* b, int ldb, int J, float* out, float alpha, int M,
                     void* stream);
 int cl_small_matmul(const float* a, int64_t sa_i, int64_t sa_j, const float* b, int64_t sb_j, int64_t sb_k, float* out,
