@@ -298,7 +298,7 @@ int make_head_map(CUtensorMap* tm, const void* ptr, int B, int H, int N, int d, 
     uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)N, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)N * ld * 2};
     uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
-    return get_tensor_map(tm, ptr, 4, dims, strides, box, true);
+    return get_tensor_map(tm, ptr, 4, dims, strides, box, 128);
 }
 
 template <int DP, int BLOCK_N, int STAGES>

@@ -27,8 +27,8 @@
 namespace clb {
 
 static constexpr int BLOCK_M = 128;
-static constexpr int BLOCK_K = 64;                       // 64 bf16 = 128 B = one swizzle row
-static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+// BLOCK_K (template BK): 64 bf16 = 128 B rows with the 128B swizzle, or 32 bf16 = 64 B rows with the 64B swizzle
+// (used for the 32-channel layers of the hint encoder, where a 3x3 tap only offers 32 contiguous K elements).
 static constexpr int NUM_EPI_WARPS = 8;
 static constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 static constexpr int STAGE_ROW_BYTES = 128;              // epilogue staging: 32 fp32 columns per row
@@ -58,10 +58,15 @@ struct GemmParams {
     int out_fp32;
 };
 
-template <int BN, int EXT>
+template <int BN, int EXT, int BK>
 struct GemmCfg {
     static constexpr int UMMA_N = BN + EXT;
-    static constexpr int B_STAGE_BYTES = UMMA_N * BLOCK_K * 2;
+    static constexpr int ROW_BYTES = BK * 2;
+    static constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
+    static constexpr int B_STAGE_BYTES = UMMA_N * ROW_BYTES;
+    static constexpr int SBO = 8 * ROW_BYTES;                  // 8-row swizzle atom
+    static constexpr int LAYOUT = (BK == 64) ? 2 : 4;          // UMMA layout type: 128B / 64B swizzle
+    static_assert(BK == 64 || BK == 32, "BK");
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int BUF_COLS = (UMMA_N + 31) / 32 * 32;
     static constexpr int TMEM_COLS = (2 * BUF_COLS <= 32) ? 32 : (2 * BUF_COLS <= 64) ? 64 : (2 * BUF_COLS <= 128) ? 128
@@ -93,11 +98,12 @@ __device__ __forceinline__ void decode_row(const GemmParams& p, int m_blk, int r
     }
 }
 
-template <int BN, int EXT>
+template <int BN, int EXT, int BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmE, const GemmParams p, const int num_stages) {
-    using Cfg = GemmCfg<BN, EXT>;
+    using Cfg = GemmCfg<BN, EXT, BK>;
+    constexpr int A_STAGE_BYTES = Cfg::A_STAGE_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve (base is 1024-aligned by the runtime for dynamic smem declared __align__(1024); re-align anyway)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -164,21 +170,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
                     if (p.a_mode == 0) {
-                        tma_load_2d(&tmA, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
+                        tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BLOCK_M);
                     } else {
                         const int tap = kb / p.cblocks, cb = kb % p.cblocks;
                         const int ky = tap / 3, kx = tap % 3;
                         if (p.a_mode == 1) {
-                            tma_load_4d(&tmA, &full_bar[stage], sa, cb * BLOCK_K, tw * p.bw + kx - 1,
+                            tma_load_4d(&tmA, &full_bar[stage], sa, cb * BK, tw * p.bw + kx - 1,
                                         th * p.bh + ky - 1, tn * p.bn);
                         } else {
                             const int iy = ky - p.pad_lo, ix = kx - p.pad_lo;
-                            tma_load_5d(&tmA, &full_bar[stage], sa, (ix & 1) * p.C + cb * BLOCK_K,
+                            tma_load_5d(&tmA, &full_bar[stage], sa, (ix & 1) * p.C + cb * BK,
                                         tw * p.bw + (ix >> 1), iy & 1, th * p.bh + (iy >> 1), tn * p.bn);
                         }
                     }
-                    tma_load_2d(&tmB, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BN);
-                    if (EXT) tma_load_2d(&tmE, &full_bar[stage], sb + BN * 128, kb * BLOCK_K, 0);
+                    tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * BN);
+                    if (EXT) tma_load_2d(&tmE, &full_bar[stage], sb + BN * Cfg::ROW_BYTES, kb * BK, 0);
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -202,9 +208,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                     const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024, 2);
-                        const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, 1024, 2);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t adesc = make_smem_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                        const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
                         tc_mma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
@@ -347,10 +353,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // host side
 // =====================================================================================================
 
-template <int BN, int EXT>
+template <int BN, int EXT, int BK = 64>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tE, const GemmParams& p,
                        cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, EXT>;
+    using Cfg = GemmCfg<BN, EXT, BK>;
     const int up_bytes = (p.lora_up != nullptr) ? ((p.N * p.lora_rp * 4 + 15) & ~15) : 0;
     const int fixed = 1024 /*align slack*/ + EPI_STAGING_BYTES + up_bytes + 256 /*barriers*/;
     int stages = (232448 - fixed) / Cfg::STAGE_BYTES;
@@ -359,13 +365,13 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     const int smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
     static bool attr_done = false;
     if (!attr_done) {
-        CL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        CL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_done = true;
     }
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
     int grid = num_sms();
     if (grid > num_tiles) grid = num_tiles;
-    gemm_tc_kernel<BN, EXT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tA, tB, tE, p, stages);
+    gemm_tc_kernel<BN, EXT, BK><<<grid, NUM_THREADS, smem_bytes, stream>>>(tA, tB, tE, p, stages);
     count_launch();
     CL_CUDA_CHECK(cudaGetLastError());
     return CL_OK;
@@ -392,7 +398,10 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     memset(&p, 0, sizeof(p));
     p.M = a->M; p.N = a->N; p.K = a->K;
     p.a_mode = a->a_mode;
-    p.num_k_blocks = (a->K + BLOCK_K - 1) / BLOCK_K;
+    // K-block: 64 (128B swizzle) unless this is a conv whose channel count only allows 32-element K runs
+    const int BK = (a->a_mode != 0 && a->C % 64 != 0) ? 32 : 64;
+    const int swz = (BK == 64) ? 128 : 64;
+    p.num_k_blocks = (a->K + BK - 1) / BK;
     CUtensorMap tA, tB, tE;
     memset(&tE, 0, sizeof(tE));
 
@@ -401,14 +410,14 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
         p.num_m_blocks = (a->M + BLOCK_M - 1) / BLOCK_M;
         uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
         uint64_t strides[1] = {(uint64_t)a->lda * 2};
-        uint32_t box[2] = {BLOCK_K, BLOCK_M};
-        CL_CHECK(get_tensor_map(&tA, a->a, 2, dims, strides, box, /*swizzle128=*/true));
+        uint32_t box[2] = {(uint32_t)BK, BLOCK_M};
+        CL_CHECK(get_tensor_map(&tA, a->a, 2, dims, strides, box, swz));
     } else if (a->a_mode == 1 || a->a_mode == 2) {
-        if (a->C % 64 != 0) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: conv C must be a multiple of 64");
+        if (a->C % 32 != 0) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: conv C must be a multiple of 32");
         if (a->K != 9 * a->C) return set_error(CL_ERR_INVALID, "cl_gemm: conv K must be 9*C");
         const int s = (a->a_mode == 2) ? 2 : 1;
         if (a->H % s || a->W % s) return set_error(CL_ERR_INVALID, "cl_gemm: stride-2 conv needs even H, W");
-        p.n_img = a->n_img; p.Ho = a->H / s; p.Wo = a->W / s; p.C = a->C; p.cblocks = a->C / 64;
+        p.n_img = a->n_img; p.Ho = a->H / s; p.Wo = a->W / s; p.C = a->C; p.cblocks = a->C / BK;
         p.pad_lo = a->pad_lo;
         if (a->M != p.n_img * p.Ho * p.Wo) return set_error(CL_ERR_INVALID, "cl_gemm: conv M != n*Ho*Wo");
         int bw = 128;
@@ -424,13 +433,13 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
         if (a->a_mode == 1) {
             uint64_t dims[4] = {C, W, H, NI};
             uint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-            uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
-            CL_CHECK(get_tensor_map(&tA, a->a, 4, dims, strides, box, true));
+            uint32_t box[4] = {(uint32_t)BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+            CL_CHECK(get_tensor_map(&tA, a->a, 4, dims, strides, box, swz));
         } else {
             uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, NI};
             uint64_t strides[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
-            uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bn};
-            CL_CHECK(get_tensor_map(&tA, a->a, 5, dims, strides, box, true));
+            uint32_t box[5] = {(uint32_t)BK, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bn};
+            CL_CHECK(get_tensor_map(&tA, a->a, 5, dims, strides, box, swz));
         }
     } else {
         return set_error(CL_ERR_INVALID, "cl_gemm: bad a_mode");
@@ -443,6 +452,7 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
         else if (a->N % 256 == 0) bn_sel = 256;
         else if (a->N % 160 == 0) bn_sel = 160;
         else if (a->N % 128 == 0) bn_sel = 128;
+        else if (a->N <= 32 && BK == 32) bn_sel = 32;
         else if (a->N <= 64) bn_sel = 64;
         else if (a->N <= 128) bn_sel = 128;
         else bn_sel = 160;
@@ -451,15 +461,15 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     {
         uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
         uint64_t strides[1] = {(uint64_t)a->ldb * 2};
-        uint32_t box[2] = {BLOCK_K, (uint32_t)bn_sel};
-        CL_CHECK(get_tensor_map(&tB, a->b, 2, dims, strides, box, true));
+        uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn_sel};
+        CL_CHECK(get_tensor_map(&tB, a->b, 2, dims, strides, box, swz));
     }
     if (lora) {
         if (a->ldb_ext % 8 != 0) return set_error(CL_ERR_INVALID, "cl_gemm: ldb_ext must be a multiple of 8");
         uint64_t dims[2] = {(uint64_t)a->K, 16};
         uint64_t strides[1] = {(uint64_t)a->ldb_ext * 2};
-        uint32_t box[2] = {BLOCK_K, 16};
-        CL_CHECK(get_tensor_map(&tE, a->ext, 2, dims, strides, box, true));
+        uint32_t box[2] = {(uint32_t)BK, 16};
+        CL_CHECK(get_tensor_map(&tE, a->ext, 2, dims, strides, box, swz));
     }
 
     p.bias = a->bias; p.row_bias = a->row_bias; p.rows_per_group = a->rows_per_group;
@@ -470,6 +480,15 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     if (p.row_bias && p.rows_per_group <= 0) return set_error(CL_ERR_INVALID, "cl_gemm: rows_per_group");
     if ((p.ldd % 4) || (p.residual && (p.ldr % 4))) return set_error(CL_ERR_INVALID, "cl_gemm: ldd/ldr % 4");
 
+    if (BK == 32) {
+        if (lora) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: LoRA epilogue is not instantiated for 32-channel convs");
+        switch (bn_sel) {
+            case 32: return launch_gemm<32, 0, 32>(tA, tB, tE, p, stream);
+            case 64: return launch_gemm<64, 0, 32>(tA, tB, tE, p, stream);
+            case 128: return launch_gemm<128, 0, 32>(tA, tB, tE, p, stream);
+            default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n for 32-channel convs must be 32/64/128");
+        }
+    }
     if (lora) {
         switch (bn_sel) {
             case 64: return launch_gemm<64, 16>(tA, tB, tE, p, stream);

@@ -57,7 +57,7 @@ static std::mutex g_tm_mutex;
 static std::unordered_map<std::string, CUtensorMap> g_tm_cache;
 
 int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, bool swizzle128) {
+                   const uint32_t* box, int swizzle_bytes) {
     if (rank < 1 || rank > 5) return set_error(CL_ERR_INVALID, "tensor map rank %d", rank);
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return set_error(CL_ERR_INVALID, "tensor map base not 16B aligned");
     struct Key {
@@ -67,7 +67,7 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* 
         uint32_t box[5];
     } key;
     memset(&key, 0, sizeof(key));
-    key.ptr = ptr; key.rank = rank; key.sw = swizzle128 ? 1 : 0;
+    key.ptr = ptr; key.rank = rank; key.sw = swizzle_bytes;
     for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) {
         key.strides[i] = strides_bytes[i];
@@ -89,7 +89,7 @@ int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* 
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdims, gstr, gbox,
                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         return set_error(CL_ERR_CUDA,

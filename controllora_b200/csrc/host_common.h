@@ -15,7 +15,7 @@ int num_sms();
 // Encode (or fetch from the cache) a tiled bf16 tensor map.  dims/box are innermost-first, strides are the byte
 // strides of dims 1..rank-1.  Returns CL_OK or a negative status.
 int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, bool swizzle128);
+                   const uint32_t* box, int swizzle_bytes /* 0, 64 or 128 */);
 
 }  // namespace clb
 
