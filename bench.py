@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — ControlLoRA training throughput on B200 (the BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (one process per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm's CPU path (oracle port) on host cores
+
+One "step" = hint-encoder fwd + SD-1.5 UNet fwd + MSE + backward (dX, LoRA dA/dB, hint-encoder dW) + gradient
+all-reduce (N > 1) + clip_grad_norm + AdamW, on synthetic 512x512 inputs (64x64 latents, 77x768 text states), batch 8
+per GPU, random-init weights of the SD-1.5 / ControlLoRA architecture (no checkpoints are reachable offline).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "train_images_per_sec_512px_bs8_per_gpu"
+UNIT = "images/s"
+# algorithmic work per image (SURVEY.md §8d / BASELINE.md §2)
+GFLOP_PER_IMAGE_STEP = 1794.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="diffusiondb-canny-v2", help="ControlLoRA config name (controllora_b200.configs.NAMED)")
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def synth_inputs(torch, B, seed_off=0, device="cpu"):
+    """SURVEY.md §8d synthetic tensors: latents / text states ~ N(0,1), canny-like {-1,+1} guide with ~8% edge pixels."""
+    g = lambda s: torch.Generator().manual_seed(s + 1000 * seed_off)
+    x = torch.randn(B, 4, 64, 64, generator=g(0))
+    t = torch.randint(0, 1000, (B,), generator=g(1)).float()
+    e = torch.randn(B, 77, 768, generator=g(2))
+    edge = (torch.rand(B, 1, 512, 512, generator=g(3)) < 0.08).float() * 2 - 1
+    guide = edge.expand(B, 3, 512, 512).contiguous()
+    tgt = torch.randn(B, 4, 64, 64, generator=g(4))
+    return x, t, e, guide, tgt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md: 1.4 PF sustained)"
+
+
+# ------------------------------------------------------------------------------------------------------ CPU oracle arm
+def cpu_train_step_factory(config_name: str):
+    """The reference algorithm on the host cores: oracle port of diffusers' UNet + models.py (oracle/), fp32, one image."""
+    import torch
+    from oracle import models_ref as MR
+    from oracle import unet_ref as UR
+    from controllora_b200.configs import NAMED
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    unet = UR.UNet2DConditionModel()
+    UR.init_synthetic_(unet, seed=1)
+    unet.requires_grad_(False)
+    cl = MR.ControlLoRA.from_config(NAMED[config_name])
+    MR.randomize_lora_up_(cl, seed=3)
+    MR.wire_processors(unet, cl)
+    opt = torch.optim.AdamW(cl.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    x, t, e, guide, tgt = synth_inputs(torch, 1)
+
+    def step():
+        cl(guide)
+        loss = torch.nn.functional.mse_loss(unet(x, t.long(), e).sample, tgt)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(cl.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        return float(loss)
+
+    return step
+
+
+def cpu_baseline(config_name: str, budget_s: float = 25.0, max_steps: int = 2):
+    step = cpu_train_step_factory(config_name)
+    t0 = time.time()
+    step()                      # warm-up (allocator, thread pool)
+    warm = time.time() - t0
+    n = 1 if warm > budget_s / 2 else max_steps
+    t0 = time.time()
+    for _ in range(n):
+        step()
+    dt = (time.time() - t0) / n
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} full train step(s) of ONE 512x512 image (batch 1) through the fp32 oracle port (oracle/), "
+                      f"torch CPU with {os.cpu_count()} threads; {dt:.1f} s/step"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step = cpu_train_step_factory(a.config)
+    t0 = time.time()
+    step()
+    first = time.time() - t0
+    budget = 150.0
+    w_eff = 0 if first > 30 else min(a.warmup, 1)
+    for _ in range(w_eff):
+        step()
+    k_eff = max(1, min(a.steps, int(budget / max(first, 1e-3))))
+    t0 = time.time()
+    for _ in range(k_eff):
+        step()
+    dt = (time.time() - t0) / k_eff
+    v = 1.0 / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": k_eff, "warmup": w_eff + 1,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{a.config} ControlLoRA train step, SD-1.5 UNet 512x512 (64x64 latents), CPU sample = batch 1"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{k_eff} timed train step(s) of one 512x512 image each ({a.steps} requested; bounded to ~150 s), "
+                                   f"fp32 oracle port of the reference (diffusers is not installable offline), {os.cpu_count()} threads"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import controllora_b200 as cb
+    from controllora_b200 import _lib, ops
+    from controllora_b200.configs import NAMED, wire_processors
+    from controllora_b200.trainer import Trainer
+
+    dev = torch.device("cuda", local)
+    B = a.batch
+    unet = cb.UNet2DConditionModel.synthetic(dev, seed=0)
+    cl = cb.ControlLoRA.from_config(NAMED[a.config]).to(dev)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():       # LoRA `up` weights are zero-initialised: give them values so no path is trivially dead
+        for n_, p_ in cl.named_parameters():
+            if n_.endswith("up.weight"):
+                p_.copy_((0.02 * torch.randn(p_.shape, generator=g)).to(dev))
+    wire_processors(unet, cl)
+    tr = Trainer(unet, cl, lr=1e-4)
+    host = synth_inputs(torch, B, seed_off=rank)
+    x, t, e, guide, tgt = (h.to(dev) for h in host)
+    e = e.to(torch.bfloat16)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        loss = tr.step(x, t, e, guide, tgt)
+    barrier()
+    # ---------------- timed region: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        loss = tr.step(x, t, e, guide, tgt)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = (_lib.launch_count() - n0) // max(a.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax) / a.steps
+    value = world * B / (ms_step / 1e3)
+    final_loss = float(loss)
+
+    # ---------------- end-to-end: host (pinned) buffers in, loss out, every step
+    pinned = [h.pin_memory() for h in host]
+    h2d = sum(p.numel() * p.element_size() for p in pinned)
+    dbuf = [torch.empty_like(p, device=dev) for p in pinned]
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        for d, p in zip(dbuf, pinned):
+            d.copy_(p, non_blocking=True)
+        l = tr.step(dbuf[0], dbuf[1], ops.f32_to_bf16(dbuf[2]), dbuf[3], dbuf[4])
+        loss_host.copy_(l, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * a.steps / float(dt)
+
+    # ---------------- roofline of the dominant kernel family (tcgen05 GEMM / implicit-GEMM conv): live CUDA-event timing
+    roof = None
+    if rank == 0 and not a.no_roofline:
+        peak_tf, peak_hbm, which = measured_peaks()
+        rec = []
+        orig = ops.gemm
+
+        def timed_gemm(A_, B_, **kw):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            r = orig(A_, B_, **kw)
+            s1.record()
+            conv = kw.get("conv_stride", 0)
+            M = A_.shape[0] if not conv else A_.shape[0] * A_.shape[1] * A_.shape[2] // (conv * conv)
+            N, K = B_.shape
+            fl = 2.0 * M * N * K + (2.0 * M * 16 * K if kw.get("lora_up") is not None else 0.0)
+            rec.append((fl, s0, s1))
+            return r
+
+        ops.gemm = timed_gemm
+        import controllora_b200.engine as E_, controllora_b200.lora_runtime as LR_, controllora_b200.hint_encoder as HE_
+        tr.step(x, t, e, guide, tgt)
+        torch.cuda.synchronize()
+        ops.gemm = orig
+        fl = sum(r[0] for r in rec)
+        tm = sum(r[1].elapsed_time(r[2]) for r in rec)
+        ach = fl / (tm * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN,EXT,BK> (all fused linear / LoRA / implicit-GEMM conv launches of one step)",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "launches_per_step": len(rec), "gemm_ms_per_step": tm, "algorithmic_gflop_per_step": fl / 1e9, "peak_source": which,
+                "step_model_flops_utilisation": (GFLOP_PER_IMAGE_STEP * 1e9 * B / (ms_step * 1e-3)) / (peak_tf * 1e12)}
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                cpu = cpu_baseline(a.config)
+            except Exception as ex:  # the baseline must never take the measurement down
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{a.config} ControlLoRA train step on the SD-1.5 UNet, 512x512 (64x64 latents, 77x768 text states), "
+                                   f"batch {B}/GPU, hint encoder + UNet fwd/bwd + clip + AdamW" + (" + NCCL all-reduce of the flat grad arena" if world > 1 else ""),
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2_policy": "no explicit flush: each step streams 1.7 GB of frozen weights plus >5 GB of activations, far beyond the 126 MB L2",
+                       "weights": "random-init (seeded), SD-1.5 / ControlLoRA shapes", "final_loss": final_loss},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if roof is not None:
+            out["roofline"] = roof
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

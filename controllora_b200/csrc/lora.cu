@@ -233,17 +233,24 @@ skinny_small_kernel(const float* __restrict__ a, int lda, int I, const float* __
 
 // ------------------------------------------------------------------------------------------ weight-space tiny matmul (fp32)
 // out[i*so_i + k*so_k] (+)= alpha * sum_j a[i*sa_i + j*sa_j] * b[j*sb_j + k*sb_k]
+// one warp per output element (the reduction length J is up to the hidden size, the outputs are few)
 __global__ void __launch_bounds__(256)
 small_matmul_kernel(const float* __restrict__ a, long long sa_i, long long sa_j, const float* __restrict__ b, long long sb_j,
                     long long sb_k, float* __restrict__ out, long long so_i, long long so_k, int I, int J, int K, float alpha,
                     int accumulate) {
     const long long total = (long long)I * K;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long t = warp0; t < total; t += nwarps) {
         const int i = (int)(t / K), k = (int)(t % K);
         float s = 0.f;
-        for (int j = 0; j < J; ++j) s += a[i * sa_i + j * sa_j] * b[j * sb_j + k * sb_k];
-        float* o = out + i * so_i + k * so_k;
-        *o = accumulate ? *o + alpha * s : alpha * s;
+        for (int j = lane; j < J; j += 32) s += a[i * sa_i + j * sa_j] * b[j * sb_j + k * sb_k];
+        s = warp_sum(s);
+        if (lane == 0) {
+            float* o = out + i * so_i + k * so_k;
+            *o = accumulate ? *o + alpha * s : alpha * s;
+        }
     }
 }
 
@@ -276,9 +283,9 @@ extern "C" int cl_skinny_atb(const float* a, int lda, int r, const void* b, int6
     if (rows_par < 1) rows_par = 1;
     int threads = ((rows_par * chunks + 31) / 32) * 32;
     if (threads > 512) { rows_par = 1; threads = ((chunks + 31) / 32) * 32; }
-    int ctas = num_sms() * 2;
+    int ctas = num_sms();
     int rows_per_cta = (M + ctas - 1) / ctas;
-    if (rows_per_cta < rows_par * 4) rows_per_cta = rows_par * 4;
+    if (rows_per_cta < rows_par * 16) rows_per_cta = rows_par * 16;
     const int grid = (M + rows_per_cta - 1) / rows_per_cta;
     const __nv_bfloat16* bb = reinterpret_cast<const __nv_bfloat16*>(b);
 #define SK_CASE(R)                                                                                                      \
@@ -359,9 +366,9 @@ extern "C" int cl_small_matmul(const float* a, int64_t sa_i, int64_t sa_j, const
                                int64_t so_i, int64_t so_k, int I, int J, int K, float alpha, int accumulate, void* stream_) {
     STREAM;
     if (!a || !b || !out) return set_error(CL_ERR_INVALID, "cl_small_matmul: null");
-    const long long total = (long long)I * K;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+    const long long total = (long long)I * K;          // one warp per output
+    int blocks = (int)((total + 7) / 8);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     small_matmul_kernel<<<blocks, 256, 0, stream>>>(a, sa_i, sa_j, b, sb_j, sb_k, out, so_i, so_k, I, J, K, alpha, accumulate);
     DONE();
 }

@@ -126,14 +126,24 @@ gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
     }
 }
 
-// forward apply: y = act((x - mean) * rstd * gamma + beta); writes float stats {mean, rstd} for the backward pass.
+// ws (fp64 sums) -> stats {mean, rstd} in fp32, one thread per (image, group)
+__global__ void gn_finalize_kernel(const double* __restrict__ ws, float* __restrict__ stats, int total, double inv_m, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const double mu = ws[2 * i] * inv_m;
+    double var = ws[2 * i + 1] * inv_m - mu * mu;
+    if (var < 0.0) var = 0.0;
+    stats[2 * i] = (float)mu;
+    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// forward apply: y = act((x - mean) * rstd * gamma + beta) with the fp32 stats {mean, rstd} of gn_finalize_kernel.
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const double* __restrict__ ws, float* __restrict__ stats, __nv_bfloat16* __restrict__ y, int HW, int C,
-                int G, float eps, int silu, long long total_chunks) {
+                const float* __restrict__ stats, __nv_bfloat16* __restrict__ y, int HW, int C, int G, int silu,
+                long long total_chunks) {
     const int chunks = C / 8;
     const int cpg = C / G;
-    const double inv_m = 1.0 / ((double)HW * cpg);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks;
          i += (long long)gridDim.x * blockDim.x) {
         const int chunk = (int)(i % chunks);
@@ -145,17 +155,9 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int g = (c0 + j) / cpg;
-            const double s0 = ws[(n * G + g) * 2], s1 = ws[(n * G + g) * 2 + 1];
-            const double mu = s0 * inv_m;
-            double var = s1 * inv_m - mu * mu;
-            if (var < 0.0) var = 0.0;
-            const float rs = (float)(1.0 / sqrt(var + (double)eps));
-            const float z = (xv[j] - (float)mu) * rs * gamma[c0 + j] + beta[c0 + j];
+            const float mu = stats[(n * G + g) * 2], rs = stats[(n * G + g) * 2 + 1];
+            const float z = (xv[j] - mu) * rs * gamma[c0 + j] + beta[c0 + j];
             o[j] = silu ? silu_f(z) : z;
-            if (stats != nullptr && (row % HW) == 0 && ((c0 + j) % cpg) == 0) {
-                stats[(n * G + g) * 2] = (float)mu;
-                stats[(n * G + g) * 2 + 1] = rs;
-            }
         }
         store8(y + row * C + c0, o);
     }
@@ -300,7 +302,7 @@ static int gn_launch_geometry(int HW, int C, int n, int& threads, int& rows_per_
     threads = ((rows_par * chunks + 31) / 32) * 32;
     if (threads > 512) { rows_par = 1; threads = ((chunks + 31) / 32) * 32; }
     // aim for ~4 CTAs per SM across the batch
-    int target_ctas = (num_sms() * 4 + n - 1) / n;
+    int target_ctas = (num_sms() * 2 + n - 1) / n;
     rows_per_cta = (HW + target_ctas - 1) / target_ctas;
     if (rows_per_cta < rows_par) rows_per_cta = rows_par;
     grid_x = (HW + rows_per_cta - 1) / rows_per_cta;
@@ -321,9 +323,11 @@ extern "C" int cl_groupnorm_fwd(const void* x, const float* gamma, const float* 
     const long long total = (long long)n * HW * (C / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-    gn_apply_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, ws, stats,
-                                                reinterpret_cast<__nv_bfloat16*>(y), HW, C, G, eps, silu, total);
-    count_launch(2);
+    if (stats == nullptr) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: stats buffer is required");
+    gn_finalize_kernel<<<(n * G + 127) / 128, 128, 0, stream>>>(ws, stats, n * G, 1.0 / ((double)HW * (C / G)), eps);
+    gn_apply_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, stats,
+                                                reinterpret_cast<__nv_bfloat16*>(y), HW, C, G, silu, total);
+    count_launch(3);
     CL_CUDA_CHECK(cudaGetLastError());
     return CL_OK;
 }

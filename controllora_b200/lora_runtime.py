@@ -70,7 +70,7 @@ class LoraRuntime:
         self.v2_plan = ops.PackPlan(device)     # V2 hidden-state-update operands
         self.level_plan = ops.PackPlan(device)  # stacked control-down operands per level (rebuilt when levels change)
         self.layers: Dict[str, LayerPlan] = {}
-        self.levels: Dict[int, _LevelCtx] = {}
+        self.level_list: List[_LevelCtx] = []
         self.signature = None
         self._build()
 
@@ -146,7 +146,8 @@ class LoraRuntime:
                 cs = lp.proc.control_states
                 assert cs is not None, "inject_control_states() must run before the UNet forward (models.py:227)"
                 groups.setdefault(cs.data_ptr(), []).append(lp)
-        key = tuple((k, tuple(id(lp) for lp in v)) for k, v in groups.items())
+        # level structure = which processors share a control tensor (pointer values change every step, membership not)
+        key = tuple(tuple(id(lp) for lp in v) for v in groups.values())
         if getattr(self, "_level_key", None) != key:
             self._build_levels(groups, control_vars)
             self._level_key = key
@@ -154,10 +155,11 @@ class LoraRuntime:
         self.v2_plan.run()
         self.level_plan.run()
         s = ctx.scale
-        for k, lv in self.levels.items():
+        for (k, lps), lv in zip(groups.items(), self.level_list):
             c = control_vars[k]
             lv.c = c
             T = c.data.shape[0] * c.data.shape[1]
+            assert c.data.shape[-1] == lv.cc
             c2 = c.data.view(T, lv.cc)
             u16 = ops.gemm(c2, lv.stack, out_fp32=True)
             lv.u = ops.hilo_combine(u16, lv.nb)
@@ -170,7 +172,7 @@ class LoraRuntime:
                 self._v1_prepare(ctx, lp)
 
     def _build_levels(self, groups, control_vars):
-        self.levels = {}
+        self.level_list = []
         plan = ops.PackPlan(self.device)
         for key, lps in groups.items():
             lv = _LevelCtx()
@@ -198,7 +200,7 @@ class LoraRuntime:
                     r = dn.shape[0]
                     # kind 2: stack_t[k, 16*blk + off + j] and [.. + 8 ..] <- bf16(dn[j, k])
                     plan.add(dn, lv.stack_t[:, 16 * blk:], 2, r, lv.cc, dn.stride(0), dn.stride(1), lv.stack_t.stride(0), off)
-            self.levels[key] = lv
+            self.level_list.append(lv)
         self.level_plan = plan
 
     # ------------------------------------------------------------------------------------------------ v1
@@ -323,7 +325,7 @@ class LoraRuntime:
 
     def finish_backward(self, ctx: Ctx):
         """After the tape ran: one GEMM per level turns the collected du blocks into d(control state)."""
-        for lv in self.levels.values():
+        for lv in getattr(self, "level_list", []):
             if lv.du is None or lv.c is None or not lv.c.rg:
                 continue
             T = lv.du.shape[0]

@@ -499,3 +499,27 @@ def rank_update(x, t, tab, alpha: float, out=None):
     out = torch.empty_like(x) if out is None else out
     _call("cl_rank_update", _p(x), _p(t), t.stride(0), _p(tab), tab.shape[1], C.c_float(alpha), _p(out), C.c_int64(M), Cc)
     return out
+
+
+def conv_wgrad(dy, x, dw, ksize: int, stride: int = 1, pad_lo: int = 1, alpha: float = 1.0):
+    """dw (fp32 [Cout, Cin, k, k], accumulated) += alpha * dY^T (*) X ; dy NHWC [n,Ho,Wo,Cout], x NHWC [n,H,W,Cin]"""
+    n, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    assert dw.is_contiguous() and dw.dtype == torch.float32
+    _call("cl_conv_wgrad", _p(dy), _p(x), _p(dw), n, H, W, Cin, Cout, ksize, stride, pad_lo, C.c_float(alpha))
+
+
+def conv_weight_prep(w, wf, wd=None):
+    Cout, Cin, k, _ = w.shape
+    _call("cl_conv_weight_prep", _p(w), _p(wf), _p(wd), Cout, Cin, k)
+
+
+def colsum(x, out, alpha: float = 1.0):
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    _call("cl_colsum", _p(x), _p(out), C.c_int64(M), Cc, C.c_float(alpha))
+
+
+def conv_in_wgrad(x, dy, dw):
+    n, Cin, H, W = x.shape
+    _call("cl_conv_in_wgrad", _p(x), _p(dy), _p(dw), n, Cin, H, W, dy.shape[-1])

@@ -1,0 +1,96 @@
+"""Fused ControlLoRA training step (the body of train_text_to_image_control_lora.py:751-796 after the VAE / text
+encoder): hint encoder -> UNet -> MSE -> backward -> (NCCL all-reduce) -> clip_grad_norm -> AdamW -> zero_grad, all as
+kernel launches on one stream with no host synchronisation.
+
+All trainable parameters are re-homed into ONE flat fp32 arena (and their gradients into another), so the data-parallel
+gradient exchange is a single ncclAllReduce and the optimizer a single kernel.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import engine as E
+from . import ops
+from .engine import Ctx, Tape, Var
+from .hint_encoder import HintEncoderEngine
+
+BF16 = torch.bfloat16
+
+
+class Trainer:
+    def __init__(self, unet, control_lora, lr: float = 1e-4, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,
+                 max_grad_norm: float = 1.0, process_group=None):
+        self.unet, self.cl = unet, control_lora
+        self.lr, self.betas, self.wd, self.eps, self.max_norm = lr, betas, weight_decay, eps, max_grad_norm
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        dev = unet.device_
+        params: List[torch.nn.Parameter] = [p for p in control_lora.parameters() if p.requires_grad]
+        seen = {id(p) for p in params}
+        for p in unet.trainable_parameters():          # e.g. stacked pre_loras that are not part of control_lora
+            if id(p) not in seen and p.requires_grad:
+                params.append(p)
+                seen.add(id(p))
+        self.params = params
+        n = sum(p.numel() for p in params)
+        pad = (-n) % 4
+        self.flat_p = torch.zeros(n + pad, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n + pad, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(n + pad, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n + pad, device=dev, dtype=torch.float32)
+        self.numel = n
+        store = unet.grad_store
+        store.bufs.clear()
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                view = self.flat_p[off:off + k].view(p.shape)
+                view.copy_(p.data.to(dev))
+                p.data = view
+                store.bufs[id(p)] = self.flat_g[off:off + k].view(p.shape)
+                store.params[id(p)] = p
+                off += k
+        unet._runtime = None                          # rebuild the LoRA runtime against the arena views
+        self.hint = HintEncoderEngine(control_lora, store.get)
+        self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.step_idx = 0
+        self.levels = None
+
+    def step(self, noisy_latents: torch.Tensor, timesteps: torch.Tensor, ehs: torch.Tensor, guide: torch.Tensor,
+             target: torch.Tensor) -> torch.Tensor:
+        """One optimizer step on device tensors: noisy_latents/target NCHW fp32, timesteps fp32 [B], ehs bf16 [B,77,768],
+        guide NCHW fp32 [B,3,512,512].  Returns the (device) loss tensor; nothing is synchronised."""
+        tape = Tape()
+        hctx = Ctx(tape=tape)
+        states = self.hint.forward(hctx, guide)
+        control = {}
+        for procs, s in zip(self.cl.lora_layers, states):
+            n, H, W, C = s.data.shape
+            c = Var(s.data.view(n, H * W, C), rg=True)       # token-matrix view of the same memory for the UNet side
+            for proc in procs:
+                proc.control_states = c.data
+            control[c.data.data_ptr()] = c
+
+            def bridge(s=s, c=c, shape=(n, H, W, C)):
+                if c.grad is not None:
+                    E.give_tensor(s, c.grad.view(shape))
+                    c.grad = None
+
+            tape.record(bridge)      # runs after every UNet backward op (incl. the per-level d-control GEMMs)
+        pred, ctx, rt = self.unet.run_engine(noisy_latents, timesteps, ehs, control, tape)
+        loss, dpred = ops.mse_loss(pred.data, target)
+        pred.grad = dpred
+        tape.backward()
+        self.step_idx += 1
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)
+        self.gnorm_sq.zero_()
+        ops.sumsq(self.flat_g, self.gnorm_sq)
+        ops.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                  self.step_idx, gnorm_sq=self.gnorm_sq, max_norm=self.max_norm, grad_scale=1.0 / self.world, zero_grad=True)
+        return loss

@@ -133,6 +133,9 @@ class UNet2DConditionModel(nn.Module):
         rt = self._get_runtime()
         ctx = Ctx(tape=tape, scale=scale)
         rt.begin(ctx, control)
+        if tape is not None:
+            # recorded before any UNet op => runs after all of them in the backward sweep
+            tape.record(lambda: rt.finish_backward(ctx))
         ehs_var = Var(ehs, rg=False)
         h = unet_forward(ctx, self.weights, sample, timesteps, ehs_var, rt.attn_fn)
         pred = conv_out_fwd(ctx, self.weights, h)
@@ -209,7 +212,6 @@ class _UNetFn(torch.autograd.Function):
         store.zero()
         fctx.pred.grad = gout.contiguous().float()
         fctx.tape.backward()
-        rt.finish_backward(fctx.ctx)
         grads = []
         for cs in fctx.ctensors:
             v = fctx.control[cs.data_ptr()]

@@ -208,6 +208,20 @@ int cl_small_matmul(const float* a, int64_t sa_i, int64_t sa_j, const float* b, 
                     int64_t so_i, int64_t so_k, int I, int J, int K, float alpha, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * K6: hint-encoder training support (the ControlLoRA conv stack of models.py:434-835 is trainable, so unlike the UNet
+ * it needs weight gradients and a per-step re-layout of its fp32 master weights).
+ *   cl_conv_wgrad:       dW[co,ci,ky,kx] += alpha * sum dY * X(shifted)   on tcgen05 (MN-major operands, split-K + RED)
+ *   cl_conv_weight_prep: w fp32 [Cout][Cin][k][k] -> wf bf16 [Cout][k*k][Cin] (forward) and wd bf16 [Cin][k*k flipped][Cout] (dX)
+ *   cl_colsum:           out[c] += alpha * sum_m x[m, c]                  (bias gradients)
+ *   cl_conv_in_wgrad:    weight gradient of the 3-channel conv_in (SIMT)
+ * ---------------------------------------------------------------------------------------------------------- */
+int cl_conv_wgrad(const void* dy, const void* x, float* dw, int n_img, int H, int W, int Cin, int Cout, int ksize, int stride,
+                  int pad_lo, float alpha, void* stream);
+int cl_conv_weight_prep(const float* w, void* wf, void* wd /* nullable */, int Cout, int Cin, int ksize, void* stream);
+int cl_colsum(const void* x, float* out, int64_t M, int C, float alpha, void* stream);
+int cl_conv_in_wgrad(const float* x, const void* dy, float* dw, int n, int Cin, int H, int W, int Cout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * K8: optimizer on the flat fp32 parameter / gradient arenas (train_text_to_image_control_lora.py:791-796:
  * clip_grad_norm_(max_norm) + torch.optim.AdamW step + zero_grad), no host synchronisation.
  *   cl_sumsq:  *out += sum x^2   (call once per arena after zeroing *out; the total grad norm)

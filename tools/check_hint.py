@@ -1,0 +1,171 @@
+"""GPU parity of the hint encoder (fwd + all parameter grads) and of one fused Trainer step against the fp32 oracle.
+usage: python tools/check_hint.py [hint_v1|hint_v2|train_v1|train_v2]"""
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+DEV = "cpu" if os.environ.get("CLB_DRYRUN") else "cuda"
+if DEV == "cpu":
+    from controllora_b200 import _lib, ops
+
+    class _Dummy:
+        def __getattr__(self, name):
+            return lambda *a, **k: 0
+
+    _lib.lib = lambda: _Dummy()
+    ops._req = lambda *a, **k: None
+    ops._stream = lambda: None
+
+from tools.check_unet import TINY, TINY_LORA, rel  # noqa: E402
+
+
+def hint_case(v2: bool, size=64, B=2):
+    import torch
+    from oracle import models_ref as MR
+    import controllora_b200 as cb
+
+    kw = dict(TINY_LORA)
+    if v2:
+        kw.update(lora_control_version=2, lora_pre_conv_skipped=True)
+    torch.manual_seed(0)
+    ocl = MR.ControlLoRA(**kw)
+    # non-trivial norm parameters
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for n, p in ocl.named_parameters():
+            if "norm" in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    mcl = cb.ControlLoRA(**kw)
+    mcl.load_state_dict(ocl.state_dict())
+    mcl.to(DEV)
+    guide = (torch.rand(B, 3, size, size, generator=g) * 2 - 1)
+    guide = guide.to(torch.bfloat16).float()
+    so = ocl(guide).control_states
+    wts = [torch.randn(s.shape, generator=g) for s in so]
+    lo = sum((s * w).sum() for s, w in zip(so, wts))
+    lo.backward()
+    sm = mcl(guide.to(DEV)).control_states
+    lm = sum((s.float() * w.to(DEV)).sum() for s, w in zip(sm, wts))
+    lm.backward()
+    if DEV == "cuda":
+        torch.cuda.synchronize()
+    worst = 0.0
+    for i, (a, b) in enumerate(zip(sm, so)):
+        e = rel(a, b)
+        worst = max(worst, e)
+        print(f"  control_state[{i}] {tuple(b.shape)} rel={e:.3e}")
+    rows = []
+    for (n1, p1), (n2, p2) in zip(ocl.named_parameters(), mcl.named_parameters()):
+        if n1.startswith("lora_layers"):
+            continue
+        assert p2.grad is not None, n2
+        rows.append((rel(p2.grad, p1.grad), n1, float(p1.grad.norm())))
+    rows.sort(reverse=True)
+    for e, n, nrm in rows[:10]:
+        print(f"  grad rel={e:.3e} |g|={nrm:.3e} {n}")
+    ok = worst < 2e-2 and rows[0][0] < 6e-2
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
+def train_case(v2: bool, B=2, HW=16):
+    """Two fused Trainer steps vs the oracle driven by torch.optim.AdamW + clip_grad_norm_ (the reference's step glue)."""
+    import torch
+    from oracle import models_ref as MR
+    from oracle import unet_ref as UR
+    import controllora_b200 as cb
+    from controllora_b200.trainer import Trainer
+
+    torch.manual_seed(0)
+    ounet = UR.UNet2DConditionModel(**TINY)
+    UR.init_synthetic_(ounet, seed=1)
+    with torch.no_grad():
+        for p in ounet.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+    ounet.requires_grad_(False)
+    munet = cb.UNet2DConditionModel.from_state_dict({k: v.clone() for k, v in ounet.state_dict().items()}, DEV, TINY)
+    kw = dict(TINY_LORA)
+    if v2:
+        kw.update(lora_control_version=2, lora_pre_conv_skipped=True, lora_key_states_skipped=True, lora_value_states_skipped=True)
+    ocl = MR.ControlLoRA(**kw)
+    MR.randomize_lora_up_(ocl, seed=3, std=0.05)
+    mcl = cb.ControlLoRA(**kw)
+    mcl.load_state_dict(ocl.state_dict())
+    mcl.to(DEV)
+    MR.wire_processors(ounet, ocl)
+    MR.wire_processors(munet, mcl)
+    opt = torch.optim.AdamW(ocl.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    tr = Trainer(munet, mcl, lr=1e-4)
+    g = torch.Generator().manual_seed(5)
+    size = HW * 8
+    p0 = {n: p.detach().clone() for n, p in ocl.named_parameters()}
+    for step in range(2):
+        x = torch.randn(B, 4, HW, HW, generator=g).to(torch.bfloat16).float()
+        t = torch.randint(0, 1000, (B,), generator=g)
+        e = torch.randn(B, 77, TINY["cross_attention_dim"], generator=g).to(torch.bfloat16).float()
+        guide = (torch.rand(B, 3, size, size, generator=g) * 2 - 1).to(torch.bfloat16).float()
+        tgt = torch.randn(B, 4, HW, HW, generator=g)
+        ocl(guide)
+        lo = torch.nn.functional.mse_loss(ounet(x, t, e).sample, tgt)
+        lo.backward()
+        gn = torch.nn.utils.clip_grad_norm_(ocl.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        lm = tr.step(x.to(DEV), t.to(DEV).float(), e.to(DEV).to(torch.bfloat16), guide.to(DEV), tgt.to(DEV))
+        if DEV == "cuda":
+            torch.cuda.synchronize()
+        print(f"  step {step}: loss oracle={float(lo):.6f} ours={float(lm):.6f}  oracle grad-norm={float(gn):.4f} "
+              f"ours={float(tr.gnorm_sq.sqrt()):.4f}")
+    # compare parameter UPDATES (Adam normalises gradients, so the update direction is a sharp test)
+    num = den = 0.0
+    worst = (0.0, "")
+    for (n, po), (_, pm) in zip(ocl.named_parameters(), mcl.named_parameters()):
+        do = po.detach() - p0[n]
+        dm = pm.detach().cpu() - p0[n]
+        num += float((dm - do).pow(2).sum())
+        den += float(do.pow(2).sum())
+        e = float((dm - do).norm() / (do.norm() + 1e-12))
+        if e > worst[0] and float(do.norm()) > 1e-6:
+            worst = (e, n)
+    tot = (num / den) ** 0.5
+    print(f"  parameter-update rel (all params) = {tot:.3e}; worst tensor {worst[1]} rel={worst[0]:.3e}")
+    ok = tot < 0.35
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
+CASES = {
+    "hint_v1": lambda: hint_case(False),
+    "hint_v2": lambda: hint_case(True),
+    "train_v1": lambda: train_case(False),
+    "train_v2": lambda: train_case(True),
+}
+
+
+def main():
+    names = sys.argv[1:] or list(CASES)
+    if len(names) == 1:
+        sys.exit(0 if CASES[names[0]]() else 1)
+    res = {}
+    for v in names:
+        try:
+            r = subprocess.run([sys.executable, __file__, v], capture_output=True, text=True, timeout=600)
+            ok = r.returncode == 0 and "CASE_OK" in r.stdout
+            out = r.stdout + r.stderr
+        except subprocess.TimeoutExpired as e:
+            ok, out = False, f"TIMEOUT {e}"
+        res[v] = ok
+        print(f"=== {v}: {'PASS' if ok else 'FAIL'}")
+        lines = [l for l in out.strip().splitlines() if "Warning" not in l and "Consider using" not in l]
+        for line in (lines if ok else lines[-40:]):
+            print("    " + line)
+        sys.stdout.flush()
+    print("SUMMARY", res)
+
+
+if __name__ == "__main__":
+    main()
