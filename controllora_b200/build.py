@@ -23,7 +23,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v" if os.environ.get("CLB_PTXAS_V") else "-O3",
-]
+] + os.environ.get("CLB_EXTRA_NVCC", "").split()
 
 
 def _newer(a: Path, b: Path) -> bool:

@@ -46,6 +46,17 @@ __device__ __forceinline__ void store_row32_swz(uint8_t* tile, int chunk_stride,
     }
 }
 
+// same for 16 consecutive columns [c16*16, c16*16+16)
+__device__ __forceinline__ void store_row16_swz(uint8_t* tile, int chunk_stride, int r, int c16, const uint32_t (&pk)[8]) {
+    uint8_t* rowp = tile + (c16 >> 2) * chunk_stride + r * 128;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int chunk = (c16 & 3) * 2 + q;
+        *reinterpret_cast<uint4*>(rowp + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+}
+
 // TMEM accumulator rows -> bf16 global rows (thread = row), columns [0, d)
 template <int DP>
 __device__ __forceinline__ void store_acc_rows(uint32_t taddr, __nv_bfloat16* rowptr, bool row_ok, int d, float mul) {
@@ -82,12 +93,15 @@ struct DkvCfg {
     static constexpr int PT_BYTES = (BQ / 64) * BK * 128;       // P^T tile (and dS^T tile)
     static constexpr int SMEM_BYTES = 1024 + 2 * KV_BYTES + STAGES * STAGE_BYTES + 2 * PT_BYTES + 2 * 2 * BQ * 4 + 256;
     static constexpr int TM_ST = 0, TM_DPT = BQ, TM_DK = 2 * BQ, TM_DV = 2 * BQ + DP;
+    static constexpr int TMEM_NEED = 2 * BQ + 2 * DP;
+    static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+    static constexpr int MIN_CTAS = (TMEM_COLS <= 256 && SMEM_BYTES <= 110 * 1024) ? 2 : 1;
     static_assert(2 * BQ + 2 * DP <= 512, "TMEM");
     static_assert(BQ % 64 == 0, "BQ");
 };
 
 template <int DP, int BQ, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, (DkvCfg<DP, BQ, STAGES>::MIN_CTAS))
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdParams p) {
@@ -129,7 +143,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp_idx == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+    if (warp_idx == 2) { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -219,24 +233,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_wait(s_full, j & 1);
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < BQ / 32; ++c) {
-                uint32_t s[32], g[32];
-                tmem_ld_32x32(tmem_base + Cfg::TM_ST + lane_off + c * 32, s);
-                tmem_ld_32x32(tmem_base + Cfg::TM_DPT + lane_off + c * 32, g);
+            for (int c = 0; c < BQ / 16; ++c) {
+                uint32_t s[16], g[16];
+                tmem_ld_32x16(tmem_base + Cfg::TM_ST + lane_off + c * 16, s);
+                tmem_ld_32x16(tmem_base + Cfg::TM_DPT + lane_off + c * 16, g);
                 tc_wait_ld();
-                uint32_t pk[16], dk_[16];
+                uint32_t pk[8], dk_[8];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -ls[c * 32 + i]));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -ls[c * 32 + i + 1]));
+                for (int i = 0; i < 16; i += 2) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -ls[c * 16 + i]));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -ls[c * 16 + i + 1]));
                     if (!key_ok) { p0 = 0.f; p1 = 0.f; }
-                    const float d0 = p0 * (__uint_as_float(g[i]) - de[c * 32 + i]) * p.scale;
-                    const float d1 = p1 * (__uint_as_float(g[i + 1]) - de[c * 32 + i + 1]) * p.scale;
+                    const float d0 = p0 * (__uint_as_float(g[i]) - de[c * 16 + i]) * p.scale;
+                    const float d1 = p1 * (__uint_as_float(g[i + 1]) - de[c * 16 + i + 1]) * p.scale;
                     pk[i >> 1] = pack_bf16x2(p0, p1);
                     dk_[i >> 1] = pack_bf16x2(d0, d1);
                 }
-                store_row32_swz(smem_pt, BK * 128, r, c, pk);
-                store_row32_swz(smem_dst, BK * 128, r, c, dk_);
+                store_row16_swz(smem_pt, BK * 128, r, c, pk);
+                store_row16_swz(smem_dst, BK * 128, r, c, dk_);
             }
             tc_fence_before();
             fence_proxy_async_smem();
@@ -251,7 +265,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (warp_idx == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp_idx == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ===================================================================================================== dQ
@@ -265,11 +279,14 @@ struct DqCfg {
     static constexpr int DS_BYTES = (BKB / 64) * BM * 128;
     static constexpr int SMEM_BYTES = 1024 + 2 * QD_BYTES + STAGES * STAGE_BYTES + DS_BYTES + 256;
     static constexpr int TM_S = 0, TM_DP = BKB, TM_DQ = 2 * BKB;
+    static constexpr int TMEM_NEED = 2 * BKB + DP;
+    static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+    static constexpr int MIN_CTAS = (TMEM_COLS <= 256 && SMEM_BYTES <= 110 * 1024) ? 2 : 1;
     static_assert(2 * BKB + DP <= 512, "TMEM");
 };
 
 template <int DP, int BKB, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, (DqCfg<DP, BKB, STAGES>::MIN_CTAS))
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const AttnBwdParams p) {
@@ -308,7 +325,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp_idx == 2) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+    if (warp_idx == 2) { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -387,24 +404,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(s_full, i & 1);
             tc_fence_after();
             const int kbase = i * BKB;
+            const bool tail = kbase + BKB > p.Nk;
 #pragma unroll
-            for (int c = 0; c < BKB / 32; ++c) {
-                uint32_t s[32], g[32];
-                tmem_ld_32x32(tmem_base + Cfg::TM_S + lane_off + c * 32, s);
-                tmem_ld_32x32(tmem_base + Cfg::TM_DP + lane_off + c * 32, g);
+            for (int c = 0; c < BKB / 16; ++c) {
+                uint32_t s[16], g[16];
+                tmem_ld_32x16(tmem_base + Cfg::TM_S + lane_off + c * 16, s);
+                tmem_ld_32x16(tmem_base + Cfg::TM_DP + lane_off + c * 16, g);
                 tc_wait_ld();
-                uint32_t dk_[16];
+                uint32_t dk_[8];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
+                for (int j = 0; j < 16; j += 2) {
                     float p0 = fast_exp2(fmaf(__uint_as_float(s[j]), p.scale_log2, -lse));
                     float p1 = fast_exp2(fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -lse));
-                    if (kbase + c * 32 + j >= p.Nk) p0 = 0.f;
-                    if (kbase + c * 32 + j + 1 >= p.Nk) p1 = 0.f;
+                    if (tail) {
+                        if (kbase + c * 16 + j >= p.Nk) p0 = 0.f;
+                        if (kbase + c * 16 + j + 1 >= p.Nk) p1 = 0.f;
+                    }
                     const float d0 = p0 * (__uint_as_float(g[j]) - delta) * p.scale;
                     const float d1 = p1 * (__uint_as_float(g[j + 1]) - delta) * p.scale;
                     dk_[j >> 1] = pack_bf16x2(d0, d1);
                 }
-                store_row32_swz(smem_ds, BM * 128, r, c, dk_);
+                store_row16_swz(smem_ds, BM * 128, r, c, dk_);
             }
             tc_fence_before();
             fence_proxy_async_smem();
@@ -418,7 +438,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp_idx == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp_idx == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ===================================================================================================== delta
@@ -513,7 +533,7 @@ extern "C" int cl_attn_bwd(const cl_attn_bwd_args* a, void* stream_) {
     if ((a->ldq % 8) || (a->ldk % 8) || (a->ldv % 8) || (a->ldo % 8) || (a->lddo % 8) || (a->dq && a->lddq % 8) ||
         (a->dk && ((a->lddk % 8) || (a->lddv % 8))))
         return set_error(CL_ERR_INVALID, "cl_attn_bwd: row strides must be multiples of 8");
-    if (a->d <= 64) return launch_attn_bwd<64, 128, 2, 128, 2>(a, stream);
+    if (a->d <= 64) return launch_attn_bwd<64, 64, 2, 64, 2>(a, stream);   // 256 TMEM columns, ~97 KB smem: two CTAs per SM
     if (a->d <= 128) return launch_attn_bwd<128, 128, 1, 128, 1>(a, stream);
     return launch_attn_bwd<192, 64, 1, 64, 2>(a, stream);
 }

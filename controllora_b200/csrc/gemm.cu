@@ -58,6 +58,21 @@ struct GemmParams {
     int out_fp32;
 };
 
+#ifdef CLB_TIMELINE
+// debug: per-SM event log  [sm][slot] = (clock64, tag)  -- tools/gemm_timeline.py prints it
+__device__ unsigned long long g_tl[160 * 256 * 2];
+__device__ unsigned int g_tl_n[160];
+__device__ __forceinline__ void tl_rec(int tag) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned int i = atomicAdd(&g_tl_n[smid], 1u);
+    if (i < 256) { g_tl[(smid * 256 + i) * 2] = clock64(); g_tl[(smid * 256 + i) * 2 + 1] = (unsigned long long)tag; }
+}
+#define TL(tag) tl_rec(tag)
+#else
+#define TL(tag)
+#endif
+
 template <int BN, int EXT, int BK>
 struct GemmCfg {
     static constexpr int UMMA_N = BN + EXT;
@@ -124,6 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
     if (warp_idx == 0 && lane == 0) {
+        TL(1);   // kernel entry
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (EXT) tma_prefetch_desc(&tmE);
@@ -164,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     th = (m_blk / p.tiles_w) % p.tiles_h;
                     tn = m_blk / (p.tiles_w * p.tiles_h);
                 }
+                TL(10);  // producer: tile start
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -199,12 +216,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 const uint32_t buf_phase = (it >> 1) & 1;
+                TL(20);  // mma: waiting for a free accumulator
                 mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
                 tc_fence_after();
+                TL(21);  // mma: accumulator free
                 const uint32_t d_tmem = tmem_base + buf * Cfg::BUF_COLS;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (kb == 0) TL(22);  // mma: first stage landed
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                     const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
@@ -217,6 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tmem_full[buf]);        // accumulator complete -> epilogue
+                TL(23);  // mma: all MMAs of the tile issued
             }
         }
     } else if (warp_idx >= 4) {
@@ -236,8 +257,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int my_m, my_grp;
             decode_row(p, m_blk, quad * 32 + lane, my_m, my_grp);
 
+            if (ew == 0 && lane == 0) TL(30);  // epilogue: waiting for the accumulator
             mbar_wait(&tmem_full[buf], buf_phase);
             tc_fence_after();
+            if (ew == 0 && lane == 0) TL(31);  // epilogue: accumulator ready
             const uint32_t t_base = tmem_base + (uint32_t(quad * 32) << 16) + buf * Cfg::BUF_COLS;
 
             float tl[8];
@@ -338,6 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            if (ew == 0 && lane == 0) TL(32);  // epilogue: tile done
         }
     }
 
@@ -380,6 +404,20 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
 }  // namespace clb
 
 using namespace clb;
+
+#ifdef CLB_TIMELINE
+extern "C" int cl_debug_timeline(unsigned long long* host_buf, unsigned int* host_n, int reset) {
+    if (reset) {
+        unsigned int z[160] = {0};
+        cudaMemcpyToSymbol(clb::g_tl_n, z, sizeof(z));
+        return 0;
+    }
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_buf, clb::g_tl, sizeof(unsigned long long) * 160 * 256 * 2);
+    cudaMemcpyFromSymbol(host_n, clb::g_tl_n, sizeof(unsigned int) * 160);
+    return 0;
+}
+#endif
 
 extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -139,10 +139,11 @@ class HintEncoderEngine:
         h = Var(y, rg=True)
         if ctx.tape is not None:
             gw, gb = self.grad_of(ci.weight), self.grad_of(ci.bias)
+            h_in = h      # `h` is re-bound below; the closure must keep conv_in's own output
 
             def bwd_in():
-                dy = h.grad
-                h.grad = None
+                dy = h_in.grad
+                h_in.grad = None
                 if dy is None:
                     return
                 ops.colsum(dy, gb)

@@ -14,6 +14,7 @@ import torch
 from . import engine as E
 from . import ops
 from .engine import Ctx, Tape, Var
+from .arena import ParamArena
 from .hint_encoder import HintEncoderEngine
 
 BF16 = torch.bfloat16
@@ -25,9 +26,6 @@ class Trainer:
         self.unet, self.cl = unet, control_lora
         self.lr, self.betas, self.wd, self.eps, self.max_norm = lr, betas, weight_decay, eps, max_grad_norm
         self.pg = process_group
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
         dev = unet.device_
         params: List[torch.nn.Parameter] = [p for p in control_lora.parameters() if p.requires_grad]
         seen = {id(p) for p in params}
@@ -36,25 +34,15 @@ class Trainer:
                 params.append(p)
                 seen.add(id(p))
         self.params = params
-        n = sum(p.numel() for p in params)
-        pad = (-n) % 4
-        self.flat_p = torch.zeros(n + pad, device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(n + pad, device=dev, dtype=torch.float32)
-        self.flat_m = torch.zeros(n + pad, device=dev, dtype=torch.float32)
-        self.flat_v = torch.zeros(n + pad, device=dev, dtype=torch.float32)
-        self.numel = n
+        self.arena = ParamArena(params, dev, process_group)
+        self.world = self.arena.world
+        self.flat_p, self.flat_g, self.flat_m, self.flat_v = self.arena.flat_p, self.arena.flat_g, self.arena.flat_m, self.arena.flat_v
+        self.numel = self.arena.numel
         store = unet.grad_store
         store.bufs.clear()
-        off = 0
-        with torch.no_grad():
-            for p in params:
-                k = p.numel()
-                view = self.flat_p[off:off + k].view(p.shape)
-                view.copy_(p.data.to(dev))
-                p.data = view
-                store.bufs[id(p)] = self.flat_g[off:off + k].view(p.shape)
-                store.params[id(p)] = p
-                off += k
+        for p in params:
+            store.bufs[id(p)] = self.arena.grad_of(p)
+            store.params[id(p)] = p
         unet._runtime = None                          # rebuild the LoRA runtime against the arena views
         self.hint = HintEncoderEngine(control_lora, store.get)
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -87,10 +75,9 @@ class Trainer:
         pred.grad = dpred
         tape.backward()
         self.step_idx += 1
-        if self.world > 1:
-            torch.distributed.all_reduce(self.flat_g, group=self.pg)
+        self.arena.all_reduce()          # one ncclAllReduce(sum) over the whole gradient arena
         self.gnorm_sq.zero_()
         ops.sumsq(self.flat_g, self.gnorm_sq)
         ops.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                  self.step_idx, gnorm_sq=self.gnorm_sq, max_norm=self.max_norm, grad_scale=1.0 / self.world, zero_grad=True)
+                  self.step_idx, gnorm_sq=self.gnorm_sq, max_norm=self.max_norm, grad_scale=self.arena.grad_scale, zero_grad=True)
         return loss

@@ -1,0 +1,114 @@
+"""GPU parity tests (pytest -m gpu): every kernel family and the assembled hot path against torch-fp32 references /
+the CPU oracle, through the C ABI.  Tolerances: bf16 storage => ~2e-3 relative per op; end-to-end tolerances below."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+# ------------------------------------------------------------------------------------------------ K1 / K4: GEMM + conv
+from tools import check_gemm, check_hint, check_ops, check_ops2, check_unet  # noqa: E402
+
+
+@pytest.mark.parametrize("case", ["plain_1tile", "plain_k320", "plain_bn64", "plain_bn160_tail", "plain_bn256", "plain_big",
+                                  "epilogue_all", "lora_r4", "lora_r4_tadd", "lora_r8_cross", "conv_s1_64", "conv_s1_small",
+                                  "conv_s2", "conv_96"])
+def test_gemm(case):
+    check_gemm.CASES[case]()
+
+
+def test_conv_32_channels_uses_bk32_path():
+    """hint-encoder shapes: 32-channel convs (64-byte swizzle / BLOCK_K = 32 variant of the kernel)."""
+    check_gemm._conv_case(2, 64, 64, 32, 32, 1, 1, True)
+    check_gemm._conv_case(2, 64, 64, 32, 64, 1, 1, False)
+    check_gemm._conv_case(2, 64, 64, 32, 32, 2, 0, False)
+
+
+# ------------------------------------------------------------------------------------------------ K2: attention
+@pytest.mark.parametrize("case", ["attn_d64_one_block", "attn_d40", "attn_cross77", "attn_d80_d160", "attn_small_d"])
+def test_attention_fwd(case):
+    check_ops.CASES[case]()
+
+
+@pytest.mark.parametrize("case", ["attn_bwd_one_block", "attn_bwd_d40", "attn_bwd_d80_d160", "attn_bwd_small_d"])
+def test_attention_bwd(case):
+    check_ops2.CASES[case]()
+
+
+def test_attention_full_size_properties():
+    """BASELINE-size self-attention (8 x 8 heads x 4096 tokens x d=40): rows of P sum to 1 => attention of constant V is
+    constant; permuting the keys/values leaves the output unchanged."""
+    from controllora_b200 import ops
+
+    B, H, N, d = 2, 8, 4096, 40
+    q = torch.randn(B, N, H * d, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, N, H * d, device="cuda").to(torch.bfloat16)
+    v = torch.ones(B, N, H * d, device="cuda", dtype=torch.bfloat16) * 0.5
+    o, lse = ops.attention_fwd(q, k, v, H, d ** -0.5)
+    assert (o.float() - 0.5).abs().max() < 4e-3
+    v2 = torch.randn(B, N, H * d, device="cuda").to(torch.bfloat16)
+    o1, _ = ops.attention_fwd(q, k, v2, H, d ** -0.5)
+    perm = torch.randperm(N, device="cuda")
+    o2, _ = ops.attention_fwd(q, k[:, perm].contiguous(), v2[:, perm].contiguous(), H, d ** -0.5)
+    assert (o1.float() - o2.float()).abs().max() < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ K5 / glue / edges / LoRA / optimizer
+@pytest.mark.parametrize("case", ["groupnorm", "layernorm", "elementwise", "edges", "conv_dgrad"])
+def test_norm_elementwise_edges(case):
+    check_ops.CASES[case]()
+
+
+@pytest.mark.parametrize("case", ["lora_kernels", "optimizer"])
+def test_lora_and_optimizer(case):
+    check_ops2.CASES[case]()
+
+
+# ------------------------------------------------------------------------------------------------ assembled hot path
+@pytest.mark.parametrize("variant", ["none", "plain", "v1", "v1_stacked", "v2"])
+def test_unet_fwd_bwd_matches_oracle(variant):
+    """Noise prediction and every LoRA / control-state gradient vs the fp32 oracle (tiny SD-style config).
+    Tolerance: bf16 activations through ~40 layers => <= 2e-2 relative on the prediction, <= 8e-2 on single gradients."""
+    assert check_unet.run(variant)
+
+
+@pytest.mark.parametrize("case", ["hint_v1", "hint_v2"])
+def test_hint_encoder_matches_oracle(case):
+    assert check_hint.CASES[case]()
+
+
+@pytest.mark.parametrize("case", ["train_v1", "train_v2"])
+def test_fused_train_step_matches_oracle(case):
+    assert check_hint.CASES[case]()
+
+
+def test_lora_zero_up_is_exact_noop_on_gpu():
+    """With diffusers' default init (up = 0) the fused epilogue must contribute exactly nothing."""
+    import controllora_b200 as cb
+    from controllora_b200.configs import wire_processors
+    from controllora_b200.unet import synthetic_state_dict
+
+    TINY, TINY_LORA = check_unet.TINY, check_unet.TINY_LORA
+    sd = synthetic_state_dict(TINY, 0)
+    u0 = cb.UNet2DConditionModel.from_state_dict(sd, "cuda", TINY)
+    u1 = cb.UNet2DConditionModel.from_state_dict(sd, "cuda", TINY)
+    cl = cb.ControlLoRA(**TINY_LORA).cuda()
+    wire_processors(u1, cl)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 16, 16, generator=g).cuda()
+    t = torch.tensor([3.0, 900.0]).cuda()
+    e = torch.randn(2, 77, 64, generator=g).cuda().to(torch.bfloat16)
+    guide = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).cuda()
+    with torch.no_grad():
+        cl(guide)
+        a = u0(x, t, e).sample
+        b = u1(x, t, e).sample
+    assert torch.equal(a, b)

@@ -1,0 +1,143 @@
+"""Host-side logic of the drop-in surface (no GPU): class surface / configs / state-dict compatibility with the
+oracle's restatement of /root/reference/models.py, processor wiring, error conventions, checkpoint round trip."""
+import json
+
+import pytest
+import torch
+
+import controllora_b200 as cb
+from controllora_b200.configs import NAMED, wire_processors
+from oracle import models_ref as MR
+
+
+@pytest.mark.parametrize("name", sorted(NAMED))
+def test_state_dict_keys_and_shapes_equal_the_reference_layout(name):
+    ours = cb.ControlLoRA.from_config(NAMED[name]).state_dict()
+    ref = MR.ControlLoRA.from_config(NAMED[name]).state_dict()
+    assert list(ours.keys()) == list(ref.keys())
+    for k in ours:
+        assert ours[k].shape == ref[k].shape, k
+
+
+def test_from_config_accepts_path_dict_and_ignores_private_keys(tmp_path):
+    cfg = {"_class_name": "ControlLoRA", "_diffusers_version": "0.13.0.dev0", "lora_rank": 4, "lora_control_version": 2,
+           "lora_pre_conv_skipped": True}
+    p = tmp_path / "c.json"
+    p.write_text(json.dumps(cfg))
+    a = cb.ControlLoRA.from_config(str(p))
+    b = cb.ControlLoRA.from_config(cfg)
+    assert type(a.lora_layers[0][0]).__name__ == "ControlLoRACrossAttnProcessorV2"
+    assert list(a.state_dict()) == list(b.state_dict())
+    with pytest.raises(TypeError):
+        cb.ControlLoRA.from_config({"not_a_key": 1})
+
+
+def test_save_and_load_pretrained_roundtrip(tmp_path):
+    m = cb.ControlLoRA.from_config(NAMED["diffusiondb-canny-v2"])
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+    m.save_pretrained(tmp_path / "bin")
+    m.save_pretrained(tmp_path / "st", safe_serialization=True)
+    for sub in ("bin", "st"):
+        r = cb.ControlLoRA.from_pretrained(tmp_path, subfolder=sub)
+        for (k1, v1), (k2, v2) in zip(m.state_dict().items(), r.state_dict().items()):
+            assert k1 == k2 and torch.equal(v1, v2)
+    saved = json.loads((tmp_path / "bin" / "config.json").read_text())
+    assert saved["_class_name"] == "ControlLoRA" and saved["lora_control_version"] == 2
+
+
+def test_lora_linear_layer_init_and_rank_check():
+    l = cb.LoRALinearLayer(64, 32, 4)
+    assert l.down.weight.shape == (4, 64) and l.up.weight.shape == (32, 4)
+    assert float(l.up.weight.abs().max()) == 0.0           # diffusers: up = 0
+    assert 0.1 < float(l.down.weight.std()) < 0.4           # ~ N(0, 1/rank)
+    with pytest.raises(ValueError):
+        cb.LoRALinearLayer(2, 64, 4)
+
+
+def test_processor_flags_and_skip_helpers():
+    p = cb.LoRACrossAttnProcessor(64, 32, rank=4, key_states_skipped=True)
+    assert not hasattr(p, "to_k_lora") and hasattr(p, "to_v_lora")
+    assert p.to_v_lora.down.weight.shape == (4, 32)
+    with pytest.raises(AssertionError):
+        p.skip_key_states(False)
+    p.skip_output_states(True)
+    assert p.output_states_skipped
+    v1 = cb.ControlLoRACrossAttnProcessor(64, None, control_self_add=True)
+    assert v1.control_self_add is False                      # models.py:180-182 quirk
+    assert v1.to_control.down.weight.shape == (4, 64)
+    cat = cb.ControlLoRACrossAttnProcessor(64, None, concat_hidden=True, control_channels=256, control_rank=8)
+    assert cat.to_control.down.weight.shape == (8, 320)
+    v2 = cb.ControlLoRACrossAttnProcessorV2(64, 32, control_channels=256)
+    assert v2.key_states_skipped and v2.value_states_skipped and v2.to_control_out.down.weight.shape == (4, 320)
+    lo = cb.LoRACrossAttnProcessor(64)
+    v1.inject_pre_lora(lo)
+    assert v1.pre_loras == [lo] and "pre_loras" not in dict(v1.named_modules())   # plain lists, not sub-modules
+
+
+def test_processors_have_no_eager_fallback():
+    p = cb.LoRACrossAttnProcessor(64)
+    with pytest.raises(NotImplementedError):
+        p(None, torch.zeros(1, 4, 64))
+
+
+def test_unet_wrapper_refuses_cpu_inputs(monkeypatch):
+    from controllora_b200.unet_module import UNet2DConditionModel
+
+    monkeypatch.delenv("CLB_DRYRUN", raising=False)
+    with pytest.raises(RuntimeError):
+        UNet2DConditionModel._prep_inputs(torch.zeros(1, 4, 8, 8), torch.tensor([1]), torch.zeros(1, 77, 64))
+
+
+TINY = dict(block_out_channels=(64, 128, 128, 128), layers_per_block=1, cross_attention_dim=64, attention_head_dim=8)
+TINY_LORA = dict(lora_block_out_channels=(64, 128, 128, 128),
+                 lora_cross_attention_dims=([None, 64] * 3, [None, 64] * 3, [None, 64] * 3, [None, 64]))
+
+
+def _tiny_unet():
+    from controllora_b200.unet import synthetic_state_dict
+
+    return cb.UNet2DConditionModel.from_state_dict(synthetic_state_dict(TINY, 0), "cpu", TINY)
+
+
+def test_attn_processor_names_and_wiring_match_the_oracle():
+    from oracle import unet_ref as UR
+
+    mu = _tiny_unet()
+    ou = UR.UNet2DConditionModel(**TINY)
+    assert list(mu.attn_processors.keys()) == list(ou.attn_processors.keys())
+    mcl = cb.ControlLoRA(**TINY_LORA)
+    ocl = MR.ControlLoRA(**TINY_LORA)
+    mp = wire_processors(mu, mcl)
+    op = MR.wire_processors(ou, ocl)
+    idx = lambda cl, p: [(i, j) for i, l in enumerate(cl.lora_layers) for j, q in enumerate(l) if q is p][0]
+    assert {k: idx(mcl, v) for k, v in mp.items()} == {k: idx(ocl, v) for k, v in op.items()}
+    with pytest.raises(ValueError):
+        mu.set_attn_processor({"only.one": mcl.lora_layers[0][0]})
+    # processors become sub-modules of the UNet wrapper as well (shared ownership, like diffusers)
+    assert any(p is mcl.lora_layers[0][0].to_q_lora.down.weight for p in mu.parameters())
+    assert mu.config.cross_attention_dim == 64 and tuple(mu.config.block_out_channels) == (64, 128, 128, 128)
+
+
+def test_synthetic_state_dict_has_diffusers_keys_and_sd15_size():
+    from controllora_b200.unet import SD15_CONFIG, synthetic_state_dict
+    from oracle import unet_ref as UR
+
+    with torch.device("meta"):
+        ref = UR.UNet2DConditionModel(**TINY)
+    sd = synthetic_state_dict(TINY, 0)
+    assert set(sd.keys()) == set(ref.state_dict().keys())
+    for k, v in ref.state_dict().items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+
+
+def test_unsupported_variants_fail_loudly():
+    from controllora_b200.lora_runtime import LoraRuntime
+    from controllora_b200.unet_module import GradStore
+
+    mu = _tiny_unet()
+    mcl = cb.ControlLoRA(lora_post_add=True, **TINY_LORA)
+    wire_processors(mu, mcl)
+    with pytest.raises(NotImplementedError):
+        LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)

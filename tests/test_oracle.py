@@ -1,0 +1,162 @@
+"""The oracle (oracle/) against its anchors: parameter counts and state-dict keys of the published reference models
+(SURVEY.md §8b/§8c), algebraic self-consistency, and the committed golden vectors."""
+import json
+import math
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import models_ref as MR
+from oracle import unet_ref as UR
+from controllora_b200.configs import NAMED
+
+ROOT = Path(__file__).resolve().parent.parent
+TINY = dict(block_out_channels=(64, 128, 128, 128), layers_per_block=1, cross_attention_dim=64, attention_head_dim=8)
+TINY_LORA = dict(lora_block_out_channels=(64, 128, 128, 128),
+                 lora_cross_attention_dims=([None, 64] * 3, [None, 64] * 3, [None, 64] * 3, [None, 64]))
+
+# README.md:7,17 ("~7M parameters / ~25M storage", "~5M / ~20M") -> exact counts, SURVEY.md §6
+PARAM_COUNTS = {"base": 6047040, "fill50k": 6047040, "diffusiondb-canny": 6047040, "mpii-pose": 6047040,
+                "post-add": 6048576, "diffusiondb-canny-v2": 5000704, "mpii-pose-v2": 5000704, "danbooru-sketch": 19810304}
+
+
+@pytest.mark.parametrize("name", sorted(PARAM_COUNTS))
+def test_controllora_param_counts(name):
+    m = MR.ControlLoRA.from_config(NAMED[name])
+    assert sum(p.numel() for p in m.parameters()) == PARAM_COUNTS[name]
+
+
+def test_unet_param_count_matches_sd15():
+    with torch.device("meta"):
+        u = UR.UNet2DConditionModel()
+    assert sum(p.numel() for p in u.parameters()) == 859_520_964           # SD-1.5 UNet
+    assert sum(p.numel() for p in u.parameters() if p.dim() >= 2) == 859_077_120   # weights in conv/linear kernels
+    keys = list(u.attn_processors.keys())
+    assert len(keys) == 32
+    # diffusers registration order: down_blocks, up_blocks, mid_block
+    assert keys[0].startswith("down_blocks.0") and keys[12].startswith("up_blocks.1") and keys[-1].startswith("mid_block")
+
+
+def test_state_dict_keys_of_published_checkpoints():
+    sd = MR.ControlLoRA.from_config(NAMED["fill50k"]).state_dict()
+    for k in ["conv_in.weight", "down_blocks.0.0.convnets.0.norm1.weight", "down_blocks.0.2.downsamplers.0.conv.bias",
+              "down_blocks.3.downsamplers.0.conv.weight", "pre_lora_layers.2.convnets.0.conv1.weight",
+              "lora_layers.0.9.to_control.up.weight", "lora_layers.3.1.to_out_lora.down.weight"]:
+        assert k in sd, k
+    assert "down_blocks.0.3.downsamplers.0.conv.weight" not in sd      # the last pyramid block has no downsampler
+    v2 = MR.ControlLoRA.from_config(NAMED["diffusiondb-canny-v2"]).state_dict()
+    assert "lora_layers.0.0.to_control_out.down.weight" in v2 and "lora_layers.0.0.to_k_lora.down.weight" not in v2
+    assert not any(k.startswith("pre_lora_layers") for k in v2)
+
+
+def _tiny_pair(**kw):
+    torch.manual_seed(0)
+    unet = UR.UNet2DConditionModel(**TINY)
+    UR.init_synthetic_(unet, seed=1)
+    cfg = dict(TINY_LORA)
+    cfg.update(kw)
+    cl = MR.ControlLoRA(**cfg)
+    return unet, cl
+
+
+def _inputs(B=2, HW=16):
+    g = torch.Generator().manual_seed(5)
+    return (torch.randn(B, 4, HW, HW, generator=g), torch.tensor([17, 801]), torch.randn(B, 77, 64, generator=g),
+            torch.rand(B, 3, HW * 8, HW * 8, generator=g) * 2 - 1)
+
+
+def test_zero_initialised_up_weights_make_lora_a_noop():
+    """SURVEY 'five facts' #5: a freshly built ControlLoRA must not change the UNet output at all."""
+    unet, cl = _tiny_pair()
+    x, t, e, guide = _inputs()
+    base = unet(x, t, e).sample
+    MR.wire_processors(unet, cl)
+    cl(guide)
+    out = unet(x, t, e).sample
+    assert torch.equal(base, out)
+    MR.randomize_lora_up_(cl, seed=3, std=0.05)
+    assert (unet(x, t, e).sample - base).abs().max() > 1e-4
+
+
+def test_control_states_shapes_and_injection():
+    unet, cl = _tiny_pair()
+    x, t, e, guide = _inputs()
+    MR.wire_processors(unet, cl)
+    states = cl(guide).control_states
+    assert [tuple(s.shape) for s in states] == [(2, 64, 16, 16), (2, 128, 8, 8), (2, 128, 4, 4), (2, 128, 2, 2)]
+    for lvl, procs in enumerate(cl.lora_layers):
+        for p in procs:
+            assert p.control_states is states[lvl]
+    # processors are wired level-wise: down_i and up_(3-i) share level i, mid is level 3 (train_...:469-487)
+    names = list(unet.attn_processors.keys())
+    assert unet.attn_processors["mid_block.attentions.0.transformer_blocks.0.attn1.processor"] is cl.lora_layers[3][0]
+    assert unet.attn_processors[names[0]] is cl.lora_layers[0][0]
+
+
+def test_v1_control_identity_used_by_the_fused_epilogue():
+    """q-path algebra behind the CUDA path: Aq (h + s Bc Ac c) == Aq h + s (Aq Bc)(Ac c)."""
+    torch.manual_seed(1)
+    T, C, r = 50, 64, 4
+    h, c = torch.randn(T, C), torch.randn(T, C)
+    Aq, Bc, Ac = torch.randn(r, C), torch.randn(C, r), torch.randn(r, C)
+    s = 0.7
+    lhs = (h + s * (c @ Ac.t()) @ Bc.t()) @ Aq.t()
+    rhs = h @ Aq.t() + s * (c @ Ac.t()) @ (Aq @ Bc).t()
+    assert torch.allclose(lhs, rhs, atol=1e-4, rtol=1e-4)
+
+
+def test_v2_rewrites_hidden_states_before_kv():
+    """models.py:369-383: V2 adds the control term to the hidden states first, so for self-attention the keys/values
+    are projected from the *updated* states (and the attention output is updated again before to_out, :415)."""
+    torch.manual_seed(0)
+    C, Cc, T = 64, 32, 10
+    attn = UR.CrossAttention(C, None, heads=4, dim_head=16)
+    p = MR.ControlLoRACrossAttnProcessorV2(C, None, rank=4, control_channels=Cc)
+    for n, w in p.named_parameters():
+        if n.endswith("up.weight"):
+            torch.nn.init.normal_(w, std=0.2)
+    h = torch.randn(2, T, C)
+    c = torch.randn(2, T, Cc)
+    p.inject_control_states(c)
+    out = p(attn, h)
+    hp = h + p.to_control(torch.cat([h, c], -1))
+    q = attn.to_q(hp) + p.to_q_lora(hp)
+    k, v = attn.to_k(hp), attn.to_v(hp)
+    o = attn.batch_to_head_dim(torch.bmm(attn.get_attention_scores(attn.head_to_batch_dim(q), attn.head_to_batch_dim(k)),
+                                         attn.head_to_batch_dim(v)))
+    o = o + p.to_control_out(torch.cat([o, c], -1))
+    want = attn.to_out[0](o) + p.to_out_lora(o)
+    assert torch.allclose(out, want, atol=1e-5)
+    k_old = attn.to_k(h)
+    assert (k - k_old).abs().max() > 1e-2
+
+
+def test_scale_kwarg_and_value_quirk():
+    """`scale` multiplies every LoRA delta except stacked adapters' value deltas (models.py:260,265)."""
+    unet, cl = _tiny_pair()
+    MR.randomize_lora_up_(cl, seed=3, std=0.05)
+    MR.wire_processors(unet, cl)
+    x, t, e, guide = _inputs()
+    cl(guide)
+    a = unet(x, t, e, cross_attention_kwargs={"scale": 1.0}).sample
+    b = unet(x, t, e, cross_attention_kwargs={"scale": 0.0}).sample
+    torch.manual_seed(0)
+    plain = UR.UNet2DConditionModel(**TINY)
+    UR.init_synthetic_(plain, seed=1)
+    assert torch.allclose(b, plain(x, t, e).sample, atol=1e-5)
+    assert (a - b).abs().max() > 1e-4
+
+
+GOLDEN = ROOT / "tests" / "golden" / "oracle_tiny.pt"
+
+
+@pytest.mark.parametrize("variant", ["v1", "v2"])
+def test_oracle_matches_committed_golden_vectors(variant):
+    """Regression pin of the oracle itself (generated by tests/golden/make_golden.py)."""
+    from tests.golden.make_golden import run_variant
+
+    gold = torch.load(GOLDEN)[variant]
+    now = run_variant(variant)
+    for k in gold:
+        assert torch.allclose(now[k], gold[k], atol=2e-5, rtol=2e-4), k
