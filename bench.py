@@ -56,52 +56,51 @@ def synth_inputs(torch, B, seed_off=0, device="cpu"):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe), polled from a thread."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0):
-        self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index=0, period_s=0.15):
+        self.idx, self.period = gpu_index, period_s
+        self.lines, self.stop_flag, self.t = [], threading.Event(), None
+
+    def _poll(self):
+        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx)]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.lines.append(out.splitlines()[0])
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        self.stop_flag.set()
+        if self.t is not None:
+            self.t.join(timeout=6)
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
+                if v.lower() == "active":
                     reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi returned no samples"], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "reasons": sorted(reasons),
+                "samples": len(sm)}
 
 
 def measured_peaks():

@@ -58,7 +58,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded spin: a protocol bug must surface as a trap (-> CUDA error), never as a hung GPU box.
 #ifndef CLB_MBAR_SPIN_LIMIT
-#define CLB_MBAR_SPIN_LIMIT (1u << 28)
+#define CLB_MBAR_SPIN_LIMIT (1u << 22)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
@@ -203,6 +203,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(t);
+}
+
+// explicit shared-space vector accesses (a generic pointer derived through integer casts makes nvcc emit the slower
+// generic LD/ST; these take the 32-bit shared address)
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_u4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // 2^x on the MUFU pipe (ex2.approx.ftz: one instruction; exp2(-inf) = +0)

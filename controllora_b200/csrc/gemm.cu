@@ -56,6 +56,7 @@ struct GemmParams {
     void* out;
     long long ldd;
     int out_fp32;
+    int b_resident;   // B (weights) tile of this CTA's n-block stays in smem for the CTA lifetime (small K)
 };
 
 #ifdef CLB_TIMELINE
@@ -72,6 +73,25 @@ __device__ __forceinline__ void tl_rec(int tag) {
 #else
 #define TL(tag)
 #endif
+
+// tile -> (m_blk, n_blk).  Streaming mode: n fastest (CTAs that run concurrently share the A rows through L2).
+// B-resident mode: a CTA keeps ONE n-block for its lifetime and walks the m-blocks.
+struct TileIter {
+    int m_blk, n_blk, step, num_m;
+    bool resident;
+    int tile, num_tiles, num_n;
+    __device__ TileIter(int num_m_blocks, int num_n_blocks, int b_resident) {
+        resident = b_resident != 0;
+        num_m = num_m_blocks; num_n = num_n_blocks; num_tiles = num_m_blocks * num_n_blocks;
+        if (resident) { n_blk = blockIdx.x % num_n; m_blk = blockIdx.x / num_n; step = gridDim.x / num_n; }
+        else { tile = blockIdx.x; m_blk = tile / num_n; n_blk = tile % num_n; step = gridDim.x; }
+    }
+    __device__ bool valid() const { return resident ? (m_blk < num_m) : (tile < num_tiles); }
+    __device__ void next() {
+        if (resident) m_blk += step;
+        else { tile += step; m_blk = tile / num_n; n_blk = tile % num_n; }
+    }
+};
 
 template <int BN, int EXT, int BK>
 struct GemmCfg {
@@ -124,7 +144,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem_a + num_stages * A_STAGE_BYTES;
-    uint8_t* smem_stage = smem_b + num_stages * Cfg::B_STAGE_BYTES;          // epilogue staging
+    const int b_slots = p.b_resident ? p.num_k_blocks : num_stages;
+    uint8_t* smem_stage = smem_b + b_slots * Cfg::B_STAGE_BYTES;             // epilogue staging
     float* smem_up = reinterpret_cast<float*>(smem_stage + EPI_STAGING_BYTES);  // [N][rp] when LoRA is on
     const int up_floats = (p.lora_up != nullptr) ? p.N * p.lora_rp : 0;
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_up) + ((up_floats * 4 + 15) & ~15));
@@ -132,11 +153,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty_bar = bars + num_stages;
     uint64_t* tmem_full = bars + 2 * num_stages;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* b_full = tmem_empty + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full + 1);
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
     if (warp_idx == 0 && lane == 0) {
         TL(1);   // kernel entry
@@ -153,6 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
         }
+        mbar_init(b_full, 1);
         fence_barrier_init();
     }
     if (warp_idx == 2) {
@@ -171,9 +193,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / p.num_n_blocks;
-                const int n_blk = tile % p.num_n_blocks;
+            TileIter ti(p.num_m_blocks, p.num_n_blocks, p.b_resident);
+            if (p.b_resident && ti.valid()) {
+                mbar_arrive_expect_tx(b_full, p.num_k_blocks * Cfg::B_STAGE_BYTES);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    uint8_t* sb = smem_b + kb * Cfg::B_STAGE_BYTES;
+                    tma_load_2d(&tmB, b_full, sb, kb * BK, ti.n_blk * BN);
+                    if (EXT) tma_load_2d(&tmE, b_full, sb + BN * Cfg::ROW_BYTES, kb * BK, 0);
+                }
+            }
+            for (; ti.valid(); ti.next()) {
+                const int m_blk = ti.m_blk;
+                const int n_blk = ti.n_blk;
                 int tw = 0, th = 0, tn = 0;
                 if (p.a_mode != 0) {
                     tw = m_blk % p.tiles_w;
@@ -183,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 TL(10);  // producer: tile start
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES);
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
                     if (p.a_mode == 0) {
@@ -200,8 +231,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         tw * p.bw + (ix >> 1), iy & 1, th * p.bh + (iy >> 1), tn * p.bn);
                         }
                     }
-                    tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * BN);
-                    if (EXT) tma_load_2d(&tmE, &full_bar[stage], sb + BN * Cfg::ROW_BYTES, kb * BK, 0);
+                    if (!p.b_resident) {
+                        tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * BN);
+                        if (EXT) tma_load_2d(&tmE, &full_bar[stage], sb + BN * Cfg::ROW_BYTES, kb * BK, 0);
+                    }
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -213,7 +246,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            TileIter ti(p.num_m_blocks, p.num_n_blocks, p.b_resident);
+            if (p.b_resident && ti.valid()) mbar_wait(b_full, 0);
+            for (; ti.valid(); ti.next(), ++it) {
                 const int buf = it & 1;
                 const uint32_t buf_phase = (it >> 1) & 1;
                 TL(20);  // mma: waiting for a free accumulator
@@ -226,7 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_fence_after();
                     if (kb == 0) TL(22);  // mma: first stage landed
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
-                    const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(smem_b + (p.b_resident ? kb : stage) * Cfg::B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adesc = make_smem_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
@@ -245,12 +280,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ew = warp_idx - 4;              // 0..7
         const int quad = warp_idx & 3;            // TMEM lane quadrant this warp may access
         const int half = ew >> 2;                 // the two warps of a quadrant split the column granules
-        uint8_t* stg = smem_stage + ew * 32 * STAGE_ROW_BYTES;
+        const uint32_t stg_addr = smem_u32(smem_stage + ew * 32 * STAGE_ROW_BYTES);
         const int rp = p.lora_rp;
+        const uint32_t up_addr = smem_u32(smem_up);
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile / p.num_n_blocks;
-            const int n_blk = tile % p.num_n_blocks;
+        for (TileIter ti(p.num_m_blocks, p.num_n_blocks, p.b_resident); ti.valid(); ti.next(), ++it) {
+            const int m_blk = ti.m_blk;
+            const int n_blk = ti.n_blk;
             const int buf = it & 1;
             const uint32_t buf_phase = (it >> 1) & 1;
             // rows: phase-1 thread owns row (quad*32 + lane); phase-2 lane handles rows (lane>>3) + 4*i
@@ -302,15 +338,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             const int n = min(col0 + c, p.N - 1);
-                            const float4 u = *reinterpret_cast<const float4*>(smem_up + n * 4);
+                            const float4 u = ld_shared_f4(up_addr + n * 16);
                             f[c] += tl[0] * u.x + tl[1] * u.y + tl[2] * u.z + tl[3] * u.w;
                         }
                     } else {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             const int n = min(col0 + c, p.N - 1);
-                            const float4 u0 = *reinterpret_cast<const float4*>(smem_up + n * 8);
-                            const float4 u1 = *reinterpret_cast<const float4*>(smem_up + n * 8 + 4);
+                            const float4 u0 = ld_shared_f4(up_addr + n * 32);
+                            const float4 u1 = ld_shared_f4(up_addr + n * 32 + 16);
                             f[c] += tl[0] * u0.x + tl[1] * u0.y + tl[2] * u0.z + tl[3] * u0.w + tl[4] * u1.x +
                                     tl[5] * u1.y + tl[6] * u1.z + tl[7] * u1.w;
                         }
@@ -319,41 +355,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // ---- phase 1 -> smem (row = lane, 8 chunks of 16 B, XOR swizzle keeps both phases conflict-free)
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 q = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    *reinterpret_cast<float4*>(stg + lane * STAGE_ROW_BYTES + ((j ^ (lane & 7)) << 4)) = q;
-                }
+                for (int j = 0; j < 8; ++j)
+                    st_shared_f4(stg_addr + lane * STAGE_ROW_BYTES + ((j ^ (lane & 7)) << 4),
+                                 make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
                 __syncwarp();
-                // ---- phase 2: lane -> (row = (lane>>3) + 4*i, chunk = lane&7): coalesced bias/residual/store
+                // ---- phase 2: lane -> (row = (lane>>3) + 4*i, chunk = lane&7): coalesced bias / residual / store.
+                //      All loads of the 8 row-iterations are issued before any use (predicated, no branches in between).
                 const int ch = lane & 7;
                 const int n0 = col0 + ch * 4;
-                float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
                 const bool col_ok = n0 < p.N;  // N % 4 == 0 is enforced on the host
+                float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (col_ok && p.bias != nullptr) bz = *reinterpret_cast<const float4*>(p.bias + n0);
+                int mrow[8];
+                float4 q[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = (lane >> 3) + 4 * i;
-                    const int m = __shfl_sync(0xffffffffu, my_m, r);
-                    const int grp = __shfl_sync(0xffffffffu, my_grp, r);
-                    if (m < 0 || !col_ok) continue;
-                    float4 q = *reinterpret_cast<const float4*>(stg + r * STAGE_ROW_BYTES + ((ch ^ (r & 7)) << 4));
-                    q.x += bz.x; q.y += bz.y; q.z += bz.z; q.w += bz.w;
-                    if (p.row_bias != nullptr) {
-                        const float4 rb = *reinterpret_cast<const float4*>(p.row_bias + (long long)grp * p.N + n0);
-                        q.x += rb.x; q.y += rb.y; q.z += rb.z; q.w += rb.w;
+                    const int m_r = __shfl_sync(0xffffffffu, my_m, r);   // every lane takes part in the shuffle
+                    mrow[i] = col_ok ? m_r : -1;
+                    q[i] = ld_shared_f4(stg_addr + r * STAGE_ROW_BYTES + ((ch ^ (r & 7)) << 4));
+                }
+                if (p.row_bias != nullptr) {
+                    float4 rb[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int grp = __shfl_sync(0xffffffffu, my_grp, (lane >> 3) + 4 * i);
+                        rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (mrow[i] >= 0) rb[i] = *reinterpret_cast<const float4*>(p.row_bias + (long long)grp * p.N + n0);
                     }
-                    if (p.residual != nullptr) {
-                        const uint2 rr = *reinterpret_cast<const uint2*>(p.residual + (long long)m * p.ldr + n0);
-                        const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y);
-                        q.x += a.x; q.y += a.y; q.z += b.x; q.w += b.y;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { q[i].x += rb[i].x; q[i].y += rb[i].y; q[i].z += rb[i].z; q[i].w += rb[i].w; }
+                }
+                if (p.residual != nullptr) {
+                    uint2 rr[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        rr[i] = make_uint2(0u, 0u);
+                        if (mrow[i] >= 0) rr[i] = *reinterpret_cast<const uint2*>(p.residual + (long long)mrow[i] * p.ldr + n0);
                     }
-                    if (p.out_fp32) {
-                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)m * p.ldd + n0) = q;
-                    } else {
-                        uint2 o;
-                        o.x = pack_bf16x2(q.x, q.y);
-                        o.y = pack_bf16x2(q.z, q.w);
-                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldd + n0) = o;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 a = unpack_bf16x2(rr[i].x), b = unpack_bf16x2(rr[i].y);
+                        q[i].x += a.x; q[i].y += a.y; q[i].z += b.x; q[i].w += b.y;
+                    }
+                }
+                if (p.out_fp32) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (mrow[i] >= 0) {
+                            float4 o = make_float4(q[i].x + bz.x, q[i].y + bz.y, q[i].z + bz.z, q[i].w + bz.w);
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)mrow[i] * p.ldd + n0) = o;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (mrow[i] >= 0) {
+                            uint2 o;
+                            o.x = pack_bf16x2(q[i].x + bz.x, q[i].y + bz.y);
+                            o.y = pack_bf16x2(q[i].z + bz.z, q[i].w + bz.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)mrow[i] * p.ldd + n0) = o;
+                        }
                     }
                 }
             }
@@ -378,23 +440,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // =====================================================================================================
 
 template <int BN, int EXT, int BK = 64>
-static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tE, const GemmParams& p,
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tE, const GemmParams& p_in,
                        cudaStream_t stream) {
     using Cfg = GemmCfg<BN, EXT, BK>;
+    GemmParams p = p_in;
     const int up_bytes = (p.lora_up != nullptr) ? ((p.N * p.lora_rp * 4 + 15) & ~15) : 0;
     const int fixed = 1024 /*align slack*/ + EPI_STAGING_BYTES + up_bytes + 256 /*barriers*/;
-    int stages = (232448 - fixed) / Cfg::STAGE_BYTES;
-    if (stages > 8) stages = 8;
-    if (stages < 2) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: not enough shared memory for 2 stages");
-    const int smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
+    int stages, smem_bytes;
+    int grid = num_sms();
+    // B-resident mode: the weight tile of one n-block fits next to >= 3 A stages and every CTA re-uses it >= 3 times
+    const int b_res_bytes = p.num_k_blocks * Cfg::B_STAGE_BYTES;
+    const int a_room = 232448 - fixed - b_res_bytes;
+    const int grid_res = (grid / p.num_n_blocks) * p.num_n_blocks;
+    if (p.a_mode == 0 && a_room >= 3 * Cfg::A_STAGE_BYTES && grid_res > 0 && grid_res * 10 >= grid * 9 &&
+        p.num_m_blocks >= 3 * (grid_res / p.num_n_blocks)) {
+        p.b_resident = 1;
+        stages = a_room / Cfg::A_STAGE_BYTES;
+        if (stages > 8) stages = 8;
+        smem_bytes = fixed + b_res_bytes + stages * Cfg::A_STAGE_BYTES;
+        grid = grid_res;
+    } else {
+        p.b_resident = 0;
+        stages = (232448 - fixed) / Cfg::STAGE_BYTES;
+        if (stages > 8) stages = 8;
+        if (stages < 2) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: not enough shared memory for 2 stages");
+        smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
+        const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+        if (grid > num_tiles) grid = num_tiles;
+    }
     static bool attr_done = false;
     if (!attr_done) {
         CL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_done = true;
     }
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-    int grid = num_sms();
-    if (grid > num_tiles) grid = num_tiles;
     gemm_tc_kernel<BN, EXT, BK><<<grid, NUM_THREADS, smem_bytes, stream>>>(tA, tB, tE, p, stages);
     count_launch();
     CL_CUDA_CHECK(cudaGetLastError());
@@ -487,6 +565,7 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     int bn_sel = a->block_n;
     if (bn_sel == 0) {
         if (lora) bn_sel = (a->N % 160 == 0) ? 160 : (a->N % 128 == 0 ? 128 : 160);
+        else if (a->a_mode == 0 && a->K <= 320 && a->N % 160 == 0 && a->M >= 8192) bn_sel = 160;  // weight tile stays smem-resident
         else if (a->N % 256 == 0) bn_sel = 256;
         else if (a->N % 160 == 0) bn_sel = 160;
         else if (a->N % 128 == 0) bn_sel = 128;

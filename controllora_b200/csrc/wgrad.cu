@@ -170,21 +170,27 @@ __global__ void conv_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat
 // out[c] += alpha * sum_m x[m, c]
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long M, int C, float alpha, int rows_per_cta) {
-    // thread -> column chunk of 8; CTA -> slab of rows
+    // thread -> column chunk of 8; CTA -> slab of rows; block-level smem reduction, then C global atomics per CTA
+    __shared__ float sh[2048];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
     const int chunks = C / 8;
     const int rows_par = blockDim.x / chunks;
     const int chunk = threadIdx.x % chunks, rsub = threadIdx.x / chunks;
-    if (rsub >= rows_par) return;
-    const long long r0 = (long long)blockIdx.x * rows_per_cta;
-    const long long r1 = min(M, r0 + rows_per_cta);
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (long long m = r0 + rsub; m < r1; m += rows_par) {
-        const uint4 u = *reinterpret_cast<const uint4*>(x + m * C + chunk * 8);
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-    }
+    if (rsub < rows_par) {
+        const long long r0 = (long long)blockIdx.x * rows_per_cta;
+        const long long r1 = min(M, r0 + rows_per_cta);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (long long m = r0 + rsub; m < r1; m += rows_par) {
+            const uint4 u = *reinterpret_cast<const uint4*>(x + m * C + chunk * 8);
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+        }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&out[chunk * 8 + j], alpha * acc[j]);
+        for (int j = 0; j < 8; ++j) atomicAdd(&sh[chunk * 8 + j], acc[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[i], alpha * sh[i]);
 }
 
 // ---------------------------------------------------------------------------------------------- conv_in weight grad

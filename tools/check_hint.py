@@ -68,7 +68,7 @@ def hint_case(v2: bool, size=64, B=2):
         scale = float(p1.grad.norm())
         if n1.endswith("bias"):
             wname = n1[:-4] + "weight"
-            scale = max(scale, 1e-3 * float(dict(ocl.named_parameters())[wname].grad.norm()))
+            scale = max(scale, 1e-2 * float(dict(ocl.named_parameters())[wname].grad.norm()))
         err = float((p2.grad.detach().float().cpu() - p1.grad).norm()) / (scale + 1e-30)
         rows.append((err, n1, float(p1.grad.norm())))
     rows.sort(reverse=True)

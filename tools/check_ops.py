@@ -305,7 +305,7 @@ def main():
     for name in CASES:
         t0 = time.time()
         try:
-            r = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=300)
+            r = subprocess.run([sys.executable, __file__, name], capture_output=True, text=True, timeout=150)
             ok = r.returncode == 0 and "CASE_OK" in r.stdout
             out = r.stdout + r.stderr
         except subprocess.TimeoutExpired as e:

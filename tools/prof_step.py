@@ -61,6 +61,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--breakdown", action="store_true")
     ap.add_argument("--fwd-only", action="store_true")
+    ap.add_argument("--trainer", action="store_true", help="time the full fused Trainer.step (hint encoder + UNet + optimizer)")
     a = ap.parse_args()
     B = a.batch
     unet, cl, ctrl = build(a.variant, B)
@@ -70,7 +71,14 @@ def main():
     e = torch.randn(B, 77, 768, generator=g).cuda().to(torch.bfloat16)
     tgt = torch.randn(B, 4, 64, 64, generator=g).cuda()
 
+    if a.trainer:
+        from controllora_b200.trainer import Trainer
+        tr = Trainer(unet, cl, lr=1e-4)
+        guide = ((torch.rand(B, 1, 512, 512, generator=g) < 0.08).float() * 2 - 1).expand(B, 3, 512, 512).contiguous().cuda()
+
     def step():
+        if a.trainer:
+            return tr.step(x, t, e, guide, tgt)
         control, _ = unet.collect_control(need_grad=not a.fwd_only)
         tape = None if a.fwd_only else Tape()
         pred, ctx, rt = unet.run_engine(x, t, e, control, tape)
@@ -90,10 +98,16 @@ def main():
             @functools.wraps(fn)
             def w(*args, **kw):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                key = name
+                if name == "gemm":
+                    A_, B_ = args[0], args[1]
+                    conv = kw.get("conv_stride", 0)
+                    M = A_.shape[0] if not conv else A_.shape[0] * A_.shape[1] * A_.shape[2] // (conv * conv)
+                    key = f"gemm{'_conv' if conv else ''}{'_lora' if kw.get('lora_up') is not None else ''} M={M} N={B_.shape[0]} K={B_.shape[1]}"
                 e0.record()
                 r = fn(*args, **kw)
                 e1.record()
-                pend.append((name, args, kw, e0, e1))
+                pend.append((key, e0, e1))     # keep no tensor references: the allocator must be able to recycle memory
                 return r
             return w
 
@@ -101,7 +115,8 @@ def main():
         for name in ["gemm", "attention_fwd", "attention_bwd", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd",
                      "geglu_fwd", "geglu_bwd", "add", "upsample2x_fwd", "upsample2x_bwd", "zero_insert2x", "concat_channels",
                      "slice_channels", "skinny_atb", "rowdot", "rowmat", "skinny_small", "small_matmul", "hilo_combine",
-                     "rank_update", "conv_in", "conv_out", "conv_out_bwd", "small_linear", "mse_loss"]:
+                     "rank_update", "conv_in", "conv_out", "conv_out_bwd", "small_linear", "mse_loss", "conv_wgrad", "colsum",
+                     "conv_weight_prep", "conv_in_wgrad", "sumsq", "adamw", "f32_to_bf16", "nchw_to_nhwc"]:
             setattr(ops, name, wrap(name, getattr(ops, name)))
 
     for i in range(2):
@@ -124,13 +139,7 @@ def main():
     print(f"variant={a.variant} B={B} fwd_only={a.fwd_only}: {ms:.2f} ms/step (GPU events), wall {wall:.2f} ms, "
           f"{(n1-n0)//a.iters} launches/step, {B/ms*1e3:.1f} img/s", flush=True)
     if a.breakdown:
-        for name, args, kw, s0, s1 in pend:
-            key = name
-            if name == "gemm":
-                A_, B_ = args[0], args[1]
-                conv = kw.get("conv_stride", 0)
-                M = A_.shape[0] if not conv else A_.shape[0] * A_.shape[1] * A_.shape[2] // (conv * conv)
-                key = f"gemm{'_conv' if conv else ''}{'_lora' if kw.get('lora_up') is not None else ''} M={M} N={B_.shape[0]} K={B_.shape[1]}"
+        for key, s0, s1 in pend:
             times[key] += s0.elapsed_time(s1) / a.iters
             counts[key] += 1
         fam = defaultdict(float)
