@@ -61,7 +61,7 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0, period_s=0.15):
+    def __init__(self, gpu_index=0, period_s=0.02):
         self.idx, self.period = gpu_index, period_s
         self.lines, self.stop_flag, self.t = [], threading.Event(), None
 
@@ -112,6 +112,35 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------------ CPU oracle arm
+_CPU_THREADS = None
+
+
+def pick_cpu_threads(torch) -> int:
+    """Use the thread count that is actually fastest for this workload's kernels on the host: torch's CPU conv / matmul
+    slow down badly when oversubscribed (128 threads measured 14x slower than 8 on the GPU box's host)."""
+    global _CPU_THREADS
+    if _CPU_THREADS is not None:
+        return _CPU_THREADS
+    ncpu = os.cpu_count() or 1
+    x = torch.randn(1, 320, 64, 64)
+    w = torch.randn(320, 320, 3, 3)
+    a = torch.randn(4096, 320)
+    b = torch.randn(320, 1280)
+    best, best_t = 1, float("inf")
+    for n in sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu}):
+        torch.set_num_threads(n)
+        for _ in range(2):
+            torch.nn.functional.conv2d(x, w, padding=1); a @ b
+        t0 = time.perf_counter()
+        for _ in range(5):
+            torch.nn.functional.conv2d(x, w, padding=1); a @ b
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    _CPU_THREADS = best
+    return best
+
+
 def cpu_train_step_factory(config_name: str):
     """The reference algorithm on the host cores: oracle port of diffusers' UNet + models.py (oracle/), fp32, one image."""
     import torch
@@ -119,7 +148,7 @@ def cpu_train_step_factory(config_name: str):
     from oracle import unet_ref as UR
     from controllora_b200.configs import NAMED
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(pick_cpu_threads(torch))
     unet = UR.UNet2DConditionModel()
     UR.init_synthetic_(unet, seed=1)
     unet.requires_grad_(False)
@@ -151,9 +180,10 @@ def cpu_baseline(config_name: str, budget_s: float = 25.0, max_steps: int = 2):
     for _ in range(n):
         step()
     dt = (time.time() - t0) / n
-    return {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+    import torch
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{n} full train step(s) of ONE 512x512 image (batch 1) through the fp32 oracle port (oracle/), "
-                      f"torch CPU with {os.cpu_count()} threads; {dt:.1f} s/step"}
+                      f"torch CPU with {torch.get_num_threads()} threads (fastest of a sweep up to {os.cpu_count()} logical CPUs); {dt:.1f} s/step"}
 
 
 def run_reference(a):
@@ -178,9 +208,10 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": k_eff, "warmup": w_eff + 1,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{a.config} ControlLoRA train step, SD-1.5 UNet 512x512 (64x64 latents), CPU sample = batch 1"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": _CPU_THREADS, "kind": "port",
                          "sample": f"{k_eff} timed train step(s) of one 512x512 image each ({a.steps} requested; bounded to ~150 s), "
-                                   f"fp32 oracle port of the reference (diffusers is not installable offline), {os.cpu_count()} threads"},
+                                   f"fp32 oracle port of the reference (diffusers is not installable offline), {_CPU_THREADS} threads "
+                                   f"(fastest of a sweep up to {os.cpu_count()} logical CPUs)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)

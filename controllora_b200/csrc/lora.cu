@@ -77,20 +77,23 @@ skinny_atb_kernel(const float* __restrict__ a, int lda, const __nv_bfloat16* __r
                 for (int i = 0; i < 8; ++i) acc[j][i] += av[j] * bv[i];
         }
     }
-    // combine the row-parallel partials of this CTA in shared memory, then one global atomic per output element
-    extern __shared__ float sh[];   // [R][C]
-    for (int i = threadIdx.x; i < R * C; i += blockDim.x) sh[i] = 0.f;
-    __syncthreads();
+    // combine the row-parallel partials of this CTA through shared memory with plain stores (shared-memory atomics cost
+    // ~2 cycles per lane and dominated this kernel), then one global RED per output element and CTA
+    extern __shared__ float sh[];   // [rows_par][R][C]
     if (active) {
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(&sh[j * C + chunk * 8 + i], acc[j][i]);
+        for (int j = 0; j < R; ++j) {
+            float* dst = sh + ((long long)rsub * R + j) * C + chunk * 8;
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
+        float s = 0.f;
+        for (int g = 0; g < rows_par; ++g) s += sh[(long long)g * R * C + i];
         const int j = i / C, c = i % C;
-        atomicAdd(&out[j * so_j + c * so_c], alpha * sh[i]);
+        atomicAdd(&out[j * so_j + c * so_c], alpha * s);
     }
 }
 
@@ -99,25 +102,30 @@ skinny_atb_kernel(const float* __restrict__ a, int lda, const __nv_bfloat16* __r
 template <int RP>
 __global__ void __launch_bounds__(256)
 rowdot_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const float* __restrict__ u, float* __restrict__ e, int M, int N) {
+    extern __shared__ float s_ut[];                 // [RP][N]  (transposed: conflict-free 16-byte reads along n)
+    for (int i = threadIdx.x; i < N * RP; i += blockDim.x) s_ut[(i % RP) * N + i / RP] = u[i];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (m >= M) return;
-    float acc[RP];
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M; m += warps_total) {
+        float acc[RP];
 #pragma unroll
-    for (int j = 0; j < RP; ++j) acc[j] = 0.f;
-    for (int n = lane * 8; n < N; n += 256) {
-        const uint4 v = *reinterpret_cast<const uint4*>(a + (long long)m * lda + n);
-        const float2 a0 = unpack_bf16x2(v.x), a1 = unpack_bf16x2(v.y), a2 = unpack_bf16x2(v.z), a3 = unpack_bf16x2(v.w);
-        const float av[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+        for (int j = 0; j < RP; ++j) acc[j] = 0.f;
+        for (int n = lane * 8; n < N; n += 256) {
+            const uint4 v = *reinterpret_cast<const uint4*>(a + (long long)m * lda + n);
+            const float2 a0 = unpack_bf16x2(v.x), a1 = unpack_bf16x2(v.y), a2 = unpack_bf16x2(v.z), a3 = unpack_bf16x2(v.w);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+            for (int j = 0; j < RP; ++j) {
+                const float4 u0 = *reinterpret_cast<const float4*>(s_ut + j * N + n);
+                const float4 u1 = *reinterpret_cast<const float4*>(s_ut + j * N + n + 4);
+                acc[j] += a0.x * u0.x + a0.y * u0.y + a1.x * u0.z + a1.y * u0.w + a2.x * u1.x + a2.y * u1.y + a3.x * u1.z + a3.y * u1.w;
+            }
+        }
 #pragma unroll
-            for (int j = 0; j < RP; ++j) acc[j] += av[i] * u[(long long)(n + i) * RP + j];
-    }
-#pragma unroll
-    for (int j = 0; j < RP; ++j) {
-        const float s = warp_sum(acc[j]);
-        if (lane == 0) e[(long long)m * RP + j] = s;
+        for (int j = 0; j < RP; ++j) {
+            const float sum = warp_sum(acc[j]);
+            if (lane == 0) e[(long long)m * RP + j] = sum;
+        }
     }
 }
 
@@ -173,20 +181,24 @@ template <int RP>
 __global__ void __launch_bounds__(256)
 rank_update_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ t, int ldt, const float* __restrict__ tab,
                    float alpha, __nv_bfloat16* __restrict__ out, long long M, int C) {
+    extern __shared__ float s_tt[];                 // [RP][C] transposed table
+    for (int i = threadIdx.x; i < C * RP; i += blockDim.x) s_tt[(i % RP) * C + i / RP] = tab[i];
+    __syncthreads();
     const int chunks = C / 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M * chunks; i += (long long)gridDim.x * blockDim.x) {
         const long long m = i / chunks;
         const int c0 = (int)(i % chunks) * 8;
-        float tv[RP];
-#pragma unroll
-        for (int j = 0; j < RP; ++j) tv[j] = alpha * t[m * ldt + j];
         const uint4 u = *reinterpret_cast<const uint4*>(x + m * C + c0);
         const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
         float xv[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-#pragma unroll
-            for (int j = 0; j < RP; ++j) xv[e] += tv[j] * tab[(long long)(c0 + e) * RP + j];
+        for (int j = 0; j < RP; ++j) {
+            const float tv = alpha * t[m * ldt + j];
+            const float4 a = *reinterpret_cast<const float4*>(s_tt + j * C + c0);
+            const float4 b = *reinterpret_cast<const float4*>(s_tt + j * C + c0 + 4);
+            xv[0] += tv * a.x; xv[1] += tv * a.y; xv[2] += tv * a.z; xv[3] += tv * a.w;
+            xv[4] += tv * b.x; xv[5] += tv * b.y; xv[6] += tv * b.z; xv[7] += tv * b.w;
+        }
         uint4 o;
         o.x = pack_bf16x2(xv[0], xv[1]); o.y = pack_bf16x2(xv[2], xv[3]);
         o.z = pack_bf16x2(xv[4], xv[5]); o.w = pack_bf16x2(xv[6], xv[7]);
@@ -290,7 +302,7 @@ extern "C" int cl_skinny_atb(const float* a, int lda, int r, const void* b, int6
     const __nv_bfloat16* bb = reinterpret_cast<const __nv_bfloat16*>(b);
 #define SK_CASE(R)                                                                                                      \
     case R: {                                                                                                           \
-        const size_t smem = (size_t)R * Ccols * sizeof(float);                                                          \
+        const size_t smem = (size_t)rows_par * R * Ccols * sizeof(float);                                               \
         static bool done = false;                                                                                       \
         if (!done) {                                                                                                    \
             CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
@@ -311,8 +323,12 @@ extern "C" int cl_rowdot(const void* a, int64_t lda, const float* u, int rp, flo
     STREAM;
     if (!a || !u || !e || N % 8) return set_error(CL_ERR_INVALID, "cl_rowdot: bad args");
     const __nv_bfloat16* aa = reinterpret_cast<const __nv_bfloat16*>(a);
-    if (rp == 4) rowdot_kernel<4><<<(M + 7) / 8, 256, 0, stream>>>(aa, lda, u, e, M, N);
-    else if (rp == 8) rowdot_kernel<8><<<(M + 7) / 8, 256, 0, stream>>>(aa, lda, u, e, M, N);
+    int blocks = (M + 7) / 8;
+    if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+    const size_t smem = (size_t)N * rp * sizeof(float);
+    if (smem > 48 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_rowdot: N * rp too large");
+    if (rp == 4) rowdot_kernel<4><<<blocks, 256, smem, stream>>>(aa, lda, u, e, M, N);
+    else if (rp == 8) rowdot_kernel<8><<<blocks, 256, smem, stream>>>(aa, lda, u, e, M, N);
     else return set_error(CL_ERR_UNSUPPORTED, "cl_rowdot: rp must be 4 or 8");
     DONE();
 }
@@ -343,11 +359,13 @@ extern "C" int cl_rank_update(const void* x, const float* t, int ldt, const floa
     if (!x || !t || !tab || !out || Ccols % 8) return set_error(CL_ERR_INVALID, "cl_rank_update: bad args");
     long long total = M * (Ccols / 8);
     int blocks = (int)((total + 255) / 256);
-    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
-    if (rp == 4) rank_update_kernel<4><<<blocks, 256, 0, stream>>>(xx, t, ldt, tab, alpha, oo, M, Ccols);
-    else if (rp == 8) rank_update_kernel<8><<<blocks, 256, 0, stream>>>(xx, t, ldt, tab, alpha, oo, M, Ccols);
+    const size_t smem = (size_t)Ccols * rp * sizeof(float);
+    if (smem > 48 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_rank_update: C * rp too large");
+    if (rp == 4) rank_update_kernel<4><<<blocks, 256, smem, stream>>>(xx, t, ldt, tab, alpha, oo, M, Ccols);
+    else if (rp == 8) rank_update_kernel<8><<<blocks, 256, smem, stream>>>(xx, t, ldt, tab, alpha, oo, M, Ccols);
     else return set_error(CL_ERR_UNSUPPORTED, "cl_rank_update: rp must be 4 or 8");
     DONE();
 }
