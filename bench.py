@@ -335,6 +335,36 @@ def run_ours(a):
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                 "launches_per_step": len(rec), "gemm_ms_per_step": tm, "algorithmic_gflop_per_step": fl / 1e9, "peak_source": which,
                 "step_model_flops_utilisation": (GFLOP_PER_IMAGE_STEP * 1e9 * B / (ms_step * 1e-3)) / (peak_tf * 1e12)}
+    # ---------------- secondary metric of BASELINE.json: denoise steps/s = UNet evaluations at the CFG batch (2B) + fused
+    #                  CFG/DDIM update per second (control injected once per image batch)
+    denoise = None
+    if rank == 0:
+        try:
+            from controllora_b200.sampler import ddim_coeffs, ddim_timesteps, sd15_alphas_cumprod
+            with torch.no_grad():
+                cl(torch.cat([guide, guide], 0))
+                x2t = torch.full((2 * B,), 500.0, device=dev)
+                e2 = torch.cat([e, e], 0)
+                lat = x.clone()
+                ac = sd15_alphas_cumprod()
+                ts = ddim_timesteps(50)
+                def dstep(t):
+                    eps2 = unet(torch.cat([lat, lat], 0), x2t.fill_(float(t)), e2).sample
+                    a_t, a_p = ddim_coeffs(t, 50, ac)
+                    ops.cfg_ddim_step(eps2, lat, 7.5, a_t, a_p)
+                for t in ts[:3]:
+                    dstep(t)
+                torch.cuda.synchronize()
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                d0.record()
+                for t in ts[3:13]:
+                    dstep(t)
+                d1.record()
+                torch.cuda.synchronize()
+                denoise = {"value": 10.0 / (d0.elapsed_time(d1) * 1e-3), "unit": "denoise steps/s",
+                           "what": f"50-step DDIM + CFG 7.5, batch {B} (UNet batch {2 * B}), 10 timed steps, {a.config} processors"}
+        except Exception as ex:
+            denoise = {"value": None, "unit": "denoise steps/s", "what": f"failed: {ex}"}
     if world > 1:
         dist.barrier()
 
@@ -360,6 +390,8 @@ def run_ours(a):
         }
         if roof is not None:
             out["roofline"] = roof
+        if denoise is not None:
+            out["aux"] = {"denoise": denoise}
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out), flush=True)

@@ -239,13 +239,21 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 tmem_ld_32x16(tmem_base + Cfg::TM_DPT + lane_off + c * 16, g);
                 tc_wait_ld();
                 uint32_t pk[8], dk_[8];
+                float lsv[16], dev[16];     // this chunk's per-query LSE / delta: broadcast 16-byte shared loads
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 l4 = *reinterpret_cast<const float4*>(ls + c * 16 + i);
+                    const float4 d4 = *reinterpret_cast<const float4*>(de + c * 16 + i);
+                    lsv[i] = l4.x; lsv[i + 1] = l4.y; lsv[i + 2] = l4.z; lsv[i + 3] = l4.w;
+                    dev[i] = d4.x; dev[i + 1] = d4.y; dev[i + 2] = d4.z; dev[i + 3] = d4.w;
+                }
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -ls[c * 16 + i]));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -ls[c * 16 + i + 1]));
+                    float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lsv[i]));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -lsv[i + 1]));
                     if (!key_ok) { p0 = 0.f; p1 = 0.f; }
-                    const float d0 = p0 * (__uint_as_float(g[i]) - de[c * 16 + i]) * p.scale;
-                    const float d1 = p1 * (__uint_as_float(g[i + 1]) - de[c * 16 + i + 1]) * p.scale;
+                    const float d0 = p0 * (__uint_as_float(g[i]) - dev[i]) * p.scale;
+                    const float d1 = p1 * (__uint_as_float(g[i + 1]) - dev[i + 1]) * p.scale;
                     pk[i >> 1] = pack_bf16x2(p0, p1);
                     dk_[i >> 1] = pack_bf16x2(d0, d1);
                 }

@@ -94,34 +94,44 @@ gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
             }
         }
     }
-    // combine: shared per-channel arrays (fp32 atomics within the CTA), then per-group fp64 atomics to global
-    __shared__ float sh0[GN_MAX_CHUNKS * 8];
-    __shared__ float sh1[GN_MAX_CHUNKS * 8];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) { sh0[i] = 0.f; sh1[i] = 0.f; }
-    __syncthreads();
-    if (active) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { atomicAdd(&sh0[c0 + j], a0[j]); atomicAdd(&sh1[c0 + j], a1[j]); }
-    }
-    __syncthreads();
+    // combine without shared-memory atomics (ATOMS costs ~2 cycles per lane): every row-group stores its per-channel
+    // partials, then the CTA sums them per channel, per group (fp64 atomics to global) and per parameter.
+    extern __shared__ float gsh[];                        // [2][rows_par + 1][C]
+    float* part0 = gsh;                                   // [rows_par][C]
+    float* part1 = gsh + (size_t)rows_par * C;            // [rows_par][C]
+    float* tot0 = gsh + (size_t)2 * rows_par * C;         // [C]
+    float* tot1 = tot0 + C;
+    auto reduce_pair = [&](const float (&x0)[8], const float (&x1)[8]) {
+        if (active) {
+            float* d0 = part0 + (size_t)rsub * C + c0;
+            float* d1 = part1 + (size_t)rsub * C + c0;
+            *reinterpret_cast<float4*>(d0) = make_float4(x0[0], x0[1], x0[2], x0[3]);
+            *reinterpret_cast<float4*>(d0 + 4) = make_float4(x0[4], x0[5], x0[6], x0[7]);
+            *reinterpret_cast<float4*>(d1) = make_float4(x1[0], x1[1], x1[2], x1[3]);
+            *reinterpret_cast<float4*>(d1 + 4) = make_float4(x1[4], x1[5], x1[6], x1[7]);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int g = 0; g < rows_par; ++g) { s0 += part0[(size_t)g * C + c]; s1 += part1[(size_t)g * C + c]; }
+            tot0[c] = s0;
+            tot1[c] = s1;
+        }
+        __syncthreads();
+    };
+    reduce_pair(a0, a1);
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         double s0 = 0.0, s1 = 0.0;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s0 += sh0[c]; s1 += sh1[c]; }
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s0 += tot0[c]; s1 += tot1[c]; }
         atomicAdd(&ws[(n * G + g) * 2], s0);
         atomicAdd(&ws[(n * G + g) * 2 + 1], s1);
     }
     if (MODE == 1 && dgamma != nullptr) {
         __syncthreads();
-        for (int i = threadIdx.x; i < C; i += blockDim.x) { sh0[i] = 0.f; sh1[i] = 0.f; }
-        __syncthreads();
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { atomicAdd(&sh0[c0 + j], g0[j]); atomicAdd(&sh1[c0 + j], g1[j]); }
-        }
-        __syncthreads();
+        reduce_pair(g0, g1);
         for (int i = threadIdx.x; i < C; i += blockDim.x) {
-            atomicAdd(&dgamma[i], sh0[i]);
-            atomicAdd(&dbeta[i], sh1[i]);
+            atomicAdd(&dgamma[i], tot0[i]);
+            atomicAdd(&dbeta[i], tot1[i]);
         }
     }
 }
@@ -317,7 +327,15 @@ extern "C" int cl_groupnorm_fwd(const void* x, const float* gamma, const float* 
     int threads, rows_per_cta, grid_x;
     CL_CHECK(gn_launch_geometry(HW, C, n, threads, rows_per_cta, grid_x));
     CL_CUDA_CHECK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * n * G, stream));
-    gn_reduce_kernel<0><<<dim3(grid_x, n), threads, 0, stream>>>(
+    const size_t rsmem = (size_t)2 * (threads / (C / 8) + 1) * C * sizeof(float);
+    {
+        static bool done = false;
+        if (!done) {
+            CL_CUDA_CHECK(cudaFuncSetAttribute(gn_reduce_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            done = true;
+        }
+    }
+    gn_reduce_kernel<0><<<dim3(grid_x, n), threads, rsmem, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, ws, nullptr, nullptr, HW, C, G,
         rows_per_cta, 0);
     const long long total = (long long)n * HW * (C / 8);
@@ -341,7 +359,15 @@ extern "C" int cl_groupnorm_bwd(const void* x, const void* dy, const float* gamm
     int threads, rows_per_cta, grid_x;
     CL_CHECK(gn_launch_geometry(HW, C, n, threads, rows_per_cta, grid_x));
     CL_CUDA_CHECK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * n * G, stream));
-    gn_reduce_kernel<1><<<dim3(grid_x, n), threads, 0, stream>>>(
+    const size_t rsmem = (size_t)2 * (threads / (C / 8) + 1) * C * sizeof(float);
+    {
+        static bool done = false;
+        if (!done) {
+            CL_CUDA_CHECK(cudaFuncSetAttribute(gn_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            done = true;
+        }
+    }
+    gn_reduce_kernel<1><<<dim3(grid_x, n), threads, rsmem, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, beta, stats, ws,
         dgamma, dbeta, HW, C, G, rows_per_cta, silu);
     const long long total = (long long)n * HW * (C / 8);

@@ -318,3 +318,29 @@ extern "C" int cl_mse_loss(const float* pred, const float* target, float* loss, 
     mse_kernel<<<blocks, 256, 0, stream>>>(pred, target, loss, dpred, n, gscale);
     DONE();
 }
+
+// ------------------------------------------------------------------------------------------ CFG + DDIM update (eta = 0)
+// eps = eps_u + g (eps_c - eps_u);  x0 = (x - sqrt(1-a_t) eps) / sqrt(a_t);  x <- sqrt(a_prev) x0 + sqrt(1-a_prev) eps
+// (classifier-free guidance as in StableDiffusionPipeline + diffusers DDIMScheduler.step, the loop of
+//  train_text_to_image_control_lora.py:829-843 / apps/gradio_canny2image.py:81-89 with BASELINE config 3's scheduler)
+namespace clb {
+__global__ void cfg_ddim_kernel(const float* __restrict__ eps2, float* __restrict__ x, long long n_half, float g, float sa_t,
+                                float s1a_t, float sa_p, float s1a_p) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_half; i += (long long)gridDim.x * blockDim.x) {
+        const float eu = eps2[i], ec = eps2[n_half + i];
+        const float e = eu + g * (ec - eu);
+        const float x0 = (x[i] - s1a_t * e) / sa_t;
+        x[i] = sa_p * x0 + s1a_p * e;
+    }
+}
+}  // namespace clb
+
+extern "C" int cl_cfg_ddim_step(const float* eps2, float* latents, int64_t n_half, float guidance, float sqrt_at, float sqrt_1m_at,
+                                float sqrt_aprev, float sqrt_1m_aprev, void* stream_) {
+    STREAM;
+    if (!eps2 || !latents) return set_error(CL_ERR_INVALID, "cl_cfg_ddim_step: null");
+    int blocks = (int)((n_half + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    clb::cfg_ddim_kernel<<<blocks, 256, 0, stream>>>(eps2, latents, n_half, guidance, sqrt_at, sqrt_1m_at, sqrt_aprev, sqrt_1m_aprev);
+    DONE();
+}

@@ -523,3 +523,11 @@ def colsum(x, out, alpha: float = 1.0):
 def conv_in_wgrad(x, dy, dw):
     n, Cin, H, W = x.shape
     _call("cl_conv_in_wgrad", _p(x), _p(dy), _p(dw), n, Cin, H, W, dy.shape[-1])
+
+
+def cfg_ddim_step(eps2, latents, guidance, a_t, a_prev):
+    """In-place DDIM (eta=0) update of `latents` [B,4,h,w] fp32 from eps2 [2B,4,h,w] = [uncond | cond]."""
+    n_half = latents.numel()
+    assert eps2.numel() == 2 * n_half and eps2.is_contiguous() and latents.is_contiguous()
+    _call("cl_cfg_ddim_step", _p(eps2), _p(latents), C.c_int64(n_half), C.c_float(guidance), C.c_float(a_t ** 0.5),
+          C.c_float((1 - a_t) ** 0.5), C.c_float(a_prev ** 0.5), C.c_float((1 - a_prev) ** 0.5))

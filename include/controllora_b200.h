@@ -171,6 +171,10 @@ int cl_timestep_embedding(const float* t, float* out, int B, int dim, void* stre
 int cl_small_linear(const float* x, const void* w, const float* bias, float* out, int Bt, int N, int K, int silu_in,
                     int silu_out, void* stream);
 int cl_mse_loss(const float* pred, const float* target, float* loss, float* dpred, int64_t n, float gscale, void* stream);
+/* classifier-free-guidance combine + DDIM (eta = 0) update of the denoise loop, one fused elementwise kernel:
+ * eps2 = [uncond | cond] noise predictions (each n_half floats), latents updated in place. */
+int cl_cfg_ddim_step(const float* eps2, float* latents, int64_t n_half, float guidance, float sqrt_at, float sqrt_1m_at,
+                     float sqrt_aprev, float sqrt_1m_aprev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * LoRA side path (diffusers LoRALinearLayer instances created at models.py:89-97,185,316-323).

@@ -112,3 +112,49 @@ def test_lora_zero_up_is_exact_noop_on_gpu():
         a = u0(x, t, e).sample
         b = u1(x, t, e).sample
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ denoise loop (CFG + DDIM)
+def test_cfg_ddim_step_matches_oracle():
+    from controllora_b200 import ops
+    from controllora_b200.sampler import ddim_coeffs, ddim_timesteps, sd15_alphas_cumprod
+    from oracle import sampler_ref as SR
+
+    g = torch.Generator().manual_seed(0)
+    eps2 = torch.randn(4, 4, 16, 16, generator=g)
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    ac = sd15_alphas_cumprod()
+    for t in ddim_timesteps(50)[:3] + ddim_timesteps(50)[-2:]:
+        xm = x.clone().cuda()
+        a_t, a_p = ddim_coeffs(t, 50, ac)
+        ops.cfg_ddim_step(eps2.cuda(), xm, 7.5, a_t, a_p)
+        ref = SR.cfg_ddim_step(eps2[:2], eps2[2:], x, t, 50, 7.5)
+        assert torch.allclose(xm.cpu(), ref, atol=1e-4, rtol=1e-4), t
+
+
+def test_ddim_loop_tracks_oracle_on_tiny_unet():
+    """3 CFG+DDIM steps (UNet batch 2B, control injected once) against the oracle UNet driven by the oracle scheduler."""
+    import controllora_b200 as cb
+    from controllora_b200.sampler import ddim_sample
+    from oracle import models_ref as MR
+    from oracle import sampler_ref as SR
+
+    ounet, munet, ocl, mcl = check_unet.build_pair("v1")
+    g = torch.Generator().manual_seed(9)
+    B, HW = 2, 16
+    guide = (torch.rand(B, 3, HW * 8, HW * 8, generator=g) * 2 - 1).to(torch.bfloat16).float()
+    cond = torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).float()
+    unc = torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).float()
+    lat0 = torch.randn(B, 4, HW, HW, generator=g)
+    steps = 3
+    with torch.no_grad():
+        ocl(torch.cat([guide, guide], 0))
+        x = lat0.clone()
+        for t in SR.timesteps(steps):
+            eps = ounet(torch.cat([x, x], 0), torch.full((2 * B,), int(t)), torch.cat([unc, cond], 0)).sample
+            x = SR.cfg_ddim_step(eps[:B], eps[B:], x, t, steps, 7.5)
+    out = ddim_sample(munet, mcl, guide.cuda(), cond.cuda().to(torch.bfloat16), unc.cuda().to(torch.bfloat16),
+                      num_inference_steps=steps, guidance_scale=7.5, latents=lat0.cuda())
+    err = float((out.cpu() - x).norm() / x.norm())
+    print("ddim 3-step latent rel err", err)
+    assert err < 6e-2
