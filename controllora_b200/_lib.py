@@ -59,6 +59,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p),
         ("row_bias", C.c_void_p),
         ("rows_per_group", C.c_int32),
+        ("ld_row_bias", C.c_int64),
         ("residual", C.c_void_p),
         ("ldr", C.c_int64),
         ("lora_up", C.c_void_p),
@@ -112,3 +113,15 @@ class PackDesc(C.Structure):
         ("ld", C.c_int32),
         ("row_off", C.c_int32),
     ]
+
+
+class SkinnyDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_int32), ("r", C.c_int32),
+        ("b", C.c_void_p), ("ldb", C.c_int64),
+        ("out", C.c_void_p), ("so_j", C.c_int64), ("so_c", C.c_int64),
+        ("alpha", C.c_float), ("M", C.c_int32), ("C", C.c_int32),
+    ]
+
+
+SKINNY_MAX = 16

@@ -59,9 +59,11 @@ __device__ __forceinline__ void store_row16_swz(uint8_t* tile, int chunk_stride,
 
 // TMEM accumulator rows -> bf16 global rows (thread = row), columns [0, d)
 template <int DP>
-__device__ __forceinline__ void store_acc_rows(uint32_t taddr, __nv_bfloat16* rowptr, bool row_ok, int d, float mul) {
+__device__ __forceinline__ void store_acc_rows(uint32_t taddr, __nv_bfloat16* rowptr, bool row_ok, int d, float mul,
+                                               int c_begin = 0, int c_step = 1) {
 #pragma unroll
     for (int c = 0; c < DP / 32; ++c) {
+        if (c < c_begin || ((c - c_begin) % c_step) != 0) continue;   // (warp-uniform) this warp's share of the columns
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tc_wait_ld();
@@ -100,8 +102,12 @@ struct DkvCfg {
     static_assert(BQ % 64 == 0, "BQ");
 };
 
+// 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 4-11 softmax (two warps per TMEM lane quadrant, each takes half of the columns:
+// with one softmax warp per SM sub-partition the dependent tcgen05.ld -> exp -> st.shared chains left the issue slots idle)
+static constexpr int BWD_THREADS = 384;
+
 template <int DP, int BQ, int STAGES>
-__global__ void __launch_bounds__(256, (DkvCfg<DP, BQ, STAGES>::MIN_CTAS))
+__global__ void __launch_bounds__(BWD_THREADS, (DkvCfg<DP, BQ, STAGES>::MIN_CTAS))
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdParams p) {
@@ -139,7 +145,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_init(kv_full, 1);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
         mbar_init(s_full, 1);
-        mbar_init(p_full, 4);
+        mbar_init(p_full, 8);
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -216,7 +222,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     } else if (warp_idx >= 4) {
         const int quad = warp_idx & 3;
         const int r = quad * 32 + lane;                // key row within the block
-        const int st = threadIdx.x - 128;              // 0..127
+        const int half = (warp_idx - 4) >> 2;          // which half of the query columns this warp converts
+        const int st = threadIdx.x - 128;              // 0..255
         const uint32_t lane_off = uint32_t(quad * 32) << 16;
         const bool key_ok = (k0 + r) < p.Nk;
         const long long stat_base = ((long long)b * p.H + h) * p.Nq;
@@ -229,11 +236,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 ls[st] = (q < p.Nq) ? p.lse[stat_base + q] : INFINITY;   // +inf -> P = 0 for padded queries
                 de[st] = (q < p.Nq) ? p.delta[stat_base + q] : 0.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(s_full, j & 1);
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < BQ / 16; ++c) {
+            for (int c = half * (BQ / 32); c < (half + 1) * (BQ / 32); ++c) {
                 uint32_t s[16], g[16];
                 tmem_ld_32x16(tmem_base + Cfg::TM_ST + lane_off + c * 16, s);
                 tmem_ld_32x16(tmem_base + Cfg::TM_DPT + lane_off + c * 16, g);
@@ -268,8 +275,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const long long row = (long long)b * p.Nk + k0 + r;
-        store_acc_rows<DP>(tmem_base + Cfg::TM_DK + lane_off, p.dk + row * p.lddk + h * p.d, key_ok, p.d, 1.f);
-        store_acc_rows<DP>(tmem_base + Cfg::TM_DV + lane_off, p.dv + row * p.lddv + h * p.d, key_ok, p.d, 1.f);
+        if (half == 0) store_acc_rows<DP>(tmem_base + Cfg::TM_DK + lane_off, p.dk + row * p.lddk + h * p.d, key_ok, p.d, 1.f);
+        else store_acc_rows<DP>(tmem_base + Cfg::TM_DV + lane_off, p.dv + row * p.lddv + h * p.d, key_ok, p.d, 1.f);
     }
     tc_fence_before();
     __syncthreads();
@@ -294,7 +301,7 @@ struct DqCfg {
 };
 
 template <int DP, int BKB, int STAGES>
-__global__ void __launch_bounds__(256, (DqCfg<DP, BKB, STAGES>::MIN_CTAS))
+__global__ void __launch_bounds__(BWD_THREADS, (DqCfg<DP, BKB, STAGES>::MIN_CTAS))
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const AttnBwdParams p) {
@@ -329,7 +336,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(q_full, 1);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
         mbar_init(s_full, 1);
-        mbar_init(p_full, 4);
+        mbar_init(p_full, 8);
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -403,6 +410,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int quad = warp_idx & 3;
         const int r = quad * 32 + lane;
         const uint32_t lane_off = uint32_t(quad * 32) << 16;
+        const int half = (warp_idx - 4) >> 2;
         const int q = q0 + r;
         const bool q_ok = q < p.Nq;
         const long long stat = ((long long)b * p.H + h) * p.Nq + q;
@@ -414,7 +422,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const int kbase = i * BKB;
             const bool tail = kbase + BKB > p.Nk;
 #pragma unroll
-            for (int c = 0; c < BKB / 16; ++c) {
+            for (int c = half * (BKB / 32); c < (half + 1) * (BKB / 32); ++c) {
                 uint32_t s[16], g[16];
                 tmem_ld_32x16(tmem_base + Cfg::TM_S + lane_off + c * 16, s);
                 tmem_ld_32x16(tmem_base + Cfg::TM_DP + lane_off + c * 16, g);
@@ -442,7 +450,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const long long row = (long long)b * p.Nq + q;
-        store_acc_rows<DP>(tmem_base + Cfg::TM_DQ + lane_off, p.dq + row * p.lddq + h * p.d, q_ok, p.d, 1.f);
+        store_acc_rows<DP>(tmem_base + Cfg::TM_DQ + lane_off, p.dq + row * p.lddq + h * p.d, q_ok, p.d, 1.f, half, 2);
     }
     tc_fence_before();
     __syncthreads();
@@ -505,7 +513,7 @@ static int launch_attn_bwd(const cl_attn_bwd_args* a, cudaStream_t stream) {
             done = true;
         }
         p.num_blocks = (a->Nk + 127) / 128;
-        attn_bwd_dkv_kernel<DP, BQ, STAGES_KV><<<a->B * a->H * p.num_blocks, 256, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+        attn_bwd_dkv_kernel<DP, BQ, STAGES_KV><<<a->B * a->H * p.num_blocks, BWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
         count_launch();
     }
     if (a->dq != nullptr) {
@@ -521,7 +529,7 @@ static int launch_attn_bwd(const cl_attn_bwd_args* a, cudaStream_t stream) {
             done = true;
         }
         p.num_blocks = (a->Nq + 127) / 128;
-        attn_bwd_dq_kernel<DP, BKB, STAGES_Q><<<a->B * a->H * p.num_blocks, 256, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+        attn_bwd_dq_kernel<DP, BKB, STAGES_Q><<<a->B * a->H * p.num_blocks, BWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
         count_launch();
     }
     CL_CUDA_CHECK(cudaGetLastError());

@@ -46,6 +46,7 @@ struct GemmParams {
     const float* bias;
     const float* row_bias;
     int rows_per_group;
+    long long ld_rb;
     const __nv_bfloat16* residual;
     long long ldr;
     const float* lora_up;
@@ -381,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int i = 0; i < 8; ++i) {
                         const int grp = __shfl_sync(0xffffffffu, my_grp, (lane >> 3) + 4 * i);
                         rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (mrow[i] >= 0) rb[i] = *reinterpret_cast<const float4*>(p.row_bias + (long long)grp * p.N + n0);
+                        if (mrow[i] >= 0) rb[i] = *reinterpret_cast<const float4*>(p.row_bias + (long long)grp * p.ld_rb + n0);
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { q[i].x += rb[i].x; q[i].y += rb[i].y; q[i].z += rb[i].z; q[i].w += rb[i].w; }
@@ -590,6 +591,8 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     }
 
     p.bias = a->bias; p.row_bias = a->row_bias; p.rows_per_group = a->rows_per_group;
+    p.ld_rb = a->ld_row_bias > 0 ? a->ld_row_bias : a->N;
+    if (p.row_bias && (p.ld_rb % 4)) return set_error(CL_ERR_INVALID, "cl_gemm: ld_row_bias must be a multiple of 4");
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.ldr = a->ldr;
     p.lora_up = a->lora_up; p.lora_rp = lora ? a->lora_rp : 4; p.lora_scale = a->lora_scale;
     p.t_add = a->t_add; p.t_out = a->t_out;

@@ -97,6 +97,69 @@ skinny_atb_kernel(const float* __restrict__ a, int lda, const __nv_bfloat16* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------ batched skinny reductions
+// Up to CL_SKINNY_MAX independent  out[j, c] += alpha * sum_m a[m, j] * b[m, c]  problems in ONE launch (blockIdx.y selects
+// the problem): the dA / dB reductions of all LoRA adapters of an attention layer are tiny, launch-latency-bound kernels
+// when issued one by one.
+struct SkinnyBatch {
+    cl_skinny_desc d[CL_SKINNY_MAX];
+};
+
+__global__ void __launch_bounds__(512)
+skinny_atb_batch_kernel(const __grid_constant__ SkinnyBatch batch, int slabs) {
+    const cl_skinny_desc& d = batch.d[blockIdx.y];
+    const int C = d.C, M = d.M, R = d.r;
+    const int chunks = C / 8;
+    const int rows_par = blockDim.x / chunks;
+    const int chunk = threadIdx.x % chunks;
+    const int rsub = threadIdx.x / chunks;
+    const bool active = rsub < rows_par;
+    const int rows_per_cta = (M + slabs - 1) / slabs;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int row1 = min(M, row0 + rows_per_cta);
+    if (row0 >= M) return;
+    const float* a = d.a;
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(d.b);
+    float acc[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+    if (active) {
+        for (int m = row0 + rsub; m < row1; m += rows_par) {
+            const uint4 u = *reinterpret_cast<const uint4*>(b + (long long)m * d.ldb + chunk * 8);
+            const float2 b0 = unpack_bf16x2(u.x), b1 = unpack_bf16x2(u.y), b2 = unpack_bf16x2(u.z), b3 = unpack_bf16x2(u.w);
+            const float bv[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < R) {
+                    const float av = a[(long long)m * d.lda + j];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[j][i] += av * bv[i];
+                }
+            }
+        }
+    }
+    extern __shared__ float sh[];   // [rows_par][R][C]
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < R) {
+                float* dst = sh + ((long long)rsub * R + j) * C + chunk * 8;
+                *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
+        float s = 0.f;
+        for (int g = 0; g < rows_par; ++g) s += sh[(long long)g * R * C + i];
+        const int j = i / C, c = i % C;
+        atomicAdd(&d.out[j * d.so_j + c * d.so_c], d.alpha * s);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ e[m, j] = sum_n a[m, n] * u[n*rp + j]
 // a bf16 [M, lda], u fp32 [N, rp]; one warp per row.
 template <int RP>
@@ -316,6 +379,36 @@ extern "C" int cl_skinny_atb(const float* a, int lda, int r, const void* b, int6
         default: return set_error(CL_ERR_UNSUPPORTED, "cl_skinny_atb: r must be 1..4 or 8");
     }
 #undef SK_CASE
+    DONE();
+}
+
+extern "C" int cl_skinny_atb_batch(const cl_skinny_desc* descs, int n, void* stream_) {
+    STREAM;
+    if (!descs || n < 1 || n > CL_SKINNY_MAX) return set_error(CL_ERR_INVALID, "cl_skinny_atb_batch: 1..%d descriptors", CL_SKINNY_MAX);
+    SkinnyBatch batch;
+    size_t smem = 0;
+    int max_m = 0;
+    for (int i = 0; i < n; ++i) {
+        const cl_skinny_desc& d = descs[i];
+        if (!d.a || !d.b || !d.out || d.C % 8 || d.C / 8 > 512 || d.r < 1 || d.r > 8 || d.M < 1)
+            return set_error(CL_ERR_INVALID, "cl_skinny_atb_batch: bad descriptor %d", i);
+        batch.d[i] = d;
+        const int rows_par = 512 / (d.C / 8);
+        const size_t need = (size_t)(rows_par < 1 ? 1 : rows_par) * d.r * d.C * sizeof(float);
+        if (need > smem) smem = need;
+        if (d.M > max_m) max_m = d.M;
+    }
+    if (smem > 200 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_skinny_atb_batch: shared memory");
+    static bool done = false;
+    if (!done) {
+        CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        done = true;
+    }
+    // ~one wave of CTAs in total; every problem gets the same number of row slabs
+    int slabs = (num_sms() + n - 1) / n;
+    if (slabs > (max_m + 63) / 64) slabs = (max_m + 63) / 64;
+    if (slabs < 1) slabs = 1;
+    skinny_atb_batch_kernel<<<dim3(slabs, n), 512, smem, stream>>>(batch, slabs);
     DONE();
 }
 

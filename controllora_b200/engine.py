@@ -69,6 +69,7 @@ class Tape:
     def backward(self) -> None:
         while self.fns:
             self.fns.pop()()
+        ops.SKINNY.flush()      # batched LoRA dA/dB reductions still queued
 
 
 # ---------------------------------------------------------------------------------------------------- frozen weights
@@ -218,8 +219,8 @@ def linear(ctx: Ctx, x: Var, lw: LinearW, *, residual: Optional[Var] = None, slo
                 for a in slot.adapters:
                     r = a.down.shape[0]
                     # dB[n, j] += s * sum_m dy[m, n] * t[m, j] ; dA[j, k] += s * sum_m e[m, j] * x[m, k]
-                    ops.skinny_atb(t_out[:, a.col:], r, dy2, a.up_grad, 1, r, scale)
-                    ops.skinny_atb(e[:, a.col:], r, x2, a.down_grad, K, 1, scale)
+                    ops.SKINNY.add(t_out[:, a.col:], r, dy2, a.up_grad, 1, r, scale)
+                    ops.SKINNY.add(e[:, a.col:], r, x2, a.down_grad, K, 1, scale)
                 if on_slot_bwd is not None:
                     on_slot_bwd(e, t_out, dy2)
 

@@ -240,7 +240,7 @@ class LoraRuntime:
         T = u.shape[0]
         du = torch.empty(T, rc, device=self.device, dtype=torch.float32)
         ops.rowmat(ea, lp.M, 1, rc, rc, r, s * s, du, rc)                           # du = s^2 e M
-        ops.skinny_atb(du, rc, lv.c.data.view(T, lv.cc), self.grad_of(Ac), lv.cc, 1, 1.0)   # dAc += du^T c
+        ops.SKINNY.add(du, rc, lv.c.data.view(T, lv.cc), self.grad_of(Ac), lv.cc, 1, 1.0)   # dAc += du^T c
         if lv.du is not None:
             i = lp.col // 4
             ops.rowmat(ea, lp.M, 1, rc, rc, r, s * s, lv.du, 16 * lv.nb, out_mode=1, col_off=16 * (i // 2) + 4 * (i % 2), lo_off=8)
@@ -272,11 +272,11 @@ class LoraRuntime:
                 dy2 = dy.view(T, C)
                 dt = ops.rowdot(dy2, lp.v2_up[which])                           # [T, 4] = dy Bc   (unscaled)
                 # dBc[c, j] += s * sum_m dy[m, c] t[m, j]
-                ops.skinny_atb(t, rc, dy2, self.grad_of(up), 1, rc, s)
+                ops.SKINNY.add(t, rc, dy2, self.grad_of(up), 1, rc, s)
                 # dAc_h[j, k] += s * sum_m dt[m, j] h[m, k] ; dAc_c likewise with c
                 gdown = self.grad_of(down)
-                ops.skinny_atb(dt, rc, h2, gdown, C + lv.cc, 1, s)
-                ops.skinny_atb(dt, rc, lv.c.data.view(T, lv.cc), gdown[:, C:], C + lv.cc, 1, s)
+                ops.SKINNY.add(dt, rc, h2, gdown, C + lv.cc, 1, s)
+                ops.SKINNY.add(dt, rc, lv.c.data.view(T, lv.cc), gdown[:, C:], C + lv.cc, 1, s)
                 # dh = dy + s * dt Ac_h
                 if h.rg:
                     E.give_tensor(h, ops.rank_update(dy, dt, lp.v2_down_tab[which], s))

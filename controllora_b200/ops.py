@@ -86,9 +86,10 @@ def gemm(
         args.bias = _ptr(bias)
     if row_bias is not None:
         _req(row_bias, torch.float32, "row_bias")
-        assert row_bias.is_contiguous() and row_bias.shape[-1] == N
+        assert row_bias.dim() == 2 and row_bias.stride(1) == 1 and row_bias.shape[-1] == N
         args.row_bias = _ptr(row_bias)
         args.rows_per_group = rows_per_group
+        args.ld_row_bias = row_bias.stride(0)
     if residual is not None:
         _req(residual, BF16, "residual")
         r2 = residual.view(-1, N) if residual.is_contiguous() else residual
@@ -531,3 +532,37 @@ def cfg_ddim_step(eps2, latents, guidance, a_t, a_prev):
     assert eps2.numel() == 2 * n_half and eps2.is_contiguous() and latents.is_contiguous()
     _call("cl_cfg_ddim_step", _p(eps2), _p(latents), C.c_int64(n_half), C.c_float(guidance), C.c_float(a_t ** 0.5),
           C.c_float((1 - a_t) ** 0.5), C.c_float(a_prev ** 0.5), C.c_float((1 - a_prev) ** 0.5))
+
+
+class SkinnyQueue:
+    """Collects the rank-r gradient reductions (dA / dB of every LoRA adapter) and issues them CL_SKINNY_MAX at a time
+    through cl_skinny_atb_batch.  The queue keeps the operand tensors alive until the launch is enqueued."""
+
+    def __init__(self):
+        from ._lib import SKINNY_MAX, SkinnyDesc
+
+        self._Desc, self._max = SkinnyDesc, SKINNY_MAX
+        self.descs, self.keep = [], []
+
+    def add(self, a, r: int, b, out, so_j: int, so_c: int, alpha: float):
+        b2 = b.view(-1, b.shape[-1]) if b.is_contiguous() else b
+        assert b2.stride(1) == 1 and b2.shape[0] == a.shape[0]
+        d = self._Desc()
+        d.a, d.lda, d.r = a.data_ptr(), a.stride(0), r
+        d.b, d.ldb = b2.data_ptr(), b2.stride(0)
+        d.out, d.so_j, d.so_c = out.data_ptr(), so_j, so_c
+        d.alpha, d.M, d.C = float(alpha), b2.shape[0], b2.shape[1]
+        self.descs.append(d)
+        self.keep.append((a, b, out))
+        if len(self.descs) >= self._max:
+            self.flush()
+
+    def flush(self):
+        if not self.descs:
+            return
+        arr = (self._Desc * len(self.descs))(*self.descs)
+        _call("cl_skinny_atb_batch", arr, len(self.descs))
+        self.descs, self.keep = [], []
+
+
+SKINNY = SkinnyQueue()

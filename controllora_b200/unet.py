@@ -125,6 +125,7 @@ class UNetWeights:
         self.mid = SimpleNamespace(
             resnets=[_Resnet(sd, "mid_block.resnets.0.", dev, True), _Resnet(sd, "mid_block.resnets.1.", dev, True)],
             attn=_Transformer(sd, "mid_block.attentions.0.", "mid_block.attentions.0.", dev, heads, True))
+        self.temb_cat = None
         self.norm_out = NormW.make(sd["conv_norm_out.weight"], sd["conv_norm_out.bias"], dev)
         self.conv_out_w = sd["conv_out.weight"].to(device=dev, dtype=BF16).permute(0, 2, 3, 1).contiguous()
         self.conv_out_b = sd["conv_out.bias"].to(device=dev, dtype=BF16).float().contiguous()
@@ -187,8 +188,17 @@ def unet_forward(ctx: Ctx, W: UNetWeights, sample: torch.Tensor, timesteps: torc
     temb = ops.timestep_embedding(timesteps, ch0)
     temb = ops.small_linear(temb, W.time1.w, W.time1.bias, silu_out=True)
     temb = ops.small_linear(temb, W.time2.w, W.time2.bias)
+    # every ResnetBlock2D.time_emb_proj in ONE launch: the stacked [sum(Cout), 1280] matrix is built once; each resnet's conv1
+    # epilogue then reads its slice of the [B, sum(Cout)] result (row pitch = sum(Cout))
+    if W.temb_cat is None:
+        rs = W.all_resnets()
+        W.temb_cat = (torch.cat([r.temb.w for r in rs], 0).contiguous(), torch.cat([r.temb.bias for r in rs], 0).contiguous())
+        off = 0
+        for r in rs:
+            r.temb_off, off = off, off + r.temb.w.shape[0]
+    tall = ops.small_linear(temb, W.temb_cat[0], W.temb_cat[1], silu_in=True)
     for r in W.all_resnets():
-        r.row_bias = ops.small_linear(temb, r.temb.w, r.temb.bias, silu_in=True)
+        r.row_bias = tall[:, r.temb_off:r.temb_off + r.temb.w.shape[0]]
     h = Var(ops.conv_in(sample, W.conv_in.w.view(ch0, 3, 3, -1), W.conv_in.bias, ch0), rg=False)
     skips = [h]
     for blk in W.down:

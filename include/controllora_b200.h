@@ -68,8 +68,9 @@ typedef struct {
     int64_t ldb_ext;
     /* epilogue */
     const float* bias;       /* [N] or NULL */
-    const float* row_bias;   /* [n_groups, N] or NULL; group of row m = m / rows_per_group */
+    const float* row_bias;   /* [n_groups, >= N] (row pitch ld_row_bias, 0 = N) or NULL; group of row m = m / rows_per_group */
     int32_t rows_per_group;
+    int64_t ld_row_bias;
     const void* residual;    /* bf16 [M, N] pitch ldr, or NULL; may alias out */
     int64_t ldr;
     const float* lora_up;    /* fp32 [N, lora_rp] or NULL */
@@ -200,6 +201,15 @@ typedef struct {
 int cl_lora_pack_batch(const cl_pack_desc* descs_dev, int n_desc, int max_elems, void* stream);
 int cl_skinny_atb(const float* a, int lda, int r, const void* b, int64_t ldb, float* out, int64_t so_j, int64_t so_c,
                   float alpha, int M, int C, void* stream);
+/* batched form: up to CL_SKINNY_MAX independent skinny reductions in one launch (descs is a HOST array, passed by value) */
+#define CL_SKINNY_MAX 16
+typedef struct {
+    const float* a; int32_t lda; int32_t r;   /* fp32 [M, lda], first r (<= 8) columns used */
+    const void* b; int64_t ldb;               /* bf16 [M, ldb], C columns */
+    float* out; int64_t so_j, so_c;           /* out[j*so_j + c*so_c] += ... */
+    float alpha; int32_t M, C;
+} cl_skinny_desc;
+int cl_skinny_atb_batch(const cl_skinny_desc* descs, int n, void* stream);
 int cl_rowdot(const void* a, int64_t lda, const float* u, int rp, float* e, int M, int N, void* stream);
 int cl_rowmat(const float* a, int lda, const float* w, int sw_i, int sw_j, int I, int J, float alpha, void* out, int ldo,
               int out_mode, int col_off, int lo_off, int accumulate, int M, void* stream);
