@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     return ap.parse_args()
 
 
@@ -243,7 +244,7 @@ def run_ours(a):
             if n_.endswith("up.weight"):
                 p_.copy_((0.02 * torch.randn(p_.shape, generator=g)).to(dev))
     wire_processors(unet, cl)
-    tr = Trainer(unet, cl, lr=1e-4)
+    tr = Trainer(unet, cl, lr=1e-4, cuda_graph=not a.no_graph)   # fwd/bwd captured once, replayed every step
     host = synth_inputs(torch, B, seed_off=rank)
     x, t, e, guide, tgt = (h.to(dev) for h in host)
     e = e.to(torch.bfloat16)
@@ -270,6 +271,8 @@ def run_ours(a):
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = (_lib.launch_count() - n0) // max(a.steps, 1)
+    if tr.cuda_graph and tr.launches_per_step:
+        launches = tr.launches_per_step      # kernels inside the replayed graph (counted at capture) + optimizer launches
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -325,7 +328,7 @@ def run_ours(a):
 
         ops.gemm = timed_gemm
         import controllora_b200.engine as E_, controllora_b200.lora_runtime as LR_, controllora_b200.hint_encoder as HE_
-        tr.step(x, t, e, guide, tgt)
+        tr.step(x, t, e, guide, tgt, eager=True)     # uncaptured pass so that every GEMM launch can be bracketed by events
         torch.cuda.synchronize()
         ops.gemm = orig
         fl = sum(r[0] for r in rec)
@@ -382,6 +385,7 @@ def run_ours(a):
             "config": {"workload": f"{a.config} ControlLoRA train step on the SD-1.5 UNet, 512x512 (64x64 latents, 77x768 text states), "
                                    f"batch {B}/GPU, hint encoder + UNet fwd/bwd + clip + AdamW" + (" + NCCL all-reduce of the flat grad arena" if world > 1 else ""),
                        "global_batch": world * B, "parallelism": f"dp{world}",
+                       "cuda_graph": bool(tr.cuda_graph and tr._graph is not None),
                        "l2_policy": "no explicit flush: each step streams 1.7 GB of frozen weights plus >5 GB of activations, far beyond the 126 MB L2",
                        "weights": "random-init (seeded), SD-1.5 / ControlLoRA shapes", "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},

@@ -71,6 +71,8 @@ class GemmArgs(C.Structure):
         ("ldd", C.c_int64),
         ("out_fp32", C.c_int32),
         ("block_n", C.c_int32),
+        ("split_k", C.c_int32),
+        ("split_ws", C.c_void_p),
     ]
 
 

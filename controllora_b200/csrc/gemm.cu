@@ -58,6 +58,10 @@ struct GemmParams {
     long long ldd;
     int out_fp32;
     int b_resident;   // B (weights) tile of this CTA's n-block stays in smem for the CTA lifetime (small K)
+    // split-K (streaming mode only): tile space is (m, n, split); split s covers k-blocks [s*kb_per_split, ...) and stores
+    // its fp32 partial tile to split_ws[s][M][N]; splitk_finish_kernel sums the partials and applies the epilogue.
+    int splits, kb_per_split;
+    float* split_ws;
 };
 
 #ifdef CLB_TIMELINE
@@ -78,20 +82,30 @@ __device__ __forceinline__ void tl_rec(int tag) {
 // tile -> (m_blk, n_blk).  Streaming mode: n fastest (CTAs that run concurrently share the A rows through L2).
 // B-resident mode: a CTA keeps ONE n-block for its lifetime and walks the m-blocks.
 struct TileIter {
-    int m_blk, n_blk, step, num_m;
+    int m_blk, n_blk, split, step, num_m;
     bool resident;
-    int tile, num_tiles, num_n;
-    __device__ TileIter(int num_m_blocks, int num_n_blocks, int b_resident) {
-        resident = b_resident != 0;
-        num_m = num_m_blocks; num_n = num_n_blocks; num_tiles = num_m_blocks * num_n_blocks;
+    int tile, num_tiles, num_n, splits, kbps, nkb;
+    __device__ TileIter(const GemmParams& p) {
+        resident = p.b_resident != 0;
+        num_m = p.num_m_blocks; num_n = p.num_n_blocks; splits = p.splits; kbps = p.kb_per_split; nkb = p.num_k_blocks;
+        num_tiles = num_m * num_n * splits;
+        split = 0; tile = 0;
         if (resident) { n_blk = blockIdx.x % num_n; m_blk = blockIdx.x / num_n; step = gridDim.x / num_n; }
-        else { tile = blockIdx.x; m_blk = tile / num_n; n_blk = tile % num_n; step = gridDim.x; }
+        else { tile = blockIdx.x; step = gridDim.x; decode(); }
+    }
+    __device__ void decode() {
+        const int t2 = tile / splits;
+        split = tile - t2 * splits;
+        m_blk = t2 / num_n;
+        n_blk = t2 - m_blk * num_n;
     }
     __device__ bool valid() const { return resident ? (m_blk < num_m) : (tile < num_tiles); }
     __device__ void next() {
         if (resident) m_blk += step;
-        else { tile += step; m_blk = tile / num_n; n_blk = tile % num_n; }
+        else { tile += step; decode(); }
     }
+    __device__ int kb_begin() const { return split * kbps; }
+    __device__ int kb_end() const { return min(nkb, (split + 1) * kbps); }
 };
 
 template <int BN, int EXT, int BK>
@@ -194,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            TileIter ti(p.num_m_blocks, p.num_n_blocks, p.b_resident);
+            TileIter ti(p);
             if (p.b_resident && ti.valid()) {
                 mbar_arrive_expect_tx(b_full, p.num_k_blocks * Cfg::B_STAGE_BYTES);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -213,7 +227,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tn = m_blk / (p.tiles_w * p.tiles_h);
                 }
                 TL(10);  // producer: tile start
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int kb1 = ti.kb_end();
+                for (int kb = ti.kb_begin(); kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES);
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
@@ -247,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            TileIter ti(p.num_m_blocks, p.num_n_blocks, p.b_resident);
+            TileIter ti(p);
             if (p.b_resident && ti.valid()) mbar_wait(b_full, 0);
             for (; ti.valid(); ti.next(), ++it) {
                 const int buf = it & 1;
@@ -257,17 +272,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 TL(21);  // mma: accumulator free
                 const uint32_t d_tmem = tmem_base + buf * Cfg::BUF_COLS;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int kb0 = ti.kb_begin(), kb1 = ti.kb_end();
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    if (kb == 0) TL(22);  // mma: first stage landed
+                    if (kb == kb0) TL(22);  // mma: first stage landed
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                     const uint32_t sb = smem_u32(smem_b + (p.b_resident ? kb : stage) * Cfg::B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adesc = make_smem_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
                         const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                        tc_mma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_ss(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
                     tc_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
@@ -285,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int rp = p.lora_rp;
         const uint32_t up_addr = smem_u32(smem_up);
         int it = 0;
-        for (TileIter ti(p.num_m_blocks, p.num_n_blocks, p.b_resident); ti.valid(); ti.next(), ++it) {
+        for (TileIter ti(p); ti.valid(); ti.next(), ++it) {
             const int m_blk = ti.m_blk;
             const int n_blk = ti.n_blk;
             const int buf = it & 1;
@@ -400,7 +416,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         q[i].x += a.x; q[i].y += a.y; q[i].z += b.x; q[i].w += b.y;
                     }
                 }
-                if (p.out_fp32) {
+                if (p.splits > 1) {
+                    float* part = p.split_ws + (long long)ti.split * p.M * p.N;   // host cleared bias/row_bias/residual
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (mrow[i] >= 0) *reinterpret_cast<float4*>(part + (long long)mrow[i] * p.N + n0) = q[i];
+                } else if (p.out_fp32) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         if (mrow[i] >= 0) {
@@ -436,6 +457,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// out = epilogue(sum_s ws[s]) for the split-K path: one thread per 4 output columns.
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ ws, int splits, int M, int N, const float* __restrict__ bias,
+                     const float* __restrict__ row_bias, int rows_per_group, long long ld_rb,
+                     const __nv_bfloat16* __restrict__ residual, long long ldr, void* __restrict__ out, long long ldd,
+                     int out_fp32) {
+    const int nq = N >> 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)M * nq) return;
+    const int m = (int)(idx / nq);
+    const int n0 = (int)(idx - (long long)m * nq) * 4;
+    const long long MN = (long long)M * N;
+    const float* src = ws + (long long)m * N + n0;
+    float4 acc = *reinterpret_cast<const float4*>(src);
+    for (int s = 1; s < splits; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(src + s * MN);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (row_bias != nullptr) {
+        const float4 v = *reinterpret_cast<const float4*>(row_bias + (long long)(m / rows_per_group) * ld_rb + n0);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (residual != nullptr) {
+        const uint2 rr = *reinterpret_cast<const uint2*>(residual + (long long)m * ldr + n0);
+        const float2 a = unpack_bf16x2(rr.x), b = unpack_bf16x2(rr.y);
+        acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
+    }
+    if (bias != nullptr) {
+        const float4 v = *reinterpret_cast<const float4*>(bias + n0);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (out_fp32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (long long)m * ldd + n0) = acc;
+    } else {
+        uint2 o;
+        o.x = pack_bf16x2(acc.x, acc.y);
+        o.y = pack_bf16x2(acc.z, acc.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (long long)m * ldd + n0) = o;
+    }
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -453,7 +515,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     const int b_res_bytes = p.num_k_blocks * Cfg::B_STAGE_BYTES;
     const int a_room = 232448 - fixed - b_res_bytes;
     const int grid_res = (grid / p.num_n_blocks) * p.num_n_blocks;
-    if (p.a_mode == 0 && a_room >= 3 * Cfg::A_STAGE_BYTES && grid_res > 0 && grid_res * 10 >= grid * 9 &&
+    if (p.splits == 1 && p.a_mode == 0 && a_room >= 3 * Cfg::A_STAGE_BYTES && grid_res > 0 && grid_res * 10 >= grid * 9 &&
         p.num_m_blocks >= 3 * (grid_res / p.num_n_blocks)) {
         p.b_resident = 1;
         stages = a_room / Cfg::A_STAGE_BYTES;
@@ -466,9 +528,11 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
         if (stages > 8) stages = 8;
         if (stages < 2) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: not enough shared memory for 2 stages");
         smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
-        const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+        const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
         if (grid > num_tiles) grid = num_tiles;
     }
+    const GemmParams full = p;
+    if (p.splits > 1) { p.bias = nullptr; p.row_bias = nullptr; p.residual = nullptr; }
     static bool attr_done = false;
     if (!attr_done) {
         CL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -476,6 +540,13 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     }
     gemm_tc_kernel<BN, EXT, BK><<<grid, NUM_THREADS, smem_bytes, stream>>>(tA, tB, tE, p, stages);
     count_launch();
+    if (p.splits > 1) {
+        const long long quads = (long long)p.M * (p.N / 4);
+        splitk_finish_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(
+            p.split_ws, p.splits, p.M, p.N, full.bias, full.row_bias, full.rows_per_group, full.ld_rb, full.residual,
+            full.ldr, full.out, full.ldd, full.out_fp32);
+        count_launch();
+    }
     CL_CUDA_CHECK(cudaGetLastError());
     return CL_OK;
 }
@@ -498,6 +569,64 @@ extern "C" int cl_debug_timeline(unsigned long long* host_buf, unsigned int* hos
 }
 #endif
 
+// Output-tile plan: block_n and the number of K splits.  Cost model (the 1-CTA mainloop is bound by the L2->SM stream of
+// A and B rows): a CTA moves (128 + bn) rows per k-block and the kernel runs `waves` rounds of tiles, so
+//   cost = waves(tiles * splits) * (128 + bn + 32) * ceil(nkb / splits)          (+32: per-tile epilogue / ramp)
+// Splitting K is only considered when the (m, n) tiles leave more than half of the SMs idle and every split keeps
+// >= 8 k-blocks.  The caller provides split_ws = splits * M * N floats (cl_gemm_split_hint tells how many).
+struct TilePlan { int bn, splits; };
+
+static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool allow_split) {
+    const bool lora = a->lora_up != nullptr;
+    const int nkb = (a->K + BK - 1) / BK;
+    const int sms = num_sms();
+    TilePlan best = {0, 1};
+    if (a->block_n != 0) best.bn = a->block_n;
+    else if (!lora && a->a_mode == 0 && a->K <= 320 && a->N % 160 == 0 && a->M >= 8192) best.bn = 160;  // weights stay smem-resident
+    long long best_cost = -1;
+    static const int cands[5] = {256, 160, 128, 64, 32};
+    for (int ci = 0; ci < 5; ++ci) {
+        const int bn = cands[ci];
+        if (best.bn != 0 && bn != best.bn) continue;           // fixed by the caller / the resident rule
+        if (best.bn == 0) {
+            if (a->N % bn != 0) continue;
+            if (lora && bn > 160) continue;
+            if (BK == 32 ? (bn > 128) : (bn < 64)) continue;   // instantiated variants
+            if (lora && bn < 64) continue;
+        }
+        const int tiles = num_m_blocks * ((a->N + bn - 1) / bn);
+        int splits = 1;
+        if (allow_split && !lora && tiles * 2 <= sms) {
+            splits = sms / tiles;
+            if (splits > nkb / 8) splits = nkb / 8;
+            if (splits > 16) splits = 16;
+            if (splits < 2) splits = 1;
+        }
+        const int kbps = (nkb + splits - 1) / splits;
+        splits = (nkb + kbps - 1) / kbps;
+        const long long waves = ((long long)tiles * splits + sms - 1) / sms;
+        const long long cost = waves * (128 + bn + 32) * kbps;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = {bn, splits}; }
+    }
+    if (best_cost < 0) {   // no candidate divides N: tail tiles
+        if (lora) best.bn = (a->N % 128 == 0) ? 128 : 160;
+        else if (a->N <= 32 && BK == 32) best.bn = 32;
+        else if (a->N <= 64) best.bn = 64;
+        else if (a->N <= 128 || BK == 32) best.bn = 128;
+        else best.bn = 160;
+        best.splits = 1;
+    }
+    return best;
+}
+
+static inline int gemm_block_k(const cl_gemm_args* a) { return (a->a_mode != 0 && a->C % 64 != 0) ? 32 : 64; }
+
+extern "C" int cl_gemm_split_hint(const cl_gemm_args* a) {
+    if (a == nullptr || a->lora_up != nullptr || a->M <= 0 || a->N <= 0 || a->K <= 0) return 1;
+    // conv tiles may pad M when the image does not tile evenly; cl_gemm re-plans with the exact count and clamps
+    return plan_tiles(a, gemm_block_k(a), (a->M + BLOCK_M - 1) / BLOCK_M, true).splits;
+}
+
 extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (a == nullptr || a->a == nullptr || a->b == nullptr || a->out == nullptr)
@@ -516,7 +645,7 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     p.M = a->M; p.N = a->N; p.K = a->K;
     p.a_mode = a->a_mode;
     // K-block: 64 (128B swizzle) unless this is a conv whose channel count only allows 32-element K runs
-    const int BK = (a->a_mode != 0 && a->C % 64 != 0) ? 32 : 64;
+    const int BK = gemm_block_k(a);
     const int swz = (BK == 64) ? 128 : 64;
     p.num_k_blocks = (a->K + BK - 1) / BK;
     CUtensorMap tA, tB, tE;
@@ -562,20 +691,20 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
         return set_error(CL_ERR_INVALID, "cl_gemm: bad a_mode");
     }
 
-    // block_n choice: LoRA needs UMMA_N = BN + 16 <= 256.
-    int bn_sel = a->block_n;
-    if (bn_sel == 0) {
-        if (lora) bn_sel = (a->N % 160 == 0) ? 160 : (a->N % 128 == 0 ? 128 : 160);
-        else if (a->a_mode == 0 && a->K <= 320 && a->N % 160 == 0 && a->M >= 8192) bn_sel = 160;  // weight tile stays smem-resident
-        else if (a->N % 256 == 0) bn_sel = 256;
-        else if (a->N % 160 == 0) bn_sel = 160;
-        else if (a->N % 128 == 0) bn_sel = 128;
-        else if (a->N <= 32 && BK == 32) bn_sel = 32;
-        else if (a->N <= 64) bn_sel = 64;
-        else if (a->N <= 128) bn_sel = 128;
-        else bn_sel = 160;
-    }
+    // block_n / split choice: LoRA needs UMMA_N = BN + 16 <= 256.
+    if (a->split_k > 1 && lora) return set_error(CL_ERR_INVALID, "cl_gemm: split_k cannot be combined with the LoRA epilogue");
+    if (a->split_k > 1 && a->split_ws == nullptr) return set_error(CL_ERR_INVALID, "cl_gemm: split_k needs split_ws");
+    const TilePlan plan = plan_tiles(a, BK, p.num_m_blocks, a->split_k > 1);
+    const int bn_sel = plan.bn;
     p.num_n_blocks = (a->N + bn_sel - 1) / bn_sel;
+    p.splits = 1;
+    p.kb_per_split = p.num_k_blocks;
+    if (plan.splits > 1) {
+        const int want = plan.splits < a->split_k ? plan.splits : a->split_k;   // split_ws holds a->split_k partials
+        p.kb_per_split = (p.num_k_blocks + want - 1) / want;
+        p.splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;     // no empty split
+        p.split_ws = reinterpret_cast<float*>(a->split_ws);
+    }
     {
         uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
         uint64_t strides[1] = {(uint64_t)a->ldb * 2};

@@ -35,9 +35,20 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
 
 static constexpr int GN_MAX_CHUNKS = 512;  // C <= 4096
 
+// Per-thread channel constants: thread t owns channels [c0, c0+8) for its whole slab, so everything that depends only
+// on (image, channel) is computed once and the row loop is load -> fma -> (store), unrolled for memory-level
+// parallelism (one 16-byte load in flight per thread caps a 1024-thread SM at ~20 GB/s; four reach the HBM limit).
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+
 // mode 0: forward statistics      -> ws[(n*G+g)*2 + {0,1}] += {sum x, sum x^2}
 // mode 1: backward reductions     -> ws[(n*G+g)*2 + {0,1}] += {sum dz*gamma, sum dz*gamma*xhat},
 //                                    dgamma[c] += sum dz*xhat, dbeta[c] += sum dz   (when dgamma != nullptr)
+// In mode 1 the group sums are gamma-weighted channel sums of the dgamma/dbeta partials, so only those accumulate.
 template <int MODE>
 __global__ void __launch_bounds__(512)
 gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
@@ -55,43 +66,74 @@ gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
     const bool active = rsub < rows_par;
     const int c0 = chunk * 8;
 
-    float a0[8], a1[8];  // MODE 0: sum, sumsq.  MODE 1: dz*gamma, dz*gamma*xhat
-    float g0[8], g1[8];  // MODE 1: dgamma / dbeta partials
-    float gam[8], bet[8], mean[8], rstd[8];
+    float a0[8], a1[8];  // MODE 0: sum, sumsq.  MODE 1: sum dz*xhat, sum dz
+    float ga[8], gb[8], rs[8], nm[8];   // MODE 1: z = xh*ga + gb, xh = x*rs + nm
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a0[j] = a1[j] = g0[j] = g1[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { a0[j] = a1[j] = 0.f; }
     if (MODE == 1 && active) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            gam[j] = gamma[c0 + j];
-            bet[j] = beta[c0 + j];
+            ga[j] = gamma[c0 + j];
+            gb[j] = beta[c0 + j];
             const int g = (c0 + j) / cpg;
-            mean[j] = stats[(n * G + g) * 2];
-            rstd[j] = stats[(n * G + g) * 2 + 1];
+            const float mu = stats[(n * G + g) * 2];
+            rs[j] = stats[(n * G + g) * 2 + 1];
+            nm[j] = -mu * rs[j];
         }
     }
     if (active) {
-        for (int r = row0 + rsub; r < row1; r += rows_par) {
-            const long long off = ((long long)n * HW + r) * C + c0;
-            float xv[8];
-            load8(x + off, xv);
-            if (MODE == 0) {
+        const __nv_bfloat16* xp = x + (long long)n * HW * C + c0;
+        const __nv_bfloat16* dp = dy + (long long)n * HW * C + c0;
+        const long long rstep = (long long)rows_par * C;
+        int r = row0 + rsub;
+        if (MODE == 0) {
+            for (; r + 3 * rows_par < row1; r += 4 * rows_par) {
+                uint4 u[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] += xv[j] * xv[j]; }
-            } else {
-                float dv[8];
-                load8(dy + off, dv);
+                for (int k = 0; k < 4; ++k) u[k] = ldg16(xp + (long long)r * C + k * rstep);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float xh = (xv[j] - mean[j]) * rstd[j];
-                    float dz = dv[j];
-                    if (silu) dz *= silu_grad_f(xh * gam[j] + bet[j]);
-                    a0[j] += dz * gam[j];
-                    a1[j] += dz * gam[j] * xh;
-                    g0[j] += dz * xh;
-                    g1[j] += dz;
+                for (int k = 0; k < 4; ++k) {
+                    float xv[8];
+                    unpack8(u[k], xv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
                 }
             }
+            for (; r < row1; r += rows_par) {
+                float xv[8];
+                unpack8(ldg16(xp + (long long)r * C), xv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
+            }
+        } else {
+            auto acc = [&](const uint4& ux, const uint4& ud) {
+                float xv[8], dv[8];
+                unpack8(ux, xv);
+                unpack8(ud, dv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = fmaf(xv[j], rs[j], nm[j]);
+                    float dz = dv[j];
+                    if (silu) {
+                        const float z = fmaf(xh, ga[j], gb[j]);
+                        const float s = fast_sigmoid(z);
+                        dz *= s * (1.f + z * (1.f - s));
+                    }
+                    a0[j] = fmaf(dz, xh, a0[j]);
+                    a1[j] += dz;
+                }
+            };
+            for (; r + 3 * rows_par < row1; r += 4 * rows_par) {
+                uint4 ux[4], ud[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ux[k] = ldg16(xp + (long long)r * C + k * rstep);
+                    ud[k] = ldg16(dp + (long long)r * C + k * rstep);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc(ux[k], ud[k]);
+            }
+            for (; r < row1; r += rows_par) acc(ldg16(xp + (long long)r * C), ldg16(dp + (long long)r * C));
         }
     }
     // combine without shared-memory atomics (ATOMS costs ~2 cycles per lane): every row-group stores its per-channel
@@ -101,34 +143,37 @@ gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
     float* part1 = gsh + (size_t)rows_par * C;            // [rows_par][C]
     float* tot0 = gsh + (size_t)2 * rows_par * C;         // [C]
     float* tot1 = tot0 + C;
-    auto reduce_pair = [&](const float (&x0)[8], const float (&x1)[8]) {
-        if (active) {
-            float* d0 = part0 + (size_t)rsub * C + c0;
-            float* d1 = part1 + (size_t)rsub * C + c0;
-            *reinterpret_cast<float4*>(d0) = make_float4(x0[0], x0[1], x0[2], x0[3]);
-            *reinterpret_cast<float4*>(d0 + 4) = make_float4(x0[4], x0[5], x0[6], x0[7]);
-            *reinterpret_cast<float4*>(d1) = make_float4(x1[0], x1[1], x1[2], x1[3]);
-            *reinterpret_cast<float4*>(d1 + 4) = make_float4(x1[4], x1[5], x1[6], x1[7]);
-        }
-        __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            float s0 = 0.f, s1 = 0.f;
-            for (int g = 0; g < rows_par; ++g) { s0 += part0[(size_t)g * C + c]; s1 += part1[(size_t)g * C + c]; }
-            tot0[c] = s0;
-            tot1[c] = s1;
-        }
-        __syncthreads();
-    };
-    reduce_pair(a0, a1);
+    if (active) {
+        float* d0 = part0 + (size_t)rsub * C + c0;
+        float* d1 = part1 + (size_t)rsub * C + c0;
+        *reinterpret_cast<float4*>(d0) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+        *reinterpret_cast<float4*>(d0 + 4) = make_float4(a0[4], a0[5], a0[6], a0[7]);
+        *reinterpret_cast<float4*>(d1) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+        *reinterpret_cast<float4*>(d1 + 4) = make_float4(a1[4], a1[5], a1[6], a1[7]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int g = 0; g < rows_par; ++g) { s0 += part0[(size_t)g * C + c]; s1 += part1[(size_t)g * C + c]; }
+        tot0[c] = s0;
+        tot1[c] = s1;
+    }
+    __syncthreads();
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         double s0 = 0.0, s1 = 0.0;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s0 += tot0[c]; s1 += tot1[c]; }
+        if (MODE == 0) {
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s0 += tot0[c]; s1 += tot1[c]; }
+        } else {
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+                const float gm = gamma[c];
+                s0 += (double)(gm * tot1[c]);   // sum dz*gamma
+                s1 += (double)(gm * tot0[c]);   // sum dz*gamma*xhat
+            }
+        }
         atomicAdd(&ws[(n * G + g) * 2], s0);
         atomicAdd(&ws[(n * G + g) * 2 + 1], s1);
     }
     if (MODE == 1 && dgamma != nullptr) {
-        __syncthreads();
-        reduce_pair(g0, g1);
         for (int i = threadIdx.x; i < C; i += blockDim.x) {
             atomicAdd(&dgamma[i], tot0[i]);
             atomicAdd(&dbeta[i], tot1[i]);
@@ -148,63 +193,117 @@ __global__ void gn_finalize_kernel(const double* __restrict__ ws, float* __restr
 }
 
 // forward apply: y = act((x - mean) * rstd * gamma + beta) with the fp32 stats {mean, rstd} of gn_finalize_kernel.
-__global__ void __launch_bounds__(256)
+// Same slab geometry as the reduction: the affine pair (scale, shift) per owned channel lives in registers.
+__global__ void __launch_bounds__(512)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ stats, __nv_bfloat16* __restrict__ y, int HW, int C, int G, int silu,
-                long long total_chunks) {
+                int rows_per_cta) {
+    const int n = blockIdx.y;
     const int chunks = C / 8;
     const int cpg = C / G;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int chunk = (int)(i % chunks);
-        const long long row = i / chunks;
-        const int n = (int)(row / HW);
-        const int c0 = chunk * 8;
+    const int rows_par = blockDim.x / chunks;
+    const int chunk = threadIdx.x % chunks;
+    const int rsub = threadIdx.x / chunks;
+    if (rsub >= rows_par) return;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int row1 = min(HW, row0 + rows_per_cta);
+    const int c0 = chunk * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int g = (c0 + j) / cpg;
+        const float mu = stats[(n * G + g) * 2], rs = stats[(n * G + g) * 2 + 1];
+        sc[j] = rs * gamma[c0 + j];
+        sh[j] = fmaf(-mu, sc[j], beta[c0 + j]);
+    }
+    const __nv_bfloat16* xp = x + (long long)n * HW * C + c0;
+    __nv_bfloat16* yp = y + (long long)n * HW * C + c0;
+    const long long rstep = (long long)rows_par * C;
+    auto emit = [&](const uint4& u, __nv_bfloat16* dst) {
         float xv[8], o[8];
-        load8(x + row * C + c0, xv);
+        unpack8(u, xv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int g = (c0 + j) / cpg;
-            const float mu = stats[(n * G + g) * 2], rs = stats[(n * G + g) * 2 + 1];
-            const float z = (xv[j] - mu) * rs * gamma[c0 + j] + beta[c0 + j];
-            o[j] = silu ? silu_f(z) : z;
+            const float z = fmaf(xv[j], sc[j], sh[j]);
+            o[j] = silu ? z * fast_sigmoid(z) : z;
         }
-        store8(y + row * C + c0, o);
+        store8(dst, o);
+    };
+    int r = row0 + rsub;
+    for (; r + 3 * rows_par < row1; r += 4 * rows_par) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = ldg16(xp + (long long)r * C + k * rstep);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) emit(u[k], yp + (long long)r * C + k * rstep);
     }
+    for (; r < row1; r += rows_par) emit(ldg16(xp + (long long)r * C), yp + (long long)r * C);
 }
 
 // backward apply: dx (+)= rstd * (dz*gamma - s1/m - xhat * s2/m)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
                     const double* __restrict__ ws, __nv_bfloat16* __restrict__ dx, int HW, int C, int G, int silu,
-                    int accumulate, long long total_chunks) {
+                    int accumulate, int rows_per_cta) {
+    const int n = blockIdx.y;
     const int chunks = C / 8;
     const int cpg = C / G;
+    const int rows_par = blockDim.x / chunks;
+    const int chunk = threadIdx.x % chunks;
+    const int rsub = threadIdx.x / chunks;
+    if (rsub >= rows_par) return;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int row1 = min(HW, row0 + rows_per_cta);
+    const int c0 = chunk * 8;
     const float inv_m = 1.f / ((float)HW * cpg);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int chunk = (int)(i % chunks);
-        const long long row = i / chunks;
-        const int n = (int)(row / HW);
-        const int c0 = chunk * 8;
+    // dx = dz*A - K1 - x*K2 with A = rs*gamma, K2 = rs^2*s2/m, K1 = rs*s1/m - mu*K2;  z = x*A + Bz, Bz = beta - mu*A
+    float A[8], Bz[8], K1[8], K2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int g = (c0 + j) / cpg;
+        const float mu = stats[(n * G + g) * 2];
+        const float rs = stats[(n * G + g) * 2 + 1];
+        A[j] = rs * gamma[c0 + j];
+        Bz[j] = fmaf(-mu, A[j], beta[c0 + j]);
+        K2[j] = rs * rs * (float)ws[(n * G + g) * 2 + 1] * inv_m;
+        K1[j] = fmaf(-mu, K2[j], rs * (float)ws[(n * G + g) * 2] * inv_m);
+    }
+    const __nv_bfloat16* xp = x + (long long)n * HW * C + c0;
+    const __nv_bfloat16* dp = dy + (long long)n * HW * C + c0;
+    __nv_bfloat16* op = dx + (long long)n * HW * C + c0;
+    const long long rstep = (long long)rows_par * C;
+    auto emit = [&](const uint4& ux, const uint4& ud, __nv_bfloat16* dst) {
         float xv[8], dv[8], o[8];
-        load8(x + row * C + c0, xv);
-        load8(dy + row * C + c0, dv);
-        if (accumulate) load8(dx + row * C + c0, o);
+        unpack8(ux, xv);
+        unpack8(ud, dv);
+        if (accumulate) load8(dst, o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int g = (c0 + j) / cpg;
-            const float mu = stats[(n * G + g) * 2], rs = stats[(n * G + g) * 2 + 1];
-            const float s1 = (float)ws[(n * G + g) * 2] * inv_m, s2 = (float)ws[(n * G + g) * 2 + 1] * inv_m;
-            const float xh = (xv[j] - mu) * rs;
             float dz = dv[j];
-            if (silu) dz *= silu_grad_f(xh * gamma[c0 + j] + beta[c0 + j]);
-            const float d = rs * (dz * gamma[c0 + j] - s1 - xh * s2);
+            if (silu) {
+                const float z = fmaf(xv[j], A[j], Bz[j]);
+                const float s = fast_sigmoid(z);
+                dz *= s * (1.f + z * (1.f - s));
+            }
+            const float d = fmaf(dz, A[j], -fmaf(xv[j], K2[j], K1[j]));
             o[j] = accumulate ? o[j] + d : d;
         }
-        store8(dx + row * C + c0, o);
+        store8(dst, o);
+    };
+    int r = row0 + rsub;
+    for (; r + 3 * rows_par < row1; r += 4 * rows_par) {
+        uint4 ux[4], ud[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ux[k] = ldg16(xp + (long long)r * C + k * rstep);
+            ud[k] = ldg16(dp + (long long)r * C + k * rstep);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) emit(ux[k], ud[k], op + (long long)r * C + k * rstep);
     }
+    for (; r < row1; r += rows_par)
+        emit(ldg16(xp + (long long)r * C), ldg16(dp + (long long)r * C), op + (long long)r * C);
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
@@ -304,15 +403,15 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
 
 using namespace clb;
 
-static int gn_launch_geometry(int HW, int C, int n, int& threads, int& rows_per_cta, int& grid_x) {
+static int gn_launch_geometry(int HW, int C, int n, int& threads, int& rows_per_cta, int& grid_x, int ctas_per_sm = 2) {
     const int chunks = C / 8;
     if (C % 8 != 0 || chunks > GN_MAX_CHUNKS) return set_error(CL_ERR_UNSUPPORTED, "groupnorm: C must be a multiple of 8 and <= 4096");
     int rows_par = 512 / chunks;
     if (rows_par < 1) rows_par = 1;
     threads = ((rows_par * chunks + 31) / 32) * 32;
     if (threads > 512) { rows_par = 1; threads = ((chunks + 31) / 32) * 32; }
-    // aim for ~4 CTAs per SM across the batch
-    int target_ctas = (num_sms() * 2 + n - 1) / n;
+    // one wave of ctas_per_sm CTAs per SM across the batch
+    int target_ctas = (num_sms() * ctas_per_sm + n - 1) / n;
     rows_per_cta = (HW + target_ctas - 1) / target_ctas;
     if (rows_per_cta < rows_par) rows_per_cta = rows_par;
     grid_x = (HW + rows_per_cta - 1) / rows_per_cta;
@@ -338,13 +437,13 @@ extern "C" int cl_groupnorm_fwd(const void* x, const float* gamma, const float* 
     gn_reduce_kernel<0><<<dim3(grid_x, n), threads, rsmem, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, ws, nullptr, nullptr, HW, C, G,
         rows_per_cta, 0);
-    const long long total = (long long)n * HW * (C / 8);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
     if (stats == nullptr) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: stats buffer is required");
     gn_finalize_kernel<<<(n * G + 127) / 128, 128, 0, stream>>>(ws, stats, n * G, 1.0 / ((double)HW * (C / G)), eps);
-    gn_apply_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, stats,
-                                                reinterpret_cast<__nv_bfloat16*>(y), HW, C, G, silu, total);
+    int a_threads, a_rows, a_grid;
+    CL_CHECK(gn_launch_geometry(HW, C, n, a_threads, a_rows, a_grid, 8));
+    gn_apply_kernel<<<dim3(a_grid, n), a_threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+                                                               stats, reinterpret_cast<__nv_bfloat16*>(y), HW, C, G,
+                                                               silu, a_rows);
     count_launch(3);
     CL_CUDA_CHECK(cudaGetLastError());
     return CL_OK;
@@ -370,12 +469,11 @@ extern "C" int cl_groupnorm_bwd(const void* x, const void* dy, const float* gamm
     gn_reduce_kernel<1><<<dim3(grid_x, n), threads, rsmem, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, beta, stats, ws,
         dgamma, dbeta, HW, C, G, rows_per_cta, silu);
-    const long long total = (long long)n * HW * (C / 8);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-    gn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(
+    int a_threads, a_rows, a_grid;
+    CL_CHECK(gn_launch_geometry(HW, C, n, a_threads, a_rows, a_grid, 8));
+    gn_bwd_apply_kernel<<<dim3(a_grid, n), a_threads, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, beta, stats, ws,
-        reinterpret_cast<__nv_bfloat16*>(dx), HW, C, G, silu, accumulate, total);
+        reinterpret_cast<__nv_bfloat16*>(dx), HW, C, G, silu, accumulate, a_rows);
     count_launch(2);
     CL_CUDA_CHECK(cudaGetLastError());
     return CL_OK;

@@ -115,8 +115,28 @@ def gemm(
             assert t_out.is_contiguous() and t_out.shape == (M, lora_up.shape[1])
             args.t_out = _ptr(t_out)
     args.block_n = block_n
-    check(_lib.lib().cl_gemm(C.byref(args), _stream()), "cl_gemm")
+    lib = _lib.lib()
+    if lora_up is None and M <= 4096 and K >= 2048:
+        # few output tiles, deep K: cut K across otherwise idle SMs (deterministic partial-tile sums, no atomics)
+        splits = lib.cl_gemm_split_hint(C.byref(args))
+        if splits > 1:
+            ws = _split_ws(splits * M * N, a.device)
+            args.split_k = splits
+            args.split_ws = _ptr(ws)
+    check(lib.cl_gemm(C.byref(args), _stream()), "cl_gemm")
     return out
+
+
+_SPLIT_WS = {}
+
+
+def _split_ws(numel: int, device) -> torch.Tensor:
+    """fp32 scratch for split-K partial tiles, one growing buffer per device (stream-ordered re-use)."""
+    buf = _SPLIT_WS.get(device)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(max(numel, 1 << 22), device=device, dtype=torch.float32)
+        _SPLIT_WS[device] = buf
+    return buf
 
 
 def split_bf16_ext(down: torch.Tensor, k: int) -> torch.Tensor:

@@ -22,7 +22,7 @@ BF16 = torch.bfloat16
 
 class Trainer:
     def __init__(self, unet, control_lora, lr: float = 1e-4, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,
-                 max_grad_norm: float = 1.0, process_group=None):
+                 max_grad_norm: float = 1.0, process_group=None, cuda_graph: bool = False, graph_warmup: int = 2):
         self.unet, self.cl = unet, control_lora
         self.lr, self.betas, self.wd, self.eps, self.max_norm = lr, betas, weight_decay, eps, max_grad_norm
         self.pg = process_group
@@ -48,11 +48,59 @@ class Trainer:
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
         self.step_idx = 0
         self.levels = None
+        # CUDA-graph mode: the forward/backward (~1800 launches) is captured once and replayed, so the step costs the
+        # host one graph launch instead of ~40 ms of Python/ctypes work and cannot become launch-bound.
+        self.cuda_graph = bool(cuda_graph)
+        self.graph_warmup = int(graph_warmup)
+        self._graph = None
+        self._static = None          # static input buffers the captured kernels read
+        self._static_loss = None
+        self._eager_calls = 0
+        self.launches_per_step = None    # kernel launches of one step (counted while capturing / running eagerly)
 
     def step(self, noisy_latents: torch.Tensor, timesteps: torch.Tensor, ehs: torch.Tensor, guide: torch.Tensor,
-             target: torch.Tensor) -> torch.Tensor:
+             target: torch.Tensor, eager: bool = False) -> torch.Tensor:
         """One optimizer step on device tensors: noisy_latents/target NCHW fp32, timesteps fp32 [B], ehs bf16 [B,77,768],
-        guide NCHW fp32 [B,3,512,512].  Returns the (device) loss tensor; nothing is synchronised."""
+        guide NCHW fp32 [B,3,512,512].  Returns the (device) loss tensor; nothing is synchronised.
+
+        With cuda_graph=True the first `graph_warmup` calls run eagerly, the next call captures the forward/backward
+        into a CUDA graph (inputs are copied into static buffers first) and every later call replays it; the gradient
+        all-reduce and the optimizer kernels stay outside the graph (NCCL's watchdog thread must not meet a global
+        capture, and the AdamW bias correction is a host scalar).  eager=True forces the uncaptured path."""
+        from . import _lib
+
+        if not self.cuda_graph or eager:
+            n0 = _lib.launch_count()
+            loss = self._forward_backward(noisy_latents, timesteps, ehs, guide, target)
+            self._optimizer_tail()
+            self.launches_per_step = int(_lib.launch_count() - n0)
+            return loss
+        args = (noisy_latents, timesteps, ehs, guide, target)
+        if self._static is None:
+            self._static = [torch.empty_like(a_).copy_(a_) for a_ in args]
+        else:
+            for st, a_ in zip(self._static, args):
+                if st.shape != a_.shape or st.dtype != a_.dtype:
+                    raise ValueError("Trainer(cuda_graph=True): input shapes/dtypes must not change between steps")
+                if st.data_ptr() != a_.data_ptr():
+                    st.copy_(a_, non_blocking=True)
+        if self._graph is None and self._eager_calls < self.graph_warmup:
+            self._eager_calls += 1
+            loss = self._forward_backward(*self._static)
+            self._optimizer_tail()
+            return loss
+        if self._graph is None:
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                self._static_loss = self._forward_backward(*self._static)
+            self.launches_per_step = int(_lib.launch_count() - n0) + 2   # + sumsq + adamw outside the graph
+            self._graph = graph
+        self._graph.replay()
+        self._optimizer_tail()
+        return self._static_loss
+
+    def _forward_backward(self, noisy_latents, timesteps, ehs, guide, target) -> torch.Tensor:
         tape = Tape()
         hctx = Ctx(tape=tape)
         states = self.hint.forward(hctx, guide)
@@ -74,10 +122,12 @@ class Trainer:
         loss, dpred = ops.mse_loss(pred.data, target)
         pred.grad = dpred
         tape.backward()
+        return loss
+
+    def _optimizer_tail(self) -> None:
         self.step_idx += 1
         self.arena.all_reduce()          # one ncclAllReduce(sum) over the whole gradient arena
         self.gnorm_sq.zero_()
         ops.sumsq(self.flat_g, self.gnorm_sq)
         ops.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                   self.step_idx, gnorm_sq=self.gnorm_sq, max_norm=self.max_norm, grad_scale=self.arena.grad_scale, zero_grad=True)
-        return loss

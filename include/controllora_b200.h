@@ -82,9 +82,15 @@ typedef struct {
     int64_t ldd;
     int32_t out_fp32;
     int32_t block_n;         /* 0 = auto */
+    int32_t split_k;         /* <= 1: none.  > 1: K is cut into this many ranges, each CTA stores an fp32 partial tile
+                                to split_ws and a second kernel sums them and applies bias / row_bias / residual
+                                (deterministic: no atomics).  Not available with the LoRA epilogue. */
+    void* split_ws;          /* device fp32 [split_k][M][N], required when split_k > 1 */
 } cl_gemm_args;
 
 int cl_gemm(const cl_gemm_args* args, void* stream);
+/* Split count cl_gemm's heuristic recommends for these arguments (1 = none); size split_ws with it. */
+int cl_gemm_split_hint(const cl_gemm_args* args);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K2: fused attention  O = softmax(Q K^T * scale) V  per (batch, head), probabilities never leave the SM.

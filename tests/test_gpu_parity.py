@@ -20,7 +20,7 @@ from tools import check_gemm, check_hint, check_ops, check_ops2, check_unet  # n
 
 @pytest.mark.parametrize("case", ["plain_1tile", "plain_k320", "plain_bn64", "plain_bn160_tail", "plain_bn256", "plain_big",
                                   "epilogue_all", "lora_r4", "lora_r4_tadd", "lora_r8_cross", "conv_s1_64", "conv_s1_small",
-                                  "conv_s2", "conv_96"])
+                                  "conv_s2", "conv_96", "split_k"])
 def test_gemm(case):
     check_gemm.CASES[case]()
 
@@ -33,7 +33,7 @@ def test_conv_32_channels_uses_bk32_path():
 
 
 # ------------------------------------------------------------------------------------------------ K2: attention
-@pytest.mark.parametrize("case", ["attn_d64_one_block", "attn_d40", "attn_cross77", "attn_d80_d160", "attn_small_d"])
+@pytest.mark.parametrize("case", ["attn_d64_one_block", "attn_d40", "attn_cross77", "attn_d80_d160", "attn_small_d", "attn_paired"])
 def test_attention_fwd(case):
     check_ops.CASES[case]()
 
@@ -88,6 +88,11 @@ def test_hint_encoder_matches_oracle(case):
 @pytest.mark.parametrize("case", ["train_v1", "train_v2"])
 def test_fused_train_step_matches_oracle(case):
     assert check_hint.CASES[case]()
+
+
+def test_cuda_graph_train_step_matches_eager():
+    """Trainer(cuda_graph=True): warm-up, capture and replays give the same losses / parameters as the eager step."""
+    assert check_hint.CASES["graph_v2"]()
 
 
 def test_lora_zero_up_is_exact_noop_on_gpu():

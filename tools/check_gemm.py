@@ -208,6 +208,33 @@ def conv_96():
 
 
 @case
+def split_k():
+    """Few output tiles + deep K: ops.gemm cuts K across CTAs (fp32 partial tiles + finishing kernel).  Checks the
+    epilogue (bias / row_bias / residual, bf16 and fp32 out), an uneven split and run-to-run bit stability."""
+    torch = _setup()
+    from controllora_b200 import ops
+
+    for (M, N, K) in [(512, 1280, 5120), (200, 640, 2112), (128, 320, 11520)]:
+        a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        b = (torch.randn(N, K, device="cuda") / K**0.5).to(torch.bfloat16)
+        bias = torch.randn(N, device="cuda")
+        rb = torch.randn(8, N, device="cuda")
+        res = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+        rpg = (M + 7) // 8
+        grp = torch.arange(M, device="cuda") // rpg
+        ref = _gemm_ref(a, b) + bias + rb[grp] + res.float()
+        out = ops.gemm(a, b, bias=bias, row_bias=rb, rows_per_group=rpg, residual=res)
+        out_b = ops.gemm(a, b, bias=bias, row_bias=rb, rows_per_group=rpg, residual=res)
+        out32 = ops.gemm(a, b, bias=bias, row_bias=rb, rows_per_group=rpg, residual=res, out_fp32=True)
+        torch.cuda.synchronize()
+        print(f"split-K M={M} N={N} K={K}: bf16 rel={_rel(out, ref):.3e} fp32 rel={_rel(out32, ref):.3e}")
+        assert _rel(out, ref) < 4e-3 and _rel(out32, ref) < 1e-5
+        assert torch.equal(out, out_b)
+    _conv_case(8, 8, 8, 2560, 1280, 1, 1, True)
+    _conv_case(8, 8, 8, 1280, 1280, 1, 1, True)
+
+
+@case
 def perf():
     torch = _setup()
     from controllora_b200 import ops

@@ -145,7 +145,60 @@ def train_case(v2: bool, B=2, HW=16):
     return ok
 
 
+def graph_case(v2: bool = True, B=2, HW=16, steps=5):
+    """Trainer(cuda_graph=True) (2 eager warm-up steps, capture, replays) against the eager Trainer on the same
+    per-step inputs: the same kernels run in the same order, so losses and parameters must agree to fp32 atomics noise."""
+    import torch
+    from oracle import unet_ref as UR
+    import controllora_b200 as cb
+    from controllora_b200.configs import wire_processors
+    from controllora_b200.trainer import Trainer
+
+    torch.manual_seed(0)
+    ounet = UR.UNet2DConditionModel(**TINY)
+    UR.init_synthetic_(ounet, seed=1)
+    sd = {k: v.detach().clone() for k, v in ounet.state_dict().items()}
+    kw = dict(TINY_LORA)
+    if v2:
+        kw.update(lora_control_version=2, lora_pre_conv_skipped=True, lora_key_states_skipped=True, lora_value_states_skipped=True)
+    trainers = []
+    for use_graph in (False, True):
+        unet = cb.UNet2DConditionModel.from_state_dict({k: v.clone() for k, v in sd.items()}, DEV, TINY)
+        torch.manual_seed(7)
+        cl = cb.ControlLoRA(**kw)
+        g = torch.Generator().manual_seed(3)
+        with torch.no_grad():
+            for n_, p_ in cl.named_parameters():
+                if n_.endswith("up.weight"):
+                    p_.copy_(0.05 * torch.randn(p_.shape, generator=g))
+        cl.to(DEV)
+        wire_processors(unet, cl)
+        trainers.append((Trainer(unet, cl, lr=1e-3, cuda_graph=use_graph), cl))
+    g = torch.Generator().manual_seed(5)
+    size = HW * 8
+    ok = True
+    for step in range(steps):
+        x = torch.randn(B, 4, HW, HW, generator=g).to(DEV)
+        t = torch.randint(0, 1000, (B,), generator=g).float().to(DEV)
+        e = torch.randn(B, 77, TINY["cross_attention_dim"], generator=g).to(DEV).to(torch.bfloat16)
+        guide = (torch.rand(B, 3, size, size, generator=g) * 2 - 1).to(DEV)
+        tgt = torch.randn(B, 4, HW, HW, generator=g).to(DEV)
+        losses = [float(tr.step(x, t, e, guide, tgt)) for tr, _ in trainers]
+        print(f"  step {step}: loss eager={losses[0]:.6f} graph={losses[1]:.6f} captured={trainers[1][0]._graph is not None}")
+        ok = ok and abs(losses[0] - losses[1]) <= 2e-3 * abs(losses[0]) + 1e-6
+    num = den = 0.0
+    for (n, pe), (_, pg) in zip(trainers[0][1].named_parameters(), trainers[1][1].named_parameters()):
+        num += float((pe.detach() - pg.detach()).pow(2).sum())
+        den += float(pe.detach().pow(2).sum())
+    rel = (num / den) ** 0.5
+    print(f"  parameter rel diff eager vs graph after {steps} steps = {rel:.3e}; launches/step = {trainers[1][0].launches_per_step}")
+    ok = ok and rel < 2e-3 and trainers[1][0]._graph is not None
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
 CASES = {
+    "graph_v2": lambda: graph_case(True),
     "hint_v1": lambda: hint_case(False),
     "hint_v2": lambda: hint_case(True),
     "train_v1": lambda: train_case(False),

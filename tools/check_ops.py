@@ -89,6 +89,32 @@ def attn_small_d():
 
 
 @case
+def attn_paired():
+    """Paired-tile forward kernel (d <= 64, Nq > 128): ragged query/key counts (second tile partly / fully out of
+    range), many key blocks, and keys whose magnitude jumps in later blocks so that the lazy O rescale (row max
+    growing by more than 2^8) actually runs."""
+    torch = _setup()
+    from controllora_b200 import ops
+
+    _attn_case(1, 2, 200, 300, 40)
+    _attn_case(2, 3, 300, 77, 64)
+    _attn_case(1, 2, 640, 1000, 8)
+    B, H, N, d = 2, 4, 512, 40
+    q = torch.randn(B, N, H * d, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, N, H * d, device="cuda")
+    k[:, 128:256] *= 6.0
+    k[:, 384:] *= 30.0
+    k = k.to(torch.bfloat16)
+    v = torch.randn(B, N, H * d, device="cuda").to(torch.bfloat16)
+    o, lse = ops.attention_fwd(q, k, v, H, d**-0.5)
+    torch.cuda.synchronize()
+    ro, rl = _attn_ref(q, k, v, H, d**-0.5)
+    eo, el = _rel(o, ro), float((lse - rl).abs().max())
+    print(f"attn growing-max: o rel={eo:.3e} lse maxabs={el:.3e}")
+    assert eo < 6e-3 and el < 5e-2, (eo, el)
+
+
+@case
 def attn_perf():
     torch = _setup()
     from controllora_b200 import ops
