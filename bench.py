@@ -254,9 +254,15 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def trace(msg):           # CLB_BENCH_TRACE=1: per-rank phase markers on stderr (to locate a multi-rank stall)
+        if os.environ.get("CLB_BENCH_TRACE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    trace("warm-up")
     for _ in range(max(a.warmup, 3)):
         loss = tr.step(x, t, e, guide, tgt)
     barrier()
+    trace("timed region")
     # ---------------- timed region: inputs resident in HBM
     sampler = ClockSampler(local)
     if rank == 0:
@@ -281,6 +287,7 @@ def run_ours(a):
     value = world * B / (ms_step / 1e3)
     final_loss = float(loss)
 
+    trace("end-to-end region")
     # ---------------- end-to-end: host (pinned) buffers in, loss out, every step
     pinned = [h.pin_memory() for h in host]
     h2d = sum(p.numel() * p.element_size() for p in pinned)
@@ -308,8 +315,12 @@ def run_ours(a):
     e2e_value = world * B * a.steps / float(dt)
 
     # ---------------- roofline of the dominant kernel family (tcgen05 GEMM / implicit-GEMM conv): live CUDA-event timing
+    trace("roofline passes")
     roof = None
-    if rank == 0 and not a.no_roofline:
+    if world > 1 and not a.no_roofline:
+        # the eager passes below contain the gradient all-reduce: every rank has to run them (only rank 0 keeps the timings)
+        barrier()
+    if not a.no_roofline:
         peak_tf, peak_hbm, which = measured_peaks()
         rec = []
         orig = ops.gemm
@@ -328,18 +339,25 @@ def run_ours(a):
 
         ops.gemm = timed_gemm
         import controllora_b200.engine as E_, controllora_b200.lora_runtime as LR_, controllora_b200.hint_encoder as HE_
-        tr.step(x, t, e, guide, tgt, eager=True)     # uncaptured pass so that every GEMM launch can be bracketed by events
+        # uncaptured passes so that every GEMM launch can be bracketed by events; the first one only re-warms the caching
+        # allocator (the graph capture emptied it), the second one is measured
+        tr.step(x, t, e, guide, tgt, eager=True)
+        torch.cuda.synchronize()
+        rec.clear()
+        tr.step(x, t, e, guide, tgt, eager=True)
         torch.cuda.synchronize()
         ops.gemm = orig
         fl = sum(r[0] for r in rec)
         tm = sum(r[1].elapsed_time(r[2]) for r in rec)
         ach = fl / (tm * 1e-3) / 1e12
+    if rank == 0 and not a.no_roofline:
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN,EXT,BK> (all fused linear / LoRA / implicit-GEMM conv launches of one step)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                 "launches_per_step": len(rec), "gemm_ms_per_step": tm, "algorithmic_gflop_per_step": fl / 1e9, "peak_source": which,
                 "step_model_flops_utilisation": (GFLOP_PER_IMAGE_STEP * 1e9 * B / (ms_step * 1e-3)) / (peak_tf * 1e12)}
     # ---------------- secondary metric of BASELINE.json: denoise steps/s = UNet evaluations at the CFG batch (2B) + fused
     #                  CFG/DDIM update per second (control injected once per image batch)
+    trace("denoise")
     denoise = None
     if rank == 0:
         try:
@@ -370,6 +388,7 @@ def run_ours(a):
             denoise = {"value": None, "unit": "denoise steps/s", "what": f"failed: {ex}"}
     if world > 1:
         dist.barrier()
+    trace("report")
 
     if rank == 0:
         cpu = None

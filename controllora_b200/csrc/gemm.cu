@@ -15,6 +15,7 @@
 // Replaces the cuBLAS/cuDNN calls behind models.py:124-147,231-282,373-423 (attention projections + LoRA side
 // path) and diffusers' FeedForward / ResnetBlock2D / Transformer2DModel projections.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <string>
@@ -85,13 +86,14 @@ struct TileIter {
     int m_blk, n_blk, split, step, num_m;
     bool resident;
     int tile, num_tiles, num_n, splits, kbps, nkb;
-    __device__ TileIter(const GemmParams& p) {
+    // cta / num_ctas: index and count of the scheduling units (CTAs, or CTA pairs); num_m_units: m-blocks per unit row
+    __device__ TileIter(const GemmParams& p, int cta, int num_ctas, int num_m_units) {
         resident = p.b_resident != 0;
-        num_m = p.num_m_blocks; num_n = p.num_n_blocks; splits = p.splits; kbps = p.kb_per_split; nkb = p.num_k_blocks;
+        num_m = num_m_units; num_n = p.num_n_blocks; splits = p.splits; kbps = p.kb_per_split; nkb = p.num_k_blocks;
         num_tiles = num_m * num_n * splits;
         split = 0; tile = 0;
-        if (resident) { n_blk = blockIdx.x % num_n; m_blk = blockIdx.x / num_n; step = gridDim.x / num_n; }
-        else { tile = blockIdx.x; step = gridDim.x; decode(); }
+        if (resident) { n_blk = cta % num_n; m_blk = cta / num_n; step = num_ctas / num_n; }
+        else { tile = cta; step = num_ctas; decode(); }
     }
     __device__ void decode() {
         const int t2 = tile / splits;
@@ -108,12 +110,17 @@ struct TileIter {
     __device__ int kb_end() const { return min(nkb, (split + 1) * kbps); }
 };
 
-template <int BN, int EXT, int BK>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile: each
+// CTA stages its own 128 A rows and HALF of the B rows, the leader's single MMA thread drives both tensor cores, and
+// each CTA ends up with its 128 x BN accumulator rows in its own TMEM -> 1.5x less L2->SM traffic per flop at BN = 256.
+template <int BN, int EXT, int BK, int CG = 1>
 struct GemmCfg {
     static constexpr int UMMA_N = BN + EXT;
     static constexpr int ROW_BYTES = BK * 2;
     static constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
-    static constexpr int B_STAGE_BYTES = UMMA_N * ROW_BYTES;
+    static constexpr int B_ROWS = UMMA_N / CG;                 // B rows staged by one CTA
+    static constexpr int B_STAGE_BYTES = B_ROWS * ROW_BYTES;
+    static_assert(CG == 1 || (CG == 2 && EXT == 0 && (BN / 2) % 8 == 0), "CTA-pair variant: no LoRA rows, BN/2 % 8 == 0");
     static constexpr int SBO = 8 * ROW_BYTES;                  // 8-row swizzle atom
     static constexpr int LAYOUT = (BK == 64) ? 2 : 4;          // UMMA layout type: 128B / 64B swizzle
     static_assert(BK == 64 || BK == 32, "BK");
@@ -148,11 +155,15 @@ __device__ __forceinline__ void decode_row(const GemmParams& p, int m_blk, int r
     }
 }
 
-template <int BN, int EXT, int BK>
+template <int BN, int EXT, int BK, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmE, const GemmParams p, const int num_stages) {
-    using Cfg = GemmCfg<BN, EXT, BK>;
+    using Cfg = GemmCfg<BN, EXT, BK, CG>;
+    const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;      // 0 = leader of the pair
+    const int sched_cta = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int sched_n = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int sched_m = (CG == 2) ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;
     constexpr int A_STAGE_BYTES = Cfg::A_STAGE_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve (base is 1024-aligned by the runtime for dynamic smem declared __align__(1024); re-align anyway)
@@ -187,19 +198,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+            mbar_init(&tmem_empty[i], CG * NUM_EPI_WARPS);   // pair: both CTAs' epilogues release the leader's barrier
         }
         mbar_init(b_full, 1);
         fence_barrier_init();
     }
     if (warp_idx == 2) {
-        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (CG == 2) { tmem_alloc_cg2(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
+        else { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     // LoRA-up table -> smem (persistent for the CTA lifetime)
     for (int i = threadIdx.x; i < up_floats; i += NUM_THREADS) smem_up[i] = p.lora_up[i];
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / TMA credit
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -208,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            TileIter ti(p);
+            TileIter ti(p, sched_cta, sched_n, sched_m);
             if (p.b_resident && ti.valid()) {
                 mbar_arrive_expect_tx(b_full, p.num_k_blocks * Cfg::B_STAGE_BYTES);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -218,7 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             for (; ti.valid(); ti.next()) {
-                const int m_blk = ti.m_blk;
+                const int m_blk = (CG == 2) ? ti.m_blk * 2 + cta_rank : ti.m_blk;
                 const int n_blk = ti.n_blk;
                 int tw = 0, th = 0, tn = 0;
                 if (p.a_mode != 0) {
@@ -230,9 +242,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int kb1 = ti.kb_end();
                 for (int kb = ti.kb_begin(); kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES);
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+                    if (CG == 2) {
+                        // both CTAs' bytes are credited to the LEADER's full barrier (one arrival: the leader's producer)
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                        const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if (p.a_mode == 0) {
+                            tma_load_2d_cg2(&tmA, fb, sa, kb * BK, m_blk * BLOCK_M);
+                        } else {
+                            const int tap = kb / p.cblocks, cb = kb % p.cblocks;
+                            const int ky = tap / 3, kx = tap % 3;
+                            if (p.a_mode == 1) {
+                                tma_load_4d_cg2(&tmA, fb, sa, cb * BK, tw * p.bw + kx - 1, th * p.bh + ky - 1, tn * p.bn);
+                            } else {
+                                const int iy = ky - p.pad_lo, ix = kx - p.pad_lo;
+                                tma_load_5d_cg2(&tmA, fb, sa, (ix & 1) * p.C + cb * BK, tw * p.bw + (ix >> 1), iy & 1,
+                                                th * p.bh + (iy >> 1), tn * p.bn);
+                            }
+                        }
+                        tma_load_2d_cg2(&tmB, fb, sb, kb * BK, n_blk * BN + cta_rank * Cfg::B_ROWS);
+                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES);
                     if (p.a_mode == 0) {
                         tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BLOCK_M);
                     } else {
@@ -257,12 +290,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp_idx == 1) {
         // ===================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, Cfg::UMMA_N, 0, 0);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, Cfg::UMMA_N, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            TileIter ti(p);
+            TileIter ti(p, sched_cta, sched_n, sched_m);
             if (p.b_resident && ti.valid()) mbar_wait(b_full, 0);
             for (; ti.valid(); ti.next(), ++it) {
                 const int buf = it & 1;
@@ -283,12 +316,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adesc = make_smem_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
                         const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                        tc_mma_ss(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        if (CG == 2) tc_mma_ss_cg2(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        else tc_mma_ss(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
-                    tc_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+                    // smem slot is free once these MMAs retire (pair: in both CTAs)
+                    if (CG == 2) tc_commit_cg2(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tmem_full[buf]);        // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (pair: each CTA drains its own 128 rows)
+                if (CG == 2) tc_commit_cg2(&tmem_full[buf], 3); else tc_commit(&tmem_full[buf]);
                 TL(23);  // mma: all MMAs of the tile issued
             }
         }
@@ -301,8 +337,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int rp = p.lora_rp;
         const uint32_t up_addr = smem_u32(smem_up);
         int it = 0;
-        for (TileIter ti(p); ti.valid(); ti.next(), ++it) {
-            const int m_blk = ti.m_blk;
+        for (TileIter ti(p, sched_cta, sched_n, sched_m); ti.valid(); ti.next(), ++it) {
+            const int m_blk = (CG == 2) ? ti.m_blk * 2 + cta_rank : ti.m_blk;
             const int n_blk = ti.n_blk;
             const int buf = it & 1;
             const uint32_t buf_phase = (it >> 1) & 1;
@@ -444,16 +480,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // all TMEM reads of this buffer are complete (tc_wait_ld above) -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[buf]), 0));
+                else mbar_arrive(&tmem_empty[buf]);
+            }
             if (ew == 0 && lane == 0) TL(32);  // epilogue: tile done
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the leader's MMAs read the peer's smem: nobody leaves before both epilogues end
+    else __syncthreads();
     if (warp_idx == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -502,10 +543,10 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, int M, int N, con
 // host side
 // =====================================================================================================
 
-template <int BN, int EXT, int BK = 64>
+template <int BN, int EXT, int BK = 64, int CG = 1>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tE, const GemmParams& p_in,
                        cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, EXT, BK>;
+    using Cfg = GemmCfg<BN, EXT, BK, CG>;
     GemmParams p = p_in;
     const int up_bytes = (p.lora_up != nullptr) ? ((p.N * p.lora_rp * 4 + 15) & ~15) : 0;
     const int fixed = 1024 /*align slack*/ + EPI_STAGING_BYTES + up_bytes + 256 /*barriers*/;
@@ -515,7 +556,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     const int b_res_bytes = p.num_k_blocks * Cfg::B_STAGE_BYTES;
     const int a_room = 232448 - fixed - b_res_bytes;
     const int grid_res = (grid / p.num_n_blocks) * p.num_n_blocks;
-    if (p.splits == 1 && p.a_mode == 0 && a_room >= 3 * Cfg::A_STAGE_BYTES && grid_res > 0 && grid_res * 10 >= grid * 9 &&
+    if (CG == 1 && p.splits == 1 && p.a_mode == 0 && a_room >= 3 * Cfg::A_STAGE_BYTES && grid_res > 0 && grid_res * 10 >= grid * 9 &&
         p.num_m_blocks >= 3 * (grid_res / p.num_n_blocks)) {
         p.b_resident = 1;
         stages = a_room / Cfg::A_STAGE_BYTES;
@@ -528,17 +569,35 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
         if (stages > 8) stages = 8;
         if (stages < 2) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: not enough shared memory for 2 stages");
         smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
-        const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.splits;
+        const int m_units = (CG == 2) ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;
+        const int num_tiles = m_units * p.num_n_blocks * p.splits;
+        if (CG == 2) grid /= 2;                       // scheduling units are CTA pairs
         if (grid > num_tiles) grid = num_tiles;
+        grid *= CG;
     }
     const GemmParams full = p;
     if (p.splits > 1) { p.bias = nullptr; p.row_bias = nullptr; p.residual = nullptr; }
     static bool attr_done = false;
     if (!attr_done) {
-        CL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        CL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT, BK, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_done = true;
     }
-    gemm_tc_kernel<BN, EXT, BK><<<grid, NUM_THREADS, smem_bytes, stream>>>(tA, tB, tE, p, stages);
+    if (CG == 2) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EXT, BK, CG>, tA, tB, tE, p, stages));
+    } else {
+        gemm_tc_kernel<BN, EXT, BK, CG><<<grid, NUM_THREADS, smem_bytes, stream>>>(tA, tB, tE, p, stages);
+    }
     count_launch();
     if (p.splits > 1) {
         const long long quads = (long long)p.M * (p.N / 4);
@@ -576,10 +635,23 @@ extern "C" int cl_debug_timeline(unsigned long long* host_buf, unsigned int* hos
 // >= 8 k-blocks.  The caller provides split_ws = splits * M * N floats (cl_gemm_split_hint tells how many).
 struct TilePlan { int bn, splits; };
 
+static inline int gemm_block_k(const cl_gemm_args* a) { return (a->a_mode != 0 && a->C % 64 != 0) ? 32 : 64; }
+
+// CTA pairs (cta_group::2) serve everything except the LoRA epilogue, the 32-channel convs and the smem-resident small-K
+// case; CLB_GEMM_2CTA=0 falls back to single-CTA tiles.
+static int gemm_cta_group(const cl_gemm_args* a, int BK, int num_m_blocks) {
+    static const int pair_enabled = [] { const char* e = getenv("CLB_GEMM_2CTA"); return (e && e[0] == '0') ? 0 : 1; }();
+    const bool small_k_resident = a->a_mode == 0 && a->K <= 320 && a->N % 160 == 0 && a->M >= 8192;
+    // K >= 2048: measured on B200, pairs cut the L2->SM traffic by 1.3-1.5x everywhere but only pay for their cluster
+    // launch / cross-CTA signalling on deep-K tiles (convs, FFN-down); short-K GEMMs stay on single CTAs.
+    return (pair_enabled && a->lora_up == nullptr && BK == 64 && !small_k_resident && num_m_blocks >= 2 && a->K >= 2048) ? 2 : 1;
+}
+
 static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool allow_split) {
     const bool lora = a->lora_up != nullptr;
     const int nkb = (a->K + BK - 1) / BK;
-    const int sms = num_sms();
+    const int cg = gemm_cta_group(a, BK, num_m_blocks);
+    const int sms = num_sms() / cg;                        // scheduling units: CTAs or CTA pairs
     TilePlan best = {0, 1};
     if (a->block_n != 0) best.bn = a->block_n;
     else if (!lora && a->a_mode == 0 && a->K <= 320 && a->N % 160 == 0 && a->M >= 8192) best.bn = 160;  // weights stay smem-resident
@@ -594,7 +666,7 @@ static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool
             if (BK == 32 ? (bn > 128) : (bn < 64)) continue;   // instantiated variants
             if (lora && bn < 64) continue;
         }
-        const int tiles = num_m_blocks * ((a->N + bn - 1) / bn);
+        const int tiles = ((num_m_blocks + cg - 1) / cg) * ((a->N + bn - 1) / bn);
         int splits = 1;
         if (allow_split && !lora && tiles * 2 <= sms) {
             splits = sms / tiles;
@@ -605,7 +677,7 @@ static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool
         const int kbps = (nkb + splits - 1) / splits;
         splits = (nkb + kbps - 1) / kbps;
         const long long waves = ((long long)tiles * splits + sms - 1) / sms;
-        const long long cost = waves * (128 + bn + 32) * kbps;
+        const long long cost = waves * (128 + bn / cg + 32) * kbps;   // rows a CTA pulls from L2 per k-block
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = {bn, splits}; }
     }
     if (best_cost < 0) {   // no candidate divides N: tail tiles
@@ -618,8 +690,6 @@ static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool
     }
     return best;
 }
-
-static inline int gemm_block_k(const cl_gemm_args* a) { return (a->a_mode != 0 && a->C % 64 != 0) ? 32 : 64; }
 
 extern "C" int cl_gemm_split_hint(const cl_gemm_args* a) {
     if (a == nullptr || a->lora_up != nullptr || a->M <= 0 || a->N <= 0 || a->K <= 0) return 1;
@@ -696,6 +766,7 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     if (a->split_k > 1 && a->split_ws == nullptr) return set_error(CL_ERR_INVALID, "cl_gemm: split_k needs split_ws");
     const TilePlan plan = plan_tiles(a, BK, p.num_m_blocks, a->split_k > 1);
     const int bn_sel = plan.bn;
+    const int cg = (bn_sel >= 64) ? gemm_cta_group(a, BK, p.num_m_blocks) : 1;
     p.num_n_blocks = (a->N + bn_sel - 1) / bn_sel;
     p.splits = 1;
     p.kb_per_split = p.num_k_blocks;
@@ -708,7 +779,7 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     {
         uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
         uint64_t strides[1] = {(uint64_t)a->ldb * 2};
-        uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn_sel};
+        uint32_t box[2] = {(uint32_t)BK, (uint32_t)(bn_sel / cg)};     // a CTA of a pair stages half of the B rows
         CL_CHECK(get_tensor_map(&tB, a->b, 2, dims, strides, box, swz));
     }
     if (lora) {
@@ -744,6 +815,15 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
             case 128: return launch_gemm<128, 16>(tA, tB, tE, p, stream);
             case 160: return launch_gemm<160, 16>(tA, tB, tE, p, stream);
             default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n for LoRA must be 64/128/160");
+        }
+    }
+    if (cg == 2) {
+        switch (bn_sel) {
+            case 64: return launch_gemm<64, 0, 64, 2>(tA, tB, tE, p, stream);
+            case 128: return launch_gemm<128, 0, 64, 2>(tA, tB, tE, p, stream);
+            case 160: return launch_gemm<160, 0, 64, 2>(tA, tB, tE, p, stream);
+            case 256: return launch_gemm<256, 0, 64, 2>(tA, tB, tE, p, stream);
+            default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n must be 64/128/160/256");
         }
     }
     switch (bn_sel) {
