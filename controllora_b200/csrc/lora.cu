@@ -105,6 +105,9 @@ struct SkinnyBatch {
     cl_skinny_desc d[CL_SKINNY_MAX];
 };
 
+// RT: compile-time bound on the rank (4 or 8); U: rows in flight per thread.  All U row loads (16 B of b, the RT
+// coefficients of a) are issued before the FMAs: with one load in flight per thread the kernel ran at ~25 % of HBM speed.
+template <int RT, int U>
 __global__ void __launch_bounds__(512)
 skinny_atb_batch_kernel(const __grid_constant__ SkinnyBatch batch, int slabs) {
     const cl_skinny_desc& d = batch.d[blockIdx.y];
@@ -119,31 +122,51 @@ skinny_atb_batch_kernel(const __grid_constant__ SkinnyBatch batch, int slabs) {
     const int row1 = min(M, row0 + rows_per_cta);
     if (row0 >= M) return;
     const float* a = d.a;
-    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(d.b);
-    float acc[8][8];
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(d.b) + chunk * 8;
+    const bool vec_a = ((reinterpret_cast<uintptr_t>(a) & 15) == 0) && (d.lda % 4 == 0) && (d.lda >= RT);
+    float acc[RT][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < RT; ++j)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
     if (active) {
-        for (int m = row0 + rsub; m < row1; m += rows_par) {
-            const uint4 u = *reinterpret_cast<const uint4*>(b + (long long)m * d.ldb + chunk * 8);
-            const float2 b0 = unpack_bf16x2(u.x), b1 = unpack_bf16x2(u.y), b2 = unpack_bf16x2(u.z), b3 = unpack_bf16x2(u.w);
-            const float bv[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+        for (int m = row0 + rsub; m < row1; m += U * rows_par) {
+            uint4 u[U];
+            float av[U][RT];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < R) {
-                    const float av = a[(long long)m * d.lda + j];
+            for (int k = 0; k < U; ++k) {
+                const int mk = m + k * rows_par;
+                const bool ok = mk < row1;
+                const long long mc = ok ? mk : (row1 - 1);      // clamp: a padded row contributes with zero coefficients
+                u[k] = __ldg(reinterpret_cast<const uint4*>(b + mc * d.ldb));
+                if (vec_a) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[j][i] += av * bv[i];
+                    for (int q = 0; q < RT / 4; ++q) {
+                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(a + mc * d.lda + 4 * q));
+                        av[k][4 * q] = ok ? t4.x : 0.f; av[k][4 * q + 1] = ok ? t4.y : 0.f;
+                        av[k][4 * q + 2] = ok ? t4.z : 0.f; av[k][4 * q + 3] = ok ? t4.w : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < RT; ++j) av[k][j] = (ok && j < R) ? a[mc * d.lda + j] : 0.f;
                 }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const float2 b0 = unpack_bf16x2(u[k].x), b1 = unpack_bf16x2(u[k].y), b2 = unpack_bf16x2(u[k].z),
+                             b3 = unpack_bf16x2(u[k].w);
+                const float bv[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+#pragma unroll
+                for (int j = 0; j < RT; ++j)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(av[k][j], bv[i], acc[j][i]);
             }
         }
     }
     extern __shared__ float sh[];   // [rows_par][R][C]
     if (active) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < RT; ++j) {
             if (j < R) {
                 float* dst = sh + ((long long)rsub * R + j) * C + chunk * 8;
                 *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
@@ -248,15 +271,27 @@ rank_update_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     for (int i = threadIdx.x; i < C * RP; i += blockDim.x) s_tt[(i % RP) * C + i / RP] = tab[i];
     __syncthreads();
     const int chunks = C / 8;
+    const bool vec_t = ((reinterpret_cast<uintptr_t>(t) & 15) == 0) && (ldt % 4 == 0);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M * chunks; i += (long long)gridDim.x * blockDim.x) {
         const long long m = i / chunks;
         const int c0 = (int)(i % chunks) * 8;
         const uint4 u = *reinterpret_cast<const uint4*>(x + m * C + c0);
         const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
         float xv[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+        float tr[RP];
+        if (vec_t) {
+#pragma unroll
+            for (int q = 0; q < RP / 4; ++q) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(t + m * ldt + 4 * q));
+                tr[4 * q] = t4.x; tr[4 * q + 1] = t4.y; tr[4 * q + 2] = t4.z; tr[4 * q + 3] = t4.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RP; ++j) tr[j] = t[m * ldt + j];
+        }
 #pragma unroll
         for (int j = 0; j < RP; ++j) {
-            const float tv = alpha * t[m * ldt + j];
+            const float tv = alpha * tr[j];
             const float4 a = *reinterpret_cast<const float4*>(s_tt + j * C + c0);
             const float4 b = *reinterpret_cast<const float4*>(s_tt + j * C + c0 + 4);
             xv[0] += tv * a.x; xv[1] += tv * a.y; xv[2] += tv * a.z; xv[3] += tv * a.w;
@@ -266,6 +301,129 @@ rank_update_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         o.x = pack_bf16x2(xv[0], xv[1]); o.y = pack_bf16x2(xv[2], xv[3]);
         o.z = pack_bf16x2(xv[4], xv[5]); o.w = pack_bf16x2(xv[6], xv[7]);
         *reinterpret_cast<uint4*>(out + m * C + c0) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ V2 control injection (fused)
+// forward:  t[m, :] = hi/lo-combine(th16[m, :16]) (+ uc[m, :rc]);   out[m, c] = x[m, c] + alpha * sum_{j<4} t[m, j] * tab[c*4 + j]
+// (== cl_hilo_combine + cl_rowmat(identity) + cl_rank_update in one pass: x is read once, t [M, 8] is kept for the backward)
+__global__ void __launch_bounds__(256)
+v2_inject_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ th16, const float* __restrict__ uc, int ldu,
+                     int rc, const float* __restrict__ tab, float alpha, __nv_bfloat16* __restrict__ out,
+                     float* __restrict__ t_out, long long M, int C) {
+    extern __shared__ float s_tt[];                 // [4][C] transposed table
+    for (int i = threadIdx.x; i < C * 4; i += blockDim.x) s_tt[(i % 4) * C + i / 4] = tab[i];
+    __syncthreads();
+    const int chunks = C / 8;
+    const bool vec_u = uc != nullptr && rc == 4 && ((reinterpret_cast<uintptr_t>(uc) & 15) == 0) && (ldu % 4 == 0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M * chunks; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / chunks;
+        const int chunk = (int)(i - m * chunks);
+        const int c0 = chunk * 8;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + m * C + c0));
+        const float4 hi = __ldg(reinterpret_cast<const float4*>(th16 + m * 16));
+        const float4 lo = __ldg(reinterpret_cast<const float4*>(th16 + m * 16 + 8));
+        float tv[4] = {hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w};
+        if (vec_u) {
+            const float4 u4 = __ldg(reinterpret_cast<const float4*>(uc + m * ldu));
+            tv[0] += u4.x; tv[1] += u4.y; tv[2] += u4.z; tv[3] += u4.w;
+        } else if (uc != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < rc) tv[j] += uc[m * ldu + j];
+        }
+        if (chunk == 0) {
+            const float4 hi2 = __ldg(reinterpret_cast<const float4*>(th16 + m * 16 + 4));
+            const float4 lo2 = __ldg(reinterpret_cast<const float4*>(th16 + m * 16 + 12));
+            *reinterpret_cast<float4*>(t_out + m * 8) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+            *reinterpret_cast<float4*>(t_out + m * 8 + 4) = make_float4(hi2.x + lo2.x, hi2.y + lo2.y, hi2.z + lo2.z, hi2.w + lo2.w);
+        }
+        const float2 x0 = unpack_bf16x2(u.x), x1 = unpack_bf16x2(u.y), x2 = unpack_bf16x2(u.z), x3 = unpack_bf16x2(u.w);
+        float xv[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float tj = alpha * tv[j];
+            const float4 a = *reinterpret_cast<const float4*>(s_tt + j * C + c0);
+            const float4 b = *reinterpret_cast<const float4*>(s_tt + j * C + c0 + 4);
+            xv[0] = fmaf(tj, a.x, xv[0]); xv[1] = fmaf(tj, a.y, xv[1]); xv[2] = fmaf(tj, a.z, xv[2]); xv[3] = fmaf(tj, a.w, xv[3]);
+            xv[4] = fmaf(tj, b.x, xv[4]); xv[5] = fmaf(tj, b.y, xv[5]); xv[6] = fmaf(tj, b.z, xv[6]); xv[7] = fmaf(tj, b.w, xv[7]);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(xv[0], xv[1]); o.y = pack_bf16x2(xv[2], xv[3]);
+        o.z = pack_bf16x2(xv[4], xv[5]); o.w = pack_bf16x2(xv[6], xv[7]);
+        *reinterpret_cast<uint4*>(out + m * C + c0) = o;
+    }
+}
+
+// backward (one warp per row, the row stays in registers between the two phases):
+//   dt[m, j] = sum_c dy[m, c] * up[c*4 + j]                       (== cl_rowdot)
+//   dh[m, c] = dy[m, c] + alpha * sum_j dt[m, j] * down[c*4 + j]   (== cl_rank_update), dh optional
+template <int IT>
+__global__ void __launch_bounds__(256)
+v2_inject_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ up, const float* __restrict__ down, float alpha,
+                     float* __restrict__ dt_out, __nv_bfloat16* __restrict__ dh, int M, int C) {
+    extern __shared__ float s_tab[];                // [4][C] up (transposed) | [4][C] down (transposed)
+    float* s_up = s_tab;
+    float* s_dn = s_tab + 4 * C;
+    for (int i = threadIdx.x; i < C * 4; i += blockDim.x) {
+        s_up[(i % 4) * C + i / 4] = up[i];
+        s_dn[(i % 4) * C + i / 4] = (dh != nullptr) ? down[i] : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int chunks = C / 8;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M; m += warps_total) {
+        float v[IT][8];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int ch = it * 32 + lane;
+            if (ch < chunks) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + (long long)m * C + ch * 8));
+                const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+                v[it][0] = a0.x; v[it][1] = a0.y; v[it][2] = a1.x; v[it][3] = a1.y;
+                v[it][4] = a2.x; v[it][5] = a2.y; v[it][6] = a3.x; v[it][7] = a3.y;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int ch = it * 32 + lane;
+            if (ch < chunks) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 u0 = *reinterpret_cast<const float4*>(s_up + j * C + ch * 8);
+                    const float4 u1 = *reinterpret_cast<const float4*>(s_up + j * C + ch * 8 + 4);
+                    acc[j] += v[it][0] * u0.x + v[it][1] * u0.y + v[it][2] * u0.z + v[it][3] * u0.w + v[it][4] * u1.x +
+                              v[it][5] * u1.y + v[it][6] * u1.z + v[it][7] * u1.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
+        if (lane == 0) *reinterpret_cast<float4*>(dt_out + (long long)m * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (dh != nullptr) {
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int ch = it * 32 + lane;
+                if (ch < chunks) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float tj = alpha * acc[j];
+                        const float4 d0 = *reinterpret_cast<const float4*>(s_dn + j * C + ch * 8);
+                        const float4 d1 = *reinterpret_cast<const float4*>(s_dn + j * C + ch * 8 + 4);
+                        v[it][0] = fmaf(tj, d0.x, v[it][0]); v[it][1] = fmaf(tj, d0.y, v[it][1]);
+                        v[it][2] = fmaf(tj, d0.z, v[it][2]); v[it][3] = fmaf(tj, d0.w, v[it][3]);
+                        v[it][4] = fmaf(tj, d1.x, v[it][4]); v[it][5] = fmaf(tj, d1.y, v[it][5]);
+                        v[it][6] = fmaf(tj, d1.z, v[it][6]); v[it][7] = fmaf(tj, d1.w, v[it][7]);
+                    }
+                    uint4 o;
+                    o.x = pack_bf16x2(v[it][0], v[it][1]); o.y = pack_bf16x2(v[it][2], v[it][3]);
+                    o.z = pack_bf16x2(v[it][4], v[it][5]); o.w = pack_bf16x2(v[it][6], v[it][7]);
+                    *reinterpret_cast<uint4*>(dh + (long long)m * C + ch * 8) = o;
+                }
+            }
+        }
     }
 }
 
@@ -401,14 +559,18 @@ extern "C" int cl_skinny_atb_batch(const cl_skinny_desc* descs, int n, void* str
     if (smem > 200 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_skinny_atb_batch: shared memory");
     static bool done = false;
     if (!done) {
-        CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         done = true;
     }
+    int max_r = 0;
+    for (int i = 0; i < n; ++i) max_r = descs[i].r > max_r ? descs[i].r : max_r;
     // ~one wave of CTAs in total; every problem gets the same number of row slabs
     int slabs = (num_sms() + n - 1) / n;
     if (slabs > (max_m + 63) / 64) slabs = (max_m + 63) / 64;
     if (slabs < 1) slabs = 1;
-    skinny_atb_batch_kernel<<<dim3(slabs, n), 512, smem, stream>>>(batch, slabs);
+    if (max_r <= 4) skinny_atb_batch_kernel<4, 8><<<dim3(slabs, n), 512, smem, stream>>>(batch, slabs);
+    else skinny_atb_batch_kernel<8, 2><<<dim3(slabs, n), 512, smem, stream>>>(batch, slabs);
     DONE();
 }
 
@@ -460,6 +622,36 @@ extern "C" int cl_rank_update(const void* x, const float* t, int ldt, const floa
     if (rp == 4) rank_update_kernel<4><<<blocks, 256, smem, stream>>>(xx, t, ldt, tab, alpha, oo, M, Ccols);
     else if (rp == 8) rank_update_kernel<8><<<blocks, 256, smem, stream>>>(xx, t, ldt, tab, alpha, oo, M, Ccols);
     else return set_error(CL_ERR_UNSUPPORTED, "cl_rank_update: rp must be 4 or 8");
+    DONE();
+}
+
+extern "C" int cl_v2_inject_fwd(const void* x, const float* th16, const float* uc, int ldu, int rc, const float* tab, float alpha,
+                                void* out, float* t_out, int64_t M, int Ccols, void* stream_) {
+    STREAM;
+    if (!x || !th16 || !tab || !out || !t_out || Ccols % 8 || rc < 1 || rc > 4) return set_error(CL_ERR_INVALID, "cl_v2_inject_fwd: bad args");
+    const size_t smem = (size_t)Ccols * 4 * sizeof(float);
+    if (smem > 48 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_v2_inject_fwd: C too large");
+    long long total = M * (Ccols / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    v2_inject_fwd_kernel<<<blocks, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), th16, uc, ldu, rc, tab, alpha,
+                                                        reinterpret_cast<__nv_bfloat16*>(out), t_out, M, Ccols);
+    DONE();
+}
+
+extern "C" int cl_v2_inject_bwd(const void* dy, const float* up, const float* down, float alpha, float* dt_out, void* dh, int M,
+                                int Ccols, void* stream_) {
+    STREAM;
+    if (!dy || !up || !dt_out || (dh && !down) || Ccols % 8) return set_error(CL_ERR_INVALID, "cl_v2_inject_bwd: bad args");
+    if (Ccols > 1280) return set_error(CL_ERR_UNSUPPORTED, "cl_v2_inject_bwd: C <= 1280");
+    const size_t smem = (size_t)Ccols * 8 * sizeof(float);
+    int blocks = (M + 7) / 8;
+    if (blocks > num_sms() * 6) blocks = num_sms() * 6;
+    const __nv_bfloat16* dd = reinterpret_cast<const __nv_bfloat16*>(dy);
+    __nv_bfloat16* hh = reinterpret_cast<__nv_bfloat16*>(dh);
+    if (Ccols <= 512) v2_inject_bwd_kernel<2><<<blocks, 256, smem, stream>>>(dd, up, down, alpha, dt_out, hh, M, Ccols);
+    else if (Ccols <= 768) v2_inject_bwd_kernel<3><<<blocks, 256, smem, stream>>>(dd, up, down, alpha, dt_out, hh, M, Ccols);
+    else v2_inject_bwd_kernel<5><<<blocks, 256, smem, stream>>>(dd, up, down, alpha, dt_out, hh, M, Ccols);
     DONE();
 }
 

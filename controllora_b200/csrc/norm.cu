@@ -29,32 +29,41 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm
-// Layout: x [n, HW, C]; group g = channels [g*cpg, (g+1)*cpg).  A CTA owns a slab of rows of one image; thread t
-// always handles the same 8-channel chunk (blockDim.x is a multiple of C/8), so per-channel partial sums stay in
-// registers; the per-group combine goes through shared memory and one fp64 atomic per (group, CTA).
+// Layout: x [n, HW, C]; group g = channels [g*cpg, (g+1)*cpg).  Three phases per direction, all HBM-bound:
+//   reduce   a CTA owns a slab of rows of one image, thread t always handles the same 8-channel chunk (blockDim.x is a
+//            multiple of C/8) so per-channel partial sums stay in registers; 2 CTAs per SM, 2 rows in flight per thread
+//   coef     one tiny kernel turns the sums into per-(image, channel) affine coefficient arrays
+//   apply    a flat, high-occupancy elementwise pass: one 16-byte chunk per thread-iteration, coefficients read as
+//            float4 from the (L1-resident) arrays - measured on B200, the register-resident-coefficient slab variant of
+//            this pass ran at 35 % of the HBM rate because only one 480-thread CTA fitted per SM.
+// Scratch `ws` (cl_groupnorm_ws_bytes): [n*G*2 fp64 group sums][4 x n*C fp32 coefficients][2 x n*C fp32 channel sums].
 
 static constexpr int GN_MAX_CHUNKS = 512;  // C <= 4096
 
-// Per-thread channel constants: thread t owns channels [c0, c0+8) for its whole slab, so everything that depends only
-// on (image, channel) is computed once and the row loop is load -> fma -> (store), unrolled for memory-level
-// parallelism (one 16-byte load in flight per thread caps a 1024-thread SM at ~20 GB/s; four reach the HBM limit).
 __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+__device__ __forceinline__ void ldg8f(const float* p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 __device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+__device__ __forceinline__ float silu_grad_fast(float z) {
+    const float s = fast_sigmoid(z);
+    return s * (1.f + z * (1.f - s));
+}
 
-// mode 0: forward statistics      -> ws[(n*G+g)*2 + {0,1}] += {sum x, sum x^2}
-// mode 1: backward reductions     -> ws[(n*G+g)*2 + {0,1}] += {sum dz*gamma, sum dz*gamma*xhat},
-//                                    dgamma[c] += sum dz*xhat, dbeta[c] += sum dz   (when dgamma != nullptr)
-// In mode 1 the group sums are gamma-weighted channel sums of the dgamma/dbeta partials, so only those accumulate.
+// mode 0: forward statistics   -> gsum[(n*G+g)*2 + {0,1}] += {sum x, sum x^2}                 (fp64 atomics)
+// mode 1: backward reductions  -> csum[0][n][c] += sum dz*x,  csum[1][n][c] += sum dz          (fp32 atomics)
+//         with dz = dy * silu'(x*sc + sh) when silu (sc = rstd*gamma, sh = beta - mean*sc), else dz = dy.
 template <int MODE>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                  const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
-                 double* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int HW, int C, int G,
-                 int rows_per_cta, int silu) {
+                 double* __restrict__ gsum, float* __restrict__ csum, int n_img, int HW, int C, int G, int rows_per_cta,
+                 int silu) {
     const int n = blockIdx.y;
     const int chunks = C / 8;
     const int cpg = C / G;
@@ -66,78 +75,66 @@ gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
     const bool active = rsub < rows_par;
     const int c0 = chunk * 8;
 
-    float a0[8], a1[8];  // MODE 0: sum, sumsq.  MODE 1: sum dz*xhat, sum dz
-    float ga[8], gb[8], rs[8], nm[8];   // MODE 1: z = xh*ga + gb, xh = x*rs + nm
+    float a0[8], a1[8];  // MODE 0: sum, sumsq.  MODE 1: sum dz*x, sum dz
+    float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a0[j] = a1[j] = 0.f; }
-    if (MODE == 1 && active) {
+    for (int j = 0; j < 8; ++j) { a0[j] = a1[j] = 0.f; sc[j] = sh[j] = 0.f; }
+    if (MODE == 1 && silu && active) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            ga[j] = gamma[c0 + j];
-            gb[j] = beta[c0 + j];
             const int g = (c0 + j) / cpg;
-            const float mu = stats[(n * G + g) * 2];
-            rs[j] = stats[(n * G + g) * 2 + 1];
-            nm[j] = -mu * rs[j];
+            const float mu = stats[(n * G + g) * 2], rs = stats[(n * G + g) * 2 + 1];
+            sc[j] = rs * gamma[c0 + j];
+            sh[j] = fmaf(-mu, sc[j], beta[c0 + j]);
         }
     }
     if (active) {
         const __nv_bfloat16* xp = x + (long long)n * HW * C + c0;
         const __nv_bfloat16* dp = dy + (long long)n * HW * C + c0;
-        const long long rstep = (long long)rows_par * C;
-        int r = row0 + rsub;
-        if (MODE == 0) {
-            for (; r + 3 * rows_par < row1; r += 4 * rows_par) {
-                uint4 u[4];
+        // 2 rows in flight per thread; rows past the slab are clamped for the load and skipped for the sums
+        for (int r = row0 + rsub; r < row1; r += 2 * rows_par) {
+            const int r1 = r + rows_par;
+            const bool ok1 = r1 < row1;
+            const long long o0 = (long long)r * C, o1 = (long long)(ok1 ? r1 : r) * C;
+            if (MODE == 0) {
+                const uint4 u0 = ldg16(xp + o0), u1 = ldg16(xp + o1);
+                float xv[8];
+                unpack8(u0, xv);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) u[k] = ldg16(xp + (long long)r * C + k * rstep);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float xv[8];
-                    unpack8(u[k], xv);
+                for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
+                if (ok1) {
+                    unpack8(u1, xv);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
                 }
-            }
-            for (; r < row1; r += rows_par) {
-                float xv[8];
-                unpack8(ldg16(xp + (long long)r * C), xv);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
-            }
-        } else {
-            auto acc = [&](const uint4& ux, const uint4& ud) {
+            } else {
+                const uint4 ux0 = ldg16(xp + o0), ud0 = ldg16(dp + o0), ux1 = ldg16(xp + o1), ud1 = ldg16(dp + o1);
                 float xv[8], dv[8];
-                unpack8(ux, xv);
-                unpack8(ud, dv);
+                unpack8(ux0, xv);
+                unpack8(ud0, dv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float xh = fmaf(xv[j], rs[j], nm[j]);
                     float dz = dv[j];
-                    if (silu) {
-                        const float z = fmaf(xh, ga[j], gb[j]);
-                        const float s = fast_sigmoid(z);
-                        dz *= s * (1.f + z * (1.f - s));
-                    }
-                    a0[j] = fmaf(dz, xh, a0[j]);
+                    if (silu) dz *= silu_grad_fast(fmaf(xv[j], sc[j], sh[j]));
+                    a0[j] = fmaf(dz, xv[j], a0[j]);
                     a1[j] += dz;
                 }
-            };
-            for (; r + 3 * rows_par < row1; r += 4 * rows_par) {
-                uint4 ux[4], ud[4];
+                if (ok1) {
+                    unpack8(ux1, xv);
+                    unpack8(ud1, dv);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    ux[k] = ldg16(xp + (long long)r * C + k * rstep);
-                    ud[k] = ldg16(dp + (long long)r * C + k * rstep);
+                    for (int j = 0; j < 8; ++j) {
+                        float dz = dv[j];
+                        if (silu) dz *= silu_grad_fast(fmaf(xv[j], sc[j], sh[j]));
+                        a0[j] = fmaf(dz, xv[j], a0[j]);
+                        a1[j] += dz;
+                    }
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc(ux[k], ud[k]);
             }
-            for (; r < row1; r += rows_par) acc(ldg16(xp + (long long)r * C), ldg16(dp + (long long)r * C));
         }
     }
     // combine without shared-memory atomics (ATOMS costs ~2 cycles per lane): every row-group stores its per-channel
-    // partials, then the CTA sums them per channel, per group (fp64 atomics to global) and per parameter.
+    // partials, then the CTA sums them per channel.
     extern __shared__ float gsh[];                        // [2][rows_par + 1][C]
     float* part0 = gsh;                                   // [rows_par][C]
     float* part1 = gsh + (size_t)rows_par * C;            // [rows_par][C]
@@ -155,246 +152,311 @@ gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s0 = 0.f, s1 = 0.f;
         for (int g = 0; g < rows_par; ++g) { s0 += part0[(size_t)g * C + c]; s1 += part1[(size_t)g * C + c]; }
-        tot0[c] = s0;
-        tot1[c] = s1;
+        if (MODE == 0) { tot0[c] = s0; tot1[c] = s1; }
+        else {
+            atomicAdd(&csum[(size_t)n * C + c], s0);
+            atomicAdd(&csum[(size_t)(n_img + n) * C + c], s1);
+        }
     }
-    __syncthreads();
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        double s0 = 0.0, s1 = 0.0;
-        if (MODE == 0) {
+    if (MODE == 0) {
+        __syncthreads();
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            double s0 = 0.0, s1 = 0.0;
             for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s0 += tot0[c]; s1 += tot1[c]; }
-        } else {
-            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-                const float gm = gamma[c];
-                s0 += (double)(gm * tot1[c]);   // sum dz*gamma
-                s1 += (double)(gm * tot0[c]);   // sum dz*gamma*xhat
-            }
-        }
-        atomicAdd(&ws[(n * G + g) * 2], s0);
-        atomicAdd(&ws[(n * G + g) * 2 + 1], s1);
-    }
-    if (MODE == 1 && dgamma != nullptr) {
-        for (int i = threadIdx.x; i < C; i += blockDim.x) {
-            atomicAdd(&dgamma[i], tot0[i]);
-            atomicAdd(&dbeta[i], tot1[i]);
+            atomicAdd(&gsum[(n * G + g) * 2], s0);
+            atomicAdd(&gsum[(n * G + g) * 2 + 1], s1);
         }
     }
 }
 
-// ws (fp64 sums) -> stats {mean, rstd} in fp32, one thread per (image, group)
-__global__ void gn_finalize_kernel(const double* __restrict__ ws, float* __restrict__ stats, int total, double inv_m, float eps) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const double mu = ws[2 * i] * inv_m;
-    double var = ws[2 * i + 1] * inv_m - mu * mu;
-    if (var < 0.0) var = 0.0;
-    stats[2 * i] = (float)mu;
-    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+// forward coefficients: stats {mean, rstd} per (image, group) and  y = x*sc + sh  per (image, channel).
+// coef layout: [4][n][C]; forward uses planes 0 (sc) and 1 (sh).
+__global__ void gn_fwd_coef_kernel(const double* __restrict__ gsum, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ stats, float* __restrict__ coef,
+                                   int n_img, int C, int G, double inv_m, float eps) {
+    const int n = blockIdx.x;
+    const int cpg = C / G;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const double mu = gsum[(n * G + g) * 2] * inv_m;
+        double var = gsum[(n * G + g) * 2 + 1] * inv_m - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const float rs = (float)(1.0 / sqrt(var + (double)eps));
+        const float fmu = (float)mu;
+        if (c == g * cpg) { stats[(n * G + g) * 2] = fmu; stats[(n * G + g) * 2 + 1] = rs; }
+        const float sc = rs * gamma[c];
+        coef[(size_t)n * C + c] = sc;
+        coef[(size_t)(n_img + n) * C + c] = fmaf(-fmu, sc, beta[c]);
+    }
 }
 
-// forward apply: y = act((x - mean) * rstd * gamma + beta) with the fp32 stats {mean, rstd} of gn_finalize_kernel.
-// Same slab geometry as the reduction: the affine pair (scale, shift) per owned channel lives in registers.
-__global__ void __launch_bounds__(512)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float* __restrict__ stats, __nv_bfloat16* __restrict__ y, int HW, int C, int G, int silu,
-                int rows_per_cta) {
+// y = act(x*sc + sh): flat pass, grid (blocks, n)
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef, __nv_bfloat16* __restrict__ y,
+                int n_img, int HW, int C, int silu) {
     const int n = blockIdx.y;
     const int chunks = C / 8;
-    const int cpg = C / G;
-    const int rows_par = blockDim.x / chunks;
-    const int chunk = threadIdx.x % chunks;
-    const int rsub = threadIdx.x / chunks;
-    if (rsub >= rows_par) return;
-    const int row0 = blockIdx.x * rows_per_cta;
-    const int row1 = min(HW, row0 + rows_per_cta);
-    const int c0 = chunk * 8;
-    float sc[8], sh[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int g = (c0 + j) / cpg;
-        const float mu = stats[(n * G + g) * 2], rs = stats[(n * G + g) * 2 + 1];
-        sc[j] = rs * gamma[c0 + j];
-        sh[j] = fmaf(-mu, sc[j], beta[c0 + j]);
-    }
-    const __nv_bfloat16* xp = x + (long long)n * HW * C + c0;
-    __nv_bfloat16* yp = y + (long long)n * HW * C + c0;
-    const long long rstep = (long long)rows_par * C;
-    auto emit = [&](const uint4& u, __nv_bfloat16* dst) {
-        float xv[8], o[8];
-        unpack8(u, xv);
+    const int total = HW * chunks;                      // < 2^31: HW * C / 8
+    const __nv_bfloat16* xp = x + (long long)n * HW * C;
+    __nv_bfloat16* yp = y + (long long)n * HW * C;
+    const float* scp = coef + (size_t)n * C;
+    const float* shp = coef + (size_t)(n_img + n) * C;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+        const int i1 = i + stride;
+        const bool ok1 = i1 < total;
+        const uint4 u0 = ldg16(xp + (long long)i * 8);
+        const uint4 u1 = ldg16(xp + (long long)(ok1 ? i1 : i) * 8);
+        const int c0 = (i % chunks) * 8, c1 = ((ok1 ? i1 : i) % chunks) * 8;
+        float xv[8], sc[8], sh[8], o[8];
+        unpack8(u0, xv);
+        ldg8f(scp + c0, sc);
+        ldg8f(shp + c0, sh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float z = fmaf(xv[j], sc[j], sh[j]);
             o[j] = silu ? z * fast_sigmoid(z) : z;
         }
-        store8(dst, o);
-    };
-    int r = row0 + rsub;
-    for (; r + 3 * rows_par < row1; r += 4 * rows_par) {
-        uint4 u[4];
+        store8(yp + (long long)i * 8, o);
+        if (ok1) {
+            unpack8(u1, xv);
+            ldg8f(scp + c1, sc);
+            ldg8f(shp + c1, sh);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) u[k] = ldg16(xp + (long long)r * C + k * rstep);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) emit(u[k], yp + (long long)r * C + k * rstep);
+            for (int j = 0; j < 8; ++j) {
+                const float z = fmaf(xv[j], sc[j], sh[j]);
+                o[j] = silu ? z * fast_sigmoid(z) : z;
+            }
+            store8(yp + (long long)i1 * 8, o);
+        }
     }
-    for (; r < row1; r += rows_par) emit(ldg16(xp + (long long)r * C), yp + (long long)r * C);
 }
 
-// backward apply: dx (+)= rstd * (dz*gamma - s1/m - xhat * s2/m)
+// backward coefficients, one CTA per image:  dx = dz*A - K1 - x*K2,  z = x*A + Bz  (planes 0..3 = A, Bz, K1, K2) from
+// the channel sums S1 = sum dz*x, S2 = sum dz:   sum dz*xhat = rstd*(S1 - mean*S2);   also dgamma / dbeta.
 __global__ void __launch_bounds__(512)
+gn_bwd_coef_kernel(const float* __restrict__ csum, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ stats, float* __restrict__ coef, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, int n_img, int C, int G, float inv_m) {
+    extern __shared__ float gs[];          // [2][G] group sums: sum dz*gamma, sum dz*gamma*xhat
+    const int n = blockIdx.x;
+    const int cpg = C / G;
+    for (int g = threadIdx.x; g < 2 * G; g += blockDim.x) gs[g] = 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float mu = stats[(n * G + g) * 2], rs = stats[(n * G + g) * 2 + 1];
+        const float s1 = csum[(size_t)n * C + c], s2 = csum[(size_t)(n_img + n) * C + c];
+        const float dzxh = rs * fmaf(-mu, s2, s1);          // sum dz*xhat of this channel
+        const float gm = gamma[c];
+        atomicAdd(&gs[g], gm * s2);
+        atomicAdd(&gs[G + g], gm * dzxh);
+        if (dgamma != nullptr) {
+            atomicAdd(&dgamma[c], dzxh);
+            atomicAdd(&dbeta[c], s2);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float mu = stats[(n * G + g) * 2], rs = stats[(n * G + g) * 2 + 1];
+        const float A = rs * gamma[c];
+        const float K2 = rs * rs * gs[G + g] * inv_m;
+        coef[(size_t)n * C + c] = A;
+        coef[(size_t)(n_img + n) * C + c] = fmaf(-mu, A, beta[c]);
+        coef[(size_t)(2 * n_img + n) * C + c] = fmaf(-mu, K2, rs * gs[g] * inv_m);
+        coef[(size_t)(3 * n_img + n) * C + c] = K2;
+    }
+}
+
+// dx (+)= dz*A - K1 - x*K2: flat pass, grid (blocks, n)
+__global__ void __launch_bounds__(256, 5)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
-                    const double* __restrict__ ws, __nv_bfloat16* __restrict__ dx, int HW, int C, int G, int silu,
-                    int accumulate, int rows_per_cta) {
+                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx, int n_img, int HW, int C, int silu,
+                    int accumulate) {
     const int n = blockIdx.y;
     const int chunks = C / 8;
-    const int cpg = C / G;
-    const int rows_par = blockDim.x / chunks;
-    const int chunk = threadIdx.x % chunks;
-    const int rsub = threadIdx.x / chunks;
-    if (rsub >= rows_par) return;
-    const int row0 = blockIdx.x * rows_per_cta;
-    const int row1 = min(HW, row0 + rows_per_cta);
-    const int c0 = chunk * 8;
-    const float inv_m = 1.f / ((float)HW * cpg);
-    // dx = dz*A - K1 - x*K2 with A = rs*gamma, K2 = rs^2*s2/m, K1 = rs*s1/m - mu*K2;  z = x*A + Bz, Bz = beta - mu*A
-    float A[8], Bz[8], K1[8], K2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int g = (c0 + j) / cpg;
-        const float mu = stats[(n * G + g) * 2];
-        const float rs = stats[(n * G + g) * 2 + 1];
-        A[j] = rs * gamma[c0 + j];
-        Bz[j] = fmaf(-mu, A[j], beta[c0 + j]);
-        K2[j] = rs * rs * (float)ws[(n * G + g) * 2 + 1] * inv_m;
-        K1[j] = fmaf(-mu, K2[j], rs * (float)ws[(n * G + g) * 2] * inv_m);
-    }
-    const __nv_bfloat16* xp = x + (long long)n * HW * C + c0;
-    const __nv_bfloat16* dp = dy + (long long)n * HW * C + c0;
-    __nv_bfloat16* op = dx + (long long)n * HW * C + c0;
-    const long long rstep = (long long)rows_par * C;
-    auto emit = [&](const uint4& ux, const uint4& ud, __nv_bfloat16* dst) {
-        float xv[8], dv[8], o[8];
+    const int total = HW * chunks;
+    const long long base = (long long)n * HW * C;
+    const float* Ap = coef + (size_t)n * C;
+    const float* Bp = coef + (size_t)(n_img + n) * C;
+    const float* K1p = coef + (size_t)(2 * n_img + n) * C;
+    const float* K2p = coef + (size_t)(3 * n_img + n) * C;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint4 ux = ldg16(x + base + (long long)i * 8), ud = ldg16(dy + base + (long long)i * 8);
+        const int c0 = (i % chunks) * 8;
+        float xv[8], dv[8], A[8], k[8], o[8];
         unpack8(ux, xv);
         unpack8(ud, dv);
-        if (accumulate) load8(dst, o);
+        ldg8f(Ap + c0, A);
+        if (silu) {
+            ldg8f(Bp + c0, k);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float dz = dv[j];
-            if (silu) {
-                const float z = fmaf(xv[j], A[j], Bz[j]);
-                const float s = fast_sigmoid(z);
-                dz *= s * (1.f + z * (1.f - s));
-            }
-            const float d = fmaf(dz, A[j], -fmaf(xv[j], K2[j], K1[j]));
-            o[j] = accumulate ? o[j] + d : d;
-        }
-        store8(dst, o);
-    };
-    int r = row0 + rsub;
-    for (; r + 3 * rows_par < row1; r += 4 * rows_par) {
-        uint4 ux[4], ud[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            ux[k] = ldg16(xp + (long long)r * C + k * rstep);
-            ud[k] = ldg16(dp + (long long)r * C + k * rstep);
+            for (int j = 0; j < 8; ++j) dv[j] *= silu_grad_fast(fmaf(xv[j], A[j], k[j]));
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) emit(ux[k], ud[k], op + (long long)r * C + k * rstep);
+        for (int j = 0; j < 8; ++j) o[j] = dv[j] * A[j];
+        ldg8f(K1p + c0, k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] -= k[j];
+        ldg8f(K2p + c0, k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(-xv[j], k[j], o[j]);
+        if (accumulate) {
+            float p[8];
+            load8(dx + base + (long long)i * 8, p);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += p[j];
+        }
+        store8(dx + base + (long long)i * 8, o);
     }
-    for (; r < row1; r += rows_par)
-        emit(ldg16(xp + (long long)r * C), ldg16(dp + (long long)r * C), op + (long long)r * C);
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
 // One warp per row; the row (C <= 2560) lives in registers.
 static constexpr int LN_MAX_IT = 10;  // 10 * 32 lanes * 8 = 2560 channels
 
-template <int LN_IT>
+// ROWS rows per warp are processed together: all their 16-byte loads are issued before the first reduction, which
+// doubles the bytes in flight per SM for the narrow (C = 320 / 640) rows.
+template <int LN_IT, int ROWS>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ stats, int T, int C, float eps) {
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= T) return;
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+    if (row0 >= T) return;
     const int chunks = C / 8;
-    float v[LN_IT][8];
-    float s = 0.f;
+    float v[ROWS][LN_IT][8];
+    float s[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int row = min(row0 + r, T - 1);
+        s[r] = 0.f;
+#pragma unroll
+        for (int it = 0; it < LN_IT; ++it) {
+            const int ch = it * 32 + lane;
+            if (ch < chunks) load8(x + (long long)row * C + ch * 8, v[r][it]);
+        }
+    }
+    float mu[ROWS], rs[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+        for (int it = 0; it < LN_IT; ++it) {
+            if (it * 32 + lane < chunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[r] += v[r][it][j];
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) mu[r] = warp_sum(s[r]) / C;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        float q = 0.f;
+#pragma unroll
+        for (int it = 0; it < LN_IT; ++it) {
+            if (it * 32 + lane < chunks) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float d = v[r][it][j] - mu[r]; q = fmaf(d, d, q); }
+            }
+        }
+        s[r] = q;
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) rs[r] = rsqrtf(warp_sum(s[r]) / C + eps);
 #pragma unroll
     for (int it = 0; it < LN_IT; ++it) {
         const int ch = it * 32 + lane;
         if (ch < chunks) {
-            load8(x + (long long)row * C + ch * 8, v[it]);
+            float g[8], bt[8];
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8 + 4));
+            g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+            bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s += v[it][j];
+            for (int r = 0; r < ROWS; ++r) {
+                if (row0 + r < T) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = fmaf((v[r][it][j] - mu[r]) * rs[r], g[j], bt[j]);
+                    store8(y + (long long)(row0 + r) * C + ch * 8, o);
+                }
+            }
         }
     }
-    const float mu = warp_sum(s) / C;
-    float q = 0.f;
+    if (lane == 0 && stats != nullptr) {
 #pragma unroll
-    for (int it = 0; it < LN_IT; ++it) {
-        const int ch = it * 32 + lane;
-        if (ch < chunks) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { const float d = v[it][j] - mu; q += d * d; }
-        }
+        for (int r = 0; r < ROWS; ++r)
+            if (row0 + r < T) { stats[(row0 + r) * 2] = mu[r]; stats[(row0 + r) * 2 + 1] = rs[r]; }
     }
-    const float rs = rsqrtf(warp_sum(q) / C + eps);
-#pragma unroll
-    for (int it = 0; it < LN_IT; ++it) {
-        const int ch = it * 32 + lane;
-        if (ch < chunks) {
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = (v[it][j] - mu) * rs * gamma[ch * 8 + j] + beta[ch * 8 + j];
-            store8(y + (long long)row * C + ch * 8, o);
-        }
-    }
-    if (lane == 0 && stats != nullptr) { stats[row * 2] = mu; stats[row * 2 + 1] = rs; }
 }
 
-template <int LN_IT>
+template <int LN_IT, int ROWS>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
               const float* __restrict__ gamma, const float* __restrict__ stats, __nv_bfloat16* __restrict__ dx, int T,
               int C, int accumulate) {
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= T) return;
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+    if (row0 >= T) return;
     const int chunks = C / 8;
-    const float mu = stats[row * 2], rs = stats[row * 2 + 1];
-    float xh[LN_IT][8], dg[LN_IT][8];
-    float s1 = 0.f, s2 = 0.f;
+    float xh[ROWS][LN_IT][8], dg[ROWS][LN_IT][8];
+    float mu[ROWS], rs[ROWS], s1[ROWS], s2[ROWS];
+    // raw loads of every row first (bf16 data parked in the fp32 arrays' storage after unpacking)
 #pragma unroll
-    for (int it = 0; it < LN_IT; ++it) {
-        const int ch = it * 32 + lane;
-        if (ch < chunks) {
-            float xv[8], dv[8];
-            load8(x + (long long)row * C + ch * 8, xv);
-            load8(dy + (long long)row * C + ch * 8, dv);
+    for (int r = 0; r < ROWS; ++r) {
+        const int row = min(row0 + r, T - 1);
+        mu[r] = stats[row * 2];
+        rs[r] = stats[row * 2 + 1];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                xh[it][j] = (xv[j] - mu) * rs;
-                dg[it][j] = dv[j] * gamma[ch * 8 + j];
-                s1 += dg[it][j];
-                s2 += dg[it][j] * xh[it][j];
+        for (int it = 0; it < LN_IT; ++it) {
+            const int ch = it * 32 + lane;
+            if (ch < chunks) {
+                load8(x + (long long)row * C + ch * 8, xh[r][it]);
+                load8(dy + (long long)row * C + ch * 8, dg[r][it]);
             }
         }
     }
-    s1 = warp_sum(s1) / C;
-    s2 = warp_sum(s2) / C;
 #pragma unroll
-    for (int it = 0; it < LN_IT; ++it) {
-        const int ch = it * 32 + lane;
-        if (ch < chunks) {
-            float o[8];
-            if (accumulate) load8(dx + (long long)row * C + ch * 8, o);
+    for (int r = 0; r < ROWS; ++r) {
+        s1[r] = 0.f; s2[r] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float d = rs * (dg[it][j] - s1 - xh[it][j] * s2);
-                o[j] = accumulate ? o[j] + d : d;
+        for (int it = 0; it < LN_IT; ++it) {
+            const int ch = it * 32 + lane;
+            if (ch < chunks) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[r][it][j] = (xh[r][it][j] - mu[r]) * rs[r];
+                    dg[r][it][j] *= g[j];
+                    s1[r] += dg[r][it][j];
+                    s2[r] = fmaf(dg[r][it][j], xh[r][it][j], s2[r]);
+                }
             }
-            store8(dx + (long long)row * C + ch * 8, o);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) { s1[r] = warp_sum(s1[r]) / C; s2[r] = warp_sum(s2[r]) / C; }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (row0 + r < T) {
+#pragma unroll
+            for (int it = 0; it < LN_IT; ++it) {
+                const int ch = it * 32 + lane;
+                if (ch < chunks) {
+                    float o[8];
+                    if (accumulate) load8(dx + (long long)(row0 + r) * C + ch * 8, o);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float d = rs[r] * (dg[r][it][j] - s1[r] - xh[r][it][j] * s2[r]);
+                        o[j] = accumulate ? o[j] + d : d;
+                    }
+                    store8(dx + (long long)(row0 + r) * C + ch * 8, o);
+                }
+            }
         }
     }
 }
@@ -403,29 +465,43 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
 
 using namespace clb;
 
-static int gn_launch_geometry(int HW, int C, int n, int& threads, int& rows_per_cta, int& grid_x, int ctas_per_sm = 2) {
+static int gn_launch_geometry(int HW, int C, int n, int& threads, int& rows_per_cta, int& grid_x) {
     const int chunks = C / 8;
     if (C % 8 != 0 || chunks > GN_MAX_CHUNKS) return set_error(CL_ERR_UNSUPPORTED, "groupnorm: C must be a multiple of 8 and <= 4096");
     int rows_par = 512 / chunks;
     if (rows_par < 1) rows_par = 1;
     threads = ((rows_par * chunks + 31) / 32) * 32;
     if (threads > 512) { rows_par = 1; threads = ((chunks + 31) / 32) * 32; }
-    // one wave of ctas_per_sm CTAs per SM across the batch
-    int target_ctas = (num_sms() * ctas_per_sm + n - 1) / n;
+    // ~4 CTAs per SM across the batch (2 resident at a time), but at least 4 row groups per CTA
+    int target_ctas = (num_sms() * 4 + n - 1) / n;
     rows_per_cta = (HW + target_ctas - 1) / target_ctas;
-    if (rows_per_cta < rows_par) rows_per_cta = rows_par;
+    if (rows_per_cta < 4 * rows_par) rows_per_cta = 4 * rows_par;
     grid_x = (HW + rows_per_cta - 1) / rows_per_cta;
     return CL_OK;
 }
+
+static int gn_flat_blocks(int HW, int C, int n, int per_thread) {
+    const long long total = (long long)HW * (C / 8);
+    long long blocks = (total + 256LL * per_thread - 1) / (256LL * per_thread);
+    const long long cap = ((long long)num_sms() * 16 + n - 1) / n;     // ~2 waves of 8 resident 256-thread CTAs per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+extern "C" int64_t cl_groupnorm_ws_bytes(int n, int G, int C) { return (int64_t)16 * n * G + (int64_t)24 * n * C; }
 
 extern "C" int cl_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
                                 double* ws, int n, int HW, int C, int G, float eps, int silu, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!x || !gamma || !beta || !y || !ws) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: null pointer");
+    if (stats == nullptr) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: stats buffer is required");
     if (G <= 0 || C % G != 0) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: C %% G != 0");
     int threads, rows_per_cta, grid_x;
     CL_CHECK(gn_launch_geometry(HW, C, n, threads, rows_per_cta, grid_x));
-    CL_CUDA_CHECK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * n * G, stream));
+    double* gsum = ws;
+    float* coef = reinterpret_cast<float*>(ws + (size_t)2 * n * G);
+    CL_CUDA_CHECK(cudaMemsetAsync(gsum, 0, sizeof(double) * 2 * n * G, stream));
     const size_t rsmem = (size_t)2 * (threads / (C / 8) + 1) * C * sizeof(float);
     {
         static bool done = false;
@@ -434,16 +510,12 @@ extern "C" int cl_groupnorm_fwd(const void* x, const float* gamma, const float* 
             done = true;
         }
     }
-    gn_reduce_kernel<0><<<dim3(grid_x, n), threads, rsmem, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, ws, nullptr, nullptr, HW, C, G,
-        rows_per_cta, 0);
-    if (stats == nullptr) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: stats buffer is required");
-    gn_finalize_kernel<<<(n * G + 127) / 128, 128, 0, stream>>>(ws, stats, n * G, 1.0 / ((double)HW * (C / G)), eps);
-    int a_threads, a_rows, a_grid;
-    CL_CHECK(gn_launch_geometry(HW, C, n, a_threads, a_rows, a_grid, 8));
-    gn_apply_kernel<<<dim3(a_grid, n), a_threads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
-                                                               stats, reinterpret_cast<__nv_bfloat16*>(y), HW, C, G,
-                                                               silu, a_rows);
+    const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+    gn_reduce_kernel<0><<<dim3(grid_x, n), threads, rsmem, stream>>>(xx, nullptr, nullptr, nullptr, nullptr, gsum, nullptr, n,
+                                                                      HW, C, G, rows_per_cta, 0);
+    gn_fwd_coef_kernel<<<n, 256, 0, stream>>>(gsum, gamma, beta, stats, coef, n, C, G, 1.0 / ((double)HW * (C / G)), eps);
+    gn_apply_kernel<<<dim3(gn_flat_blocks(HW, C, n, 2), n), 256, 0, stream>>>(xx, coef, reinterpret_cast<__nv_bfloat16*>(y), n,
+                                                                              HW, C, silu);
     count_launch(3);
     CL_CUDA_CHECK(cudaGetLastError());
     return CL_OK;
@@ -455,9 +527,12 @@ extern "C" int cl_groupnorm_bwd(const void* x, const void* dy, const float* gamm
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!x || !dy || !gamma || !beta || !stats || !dx || !ws) return set_error(CL_ERR_INVALID, "cl_groupnorm_bwd: null pointer");
     if (G <= 0 || C % G != 0) return set_error(CL_ERR_INVALID, "cl_groupnorm_bwd: C %% G != 0");
+    if (G > 4096) return set_error(CL_ERR_UNSUPPORTED, "cl_groupnorm_bwd: G <= 4096");
     int threads, rows_per_cta, grid_x;
     CL_CHECK(gn_launch_geometry(HW, C, n, threads, rows_per_cta, grid_x));
-    CL_CUDA_CHECK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * n * G, stream));
+    float* coef = reinterpret_cast<float*>(ws + (size_t)2 * n * G);
+    float* csum = coef + (size_t)4 * n * C;
+    CL_CUDA_CHECK(cudaMemsetAsync(csum, 0, sizeof(float) * 2 * n * C, stream));
     const size_t rsmem = (size_t)2 * (threads / (C / 8) + 1) * C * sizeof(float);
     {
         static bool done = false;
@@ -466,15 +541,15 @@ extern "C" int cl_groupnorm_bwd(const void* x, const void* dy, const float* gamm
             done = true;
         }
     }
-    gn_reduce_kernel<1><<<dim3(grid_x, n), threads, rsmem, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, beta, stats, ws,
-        dgamma, dbeta, HW, C, G, rows_per_cta, silu);
-    int a_threads, a_rows, a_grid;
-    CL_CHECK(gn_launch_geometry(HW, C, n, a_threads, a_rows, a_grid, 8));
-    gn_bwd_apply_kernel<<<dim3(a_grid, n), a_threads, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, beta, stats, ws,
-        reinterpret_cast<__nv_bfloat16*>(dx), HW, C, G, silu, accumulate, a_rows);
-    count_launch(2);
+    const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+    const __nv_bfloat16* dd = reinterpret_cast<const __nv_bfloat16*>(dy);
+    gn_reduce_kernel<1><<<dim3(grid_x, n), threads, rsmem, stream>>>(xx, dd, gamma, beta, stats, nullptr, csum, n, HW, C, G,
+                                                                      rows_per_cta, silu);
+    gn_bwd_coef_kernel<<<n, 512, 2 * G * sizeof(float), stream>>>(csum, gamma, beta, stats, coef, dgamma, dbeta, n, C, G,
+                                                                  1.f / ((float)HW * (C / G)));
+    gn_bwd_apply_kernel<<<dim3(gn_flat_blocks(HW, C, n, 1), n), 256, 0, stream>>>(xx, dd, coef, reinterpret_cast<__nv_bfloat16*>(dx),
+                                                                                  n, HW, C, silu, accumulate);
+    count_launch(3);
     CL_CUDA_CHECK(cudaGetLastError());
     return CL_OK;
 }
@@ -484,8 +559,8 @@ extern "C" int cl_layernorm_fwd(const void* x, const float* gamma, const float* 
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!x || !gamma || !beta || !y) return set_error(CL_ERR_INVALID, "cl_layernorm_fwd: null pointer");
     if (C % 8 != 0 || C > LN_MAX_IT * 256) return set_error(CL_ERR_UNSUPPORTED, "cl_layernorm_fwd: C must be a multiple of 8, <= 2560");
-#define LN_FWD(IT) ln_fwd_kernel<IT><<<(T + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), stats, T, C, eps)
-    if (C <= 512) LN_FWD(2); else if (C <= 768) LN_FWD(3); else if (C <= 1280) LN_FWD(5); else LN_FWD(10);
+#define LN_FWD(IT, R) ln_fwd_kernel<IT, R><<<(T + 8 * R - 1) / (8 * R), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), stats, T, C, eps)
+    if (C <= 512) LN_FWD(2, 2); else if (C <= 768) LN_FWD(3, 2); else if (C <= 1280) LN_FWD(5, 1); else LN_FWD(10, 1);
 #undef LN_FWD
     count_launch();
     CL_CUDA_CHECK(cudaGetLastError());
@@ -497,8 +572,8 @@ extern "C" int cl_layernorm_bwd(const void* x, const void* dy, const float* gamm
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!x || !dy || !gamma || !stats || !dx) return set_error(CL_ERR_INVALID, "cl_layernorm_bwd: null pointer");
     if (C % 8 != 0 || C > LN_MAX_IT * 256) return set_error(CL_ERR_UNSUPPORTED, "cl_layernorm_bwd: C must be a multiple of 8, <= 2560");
-#define LN_BWD(IT) ln_bwd_kernel<IT><<<(T + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, stats, reinterpret_cast<__nv_bfloat16*>(dx), T, C, accumulate)
-    if (C <= 512) LN_BWD(2); else if (C <= 768) LN_BWD(3); else if (C <= 1280) LN_BWD(5); else LN_BWD(10);
+#define LN_BWD(IT, R) ln_bwd_kernel<IT, R><<<(T + 8 * R - 1) / (8 * R), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, stats, reinterpret_cast<__nv_bfloat16*>(dx), T, C, accumulate)
+    if (C <= 512) LN_BWD(2, 1); else if (C <= 768) LN_BWD(3, 1); else if (C <= 1280) LN_BWD(5, 1); else LN_BWD(10, 1);
 #undef LN_BWD
     count_launch();
     CL_CUDA_CHECK(cudaGetLastError());

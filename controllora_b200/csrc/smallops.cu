@@ -16,41 +16,66 @@ __device__ __forceinline__ float siluf(float z) { return z / (1.f + __expf(-z));
 
 // ------------------------------------------------------------------------------------------ conv_in (3x3, Cin small)
 // x: NCHW fp32 [n, Cin, H, W] (rounded to bf16 on load == the reference's cast to weight_dtype), w: bf16 [Cout][3][3][Cin],
-// y: NHWC bf16 [n, H, W, Cout].  CTA = 32 consecutive pixels of one image row-major; thread = (pixel, co) pairs.
+// y: NHWC bf16 [n, H, W, Cout].  Thread = one output pixel x 32 output channels (blockIdx.y picks the channel group):
+// the 9*Cin inputs and the 32 accumulators live in registers, the weights are read from shared memory as broadcast
+// 16-byte loads ([k][32] layout), so the kernel is FMA-bound (~4 FMAs per shared-memory word) instead of LDS-bound.
 template <int CIN>
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
                __nv_bfloat16* __restrict__ y, int n, int H, int W, int Cout) {
     constexpr int KK = 9 * CIN;
-    extern __shared__ float sm[];
-    float* sw = sm;                 // [Cout][KK]
-    float* sx = sm + Cout * KK;     // [32][KK]
-    for (int i = threadIdx.x; i < Cout * KK; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
-    const long long pix0 = (long long)blockIdx.x * 32;
-    const long long npix = (long long)n * H * W;
-    for (int i = threadIdx.x; i < 32 * KK; i += blockDim.x) {
-        const int pl = i / KK, k = i % KK;
-        const long long pix = pix0 + pl;
-        float v = 0.f;
-        if (pix < npix) {
-            const int tap = k / CIN, ci = k % CIN;
-            const int b = (int)(pix / (H * W));
-            const int hw = (int)(pix % (H * W));
-            const int h = hw / W + tap / 3 - 1, ww = hw % W + tap % 3 - 1;
-            if (h >= 0 && h < H && ww >= 0 && ww < W)
-                v = __bfloat162float(__float2bfloat16(x[(((long long)b * CIN + ci) * H + h) * W + ww]));
-        }
-        sx[i] = v;
+    __shared__ __align__(16) float sw[KK * 32];     // [k][32 channels of this group]
+    __shared__ float sb[32];
+    const int co0 = blockIdx.y * 32;
+    for (int i = threadIdx.x; i < KK * 32; i += blockDim.x) {
+        const int k = i / 32, c = i % 32;
+        sw[i] = (co0 + c < Cout) ? __bfloat162float(w[(size_t)(co0 + c) * KK + k]) : 0.f;
     }
+    if (threadIdx.x < 32) sb[threadIdx.x] = (bias != nullptr && co0 + threadIdx.x < Cout) ? bias[co0 + threadIdx.x] : 0.f;
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * Cout; i += blockDim.x) {
-        const int pl = i / Cout, co = i % Cout;
-        const long long pix = pix0 + pl;
-        if (pix >= npix) continue;
-        float acc = bias ? bias[co] : 0.f;
+    const long long npix = (long long)n * H * W;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const int b = (int)(pix / (H * W));
+    const int hw = (int)(pix % (H * W));
+    const int h0 = hw / W, w0 = hw % W;
+    float xin[KK];
 #pragma unroll
-        for (int k = 0; k < KK; ++k) acc += sx[pl * KK + k] * sw[co * KK + k];
-        y[pix * Cout + co] = __float2bfloat16(acc);
+    for (int tap = 0; tap < 9; ++tap) {
+        const int h = h0 + tap / 3 - 1, ww = w0 + tap % 3 - 1;
+        const bool ok = h >= 0 && h < H && ww >= 0 && ww < W;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+            xin[tap * CIN + ci] = ok ? __bfloat162float(__float2bfloat16(__ldg(x + (((long long)b * CIN + ci) * H + h) * W + ww))) : 0.f;
+    }
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = sb[c];
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+        const float xv = xin[k];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 w4 = *reinterpret_cast<const float4*>(sw + k * 32 + q * 4);
+            acc[4 * q] = fmaf(xv, w4.x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(xv, w4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(xv, w4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(xv, w4.w, acc[4 * q + 3]);
+        }
+    }
+    __nv_bfloat16* yp = y + pix * Cout + co0;
+    if (co0 + 32 <= Cout) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(acc[8 * q], acc[8 * q + 1]); o.y = pack_bf16x2(acc[8 * q + 2], acc[8 * q + 3]);
+            o.z = pack_bf16x2(acc[8 * q + 4], acc[8 * q + 5]); o.w = pack_bf16x2(acc[8 * q + 6], acc[8 * q + 7]);
+            *reinterpret_cast<uint4*>(yp + 8 * q) = o;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (co0 + c < Cout) yp[c] = __float2bfloat16(acc[c]);
     }
 }
 
@@ -233,20 +258,13 @@ extern "C" int cl_conv_in(const float* x, const void* w, const float* bias, void
     STREAM;
     if (!x || !w || !y) return set_error(CL_ERR_INVALID, "cl_conv_in: null");
     const long long npix = (long long)n * H * W;
-    const int grid = (int)((npix + 31) / 32);
-    const size_t smem = (size_t)(Cout + 32) * 9 * Cin * sizeof(float);
-    if (smem > 200 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_in: weights do not fit shared memory");
+    if (Cout % 8 != 0) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_in: Cout must be a multiple of 8");
+    const dim3 grid((unsigned)((npix + 255) / 256), (unsigned)((Cout + 31) / 32));
 #define CONV_IN_CASE(CI)                                                                                         \
-    case CI: {                                                                                                   \
-        static bool done = false;                                                                                \
-        if (!done) {                                                                                             \
-            CL_CUDA_CHECK(cudaFuncSetAttribute(conv_in_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-            done = true;                                                                                         \
-        }                                                                                                        \
-        conv_in_kernel<CI><<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(w), bias,      \
-                                                        reinterpret_cast<__nv_bfloat16*>(y), n, H, W, Cout);     \
-        break;                                                                                                   \
-    }
+    case CI:                                                                                                     \
+        conv_in_kernel<CI><<<grid, 256, 0, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(w), bias,         \
+                                                     reinterpret_cast<__nv_bfloat16*>(y), n, H, W, Cout);        \
+        break;
     switch (Cin) {
         CONV_IN_CASE(3)
         CONV_IN_CASE(4)

@@ -195,61 +195,94 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
 
 // ---------------------------------------------------------------------------------------------- conv_in weight grad
 // dW[co][ci][ky][kx] += sum_pix dY[pix][co] * x[n, ci, h+ky-1, w+kx-1];  x NCHW fp32 (bf16-rounded), dY NHWC bf16.
+// A CTA walks its pixel range in blocks of 64 pixels staged in shared memory (im2col rows sx[pixel][k], dY rows
+// sdy[pixel][32 channels of blockIdx.y's group]).  Thread = (pixel subset, 4 channels, 4 taps): 16 accumulators fed by
+// two 16-byte shared loads per pixel, i.e. 8 FMAs per shared-memory instruction (the first version did 0.5).
 template <int CIN>
 __global__ void __launch_bounds__(256)
 conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, int n, int H, int W,
                      int Cout, int pix_per_cta) {
-    constexpr int KK = 9 * CIN;
-    extern __shared__ float sm[];
-    float* sx = sm;                 // [64][KK]
-    float* sdy = sm + 64 * KK;      // [64][Cout]
+    constexpr int KK = 9 * CIN, KP = (KK + 3) / 4 * 4, KG = KP / 4, TPS = 8 * KG;
+    constexpr int PS = (CIN == 3) ? 4 : 2;          // pixel subsets (PS * TPS <= 256)
+    constexpr int PB = 64, PPS = PB / PS;
+    static_assert(PS * TPS <= 256, "thread layout");
+    __shared__ __align__(16) float sx[PB][KP];
+    __shared__ __align__(16) float sdy[PB][32];
+    __shared__ float red[PS][32][KP];
+    const int tid = threadIdx.x;
+    const int sub = tid / TPS, within = tid % TPS;
+    const int cg = within / KG, kg = within % KG;
+    const bool active = sub < PS;
+    const int co0 = blockIdx.y * 32;
     const long long npix = (long long)n * H * W;
     const long long p0 = (long long)blockIdx.x * pix_per_cta;
     const long long p1 = min(npix, p0 + pix_per_cta);
-    // each thread owns outputs o = tid, tid+256, ...  (o = co*KK + k)
-    const int nout = Cout * KK;
-    float acc[8];
+    float acc[4][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (long long pb = p0; pb < p1; pb += 64) {
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
+    for (int i = tid; i < PB * (KP - KK); i += 256) sx[i / (KP - KK > 0 ? KP - KK : 1)][KK + i % (KP - KK > 0 ? KP - KK : 1)] = 0.f;   // pad taps
+    for (long long pb = p0; pb < p1; pb += PB) {
         __syncthreads();
-        for (int i = threadIdx.x; i < 64 * KK; i += blockDim.x) {
-            const int pl = i / KK, k = i % KK;
+        for (int i = tid; i < PB * 9; i += 256) {        // one (pixel, tap) per item: the coordinate math is shared by the CIN loads
+            const int pl = i / 9, tap = i % 9;
             const long long pix = pb + pl;
-            float v = 0.f;
-            if (pix < p1) {
-                const int tap = k / CIN, ci = k % CIN;
+            bool ok = pix < p1;
+            long long src = 0;
+            if (ok) {
                 const int b = (int)(pix / (H * W));
                 const int hw = (int)(pix % (H * W));
                 const int h = hw / W + tap / 3 - 1, ww = hw % W + tap % 3 - 1;
-                if (h >= 0 && h < H && ww >= 0 && ww < W)
-                    v = __bfloat162float(__float2bfloat16(x[(((long long)b * CIN + ci) * H + h) * W + ww]));
+                ok = h >= 0 && h < H && ww >= 0 && ww < W;
+                src = ((long long)b * CIN * H + h) * W + ww;
             }
-            sx[i] = v;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+                sx[pl][tap * CIN + ci] = ok ? __bfloat162float(__float2bfloat16(__ldg(x + src + (long long)ci * H * W))) : 0.f;
         }
-        for (int i = threadIdx.x; i < 64 * Cout; i += blockDim.x) {
-            const long long pix = pb + i / Cout;
-            sdy[i] = (pix < p1) ? __bfloat162float(dy[pix * Cout + i % Cout]) : 0.f;
+        for (int i = tid; i < PB * 8; i += 256) {
+            const int pl = i / 8, c4 = (i % 8) * 4;
+            const long long pix = pb + pl;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pix < p1 && co0 + c4 + 4 <= Cout) {      // Cout % 4 == 0 is enforced on the host
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(dy + pix * Cout + co0 + c4));
+                const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+                v = make_float4(a.x, a.y, c.x, c.y);
+            }
+            *reinterpret_cast<float4*>(&sdy[pl][c4]) = v;
         }
         __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (int pp = 0; pp < PPS; ++pp) {
+                const int pl = sub * PPS + pp;
+                const float4 d4 = *reinterpret_cast<const float4*>(&sdy[pl][cg * 4]);
+                const float4 x4 = *reinterpret_cast<const float4*>(&sx[pl][kg * 4]);
+                const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int o = threadIdx.x + i * 256;
-            if (o < nout) {
-                const int co = o / KK, k = o % KK;
-                float s = 0.f;
-                for (int pl = 0; pl < 64; ++pl) s += sdy[pl * Cout + co] * sx[pl * KK + k];
-                acc[i] += s;
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[c][k] = fmaf(dv[c], xv[k], acc[c][k]);
             }
         }
     }
+    if (active) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int o = threadIdx.x + i * 256;
-        if (o < nout) {
-            const int co = o / KK, k = o % KK;
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) red[sub][cg * 4 + c][kg * 4 + k] = acc[c][k];
+    }
+    __syncthreads();
+    for (int o = tid; o < 32 * KK; o += 256) {
+        const int co = o / KK, k = o % KK;
+        if (co0 + co < Cout) {
+            float v = 0.f;
+#pragma unroll
+            for (int s2 = 0; s2 < PS; ++s2) v += red[s2][co][k];
             const int tap = k / CIN, ci = k % CIN;
-            atomicAdd(&dw[((long long)co * CIN + ci) * 9 + tap], acc[i]);
+            atomicAdd(&dw[((long long)(co0 + co) * CIN + ci) * 9 + tap], v);
         }
     }
 }
@@ -351,15 +384,16 @@ extern "C" int cl_colsum(const void* x, float* out, int64_t M, int C, float alph
 extern "C" int cl_conv_in_wgrad(const float* x, const void* dy, float* dw, int n, int Cin, int H, int W, int Cout, void* stream_) {
     STREAM;
     if (!x || !dy || !dw) return set_error(CL_ERR_INVALID, "cl_conv_in_wgrad: null");
-    if (Cout * 9 * Cin > 8 * 256) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_in_wgrad: Cout*9*Cin must be <= 2048");
+    if (Cout % 4 != 0) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_in_wgrad: Cout must be a multiple of 4");
     const long long npix = (long long)n * H * W;
-    int ctas = num_sms() * 2;
-    int ppc = (int)((npix + ctas - 1) / ctas);
+    const int groups = (Cout + 31) / 32;
+    int ctas = (num_sms() * 8 + groups - 1) / groups;          // ~8 CTAs per SM over all channel groups
+    long long ppc = (npix + ctas - 1) / ctas;
     ppc = ((ppc + 63) / 64) * 64;
-    const int grid = (int)((npix + ppc - 1) / ppc);
-    const size_t smem = (size_t)64 * (9 * Cin + Cout) * sizeof(float);
-    if (Cin == 3) conv_in_wgrad_kernel<3><<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, n, H, W, Cout, ppc);
-    else if (Cin == 4) conv_in_wgrad_kernel<4><<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, n, H, W, Cout, ppc);
+    if (ppc < 256) ppc = 256;
+    const dim3 grid((unsigned)((npix + ppc - 1) / ppc), (unsigned)groups);
+    if (Cin == 3) conv_in_wgrad_kernel<3><<<grid, 256, 0, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, n, H, W, Cout, (int)ppc);
+    else if (Cin == 4) conv_in_wgrad_kernel<4><<<grid, 256, 0, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, n, H, W, Cout, (int)ppc);
     else return set_error(CL_ERR_UNSUPPORTED, "cl_conv_in_wgrad: Cin must be 3 or 4");
     DONE();
 }

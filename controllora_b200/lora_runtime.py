@@ -259,10 +259,10 @@ class LoraRuntime:
         ext = lp.v2_ext[which]
         # t = h Ac_h^T (tensor core, N = 16 hi/lo columns) + u_c
         th16 = ops.gemm(h2, ext, out_fp32=True)
-        t = ops.hilo_combine(th16, 1)                      # [T, 8], cols 0..rc-1 valid
         uc = lv.u[:, lp.col + 4 * which:]
-        ops.rowmat(uc, lp.v2_eye, 4, 1, rc, rc, 1.0, t, 8, accumulate=True)        # t[:, :rc] += u_c
-        out = Var(ops.rank_update(h.data, t, lp.v2_up[which], s), rg=True)
+        # one pass: t = hi+lo of th16 (+ u_c), h' = h + s * t Bc^T   ([T, 8] t, cols 0..rc-1 valid, kept for the backward)
+        out_data, t = ops.v2_inject_fwd(h.data, th16, uc, rc, lp.v2_up[which], s)
+        out = Var(out_data, rg=True)
         if ctx.tape is not None:
             def bwd():
                 dy = out.grad
@@ -270,7 +270,8 @@ class LoraRuntime:
                 if dy is None:
                     return
                 dy2 = dy.view(T, C)
-                dt = ops.rowdot(dy2, lp.v2_up[which])                           # [T, 4] = dy Bc   (unscaled)
+                # one pass over dy: dt = dy Bc (unscaled, [T, 4]) and dh = dy + s * dt Ac_h
+                dt, dh = ops.v2_inject_bwd(dy, lp.v2_up[which], lp.v2_down_tab[which], s, need_dh=h.rg)
                 # dBc[c, j] += s * sum_m dy[m, c] t[m, j]
                 ops.SKINNY.add(t, rc, dy2, self.grad_of(up), 1, rc, s)
                 # dAc_h[j, k] += s * sum_m dt[m, j] h[m, k] ; dAc_c likewise with c
@@ -279,7 +280,7 @@ class LoraRuntime:
                 ops.SKINNY.add(dt, rc, lv.c.data.view(T, lv.cc), gdown[:, C:], C + lv.cc, 1, s)
                 # dh = dy + s * dt Ac_h
                 if h.rg:
-                    E.give_tensor(h, ops.rank_update(dy, dt, lp.v2_down_tab[which], s))
+                    E.give_tensor(h, dh)
                 if lv.du is not None:
                     i = lp.col // 8
                     ops.rowmat(dt, lp.v2_eye, 4, 1, rc, rc, s, lv.du, 16 * lv.nb, out_mode=1, col_off=16 * i + 4 * which, lo_off=8)

@@ -166,13 +166,15 @@ def _p(t):
 _ws_cache = {}
 
 
-def _gn_ws(device, n, G):
-    key = (device, n * G)
-    ws = _ws_cache.get(key)
-    if ws is None:
-        ws = torch.empty(2 * n * G, device=device, dtype=torch.float64)
-        _ws_cache[key] = ws
-    return ws
+def _gn_ws(device, n, G, Cc):
+    """GroupNorm scratch (cl_groupnorm_ws_bytes): fp64 group sums + per-(image, channel) coefficient / sum planes."""
+    nbytes = 16 * n * G + 24 * n * Cc
+    key = (device, "gn")
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() * 8 < nbytes:
+        buf = torch.empty((nbytes + 7) // 8 + 1024, device=device, dtype=torch.float64)
+        _ws_cache[key] = buf
+    return buf
 
 
 def attention_fwd(q, k, v, heads: int, scale: float, out=None, need_lse=True):
@@ -208,7 +210,7 @@ def groupnorm_fwd(x, gamma, beta, G: int, eps: float, silu: bool, out=None):
     assert x.is_contiguous()
     y = torch.empty_like(x) if out is None else out
     stats = torch.empty(n, G, 2, device=x.device, dtype=torch.float32)
-    _call("cl_groupnorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(stats), _p(_gn_ws(x.device, n, G)),
+    _call("cl_groupnorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(stats), _p(_gn_ws(x.device, n, G, C_)),
           n, HW, C_, G, C.c_float(eps), int(silu))
     return y, stats
 
@@ -221,7 +223,7 @@ def groupnorm_bwd(x, dy, gamma, beta, stats, G: int, silu: bool, dx=None, accumu
         dx = torch.empty_like(x)
         accumulate = False
     _call("cl_groupnorm_bwd", _p(x), _p(dy), _p(gamma), _p(beta), _p(stats), _p(dx), _p(dgamma), _p(dbeta),
-          _p(_gn_ws(x.device, n, G)), n, HW, C_, G, int(silu), int(accumulate))
+          _p(_gn_ws(x.device, n, G, C_)), n, HW, C_, G, int(silu), int(accumulate))
     return dx
 
 
@@ -520,6 +522,30 @@ def rank_update(x, t, tab, alpha: float, out=None):
     out = torch.empty_like(x) if out is None else out
     _call("cl_rank_update", _p(x), _p(t), t.stride(0), _p(tab), tab.shape[1], C.c_float(alpha), _p(out), C.c_int64(M), Cc)
     return out
+
+
+def v2_inject_fwd(x, th16, uc, rc: int, tab, alpha: float):
+    """t = hilo(th16) + uc;  out = x + alpha * t[:, :4] @ tab^T.  x bf16 [..., C], th16 fp32 [M, 16], uc fp32 [M, >=rc] view,
+    tab fp32 [C, 4].  Returns (out, t [M, 8])."""
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    assert x.is_contiguous() and th16.is_contiguous() and th16.shape == (M, 16) and tab.shape == (Cc, 4)
+    out = torch.empty_like(x)
+    t = torch.empty(M, 8, device=x.device, dtype=torch.float32)
+    ldu = 0 if uc is None else uc.stride(0)
+    _call("cl_v2_inject_fwd", _p(x), _p(th16), _p(uc), ldu, rc, _p(tab), C.c_float(alpha), _p(out), _p(t), C.c_int64(M), Cc)
+    return out, t
+
+
+def v2_inject_bwd(dy, up_tab, down_tab, alpha: float, need_dh: bool):
+    """dt [M, 4] = dy @ up_tab;  dh = dy + alpha * dt @ down_tab^T (None unless need_dh)."""
+    Cc = dy.shape[-1]
+    M = dy.numel() // Cc
+    assert dy.is_contiguous()
+    dt = torch.empty(M, 4, device=dy.device, dtype=torch.float32)
+    dh = torch.empty_like(dy) if need_dh else None
+    _call("cl_v2_inject_bwd", _p(dy), _p(up_tab), _p(down_tab), C.c_float(alpha), _p(dt), _p(dh), M, Cc)
+    return dt, dh
 
 
 def conv_wgrad(dy, x, dw, ksize: int, stride: int = 1, pad_lo: int = 1, alpha: float = 1.0):

@@ -136,8 +136,10 @@ int cl_attn_bwd(const cl_attn_bwd_args* args, void* stream);
  * K5: normalisation.  GroupNorm(+SiLU) on NHWC [n, HW, C] and LayerNorm on [T, C], forward and dX backward.
  * Replaces torch.nn.GroupNorm / F.silu / LayerNorm inside diffusers ResnetBlock2D, Transformer2DModel,
  * BasicTransformerBlock, UNet conv_norm_out, and models.py:515-543 (ConvBlock2D, where dgamma/dbeta are needed).
- * `ws` is caller-provided scratch of 2*n*G doubles; `stats` (fp32 [n, G, 2] = mean, rstd) feeds the backward.
+ * `ws` is caller-provided scratch of cl_groupnorm_ws_bytes(n, G, C) bytes (group sums, per-(image, channel) affine
+ * coefficients, channel sums); `stats` (fp32 [n, G, 2] = mean, rstd) feeds the backward.
  * ---------------------------------------------------------------------------------------------------------- */
+int64_t cl_groupnorm_ws_bytes(int n, int G, int C);
 int cl_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, double* ws,
                      int n, int HW, int C, int G, float eps, int silu, void* stream);
 int cl_groupnorm_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* stats,
@@ -221,7 +223,14 @@ int cl_rowmat(const float* a, int lda, const float* w, int sw_i, int sw_j, int I
               int out_mode, int col_off, int lo_off, int accumulate, int M, void* stream);
 int cl_hilo_combine(const float* src, float* dst, int64_t M, int nb, void* stream);  /* [M,16nb] hi|lo blocks -> [M,8nb] */
 int cl_rank_update(const void* x, const float* t, int ldt, const float* tab, int rp, float alpha, void* out, int64_t M,
-                   int C, void* stream);                                            /* out = x + alpha * t * tab^T */
+                   int C, void* stream);
+/* V2 control injection (models.py:369, 415:  h' = h + s * up(down([h ; c]))) fused around the rank-4 update:
+ *   fwd: t = hi/lo-combine(th16 [M,16]) + uc [M, rc<=4];  out = x + alpha * t[:, :4] tab^T (tab fp32 [C, 4]);  t_out [M, 8] kept
+ *   bwd: dt [M, 4] = dy * up (fp32 [C, 4]);  dh = dy + alpha * dt * down^T (fp32 [C, 4]; dh nullable)                      */
+int cl_v2_inject_fwd(const void* x, const float* th16, const float* uc /* nullable */, int ldu, int rc, const float* tab,
+                     float alpha, void* out, float* t_out, int64_t M, int C, void* stream);
+int cl_v2_inject_bwd(const void* dy, const float* up, const float* down, float alpha, float* dt_out, void* dh /* nullable */,
+                     int M, int C, void* stream);                                            /* out = x + alpha * t * tab^T */
 int cl_skinny_small(const float* a, int lda, int I, const float* b, int ldb, int J, float* out, float alpha, int M,
                     void* stream);
 int cl_small_matmul(const float* a, int64_t sa_i, int64_t sa_j, const float* b, int64_t sb_j, int64_t sb_k, float* out,
