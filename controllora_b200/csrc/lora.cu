@@ -108,7 +108,7 @@ struct SkinnyBatch {
 // RT: compile-time bound on the rank (4 or 8); U: rows in flight per thread.  All U row loads (16 B of b, the RT
 // coefficients of a) are issued before the FMAs: with one load in flight per thread the kernel ran at ~25 % of HBM speed.
 template <int RT, int U>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, (RT <= 4) ? 2 : 1)
 skinny_atb_batch_kernel(const __grid_constant__ SkinnyBatch batch, int slabs) {
     const cl_skinny_desc& d = batch.d[blockIdx.y];
     const int C = d.C, M = d.M, R = d.r;
@@ -559,17 +559,17 @@ extern "C" int cl_skinny_atb_batch(const cl_skinny_desc* descs, int n, void* str
     if (smem > 200 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_skinny_atb_batch: shared memory");
     static bool done = false;
     if (!done) {
-        CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         done = true;
     }
     int max_r = 0;
     for (int i = 0; i < n; ++i) max_r = descs[i].r > max_r ? descs[i].r : max_r;
-    // ~one wave of CTAs in total; every problem gets the same number of row slabs
-    int slabs = (num_sms() + n - 1) / n;
+    // ~one wave of CTAs in total (two resident per SM for rank <= 4); every problem gets the same number of row slabs
+    int slabs = (num_sms() * (max_r <= 4 ? 2 : 1) + n - 1) / n;
     if (slabs > (max_m + 63) / 64) slabs = (max_m + 63) / 64;
     if (slabs < 1) slabs = 1;
-    if (max_r <= 4) skinny_atb_batch_kernel<4, 8><<<dim3(slabs, n), 512, smem, stream>>>(batch, slabs);
+    if (max_r <= 4) skinny_atb_batch_kernel<4, 2><<<dim3(slabs, n), 512, smem, stream>>>(batch, slabs);
     else skinny_atb_batch_kernel<8, 2><<<dim3(slabs, n), 512, smem, stream>>>(batch, slabs);
     DONE();
 }
