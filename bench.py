@@ -30,6 +30,16 @@ UNIT = "images/s"
 GFLOP_PER_IMAGE_STEP = 1794.0
 
 
+def gemm_traffic_per_launch():
+    """DRAM bytes per gemm_tc_kernel launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the GEMM launches of
+    one training step) from the committed ncu capture profiles/r01_gemm_traffic.json; None when the file is missing."""
+    try:
+        d = json.loads((Path(__file__).resolve().parent / "profiles" / "r01_gemm_traffic.json").read_text())
+        return float(d["bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -352,7 +362,7 @@ def run_ours(a):
         ach = fl / (tm * 1e-3) / 1e12
     if rank == 0 and not a.no_roofline:
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN,EXT,BK> (all fused linear / LoRA / implicit-GEMM conv launches of one step)",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": gemm_traffic_per_launch(),
                 "launches_per_step": len(rec), "gemm_ms_per_step": tm, "algorithmic_gflop_per_step": fl / 1e9, "peak_source": which,
                 "step_model_flops_utilisation": (GFLOP_PER_IMAGE_STEP * 1e9 * B / (ms_step * 1e-3)) / (peak_tf * 1e12)}
     # ---------------- secondary metric of BASELINE.json: denoise steps/s = UNet evaluations at the CFG batch (2B) + fused
