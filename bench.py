@@ -301,23 +301,44 @@ def run_ours(a):
     # ---------------- end-to-end: host (pinned) buffers in, loss out, every step
     pinned = [h.pin_memory() for h in host]
     h2d = sum(p.numel() * p.element_size() for p in pinned)
-    dbuf = [torch.empty_like(p, device=dev) for p in pinned]
+    # two device staging sets: the copy stream uploads step i+1 while the compute stream runs step i (what a training loop
+    # with a prefetching loader does); every step still moves all of its inputs host->device and its loss device->host
+    dbuf = [[torch.empty_like(p, device=dev) for p in pinned] for _ in range(2)]
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
-        for d, p in zip(dbuf, pinned):
-            d.copy_(p, non_blocking=True)
-        l = tr.step(dbuf[0], dbuf[1], ops.f32_to_bf16(dbuf[2]), dbuf[3], dbuf[4])
-        loss_host.copy_(l, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_host)
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])          # the step that last read this slot has finished with it
+            for d, p in zip(dbuf[slot], pinned):
+                d.copy_(p, non_blocking=True)
+            ready[slot].record(copy_stream)
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(nsteps):
+        cur = torch.cuda.current_stream()
+        for ev in consumed:
+            ev.record(cur)
+        prefetch(0)
+        last = None
+        for i in range(nsteps):
+            slot = i & 1
+            cur.wait_event(ready[slot])
+            if i + 1 < nsteps:
+                prefetch(slot ^ 1)
+            d = dbuf[slot]
+            l = tr.step(d[0], d[1], ops.f32_to_bf16(d[2]), d[3], d[4])
+            consumed[slot].record(cur)
+            loss_host.copy_(l, non_blocking=True)
+            cur.synchronize()
+            last = float(loss_host)
+        return last
+
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        e2e_step()
+    e2e_run(a.steps)
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(BWD_THREADS, (DkvCfg<DP, BQ, STAGES>::MIN_CTAS
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdParams p) {
+    pdl_launch_dependents();
     using Cfg = DkvCfg<DP, BQ, STAGES>;
     constexpr int BK = Cfg::BK;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -150,6 +151,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         fence_barrier_init();
     }
     if (warp_idx == 2) { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
+    pdl_wait();   // prologue above touched only smem / TMEM / kernel params
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -305,6 +307,7 @@ __global__ void __launch_bounds__(BWD_THREADS, (DqCfg<DP, BKB, STAGES>::MIN_CTAS
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const AttnBwdParams p) {
+    pdl_launch_dependents();
     using Cfg = DqCfg<DP, BKB, STAGES>;
     constexpr int BM = Cfg::BM;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -341,6 +344,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         fence_barrier_init();
     }
     if (warp_idx == 2) { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
+    pdl_wait();   // prologue above touched only smem / TMEM / kernel params
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -461,6 +465,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // delta[b, h, q] = sum_d dO[b, q, h*d + :] * O[b, q, h*d + :]
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ d_o,
                                   long long lddo, float* __restrict__ delta, int B, int H, int Nq, int d) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)B * Nq * H;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int h = (int)(i % H);
@@ -495,7 +501,7 @@ static int launch_attn_bwd(const cl_attn_bwd_args* a, cudaStream_t stream) {
         const long long total = (long long)a->B * a->Nq * a->H;
         int blocks = (int)((total + 255) / 256);
         if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-        attn_delta_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->o), a->ldo,
+        launch_k(attn_delta_kernel, blocks, 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(a->o), a->ldo,
                                                       reinterpret_cast<const __nv_bfloat16*>(a->d_o), a->lddo, a->delta,
                                                       a->B, a->H, a->Nq, a->d);
         count_launch();
@@ -513,7 +519,7 @@ static int launch_attn_bwd(const cl_attn_bwd_args* a, cudaStream_t stream) {
             done = true;
         }
         p.num_blocks = (a->Nk + 127) / 128;
-        attn_bwd_dkv_kernel<DP, BQ, STAGES_KV><<<a->B * a->H * p.num_blocks, BWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+        launch_k(attn_bwd_dkv_kernel<DP, BQ, STAGES_KV>, a->B * a->H * p.num_blocks, BWD_THREADS, Cfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p);
         count_launch();
     }
     if (a->dq != nullptr) {
@@ -529,7 +535,7 @@ static int launch_attn_bwd(const cl_attn_bwd_args* a, cudaStream_t stream) {
             done = true;
         }
         p.num_blocks = (a->Nq + 127) / 128;
-        attn_bwd_dq_kernel<DP, BKB, STAGES_Q><<<a->B * a->H * p.num_blocks, BWD_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+        launch_k(attn_bwd_dq_kernel<DP, BKB, STAGES_Q>, a->B * a->H * p.num_blocks, BWD_THREADS, Cfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p);
         count_launch();
     }
     CL_CUDA_CHECK(cudaGetLastError());

@@ -52,6 +52,7 @@ template <int DP, int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(256, (DP <= 64) ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+    pdl_launch_dependents();
     using Cfg = AttnFwdCfg<DP, BLOCK_N, STAGES>;
     constexpr int BLOCK_M = Cfg::BLOCK_M;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -102,6 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
+    pdl_wait();   // prologue above touched only smem / TMEM / kernel params
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -320,6 +322,7 @@ struct AttnFwd2Cfg {
 __global__ void __launch_bounds__(AttnFwd2Cfg::THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+    pdl_launch_dependents();
     using Cfg = AttnFwd2Cfg;
     constexpr int BLOCK_M = Cfg::BLOCK_M, BLOCK_N = Cfg::BLOCK_N, DP = Cfg::DP, STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -370,6 +373,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
+    pdl_wait();   // prologue above touched only smem / TMEM / kernel params
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -593,7 +597,7 @@ static int launch_attn_fwd(const cl_attn_fwd_args* a, cudaStream_t stream) {
         attr_done = true;
     }
     const int grid = a->B * a->H * p.num_q_blocks;
-    attn_fwd_kernel<DP, BLOCK_N, STAGES><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    launch_k(attn_fwd_kernel<DP, BLOCK_N, STAGES>, grid, 256, Cfg::SMEM_BYTES, stream, tq, tk, tv, p);
     count_launch();
     CL_CUDA_CHECK(cudaGetLastError());
     return CL_OK;
@@ -616,7 +620,7 @@ static int launch_attn_fwd2(const cl_attn_fwd_args* a, cudaStream_t stream) {
         attr_done = true;
     }
     const int grid = a->B * a->H * p.num_q_blocks;
-    attn_fwd2_kernel<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    launch_k(attn_fwd2_kernel, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, tq, tk, tv, p);
     count_launch();
     CL_CUDA_CHECK(cudaGetLastError());
     return CL_OK;

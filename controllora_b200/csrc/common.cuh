@@ -26,6 +26,13 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel starts with launch_dependents (the next kernel of the stream / graph may be scheduled as soon as all CTAs
+// of this grid have started) followed - before its first global-memory access - by wait (all memory operations of the
+// preceding grid are complete and visible).  Both are no-ops for a grid launched without the programmatic attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

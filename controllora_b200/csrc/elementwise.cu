@@ -39,6 +39,8 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 }
 
 __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ out, long long T, int F) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int ch = F / 8;
     GRID_STRIDE(i, T * ch) {
         const long long t = i / ch;
@@ -53,6 +55,8 @@ __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ p, __nv_bfloa
 }
 __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ p, const __nv_bfloat16* __restrict__ dout,
                                  __nv_bfloat16* __restrict__ dp, long long T, int F) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int ch = F / 8;
     GRID_STRIDE(i, T * ch) {
         const long long t = i / ch;
@@ -74,6 +78,8 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ p, const __nv
 // ---------------------------------------------------------------- out = a + b
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                            __nv_bfloat16* __restrict__ out, long long n8) {
+    pdl_launch_dependents();
+    pdl_wait();
     GRID_STRIDE(i, n8) {
         float x[8], y[8];
         ld8(a + i * 8, x);
@@ -86,6 +92,8 @@ __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
 
 // ---------------------------------------------------------------- nearest 2x upsample and its adjoint
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int H, int W, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int ch = C / 8;
     const long long total = (long long)n * 2 * H * 2 * W * ch;
     GRID_STRIDE(i, total) {
@@ -100,6 +108,8 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 }
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int n, int H, int W,
                                       int C, int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int ch = C / 8;
     const long long total = (long long)n * H * W * ch;
     GRID_STRIDE(i, total) {
@@ -131,6 +141,8 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv
 // out [n, 2H, 2W, C] = 0 except out[b, 2h+off, 2w+off, :] = x[b, h, w, :]
 __global__ void zero_insert2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int H, int W,
                                      int C, int off) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int ch = C / 8;
     const long long total = (long long)n * 2 * H * 2 * W * ch;
     GRID_STRIDE(i, total) {
@@ -149,6 +161,8 @@ __global__ void zero_insert2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
 // ---------------------------------------------------------------- channel concat / split on [M, C] matrices
 __global__ void concat_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                               __nv_bfloat16* __restrict__ out, long long M, int Ca, int Cb) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int ch = (Ca + Cb) / 8, cha = Ca / 8;
     GRID_STRIDE(i, M * ch) {
         const long long m = i / ch;
@@ -161,6 +175,8 @@ __global__ void concat_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
 // dst[m, :] (+)= src[m, c_off : c_off + Cd]
 __global__ void slice_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long M, int Cs,
                              int c_off, int Cd, int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int ch = Cd / 8;
     GRID_STRIDE(i, M * ch) {
         const long long m = i / ch;
@@ -181,6 +197,8 @@ __global__ void slice_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat1
 // NCHW (fp32 or bf16) -> NHWC bf16, and NHWC bf16 -> NCHW fp32 (used for control states / their gradients)
 template <typename TIn>
 __global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int C, int HW) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -196,6 +214,8 @@ __global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, __nv_bfloat16* __
 }
 __global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n, int C, int HW,
                                         int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -214,9 +234,13 @@ __global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, flo
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     GRID_STRIDE(i, n) y[i] = __float2bfloat16(x[i]);
 }
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     GRID_STRIDE(i, n) y[i] = __bfloat162float(x[i]);
 }
 
@@ -234,76 +258,76 @@ using namespace clb;
 extern "C" int cl_geglu_fwd(const void* p, void* out, int64_t T, int F, void* stream_) {
     STREAM;
     if (!p || !out || F % 8) return set_error(CL_ERR_INVALID, "cl_geglu_fwd: bad args");
-    geglu_fwd_kernel<<<ew_blocks(T * (F / 8)), 256, 0, stream>>>(BF(p), BFW(out), T, F);
+    launch_k(geglu_fwd_kernel, ew_blocks(T * (F / 8)), 256, 0, stream, BF(p), BFW(out), T, F);
     DONE();
 }
 extern "C" int cl_geglu_bwd(const void* p, const void* dout, void* dp, int64_t T, int F, void* stream_) {
     STREAM;
     if (!p || !dout || !dp || F % 8) return set_error(CL_ERR_INVALID, "cl_geglu_bwd: bad args");
-    geglu_bwd_kernel<<<ew_blocks(T * (F / 8)), 256, 0, stream>>>(BF(p), BF(dout), BFW(dp), T, F);
+    launch_k(geglu_bwd_kernel, ew_blocks(T * (F / 8)), 256, 0, stream, BF(p), BF(dout), BFW(dp), T, F);
     DONE();
 }
 extern "C" int cl_add(const void* a, const void* b, void* out, int64_t n, void* stream_) {
     STREAM;
     if (!a || !b || !out || n % 8) return set_error(CL_ERR_INVALID, "cl_add: bad args (n %% 8)");
-    add_kernel<<<ew_blocks(n / 8), 256, 0, stream>>>(BF(a), BF(b), BFW(out), n / 8);
+    launch_k(add_kernel, ew_blocks(n / 8), 256, 0, stream, BF(a), BF(b), BFW(out), n / 8);
     DONE();
 }
 extern "C" int cl_upsample2x_fwd(const void* x, void* y, int n, int H, int W, int C, void* stream_) {
     STREAM;
     if (!x || !y || C % 8) return set_error(CL_ERR_INVALID, "cl_upsample2x_fwd: bad args");
-    upsample2x_kernel<<<ew_blocks((long long)n * 4 * H * W * (C / 8)), 256, 0, stream>>>(BF(x), BFW(y), n, H, W, C);
+    launch_k(upsample2x_kernel, ew_blocks((long long)n * 4 * H * W * (C / 8)), 256, 0, stream, BF(x), BFW(y), n, H, W, C);
     DONE();
 }
 extern "C" int cl_upsample2x_bwd(const void* dy, void* dx, int n, int H, int W, int C, int accumulate, void* stream_) {
     STREAM;
     if (!dy || !dx || C % 8) return set_error(CL_ERR_INVALID, "cl_upsample2x_bwd: bad args");
-    upsample2x_bwd_kernel<<<ew_blocks((long long)n * H * W * (C / 8)), 256, 0, stream>>>(BF(dy), BFW(dx), n, H, W, C, accumulate);
+    launch_k(upsample2x_bwd_kernel, ew_blocks((long long)n * H * W * (C / 8)), 256, 0, stream, BF(dy), BFW(dx), n, H, W, C, accumulate);
     DONE();
 }
 extern "C" int cl_zero_insert2x(const void* x, void* y, int n, int H, int W, int C, int off, void* stream_) {
     STREAM;
     if (!x || !y || C % 8 || (off != 0 && off != 1)) return set_error(CL_ERR_INVALID, "cl_zero_insert2x: bad args");
-    zero_insert2x_kernel<<<ew_blocks((long long)n * 4 * H * W * (C / 8)), 256, 0, stream>>>(BF(x), BFW(y), n, H, W, C, off);
+    launch_k(zero_insert2x_kernel, ew_blocks((long long)n * 4 * H * W * (C / 8)), 256, 0, stream, BF(x), BFW(y), n, H, W, C, off);
     DONE();
 }
 extern "C" int cl_concat_channels(const void* a, const void* b, void* out, int64_t M, int Ca, int Cb, void* stream_) {
     STREAM;
     if (!a || !b || !out || Ca % 8 || Cb % 8) return set_error(CL_ERR_INVALID, "cl_concat_channels: bad args");
-    concat_kernel<<<ew_blocks(M * ((Ca + Cb) / 8)), 256, 0, stream>>>(BF(a), BF(b), BFW(out), M, Ca, Cb);
+    launch_k(concat_kernel, ew_blocks(M * ((Ca + Cb) / 8)), 256, 0, stream, BF(a), BF(b), BFW(out), M, Ca, Cb);
     DONE();
 }
 extern "C" int cl_slice_channels(const void* src, void* dst, int64_t M, int Cs, int c_off, int Cd, int accumulate,
                                  void* stream_) {
     STREAM;
     if (!src || !dst || Cs % 8 || Cd % 8 || c_off % 8 || c_off + Cd > Cs) return set_error(CL_ERR_INVALID, "cl_slice_channels: bad args");
-    slice_kernel<<<ew_blocks(M * (Cd / 8)), 256, 0, stream>>>(BF(src), BFW(dst), M, Cs, c_off, Cd, accumulate);
+    launch_k(slice_kernel, ew_blocks(M * (Cd / 8)), 256, 0, stream, BF(src), BFW(dst), M, Cs, c_off, Cd, accumulate);
     DONE();
 }
 extern "C" int cl_nchw_to_nhwc(const void* x, int x_is_fp32, void* y, int n, int C, int HW, void* stream_) {
     STREAM;
     if (!x || !y) return set_error(CL_ERR_INVALID, "cl_nchw_to_nhwc: null");
     dim3 grid((HW + 31) / 32, (C + 31) / 32, n), block(32, 8);
-    if (x_is_fp32) nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(x), BFW(y), n, C, HW);
-    else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(BF(x), BFW(y), n, C, HW);
+    if (x_is_fp32) launch_k(nchw_to_nhwc_kernel<float>, grid, block, 0, stream, reinterpret_cast<const float*>(x), BFW(y), n, C, HW);
+    else launch_k(nchw_to_nhwc_kernel<__nv_bfloat16>, grid, block, 0, stream, BF(x), BFW(y), n, C, HW);
     DONE();
 }
 extern "C" int cl_nhwc_to_nchw_f32(const void* x, float* y, int n, int C, int HW, int accumulate, void* stream_) {
     STREAM;
     if (!x || !y) return set_error(CL_ERR_INVALID, "cl_nhwc_to_nchw_f32: null");
     dim3 grid((HW + 31) / 32, (C + 31) / 32, n), block(32, 8);
-    nhwc_to_nchw_f32_kernel<<<grid, block, 0, stream>>>(BF(x), y, n, C, HW, accumulate);
+    launch_k(nhwc_to_nchw_f32_kernel, grid, block, 0, stream, BF(x), y, n, C, HW, accumulate);
     DONE();
 }
 extern "C" int cl_f32_to_bf16(const float* x, void* y, int64_t n, void* stream_) {
     STREAM;
     if (!x || !y) return set_error(CL_ERR_INVALID, "cl_f32_to_bf16: null");
-    f32_to_bf16_kernel<<<ew_blocks(n), 256, 0, stream>>>(x, BFW(y), n);
+    launch_k(f32_to_bf16_kernel, ew_blocks(n), 256, 0, stream, x, BFW(y), n);
     DONE();
 }
 extern "C" int cl_bf16_to_f32(const void* x, float* y, int64_t n, void* stream_) {
     STREAM;
     if (!x || !y) return set_error(CL_ERR_INVALID, "cl_bf16_to_f32: null");
-    bf16_to_f32_kernel<<<ew_blocks(n), 256, 0, stream>>>(BF(x), y, n);
+    launch_k(bf16_to_f32_kernel, ew_blocks(n), 256, 0, stream, BF(x), y, n);
     DONE();
 }

@@ -159,6 +159,7 @@ template <int BN, int EXT, int BK, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmE, const GemmParams p, const int num_stages) {
+    pdl_launch_dependents();
     using Cfg = GemmCfg<BN, EXT, BK, CG>;
     const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;      // 0 = leader of the pair
     const int sched_cta = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -207,6 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (CG == 2) { tmem_alloc_cg2(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
         else { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
+    pdl_wait();   // prologue above touched only smem / TMEM / kernel params
     // LoRA-up table -> smem (persistent for the CTA lifetime)
     for (int i = threadIdx.x; i < up_floats; i += NUM_THREADS) smem_up[i] = p.lora_up[i];
     tc_fence_before();
@@ -504,6 +506,8 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, int M, int N, con
                      const float* __restrict__ row_bias, int rows_per_group, long long ld_rb,
                      const __nv_bfloat16* __restrict__ residual, long long ldr, void* __restrict__ out, long long ldd,
                      int out_fp32) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int nq = N >> 2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)M * nq) return;
@@ -549,7 +553,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     using Cfg = GemmCfg<BN, EXT, BK, CG>;
     GemmParams p = p_in;
     const int up_bytes = (p.lora_up != nullptr) ? ((p.N * p.lora_rp * 4 + 15) & ~15) : 0;
-    const int fixed = 1024 /*align slack*/ + EPI_STAGING_BYTES + up_bytes + 256 /*barriers*/;
+    const int fixed = 1024 /*align slack*/ + EPI_STAGING_BYTES + up_bytes + 512 /*barriers: 2 * stages + 5 words*/;
     int stages, smem_bytes;
     int grid = num_sms();
     // B-resident mode: the weight tile of one n-block fits next to >= 3 A stages and every CTA re-uses it >= 3 times
@@ -566,7 +570,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     } else {
         p.b_resident = 0;
         stages = (232448 - fixed) / Cfg::STAGE_BYTES;
-        if (stages > 8) stages = 8;
+        if (stages > 24) stages = 24;   // small stages (32-channel convs: 10 KB) need a deep ring to keep ~190 KB in flight
         if (stages < 2) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: not enough shared memory for 2 stages");
         smem_bytes = fixed + stages * Cfg::STAGE_BYTES;
         const int m_units = (CG == 2) ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;
@@ -589,19 +593,21 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
         cfg.blockDim = dim3(NUM_THREADS);
         cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
         CL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EXT, BK, CG>, tA, tB, tE, p, stages));
     } else {
-        gemm_tc_kernel<BN, EXT, BK, CG><<<grid, NUM_THREADS, smem_bytes, stream>>>(tA, tB, tE, p, stages);
+        launch_k(gemm_tc_kernel<BN, EXT, BK, CG>, grid, NUM_THREADS, smem_bytes, stream, tA, tB, tE, p, stages);
     }
     count_launch();
     if (p.splits > 1) {
         const long long quads = (long long)p.M * (p.N / 4);
-        splitk_finish_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(
+        launch_k(splitk_finish_kernel, (unsigned)((quads + 255) / 256), 256, 0, stream, 
             p.split_ws, p.splits, p.M, p.N, full.bias, full.row_bias, full.rows_per_group, full.ld_rb, full.residual,
             full.ldr, full.out, full.ldd, full.out_fp32);
         count_launch();

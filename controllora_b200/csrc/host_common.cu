@@ -2,6 +2,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -23,6 +24,13 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    // off by default: measured on B200 (round 1, CUDA-graph replay of the train step) 47.9 ms with programmatic edges
+    // against 47.0 ms without - early-resident dependents cost more than the launch gaps they hide.  CLB_PDL=1 enables.
+    static const bool on = [] { const char* e = getenv("CLB_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
 
 int num_sms() {
     static int sms = 0;

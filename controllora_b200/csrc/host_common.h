@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/controllora_b200.h"
 
@@ -16,6 +17,28 @@ int num_sms();
 // strides of dims 1..rank-1.  Returns CL_OK or a negative status.
 int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, int swizzle_bytes /* 0, 64 or 128 */);
+
+// Programmatic dependent launch (opt-in: CLB_PDL=1): see pdl_launch_dependents / pdl_wait in common.cuh.
+bool pdl_enabled();
+
+// Launch `kernel` with the programmatic-stream-serialization attribute: inside a stream (or a captured CUDA graph) the
+// grid may start while the previous kernel drains; every kernel of this library executes griddepcontrol.wait before its
+// first global-memory access.  A launch error is left in cudaGetLastError() for the caller's check.
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace clb
 

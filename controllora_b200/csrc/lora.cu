@@ -16,6 +16,8 @@ namespace clb {
 // with src(j, k) = src[j*s_j + k*s_k].  Rows / columns not covered by any descriptor must be pre-zeroed once.
 __global__ void __launch_bounds__(256)
 lora_pack_kernel(const cl_pack_desc* __restrict__ descs, int n_desc) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int di = blockIdx.y;
     if (di >= n_desc) return;
     const cl_pack_desc d = descs[di];
@@ -51,6 +53,8 @@ template <int R>
 __global__ void __launch_bounds__(512)
 skinny_atb_kernel(const float* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b, long long ldb,
                   float* __restrict__ out, long long so_j, long long so_c, float alpha, int M, int C, int rows_per_cta) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int chunks = C / 8;
     const int rows_par = blockDim.x / chunks;
     const int chunk = threadIdx.x % chunks;
@@ -110,6 +114,8 @@ struct SkinnyBatch {
 template <int RT, int U>
 __global__ void __launch_bounds__(512, (RT <= 4) ? 2 : 1)
 skinny_atb_batch_kernel(const __grid_constant__ SkinnyBatch batch, int slabs) {
+    pdl_launch_dependents();
+    pdl_wait();
     const cl_skinny_desc& d = batch.d[blockIdx.y];
     const int C = d.C, M = d.M, R = d.r;
     const int chunks = C / 8;
@@ -188,6 +194,8 @@ skinny_atb_batch_kernel(const __grid_constant__ SkinnyBatch batch, int slabs) {
 template <int RP>
 __global__ void __launch_bounds__(256)
 rowdot_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const float* __restrict__ u, float* __restrict__ e, int M, int N) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float s_ut[];                 // [RP][N]  (transposed: conflict-free 16-byte reads along n)
     for (int i = threadIdx.x; i < N * RP; i += blockDim.x) s_ut[(i % RP) * N + i / RP] = u[i];
     __syncthreads();
@@ -221,6 +229,8 @@ rowdot_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const float* _
 __global__ void __launch_bounds__(256)
 rowmat_kernel(const float* __restrict__ a, int lda, const float* __restrict__ w, int sw_i, int sw_j, int I, int J,
               float alpha, void* __restrict__ out, int ldo, int out_mode, int col_off, int lo_off, int accumulate, int M) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sw[64];
     if (threadIdx.x < I * J) sw[threadIdx.x] = w[(threadIdx.x / J) * sw_i + (threadIdx.x % J) * sw_j];
     __syncthreads();
@@ -251,6 +261,8 @@ rowmat_kernel(const float* __restrict__ a, int lda, const float* __restrict__ w,
 // src fp32 [M, 16*nb] laid out in 16-column blocks [hi0..3 | hi4..7 | lo0..3 | lo4..7] -> dst fp32 [M, 8*nb] = hi + lo
 __global__ void __launch_bounds__(256)
 hilo_combine_kernel(const float* __restrict__ src, float* __restrict__ dst, long long M, int nb) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = M * nb * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long m = i / (nb * 8);
@@ -267,6 +279,8 @@ template <int RP>
 __global__ void __launch_bounds__(256)
 rank_update_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ t, int ldt, const float* __restrict__ tab,
                    float alpha, __nv_bfloat16* __restrict__ out, long long M, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float s_tt[];                 // [RP][C] transposed table
     for (int i = threadIdx.x; i < C * RP; i += blockDim.x) s_tt[(i % RP) * C + i / RP] = tab[i];
     __syncthreads();
@@ -311,6 +325,8 @@ __global__ void __launch_bounds__(256)
 v2_inject_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ th16, const float* __restrict__ uc, int ldu,
                      int rc, const float* __restrict__ tab, float alpha, __nv_bfloat16* __restrict__ out,
                      float* __restrict__ t_out, long long M, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float s_tt[];                 // [4][C] transposed table
     for (int i = threadIdx.x; i < C * 4; i += blockDim.x) s_tt[(i % 4) * C + i / 4] = tab[i];
     __syncthreads();
@@ -362,6 +378,8 @@ template <int IT>
 __global__ void __launch_bounds__(256)
 v2_inject_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ up, const float* __restrict__ down, float alpha,
                      float* __restrict__ dt_out, __nv_bfloat16* __restrict__ dh, int M, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float s_tab[];                // [4][C] up (transposed) | [4][C] down (transposed)
     float* s_up = s_tab;
     float* s_dn = s_tab + 4 * C;
@@ -431,6 +449,8 @@ v2_inject_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
 __global__ void __launch_bounds__(256)
 skinny_small_kernel(const float* __restrict__ a, int lda, int I, const float* __restrict__ b, int ldb, int J,
                     float* __restrict__ out, float alpha, int M) {
+    pdl_launch_dependents();
+    pdl_wait();
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -471,6 +491,8 @@ __global__ void __launch_bounds__(256)
 small_matmul_kernel(const float* __restrict__ a, long long sa_i, long long sa_j, const float* __restrict__ b, long long sb_j,
                     long long sb_k, float* __restrict__ out, long long so_i, long long so_k, int I, int J, int K, float alpha,
                     int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)I * K;
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -502,7 +524,7 @@ extern "C" int cl_lora_pack_batch(const cl_pack_desc* descs_dev, int n_desc, int
     int bx = (max_elems + 255) / 256;
     if (bx > 16) bx = 16;
     if (bx < 1) bx = 1;
-    lora_pack_kernel<<<dim3(bx, n_desc), 256, 0, stream>>>(descs_dev, n_desc);
+    launch_k(lora_pack_kernel, dim3(bx, n_desc), 256, 0, stream, descs_dev, n_desc);
     DONE();
 }
 
@@ -529,7 +551,7 @@ extern "C" int cl_skinny_atb(const float* a, int lda, int r, const void* b, int6
             CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
             done = true;                                                                                                \
         }                                                                                                               \
-        skinny_atb_kernel<R><<<grid, threads, smem, stream>>>(a, lda, bb, ldb, out, so_j, so_c, alpha, M, Ccols, rows_per_cta); \
+        launch_k(skinny_atb_kernel<R>, grid, threads, smem, stream, a, lda, bb, ldb, out, so_j, so_c, alpha, M, Ccols, rows_per_cta); \
         break;                                                                                                          \
     }
     switch (r) {
@@ -569,8 +591,8 @@ extern "C" int cl_skinny_atb_batch(const cl_skinny_desc* descs, int n, void* str
     int slabs = (num_sms() * (max_r <= 4 ? 2 : 1) + n - 1) / n;
     if (slabs > (max_m + 63) / 64) slabs = (max_m + 63) / 64;
     if (slabs < 1) slabs = 1;
-    if (max_r <= 4) skinny_atb_batch_kernel<4, 2><<<dim3(slabs, n), 512, smem, stream>>>(batch, slabs);
-    else skinny_atb_batch_kernel<8, 2><<<dim3(slabs, n), 512, smem, stream>>>(batch, slabs);
+    if (max_r <= 4) launch_k(skinny_atb_batch_kernel<4, 2>, dim3(slabs, n), 512, smem, stream, batch, slabs);
+    else launch_k(skinny_atb_batch_kernel<8, 2>, dim3(slabs, n), 512, smem, stream, batch, slabs);
     DONE();
 }
 
@@ -582,8 +604,8 @@ extern "C" int cl_rowdot(const void* a, int64_t lda, const float* u, int rp, flo
     if (blocks > num_sms() * 4) blocks = num_sms() * 4;
     const size_t smem = (size_t)N * rp * sizeof(float);
     if (smem > 48 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_rowdot: N * rp too large");
-    if (rp == 4) rowdot_kernel<4><<<blocks, 256, smem, stream>>>(aa, lda, u, e, M, N);
-    else if (rp == 8) rowdot_kernel<8><<<blocks, 256, smem, stream>>>(aa, lda, u, e, M, N);
+    if (rp == 4) launch_k(rowdot_kernel<4>, blocks, 256, smem, stream, aa, lda, u, e, M, N);
+    else if (rp == 8) launch_k(rowdot_kernel<8>, blocks, 256, smem, stream, aa, lda, u, e, M, N);
     else return set_error(CL_ERR_UNSUPPORTED, "cl_rowdot: rp must be 4 or 8");
     DONE();
 }
@@ -594,7 +616,7 @@ extern "C" int cl_rowmat(const float* a, int lda, const float* w, int sw_i, int 
     if (!a || !w || !out || I > 8 || J > 8 || I < 1 || J < 1) return set_error(CL_ERR_INVALID, "cl_rowmat: bad args");
     int blocks = (M + 255) / 256;
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    rowmat_kernel<<<blocks, 256, 0, stream>>>(a, lda, w, sw_i, sw_j, I, J, alpha, out, ldo, out_mode, col_off, lo_off, accumulate, M);
+    launch_k(rowmat_kernel, blocks, 256, 0, stream, a, lda, w, sw_i, sw_j, I, J, alpha, out, ldo, out_mode, col_off, lo_off, accumulate, M);
     DONE();
 }
 
@@ -604,7 +626,7 @@ extern "C" int cl_hilo_combine(const float* src, float* dst, int64_t M, int nb, 
     long long total = M * nb * 8;
     int blocks = (int)((total + 255) / 256);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    hilo_combine_kernel<<<blocks, 256, 0, stream>>>(src, dst, M, nb);
+    launch_k(hilo_combine_kernel, blocks, 256, 0, stream, src, dst, M, nb);
     DONE();
 }
 
@@ -619,8 +641,8 @@ extern "C" int cl_rank_update(const void* x, const float* t, int ldt, const floa
     __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
     const size_t smem = (size_t)Ccols * rp * sizeof(float);
     if (smem > 48 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_rank_update: C * rp too large");
-    if (rp == 4) rank_update_kernel<4><<<blocks, 256, smem, stream>>>(xx, t, ldt, tab, alpha, oo, M, Ccols);
-    else if (rp == 8) rank_update_kernel<8><<<blocks, 256, smem, stream>>>(xx, t, ldt, tab, alpha, oo, M, Ccols);
+    if (rp == 4) launch_k(rank_update_kernel<4>, blocks, 256, smem, stream, xx, t, ldt, tab, alpha, oo, M, Ccols);
+    else if (rp == 8) launch_k(rank_update_kernel<8>, blocks, 256, smem, stream, xx, t, ldt, tab, alpha, oo, M, Ccols);
     else return set_error(CL_ERR_UNSUPPORTED, "cl_rank_update: rp must be 4 or 8");
     DONE();
 }
@@ -634,7 +656,7 @@ extern "C" int cl_v2_inject_fwd(const void* x, const float* th16, const float* u
     long long total = M * (Ccols / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    v2_inject_fwd_kernel<<<blocks, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), th16, uc, ldu, rc, tab, alpha,
+    launch_k(v2_inject_fwd_kernel, blocks, 256, smem, stream, reinterpret_cast<const __nv_bfloat16*>(x), th16, uc, ldu, rc, tab, alpha,
                                                         reinterpret_cast<__nv_bfloat16*>(out), t_out, M, Ccols);
     DONE();
 }
@@ -649,9 +671,9 @@ extern "C" int cl_v2_inject_bwd(const void* dy, const float* up, const float* do
     if (blocks > num_sms() * 6) blocks = num_sms() * 6;
     const __nv_bfloat16* dd = reinterpret_cast<const __nv_bfloat16*>(dy);
     __nv_bfloat16* hh = reinterpret_cast<__nv_bfloat16*>(dh);
-    if (Ccols <= 512) v2_inject_bwd_kernel<2><<<blocks, 256, smem, stream>>>(dd, up, down, alpha, dt_out, hh, M, Ccols);
-    else if (Ccols <= 768) v2_inject_bwd_kernel<3><<<blocks, 256, smem, stream>>>(dd, up, down, alpha, dt_out, hh, M, Ccols);
-    else v2_inject_bwd_kernel<5><<<blocks, 256, smem, stream>>>(dd, up, down, alpha, dt_out, hh, M, Ccols);
+    if (Ccols <= 512) launch_k(v2_inject_bwd_kernel<2>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols);
+    else if (Ccols <= 768) launch_k(v2_inject_bwd_kernel<3>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols);
+    else launch_k(v2_inject_bwd_kernel<5>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols);
     DONE();
 }
 
@@ -661,7 +683,7 @@ extern "C" int cl_skinny_small(const float* a, int lda, int I, const float* b, i
     if (!a || !b || !out || I > 8 || J > 8) return set_error(CL_ERR_INVALID, "cl_skinny_small: bad args");
     int blocks = (M + 255) / 256;
     if (blocks > num_sms()) blocks = num_sms();
-    skinny_small_kernel<<<blocks, 256, 0, stream>>>(a, lda, I, b, ldb, J, out, alpha, M);
+    launch_k(skinny_small_kernel, blocks, 256, 0, stream, a, lda, I, b, ldb, J, out, alpha, M);
     DONE();
 }
 
@@ -672,6 +694,6 @@ extern "C" int cl_small_matmul(const float* a, int64_t sa_i, int64_t sa_j, const
     const long long total = (long long)I * K;          // one warp per output
     int blocks = (int)((total + 7) / 8);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    small_matmul_kernel<<<blocks, 256, 0, stream>>>(a, sa_i, sa_j, b, sb_j, sb_k, out, so_i, so_k, I, J, K, alpha, accumulate);
+    launch_k(small_matmul_kernel, blocks, 256, 0, stream, a, sa_i, sa_j, b, sb_j, sb_k, out, so_i, so_k, I, J, K, alpha, accumulate);
     DONE();
 }

@@ -64,6 +64,8 @@ gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
                  const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
                  double* __restrict__ gsum, float* __restrict__ csum, int n_img, int HW, int C, int G, int rows_per_cta,
                  int silu) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = blockIdx.y;
     const int chunks = C / 8;
     const int cpg = C / G;
@@ -174,6 +176,8 @@ gn_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
 __global__ void gn_fwd_coef_kernel(const double* __restrict__ gsum, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ stats, float* __restrict__ coef,
                                    int n_img, int C, int G, double inv_m, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = blockIdx.x;
     const int cpg = C / G;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -194,6 +198,8 @@ __global__ void gn_fwd_coef_kernel(const double* __restrict__ gsum, const float*
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ coef, __nv_bfloat16* __restrict__ y,
                 int n_img, int HW, int C, int silu) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = blockIdx.y;
     const int chunks = C / 8;
     const int total = HW * chunks;                      // < 2^31: HW * C / 8
@@ -238,6 +244,8 @@ __global__ void __launch_bounds__(512)
 gn_bwd_coef_kernel(const float* __restrict__ csum, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ stats, float* __restrict__ coef, float* __restrict__ dgamma,
                    float* __restrict__ dbeta, int n_img, int C, int G, float inv_m) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float gs[];          // [2][G] group sums: sum dz*gamma, sum dz*gamma*xhat
     const int n = blockIdx.x;
     const int cpg = C / G;
@@ -274,6 +282,8 @@ __global__ void __launch_bounds__(256, 5)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                     const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx, int n_img, int HW, int C, int silu,
                     int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = blockIdx.y;
     const int chunks = C / 8;
     const int total = HW * chunks;
@@ -323,6 +333,8 @@ template <int LN_IT, int ROWS>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ stats, int T, int C, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
     if (row0 >= T) return;
@@ -398,6 +410,8 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
               const float* __restrict__ gamma, const float* __restrict__ stats, __nv_bfloat16* __restrict__ dx, int T,
               int C, int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
     if (row0 >= T) return;
@@ -511,10 +525,10 @@ extern "C" int cl_groupnorm_fwd(const void* x, const float* gamma, const float* 
         }
     }
     const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
-    gn_reduce_kernel<0><<<dim3(grid_x, n), threads, rsmem, stream>>>(xx, nullptr, nullptr, nullptr, nullptr, gsum, nullptr, n,
+    launch_k(gn_reduce_kernel<0>, dim3(grid_x, n), threads, rsmem, stream, xx, nullptr, nullptr, nullptr, nullptr, gsum, nullptr, n,
                                                                       HW, C, G, rows_per_cta, 0);
-    gn_fwd_coef_kernel<<<n, 256, 0, stream>>>(gsum, gamma, beta, stats, coef, n, C, G, 1.0 / ((double)HW * (C / G)), eps);
-    gn_apply_kernel<<<dim3(gn_flat_blocks(HW, C, n, 2), n), 256, 0, stream>>>(xx, coef, reinterpret_cast<__nv_bfloat16*>(y), n,
+    launch_k(gn_fwd_coef_kernel, n, 256, 0, stream, gsum, gamma, beta, stats, coef, n, C, G, 1.0 / ((double)HW * (C / G)), eps);
+    launch_k(gn_apply_kernel, dim3(gn_flat_blocks(HW, C, n, 2), n), 256, 0, stream, xx, coef, reinterpret_cast<__nv_bfloat16*>(y), n,
                                                                               HW, C, silu);
     count_launch(3);
     CL_CUDA_CHECK(cudaGetLastError());
@@ -543,11 +557,11 @@ extern "C" int cl_groupnorm_bwd(const void* x, const void* dy, const float* gamm
     }
     const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
     const __nv_bfloat16* dd = reinterpret_cast<const __nv_bfloat16*>(dy);
-    gn_reduce_kernel<1><<<dim3(grid_x, n), threads, rsmem, stream>>>(xx, dd, gamma, beta, stats, nullptr, csum, n, HW, C, G,
+    launch_k(gn_reduce_kernel<1>, dim3(grid_x, n), threads, rsmem, stream, xx, dd, gamma, beta, stats, nullptr, csum, n, HW, C, G,
                                                                       rows_per_cta, silu);
-    gn_bwd_coef_kernel<<<n, 512, 2 * G * sizeof(float), stream>>>(csum, gamma, beta, stats, coef, dgamma, dbeta, n, C, G,
+    launch_k(gn_bwd_coef_kernel, n, 512, 2 * G * sizeof(float), stream, csum, gamma, beta, stats, coef, dgamma, dbeta, n, C, G,
                                                                   1.f / ((float)HW * (C / G)));
-    gn_bwd_apply_kernel<<<dim3(gn_flat_blocks(HW, C, n, 1), n), 256, 0, stream>>>(xx, dd, coef, reinterpret_cast<__nv_bfloat16*>(dx),
+    launch_k(gn_bwd_apply_kernel, dim3(gn_flat_blocks(HW, C, n, 1), n), 256, 0, stream, xx, dd, coef, reinterpret_cast<__nv_bfloat16*>(dx),
                                                                                   n, HW, C, silu, accumulate);
     count_launch(3);
     CL_CUDA_CHECK(cudaGetLastError());
@@ -559,7 +573,7 @@ extern "C" int cl_layernorm_fwd(const void* x, const float* gamma, const float* 
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!x || !gamma || !beta || !y) return set_error(CL_ERR_INVALID, "cl_layernorm_fwd: null pointer");
     if (C % 8 != 0 || C > LN_MAX_IT * 256) return set_error(CL_ERR_UNSUPPORTED, "cl_layernorm_fwd: C must be a multiple of 8, <= 2560");
-#define LN_FWD(IT, R) ln_fwd_kernel<IT, R><<<(T + 8 * R - 1) / (8 * R), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), stats, T, C, eps)
+#define LN_FWD(IT, R) launch_k(ln_fwd_kernel<IT, R>, (T + 8 * R - 1) / (8 * R), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), stats, T, C, eps)
     if (C <= 512) LN_FWD(2, 2); else if (C <= 768) LN_FWD(3, 2); else if (C <= 1280) LN_FWD(5, 1); else LN_FWD(10, 1);
 #undef LN_FWD
     count_launch();
@@ -572,7 +586,7 @@ extern "C" int cl_layernorm_bwd(const void* x, const void* dy, const float* gamm
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!x || !dy || !gamma || !stats || !dx) return set_error(CL_ERR_INVALID, "cl_layernorm_bwd: null pointer");
     if (C % 8 != 0 || C > LN_MAX_IT * 256) return set_error(CL_ERR_UNSUPPORTED, "cl_layernorm_bwd: C must be a multiple of 8, <= 2560");
-#define LN_BWD(IT, R) ln_bwd_kernel<IT, R><<<(T + 8 * R - 1) / (8 * R), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, stats, reinterpret_cast<__nv_bfloat16*>(dx), T, C, accumulate)
+#define LN_BWD(IT, R) launch_k(ln_bwd_kernel<IT, R>, (T + 8 * R - 1) / (8 * R), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma, stats, reinterpret_cast<__nv_bfloat16*>(dx), T, C, accumulate)
     if (C <= 512) LN_BWD(2, 1); else if (C <= 768) LN_BWD(3, 1); else if (C <= 1280) LN_BWD(5, 1); else LN_BWD(10, 1);
 #undef LN_BWD
     count_launch();

@@ -11,6 +11,8 @@
 namespace clb {
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     float s = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float v = x[i];
@@ -31,6 +33,8 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
              float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, const float* __restrict__ gnorm_sq,
              float max_norm, float grad_scale, int zero_grad) {
+    pdl_launch_dependents();
+    pdl_wait();
     float coef = grad_scale;
     if (gnorm_sq != nullptr && max_norm > 0.f) {
         const float total = sqrtf(*gnorm_sq) * grad_scale;
@@ -62,7 +66,7 @@ extern "C" int cl_sumsq(const float* x, int64_t n, float* out, void* stream_) {
     int blocks = (int)((n + 255) / 256);
     if (blocks > num_sms() * 4) blocks = num_sms() * 4;
     if (blocks < 1) blocks = 1;
-    sumsq_kernel<<<blocks, 256, 0, stream>>>(x, n, out);
+    launch_k(sumsq_kernel, blocks, 256, 0, stream, x, n, out);
     count_launch();
     CL_CUDA_CHECK(cudaGetLastError());
     return CL_OK;
@@ -77,7 +81,7 @@ extern "C" int cl_adamw(float* p, float* g, float* m, float* v, int64_t n, float
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
     int blocks = (int)((n + 255) / 256);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    adamw_kernel<<<blocks, 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, gnorm_sq,
+    launch_k(adamw_kernel, blocks, 256, 0, stream, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, gnorm_sq,
                                             max_norm, grad_scale, zero_grad);
     count_launch();
     CL_CUDA_CHECK(cudaGetLastError());

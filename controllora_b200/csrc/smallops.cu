@@ -23,6 +23,8 @@ template <int CIN>
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
                __nv_bfloat16* __restrict__ y, int n, int H, int W, int Cout) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int KK = 9 * CIN;
     __shared__ __align__(16) float sw[KK * 32];     // [k][32 channels of this group]
     __shared__ float sb[32];
@@ -85,6 +87,8 @@ template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_out_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
                 float* __restrict__ y, int n, int H, int W, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __nv_bfloat16 swb[];   // [COUT][9][C]
     for (int i = threadIdx.x; i < COUT * 9 * C / 8; i += blockDim.x)
         reinterpret_cast<uint4*>(swb)[i] = reinterpret_cast<const uint4*>(w)[i];
@@ -129,6 +133,8 @@ template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_out_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dx, int n,
                     int H, int W, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __nv_bfloat16 swb[];   // [COUT][9][C]
     for (int i = threadIdx.x; i < COUT * 9 * C / 8; i += blockDim.x)
         reinterpret_cast<uint4*>(swb)[i] = reinterpret_cast<const uint4*>(w)[i];
@@ -167,6 +173,8 @@ conv_out_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restric
 // ------------------------------------------------------------------------------------------ timestep embedding
 // out[b, :] = [cos(t * f_i) | sin(t * f_i)], f_i = exp(-ln(10000) * i / half)   (flip_sin_to_cos, freq_shift 0)
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int half = dim / 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
         const int b = i / half, j = i % half;
@@ -183,6 +191,8 @@ static constexpr int SL_MAXB = 8;
 __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ out, int Bt, int N, int K, int silu_in, int silu_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sxs[];  // [nb][K]
     const int b0 = blockIdx.y * SL_MAXB;
     const int nb = min(SL_MAXB, Bt - b0);
@@ -226,6 +236,8 @@ small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
 __global__ void __launch_bounds__(256)
 mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ loss,
            float* __restrict__ dpred, long long n, float gscale) {
+    pdl_launch_dependents();
+    pdl_wait();
     float s = 0.f;
     const float inv = 1.f / (float)n;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -262,7 +274,7 @@ extern "C" int cl_conv_in(const float* x, const void* w, const float* bias, void
     const dim3 grid((unsigned)((npix + 255) / 256), (unsigned)((Cout + 31) / 32));
 #define CONV_IN_CASE(CI)                                                                                         \
     case CI:                                                                                                     \
-        conv_in_kernel<CI><<<grid, 256, 0, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(w), bias,         \
+        launch_k(conv_in_kernel<CI>, grid, 256, 0, stream, x, reinterpret_cast<const __nv_bfloat16*>(w), bias,         \
                                                      reinterpret_cast<__nv_bfloat16*>(y), n, H, W, Cout);        \
         break;
     switch (Cin) {
@@ -286,7 +298,7 @@ extern "C" int cl_conv_out(const void* x, const void* w, const float* bias, floa
         done = true;
     }
     if (smem > 200 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_out: C too large");
-    conv_out_kernel<4><<<num_sms() * 4, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+    launch_k(conv_out_kernel<4>, num_sms() * 4, 256, smem, stream, reinterpret_cast<const __nv_bfloat16*>(x),
                                                             reinterpret_cast<const __nv_bfloat16*>(w), bias, y, n, H, W, C);
     DONE();
 }
@@ -302,7 +314,7 @@ extern "C" int cl_conv_out_bwd(const float* dy, const void* w, void* dx, int n, 
         done = true;
     }
     if (smem > 200 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_conv_out_bwd: C too large");
-    conv_out_bwd_kernel<4><<<num_sms() * 4, 256, smem, stream>>>(dy, reinterpret_cast<const __nv_bfloat16*>(w),
+    launch_k(conv_out_bwd_kernel<4>, num_sms() * 4, 256, smem, stream, dy, reinterpret_cast<const __nv_bfloat16*>(w),
                                                                 reinterpret_cast<__nv_bfloat16*>(dx), n, H, W, C);
     DONE();
 }
@@ -310,7 +322,7 @@ extern "C" int cl_conv_out_bwd(const float* dy, const void* w, void* dx, int n, 
 extern "C" int cl_timestep_embedding(const float* t, float* out, int B, int dim, void* stream_) {
     STREAM;
     if (!t || !out || dim % 2) return set_error(CL_ERR_INVALID, "cl_timestep_embedding: bad args");
-    timestep_embedding_kernel<<<(B * dim / 2 + 255) / 256, 256, 0, stream>>>(t, out, B, dim);
+    launch_k(timestep_embedding_kernel, (B * dim / 2 + 255) / 256, 256, 0, stream, t, out, B, dim);
     DONE();
 }
 
@@ -321,7 +333,7 @@ extern "C" int cl_small_linear(const float* x, const void* w, const float* bias,
     const size_t smem = (size_t)SL_MAXB * K * sizeof(float);
     if (smem > 48 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_small_linear: K too large");
     dim3 grid((N + 7) / 8, (Bt + SL_MAXB - 1) / SL_MAXB);
-    small_linear_kernel<<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, Bt, N, K,
+    launch_k(small_linear_kernel, grid, 256, smem, stream, x, reinterpret_cast<const __nv_bfloat16*>(w), bias, out, Bt, N, K,
                                                      silu_in, silu_out);
     DONE();
 }
@@ -333,7 +345,7 @@ extern "C" int cl_mse_loss(const float* pred, const float* target, float* loss, 
     CL_CUDA_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), stream));
     int blocks = (int)((n + 255) / 256);
     if (blocks > num_sms() * 4) blocks = num_sms() * 4;
-    mse_kernel<<<blocks, 256, 0, stream>>>(pred, target, loss, dpred, n, gscale);
+    launch_k(mse_kernel, blocks, 256, 0, stream, pred, target, loss, dpred, n, gscale);
     DONE();
 }
 
@@ -344,6 +356,8 @@ extern "C" int cl_mse_loss(const float* pred, const float* target, float* loss, 
 namespace clb {
 __global__ void cfg_ddim_kernel(const float* __restrict__ eps2, float* __restrict__ x, long long n_half, float g, float sa_t,
                                 float s1a_t, float sa_p, float s1a_p) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_half; i += (long long)gridDim.x * blockDim.x) {
         const float eu = eps2[i], ec = eps2[n_half + i];
         const float e = eu + g * (ec - eu);
@@ -359,6 +373,6 @@ extern "C" int cl_cfg_ddim_step(const float* eps2, float* latents, int64_t n_hal
     if (!eps2 || !latents) return set_error(CL_ERR_INVALID, "cl_cfg_ddim_step: null");
     int blocks = (int)((n_half + 255) / 256);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    clb::cfg_ddim_kernel<<<blocks, 256, 0, stream>>>(eps2, latents, n_half, guidance, sqrt_at, sqrt_1m_at, sqrt_aprev, sqrt_1m_aprev);
+    launch_k(clb::cfg_ddim_kernel, blocks, 256, 0, stream, eps2, latents, n_half, guidance, sqrt_at, sqrt_1m_at, sqrt_aprev, sqrt_1m_aprev);
     DONE();
 }

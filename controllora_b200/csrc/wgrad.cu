@@ -40,6 +40,7 @@ static constexpr int WG_SMEM = 1024 + WG_STAGES * WG_STAGE_BYTES + 256;
 
 __global__ void __launch_bounds__(256, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+    pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
@@ -67,6 +68,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         fence_barrier_init();
     }
     if (warp_idx == 2) { tmem_alloc(tmem_ptr_smem, 256); tmem_relinquish(); }
+    pdl_wait();   // prologue above touched only smem / TMEM / kernel params
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -155,6 +157,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 // w fp32 [Cout][Cin][k][k] -> wf bf16 [Cout][k*k][Cin]  and  wd bf16 [Cin][k*k (flipped)][Cout]
 __global__ void conv_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
                                         int Cout, int Cin, int kk) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)Cout * Cin * kk;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i % kk);
@@ -170,6 +174,8 @@ __global__ void conv_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat
 // out[c] += alpha * sum_m x[m, c]
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long M, int C, float alpha, int rows_per_cta) {
+    pdl_launch_dependents();
+    pdl_wait();
     // thread -> column chunk of 8; CTA -> slab of rows; block-level smem reduction, then C global atomics per CTA
     __shared__ float sh[2048];
     for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
@@ -202,6 +208,8 @@ template <int CIN>
 __global__ void __launch_bounds__(256)
 conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw, int n, int H, int W,
                      int Cout, int pix_per_cta) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int KK = 9 * CIN, KP = (KK + 3) / 4 * 4, KG = KP / 4, TPS = 8 * KG;
     constexpr int PS = (CIN == 3) ? 4 : 2;          // pixel subsets (PS * TPS <= 256)
     constexpr int PB = 64, PPS = PB / PS;
@@ -352,7 +360,7 @@ extern "C" int cl_conv_wgrad(const void* dy, const void* x, float* dw, int n_img
         CL_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
         done = true;
     }
-    wgrad_tc_kernel<<<dim3(splits, tiles), 256, WG_SMEM, stream>>>(tDY, tX, p);
+    launch_k(wgrad_tc_kernel, dim3(splits, tiles), 256, WG_SMEM, stream, tDY, tX, p);
     DONE();
 }
 
@@ -362,7 +370,7 @@ extern "C" int cl_conv_weight_prep(const float* w, void* wf, void* wd, int Cout,
     const long long total = (long long)Cout * Cin * ksize * ksize;
     int blocks = (int)((total + 255) / 256);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    conv_weight_prep_kernel<<<blocks, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(wf), reinterpret_cast<__nv_bfloat16*>(wd),
+    launch_k(conv_weight_prep_kernel, blocks, 256, 0, stream, w, reinterpret_cast<__nv_bfloat16*>(wf), reinterpret_cast<__nv_bfloat16*>(wd),
                                                         Cout, Cin, ksize * ksize);
     DONE();
 }
@@ -377,7 +385,7 @@ extern "C" int cl_colsum(const void* x, float* out, int64_t M, int C, float alph
     int rows_per_cta = (int)((M + ctas - 1) / ctas);
     if (rows_per_cta < rows_par * 4) rows_per_cta = rows_par * 4;
     const int grid = (int)((M + rows_per_cta - 1) / rows_per_cta);
-    colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, M, C, alpha, rows_per_cta);
+    launch_k(colsum_kernel, grid, 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), out, M, C, alpha, rows_per_cta);
     DONE();
 }
 
@@ -392,8 +400,8 @@ extern "C" int cl_conv_in_wgrad(const float* x, const void* dy, float* dw, int n
     ppc = ((ppc + 63) / 64) * 64;
     if (ppc < 256) ppc = 256;
     const dim3 grid((unsigned)((npix + ppc - 1) / ppc), (unsigned)groups);
-    if (Cin == 3) conv_in_wgrad_kernel<3><<<grid, 256, 0, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, n, H, W, Cout, (int)ppc);
-    else if (Cin == 4) conv_in_wgrad_kernel<4><<<grid, 256, 0, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, n, H, W, Cout, (int)ppc);
+    if (Cin == 3) launch_k(conv_in_wgrad_kernel<3>, grid, 256, 0, stream, x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, n, H, W, Cout, (int)ppc);
+    else if (Cin == 4) launch_k(conv_in_wgrad_kernel<4>, grid, 256, 0, stream, x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, n, H, W, Cout, (int)ppc);
     else return set_error(CL_ERR_UNSUPPORTED, "cl_conv_in_wgrad: Cin must be 3 or 4");
     DONE();
 }
