@@ -376,3 +376,35 @@ extern "C" int cl_cfg_ddim_step(const float* eps2, float* latents, int64_t n_hal
     launch_k(clb::cfg_ddim_kernel, blocks, 256, 0, stream, eps2, latents, n_half, guidance, sqrt_at, sqrt_1m_at, sqrt_aprev, sqrt_1m_aprev);
     DONE();
 }
+
+// ------------------------------------------------------------------------------------------ CFG + DPM-Solver++(2M) step
+// eps = eps_u + g (eps_c - eps_u);  x0 = (x - sigma_s eps) / alpha_s;  x <- c_x x + c_m0 x0 + c_m1 x0_prev;  x0_prev <- x0
+// (diffusers-0.13 DPMSolverMultistepScheduler.step, dpmsolver++ / midpoint / order 2, the scheduler the reference's
+//  validation loop and apps use: train_text_to_image_control_lora.py:817-823, mix_lora_and_control_lora.py:80; the five
+//  scalars come from controllora_b200/sampler.py:dpmpp_2m_coeffs)
+namespace clb {
+__global__ void cfg_dpmpp_kernel(const float* __restrict__ eps2, float* __restrict__ x, float* __restrict__ x0_prev, long long n_half,
+                                 float g, float alpha_s, float sigma_s, float c_x, float c_m0, float c_m1) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const float inv_a = 1.f / alpha_s;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_half; i += (long long)gridDim.x * blockDim.x) {
+        const float eu = eps2[i], ec = eps2[n_half + i];
+        const float e = eu + g * (ec - eu);
+        const float xv = x[i];
+        const float x0 = (xv - sigma_s * e) * inv_a;
+        x[i] = c_x * xv + c_m0 * x0 + c_m1 * x0_prev[i];
+        x0_prev[i] = x0;
+    }
+}
+}  // namespace clb
+
+extern "C" int cl_cfg_dpmpp_step(const float* eps2, float* latents, float* x0_prev, int64_t n_half, float guidance, float alpha_s,
+                                 float sigma_s, float c_x, float c_m0, float c_m1, void* stream_) {
+    STREAM;
+    if (!eps2 || !latents || !x0_prev) return set_error(CL_ERR_INVALID, "cl_cfg_dpmpp_step: null");
+    int blocks = (int)((n_half + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    launch_k(clb::cfg_dpmpp_kernel, blocks, 256, 0, stream, eps2, latents, x0_prev, n_half, guidance, alpha_s, sigma_s, c_x, c_m0, c_m1);
+    DONE();
+}

@@ -580,6 +580,17 @@ def cfg_ddim_step(eps2, latents, guidance, a_t, a_prev):
           C.c_float((1 - a_t) ** 0.5), C.c_float(a_prev ** 0.5), C.c_float((1 - a_prev) ** 0.5))
 
 
+def cfg_dpmpp_step(eps2, latents, x0_prev, guidance, alpha_s, sigma_s, c_x, c_m0, c_m1):
+    """In-place DPM-Solver++(2M) update of `latents` (and of the stored x0 prediction) from eps2 [2B,...] = [uncond | cond]."""
+    _req(eps2, torch.float32, "eps2")
+    _req(latents, torch.float32, "latents")
+    _req(x0_prev, torch.float32, "x0_prev")
+    assert eps2.is_contiguous() and latents.is_contiguous() and x0_prev.is_contiguous()
+    assert eps2.numel() == 2 * latents.numel() == 2 * x0_prev.numel()
+    _call("cl_cfg_dpmpp_step", _p(eps2), _p(latents), _p(x0_prev), C.c_int64(latents.numel()), C.c_float(guidance),
+          C.c_float(alpha_s), C.c_float(sigma_s), C.c_float(c_x), C.c_float(c_m0), C.c_float(c_m1))
+
+
 class SkinnyQueue:
     """Collects the rank-r gradient reductions (dA / dB of every LoRA adapter) and issues them CL_SKINNY_MAX at a time
     through cl_skinny_atb_batch.  The queue keeps the operand tensors alive until the launch is enqueued."""

@@ -184,6 +184,10 @@ int cl_mse_loss(const float* pred, const float* target, float* loss, float* dpre
  * eps2 = [uncond | cond] noise predictions (each n_half floats), latents updated in place. */
 int cl_cfg_ddim_step(const float* eps2, float* latents, int64_t n_half, float guidance, float sqrt_at, float sqrt_1m_at,
                      float sqrt_aprev, float sqrt_1m_aprev, void* stream);
+/* CFG + DPM-Solver++(2M) update (diffusers DPMSolverMultistepScheduler defaults; the scheduler of the reference's
+ * validation loop / apps): x0 = (x - sigma_s eps)/alpha_s; x <- c_x x + c_m0 x0 + c_m1 x0_prev; x0_prev <- x0.        */
+int cl_cfg_dpmpp_step(const float* eps2 /* [2B,...] = [uncond | cond] */, float* latents, float* x0_prev, int64_t n_half,
+                      float guidance, float alpha_s, float sigma_s, float c_x, float c_m0, float c_m1, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * LoRA side path (diffusers LoRALinearLayer instances created at models.py:89-97,185,316-323).

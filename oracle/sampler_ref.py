@@ -1,6 +1,10 @@
 """ORACLE (tests only): CFG + DDIM (eta = 0) update restated from diffusers' DDIMScheduler.step / StableDiffusionPipeline
 (the un-vendored dependency behind train_text_to_image_control_lora.py:829-843; scheduler config of SD-1.5:
-scaled_linear betas 0.00085 -> 0.012, 1000 steps, steps_offset 1, set_alpha_to_one False, epsilon prediction, no clipping)."""
+scaled_linear betas 0.00085 -> 0.012, 1000 steps, steps_offset 1, set_alpha_to_one False, epsilon prediction, no clipping),
+and the DPM-Solver++(2M) multistep update of diffusers-0.13's DPMSolverMultistepScheduler with its defaults
+(algorithm_type "dpmsolver++", solver_order 2, solver_type "midpoint", lower_order_final True, no thresholding) - the
+scheduler the reference actually swaps in for validation / inference (train_text_to_image_control_lora.py:817-823,
+mix_lora_and_control_lora.py:80, apps/gradio_canny2image.py)."""
 import torch
 
 
@@ -22,3 +26,55 @@ def cfg_ddim_step(eps_uncond, eps_cond, x, t, num_inference_steps, guidance, ac=
     a_p = ac[prev] if prev >= 0 else ac[0]
     x0 = (x - (1 - a_t).sqrt() * eps) / a_t.sqrt()
     return (a_p.sqrt() * x0 + (1 - a_p).sqrt() * eps).to(x.dtype)
+
+
+# ---------------------------------------------------------------------------------------------- DPM-Solver++ (2M)
+class DPMSolverPP2M:
+    """Stateful restatement of DPMSolverMultistepScheduler (diffusers 0.13): set_timesteps + step for epsilon prediction."""
+
+    def __init__(self, num_inference_steps, n=1000, b0=0.00085, b1=0.012, lower_order_final=True):
+        import numpy as np
+
+        ac = alphas_cumprod(n, b0, b1)
+        self.alpha_t = ac.sqrt()
+        self.sigma_t = (1 - ac).sqrt()
+        self.lambda_t = self.alpha_t.log() - self.sigma_t.log()
+        ts = np.linspace(0, n - 1, num_inference_steps + 1).round()[::-1][:-1].copy().astype(np.int64)
+        self.timesteps = [int(v) for v in ts]
+        self.model_outputs = [None, None]
+        self.lower_order_nums = 0
+        self.lower_order_final = lower_order_final
+
+    def _first_order(self, m0, s, t, x):
+        lt, ls = self.lambda_t[t], self.lambda_t[s]
+        h = lt - ls
+        return (self.sigma_t[t] / self.sigma_t[s]) * x - (self.alpha_t[t] * (torch.exp(-h) - 1.0)) * m0
+
+    def _second_order(self, m0, m1, s1, s0, t, x):
+        lt, ls0, ls1 = self.lambda_t[t], self.lambda_t[s0], self.lambda_t[s1]
+        h, h0 = lt - ls0, ls0 - ls1
+        r0 = h0 / h
+        d0, d1 = m0, (1.0 / r0) * (m0 - m1)
+        c = self.alpha_t[t] * (torch.exp(-h) - 1.0)
+        return (self.sigma_t[t] / self.sigma_t[s0]) * x - c * d0 - 0.5 * c * d1
+
+    def step(self, eps, timestep, x):
+        """eps: the (already guidance-combined) noise prediction at `timestep`; x: current sample (fp64 math inside)."""
+        i = self.timesteps.index(int(timestep))
+        n = len(self.timesteps)
+        prev = 0 if i == n - 1 else self.timesteps[i + 1]
+        final = (i == n - 1) and self.lower_order_final and n < 15
+        xd, ed = x.double(), eps.double()
+        x0 = (xd - self.sigma_t[timestep] * ed) / self.alpha_t[timestep]
+        self.model_outputs = [self.model_outputs[1], x0]
+        if self.lower_order_nums < 1 or final:
+            out = self._first_order(x0, int(timestep), prev, xd)
+        else:
+            out = self._second_order(x0, self.model_outputs[0], self.timesteps[i - 1], int(timestep), prev, xd)
+        if self.lower_order_nums < 2:
+            self.lower_order_nums += 1
+        return out.to(x.dtype)
+
+
+def cfg_combine(eps_uncond, eps_cond, guidance):
+    return eps_uncond + guidance * (eps_cond - eps_uncond)

@@ -137,6 +137,55 @@ def test_cfg_ddim_step_matches_oracle():
         assert torch.allclose(xm.cpu(), ref, atol=1e-4, rtol=1e-4), t
 
 
+def test_cfg_dpmpp_step_matches_oracle():
+    """Fused CFG + DPM-Solver++(2M) kernel against the stateful oracle scheduler over a whole 12-step trajectory
+    (first-order first and last steps, second-order in between)."""
+    from controllora_b200 import ops
+    from controllora_b200.sampler import dpm_timesteps, dpmpp_2m_coeffs, sd15_alphas_cumprod
+    from oracle import sampler_ref as SR
+
+    steps = 12
+    sched = SR.DPMSolverPP2M(steps)
+    ts = dpm_timesteps(steps)
+    ac = sd15_alphas_cumprod()
+    g = torch.Generator().manual_seed(0)
+    x_ref = torch.randn(2, 4, 16, 16, generator=g)
+    xm = x_ref.clone().cuda()
+    x0p = torch.zeros_like(xm)
+    for i, t in enumerate(ts):
+        eps2 = torch.randn(4, 4, 16, 16, generator=g)
+        x_ref = sched.step(SR.cfg_combine(eps2[:2], eps2[2:], 7.5), t, x_ref)
+        ops.cfg_dpmpp_step(eps2.cuda(), xm, x0p, 7.5, *dpmpp_2m_coeffs(i, ts, ac))
+        assert torch.allclose(xm.cpu(), x_ref, atol=2e-4, rtol=2e-4), (i, t)
+
+
+def test_dpmpp_loop_tracks_oracle_on_tiny_unet():
+    """4 CFG + DPM-Solver++(2M) steps (UNet batch 2B, control injected once) against the oracle UNet + oracle scheduler."""
+    from controllora_b200.sampler import dpmpp_sample
+    from oracle import sampler_ref as SR
+
+    ounet, munet, ocl, mcl = check_unet.build_pair("v2")
+    g = torch.Generator().manual_seed(11)
+    B, HW = 2, 16
+    guide = (torch.rand(B, 3, HW * 8, HW * 8, generator=g) * 2 - 1).to(torch.bfloat16).float()
+    cond = torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).float()
+    unc = torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).float()
+    lat0 = torch.randn(B, 4, HW, HW, generator=g)
+    steps = 4
+    sched = SR.DPMSolverPP2M(steps)
+    with torch.no_grad():
+        ocl(torch.cat([guide, guide], 0))
+        x = lat0.clone()
+        for t in sched.timesteps:
+            eps = ounet(torch.cat([x, x], 0), torch.full((2 * B,), int(t)), torch.cat([unc, cond], 0)).sample
+            x = sched.step(SR.cfg_combine(eps[:B], eps[B:], 7.5), t, x)
+    out = dpmpp_sample(munet, mcl, guide.cuda(), cond.cuda().to(torch.bfloat16), unc.cuda().to(torch.bfloat16),
+                       num_inference_steps=steps, guidance_scale=7.5, latents=lat0.cuda())
+    err = float((out.cpu() - x).norm() / x.norm())
+    print("dpm-solver++ 4-step latent rel err", err)
+    assert err < 8e-2
+
+
 def test_ddim_loop_tracks_oracle_on_tiny_unet():
     """3 CFG+DDIM steps (UNet batch 2B, control injected once) against the oracle UNet driven by the oracle scheduler."""
     import controllora_b200 as cb

@@ -141,3 +141,28 @@ def test_unsupported_variants_fail_loudly():
     wire_processors(mu, mcl)
     with pytest.raises(NotImplementedError):
         LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)
+
+
+@pytest.mark.parametrize("steps", [8, 30, 50])
+def test_dpmpp_2m_coefficients_reproduce_the_oracle_scheduler(steps):
+    """sampler.dpmpp_2m_coeffs (the five scalars the fused CFG + DPM-Solver++ kernel consumes) against the stateful
+    restatement of diffusers' DPMSolverMultistepScheduler: same timesteps, same trajectory on a synthetic eps model."""
+    from controllora_b200.sampler import dpm_timesteps, dpmpp_2m_coeffs, sd15_alphas_cumprod
+    from oracle import sampler_ref as SR
+
+    sched = SR.DPMSolverPP2M(steps)
+    ts = dpm_timesteps(steps)
+    assert ts == sched.timesteps
+    ac = sd15_alphas_cumprod()
+    g = torch.Generator().manual_seed(0)
+    x_ref = torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64)
+    x = x_ref.clone()
+    x0_prev = torch.zeros_like(x)
+    w = torch.randn(4, 4, generator=g, dtype=torch.float64) * 0.3
+    for i, t in enumerate(ts):
+        eps_fn = lambda v: torch.einsum("oc,bchw->bohw", w, v) * (0.5 + t / 2000.0)      # any deterministic "model"
+        x_ref = sched.step(eps_fn(x_ref), t, x_ref)
+        a_s, sg_s, c_x, c_m0, c_m1 = dpmpp_2m_coeffs(i, ts, ac)
+        x0 = (x - sg_s * eps_fn(x)) / a_s
+        x, x0_prev = c_x * x + c_m0 * x0 + c_m1 * x0_prev, x0
+        assert torch.allclose(x, x_ref, rtol=1e-9, atol=1e-9), (i, t)
