@@ -140,6 +140,7 @@ class LoraSlot:
         self.device = device
         self.rp = 4
         self.ext = self.up_tab = self.ext_t = self.down_tab = None
+        self.post_add = False     # models.py:125,132,135,147: the adapter reads the base projection's OUTPUT (then K == N)
 
     def add(self, down: torch.Tensor, up: torch.Tensor, mult: float = 1.0) -> Adapter:
         r = down.shape[0]
@@ -178,6 +179,8 @@ class Ctx:
 def linear(ctx: Ctx, x: Var, lw: LinearW, *, residual: Optional[Var] = None, slot: Optional[LoraSlot] = None,
            t_add: Optional[torch.Tensor] = None, on_slot_bwd: Optional[Callable] = None, out_shape=None) -> Var:
     """y = x W^T + b (+ residual) (+ scale * (x A^T + t_add) B^T).  x: [..., K] bf16."""
+    if slot is not None and slot.rank > 0 and slot.post_add:
+        return _linear_post_add(ctx, x, lw, residual, slot, t_add, on_slot_bwd, out_shape)
     K = x.data.shape[-1]
     x2 = x.data.view(-1, K)
     N = lw.w.shape[0]
@@ -223,6 +226,46 @@ def linear(ctx: Ctx, x: Var, lw: LinearW, *, residual: Optional[Var] = None, slo
                     ops.SKINNY.add(e[:, a.col:], r, x2, a.down_grad, K, 1, scale)
                 if on_slot_bwd is not None:
                     on_slot_bwd(e, t_out, dy2)
+
+        ctx.tape.record(bwd)
+    return out
+
+
+def _linear_post_add(ctx: Ctx, x: Var, lw: LinearW, residual: Optional[Var], slot: LoraSlot, t_add, on_slot_bwd, out_shape) -> Var:
+    """post_add LoRA (models.py:125,132,135,147 / :236-238):  y0 = x W^T + b;  t = y0 A^T (+ t_add);  y = y0 + s t B^T (+ res).
+    The adapter reads the projection's own output, so its rank-r product needs complete output rows: base GEMM, then the
+    same skinny-GEMM + fused rank-4 update kernels as the V2 control injection.  One adapter of rank <= 4 per projection."""
+    assert len(slot.adapters) == 1 and slot.rank <= 4 and slot.K == slot.N
+    a = slot.adapters[0]
+    r = a.down.shape[0]
+    K = x.data.shape[-1]
+    x2 = x.data.view(-1, K)
+    N = lw.w.shape[0]
+    scale = ctx.scale
+    y0 = ops.gemm(x2, lw.w, bias=lw.bias)                                   # [M, N] bf16
+    th16 = ops.gemm(y0, slot.ext, out_fp32=True)                            # hi/lo columns of y0 A^T
+    y, t = ops.v2_inject_fwd(y0, th16, t_add, r, slot.up_tab, scale)        # t [M, 8] (cols < r valid), y = y0 + s t B^T
+    if residual is not None:
+        y = ops.add(y, residual.data.view(-1, N))
+    y = y.view(*(out_shape or (*x.data.shape[:-1], N)))
+    out = Var(y, rg=True)
+    if ctx.tape is not None:
+        def bwd():
+            dy = out.grad
+            out.grad = None
+            if dy is None:
+                return
+            dy2 = dy.contiguous().view(-1, N)
+            if residual is not None:
+                give_tensor(residual, dy.view(residual.data.shape))
+            # dt = dy B (unscaled);  dy0 = dy + s dt A
+            dt, dy0 = ops.v2_inject_bwd(dy2, slot.up_tab, slot.down_tab, scale, need_dh=True)
+            ops.SKINNY.add(t, r, dy2, a.up_grad, 1, r, scale)               # dB[n, j] += s sum_m dy[m, n] t[m, j]
+            ops.SKINNY.add(dt, r, y0, a.down_grad, N, 1, scale)             # dA[j, n] += s sum_m dt[m, j] y0[m, n]
+            if x.rg:
+                give_produce(x, lambda buf, acc: ops.gemm(dy0, lw.wt, out=buf.view(-1, K), residual=buf.view(-1, K) if acc else None))
+            if on_slot_bwd is not None:
+                on_slot_bwd(dt, t, dy2)
 
         ctx.tape.record(bwd)
     return out

@@ -104,9 +104,10 @@ class LoraRuntime:
             lp.proc = p
             chain = [*getattr(p, "pre_loras", []), p, *getattr(p, "post_loras", [])]
             lp.chain = chain
+            post_add = [bool(getattr(a, "post_add", False)) for a in chain]
+            if any(post_add) and (len(chain) > 1 or _is_v2(p)):
+                raise NotImplementedError("lora_post_add=True is supported for single (unstacked) LoRA / v1 ControlLoRA processors only")
             for a in chain:
-                if getattr(a, "post_add", False):
-                    raise NotImplementedError("lora_post_add=True (configs/post-add.json) is not on the CUDA path yet")
                 if a is not p and (_is_v1(a) or _is_v2(a)):
                     raise NotImplementedError("stacking a second *Control*LoRA processor as pre/post LoRA is not supported")
             if _is_v1(p) and getattr(p, "concat_hidden", False):
@@ -114,10 +115,14 @@ class LoraRuntime:
             lp.kind = "v1" if _is_v1(p) else ("v2" if _is_v2(p) else "plain")
             C = L.to_q.w.shape[0]
             kv_in = L.to_k.w.shape[1]
+            lp.post_add = any(post_add)
             lp.q = LoraSlot(C, C, dev)
-            lp.k = LoraSlot(C, kv_in, dev)
-            lp.v = LoraSlot(C, kv_in, dev)
+            # post_add adapters read the projection's output: their `down` has C input features even for the text k / v
+            lp.k = LoraSlot(C, C if lp.post_add else kv_in, dev)
+            lp.v = LoraSlot(C, C if lp.post_add else kv_in, dev)
             lp.out = LoraSlot(C, C, dev)
+            for sl in (lp.q, lp.k, lp.v, lp.out):
+                sl.post_add = lp.post_add
             for a in chain:
                 ad = self._adapter(lp.q, a.to_q_lora)
                 if a is p:
@@ -129,8 +134,8 @@ class LoraRuntime:
                 if a is p or not a.output_states_skipped:
                     self._adapter(lp.out, a.to_out_lora)
             lp.q.finalize(self.plan, need_dx=True)
-            lp.k.finalize(self.plan, need_dx=not L.is_cross)
-            lp.v.finalize(self.plan, need_dx=not L.is_cross)
+            lp.k.finalize(self.plan, need_dx=lp.post_add or not L.is_cross)     # post_add: down_tab = A^T feeds dy0 = dy + s dt A
+            lp.v.finalize(self.plan, need_dx=lp.post_add or not L.is_cross)
             lp.out.finalize(self.plan, need_dx=True)
             if lp.kind == "v2":
                 self._v2_tables(lp)

@@ -137,10 +137,37 @@ def test_unsupported_variants_fail_loudly():
     from controllora_b200.unet_module import GradStore
 
     mu = _tiny_unet()
-    mcl = cb.ControlLoRA(lora_post_add=True, **TINY_LORA)
+    mcl = cb.ControlLoRA(lora_concat_hidden=True, **TINY_LORA)          # configs/danbooru-sketch.json flavour
     wire_processors(mu, mcl)
     with pytest.raises(NotImplementedError):
         LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)
+    # post_add stacked with a pre-LoRA is outside the supported set as well
+    mu = _tiny_unet()
+    mcl = cb.ControlLoRA(lora_post_add=True, **TINY_LORA)
+    procs = wire_processors(mu, mcl)
+    for p in procs.values():
+        p.inject_pre_lora(cb.LoRACrossAttnProcessor(p.hidden_size, p.cross_attention_dim, rank=4))
+    with pytest.raises(NotImplementedError):
+        LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)
+
+
+def test_post_add_config_builds_a_runtime_plan():
+    """lora_post_add=True (configs/post-add.json): every slot is flagged, and the text k / v adapters take C inputs."""
+    from controllora_b200.lora_runtime import LoraRuntime
+    from controllora_b200.unet_module import GradStore
+
+    mu = _tiny_unet()
+    mcl = cb.ControlLoRA(lora_post_add=True, **TINY_LORA)
+    procs = wire_processors(mu, mcl)
+    rt = LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)
+    n = 0
+    for lp in rt.layers.values():
+        if getattr(lp, "proc", None) is None:
+            continue
+        n += 1
+        assert lp.post_add and all(sl.post_add for sl in (lp.q, lp.k, lp.v, lp.out))
+        assert lp.k.K == lp.k.N and lp.v.K == lp.v.N
+    assert n == len(procs) > 0
 
 
 @pytest.mark.parametrize("steps", [8, 30, 50])

@@ -54,6 +54,8 @@ def build_pair(variant, B=2, HW=16, seed=0):
     kw = dict(TINY_LORA)
     if variant == "v2":
         kw.update(lora_control_version=2, lora_pre_conv_skipped=True)
+    if variant == "v1_post_add":
+        kw.update(lora_post_add=True)            # configs/post-add.json: every adapter reads its projection's output
     ocl = MR.ControlLoRA(**kw) if variant != "none" else None
     mcl = cb.ControlLoRA(**kw) if variant != "none" else None
     if ocl is not None:
@@ -114,7 +116,7 @@ def run(variant):
     target = torch.randn(B, 4, HW, HW, generator=g)
     ch = TINY["block_out_channels"]
     ctrl_o, ctrl_m = [], []
-    if variant in ("v1", "v1_stacked", "v2"):
+    if variant in ("v1", "v1_stacked", "v2", "v1_post_add"):
         cc = [256] * 4 if variant == "v2" else list(ch)
         for lvl in range(4):
             s = HW >> lvl
