@@ -131,3 +131,65 @@ class Trainer:
         ops.sumsq(self.flat_g, self.gnorm_sq)
         ops.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                   self.step_idx, gnorm_sq=self.gnorm_sq, max_norm=self.max_norm, grad_scale=self.arena.grad_scale, zero_grad=True)
+
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    # The reference checkpoints through accelerate: `accelerator.save_state(output_dir/checkpoint-{global_step})` every
+    # `checkpointing_steps` (train_text_to_image_control_lora.py:805-809) and resumes from the highest `checkpoint-N`
+    # (:713-735).  Same directory convention here: the ControlLoRA weights in the reference's own format
+    # (config.json + diffusion_pytorch_model.safetensors, the files of :927-929) plus the optimizer state of the flat arenas.
+    def save_checkpoint(self, output_dir, global_step: Optional[int] = None) -> str:
+        import os
+
+        step = self.step_idx if global_step is None else int(global_step)
+        path = os.path.join(str(output_dir), f"checkpoint-{step}")
+        os.makedirs(path, exist_ok=True)
+        self.cl.save_config(path)
+        self.cl.save_pretrained(path, safe_serialization=True)
+        torch.save({"step_idx": self.step_idx, "global_step": step, "numel": self.numel, "lr": self.lr, "betas": self.betas,
+                    "weight_decay": self.wd, "eps": self.eps, "max_grad_norm": self.max_norm,
+                    "exp_avg": self.flat_m[:self.numel].detach().cpu(), "exp_avg_sq": self.flat_v[:self.numel].detach().cpu(),
+                    "param_names": [n for n, _ in self.cl.named_parameters()]},
+                   os.path.join(path, "optimizer.bin"))
+        return path
+
+    @staticmethod
+    def latest_checkpoint(output_dir) -> Optional[str]:
+        """Highest `checkpoint-N` under output_dir (train_text_to_image_control_lora.py:713-721), or None."""
+        import os
+
+        if not os.path.isdir(str(output_dir)):
+            return None
+        best, best_n = None, -1
+        for d in os.listdir(str(output_dir)):
+            if d.startswith("checkpoint-") and d[len("checkpoint-"):].isdigit() and int(d[len("checkpoint-"):]) > best_n:
+                best, best_n = d, int(d[len("checkpoint-"):])
+        return None if best is None else os.path.join(str(output_dir), best)
+
+    def load_checkpoint(self, path) -> int:
+        """Restore parameters (into the flat arena the kernels read) and AdamW moments; returns the stored global step.
+        A captured CUDA graph stays valid: it reads the same arena addresses."""
+        import os
+
+        st = os.path.join(str(path), "diffusion_pytorch_model.safetensors")
+        if os.path.isfile(st):
+            from safetensors.torch import load_file
+
+            sd = load_file(st)
+        else:
+            sd = torch.load(os.path.join(str(path), "diffusion_pytorch_model.bin"), map_location="cpu")
+        own = dict(self.cl.named_parameters())
+        missing = [k for k in own if k not in sd]
+        if missing:
+            raise KeyError(f"checkpoint {path} lacks parameters: {missing[:4]}...")
+        with torch.no_grad():
+            for k, p in own.items():
+                p.data.copy_(sd[k].to(p.data.device, p.data.dtype))      # p.data is a view into flat_p
+        opt = torch.load(os.path.join(str(path), "optimizer.bin"), map_location="cpu")
+        if int(opt["numel"]) != self.numel:
+            raise ValueError("optimizer state does not match this ControlLoRA's parameter count")
+        with torch.no_grad():
+            self.flat_m[:self.numel].copy_(opt["exp_avg"].to(self.flat_m.device))
+            self.flat_v[:self.numel].copy_(opt["exp_avg_sq"].to(self.flat_v.device))
+            self.flat_g.zero_()
+        self.step_idx = int(opt["step_idx"])
+        return int(opt.get("global_step", self.step_idx))

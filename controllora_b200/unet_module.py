@@ -79,6 +79,34 @@ class UNet2DConditionModel(nn.Module):
         return cls(UNetWeights(sd, torch.device(device), config))
 
     @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None, device="cuda", **unused):
+        """Load a diffusers-format UNet directory (`<root>[/subfolder]/config.json` +
+        `diffusion_pytorch_model.safetensors` or `.bin`), the layout `UNet2DConditionModel.from_pretrained(...,
+        subfolder="unet")` reads at train_text_to_image_control_lora.py:407-409.  Local directories only (no hub access)."""
+        import json
+        import os
+
+        root = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else str(pretrained_model_name_or_path)
+        if not os.path.isdir(root):
+            raise FileNotFoundError(f"{root}: not a local directory (hub download is not available)")
+        config = None
+        cfg_path = os.path.join(root, "config.json")
+        if os.path.isfile(cfg_path):
+            with open(cfg_path) as f:
+                raw = json.load(f)
+            keep = ("block_out_channels", "layers_per_block", "cross_attention_dim", "attention_head_dim", "in_channels",
+                    "out_channels", "norm_num_groups", "norm_eps")
+            config = {k: (tuple(v) if isinstance(v, list) else v) for k, v in raw.items() if k in keep}
+        st = os.path.join(root, "diffusion_pytorch_model.safetensors")
+        if os.path.isfile(st):
+            from safetensors.torch import load_file
+
+            sd = load_file(st)
+        else:
+            sd = torch.load(os.path.join(root, "diffusion_pytorch_model.bin"), map_location="cpu")
+        return cls.from_state_dict(sd, device, config)
+
+    @classmethod
     def synthetic(cls, device="cuda", config: Optional[dict] = None, seed: int = 0):
         return cls.from_state_dict(synthetic_state_dict(config, seed), device, config)
 

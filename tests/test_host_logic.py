@@ -193,3 +193,58 @@ def test_dpmpp_2m_coefficients_reproduce_the_oracle_scheduler(steps):
         x0 = (x - sg_s * eps_fn(x)) / a_s
         x, x0_prev = c_x * x + c_m0 * x0 + c_m1 * x0_prev, x0
         assert torch.allclose(x, x_ref, rtol=1e-9, atol=1e-9), (i, t)
+
+
+def test_unet_from_pretrained_reads_a_diffusers_directory(tmp_path):
+    """config.json + diffusion_pytorch_model.safetensors under <root>/unet, the layout of train_...:407-409."""
+    import json
+    from safetensors.torch import save_file
+    from controllora_b200.unet import synthetic_state_dict
+
+    sd = synthetic_state_dict(TINY, 3)
+    root = tmp_path / "sd" / "unet"
+    root.mkdir(parents=True)
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(root / "diffusion_pytorch_model.safetensors"))
+    cfg = {k: (list(v) if isinstance(v, tuple) else v) for k, v in TINY.items()}
+    cfg.update(_class_name="UNet2DConditionModel", sample_size=64)
+    (root / "config.json").write_text(json.dumps(cfg))
+    mu = cb.UNet2DConditionModel.from_pretrained(str(tmp_path / "sd"), subfolder="unet", device="cpu")
+    assert tuple(mu.config.block_out_channels) == tuple(TINY["block_out_channels"])
+    assert list(mu.attn_processors.keys()) == list(_tiny_unet().attn_processors.keys())
+    with pytest.raises(FileNotFoundError):
+        cb.UNet2DConditionModel.from_pretrained(str(tmp_path / "nope"), subfolder="unet", device="cpu")
+
+
+def test_trainer_checkpoint_roundtrip(tmp_path):
+    """checkpoint-N directories (reference: accelerator.save_state / resume from the highest N): parameters, AdamW moments
+    and the step counter survive a save -> fresh Trainer -> load."""
+    from controllora_b200.trainer import Trainer
+
+    def make(seed):
+        torch.manual_seed(seed)
+        mu = _tiny_unet()
+        mcl = cb.ControlLoRA(**TINY_LORA)
+        wire_processors(mu, mcl)
+        return Trainer(mu, mcl, lr=1e-4), mcl
+
+    tr, cl = make(0)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        tr.flat_p[:tr.numel].copy_(torch.randn(tr.numel, generator=g))
+        tr.flat_m[:tr.numel].copy_(torch.randn(tr.numel, generator=g))
+        tr.flat_v[:tr.numel].copy_(torch.rand(tr.numel, generator=g))
+    tr.step_idx = 37
+    assert Trainer.latest_checkpoint(tmp_path) is None
+    tr.save_checkpoint(tmp_path, global_step=30)
+    p37 = tr.save_checkpoint(tmp_path)
+    assert Trainer.latest_checkpoint(tmp_path) == p37 and p37.endswith("checkpoint-37")
+    tr2, cl2 = make(5)
+    assert not torch.equal(tr2.flat_p, tr.flat_p)
+    assert tr2.load_checkpoint(p37) == 37 and tr2.step_idx == 37
+    assert torch.equal(tr2.flat_p[:tr.numel], tr.flat_p[:tr.numel])
+    assert torch.equal(tr2.flat_m, tr.flat_m) and torch.equal(tr2.flat_v, tr.flat_v)
+    for (n1, a), (n2, b) in zip(cl.named_parameters(), cl2.named_parameters()):
+        assert n1 == n2 and torch.equal(a, b)
+    # the ControlLoRA part of the checkpoint is a plain reference-format model directory
+    cl3 = cb.ControlLoRA.from_pretrained(p37)
+    assert all(torch.equal(a, b.cpu()) for a, b in zip(cl3.state_dict().values(), cl.state_dict().values()))
