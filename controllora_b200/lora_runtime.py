@@ -7,6 +7,9 @@ into one rank<=8 `LoraSlot` per projection, so a projection and all of its LoRA 
 v1 control (models.py:237-238):  q = Wq h + s Bq Aq (h + s Bc Ac c)
         = Wq h + s Bq ( Aq h  +  s (Aq Bc) (Ac c) )               -> `t_add` of the fused GEMM epilogue,
   with u = Ac c computed for all processors of a UNet level by one GEMM over the level's control state.
+v1 control with `concat_hidden` (models.py:208-214; configs/danbooru-sketch.json, control_rank 256):
+        ctrl = s Bc Ac [h ; c]  is a real two-layer MLP, so it runs as dense tcgen05 GEMMs (Ac_h, Ac_c, Bc are trainable: their
+        weight gradients are dense GEMMs too), followed by the rank-4 `to_q_lora` on h + ctrl.
 V2 control (models.py:369, 415):  h' = h + s Bc Ac [h ; c]  is a rank-r update of the hidden states (before q/k/v and
   again before to_out), done by one skinny GEMM + one rank-update kernel.
 """
@@ -110,9 +113,10 @@ class LoraRuntime:
             for a in chain:
                 if a is not p and (_is_v1(a) or _is_v2(a)):
                     raise NotImplementedError("stacking a second *Control*LoRA processor as pre/post LoRA is not supported")
-            if _is_v1(p) and getattr(p, "concat_hidden", False):
-                raise NotImplementedError("lora_concat_hidden=True for v1 processors (configs/danbooru-sketch.json) is not on the CUDA path yet")
-            lp.kind = "v1" if _is_v1(p) else ("v2" if _is_v2(p) else "plain")
+            cat = _is_v1(p) and getattr(p, "concat_hidden", False)
+            if cat and (len(chain) > 1 or any(post_add) or p.to_q_lora.down.weight.shape[0] > 4):
+                raise NotImplementedError("lora_concat_hidden=True is supported for single (unstacked, non-post_add, rank <= 4) processors only")
+            lp.kind = "v1cat" if cat else ("v1" if _is_v1(p) else ("v2" if _is_v2(p) else "plain"))
             C = L.to_q.w.shape[0]
             kv_in = L.to_k.w.shape[1]
             lp.post_add = any(post_add)
@@ -124,7 +128,10 @@ class LoraRuntime:
             for sl in (lp.q, lp.k, lp.v, lp.out):
                 sl.post_add = lp.post_add
             for a in chain:
-                ad = self._adapter(lp.q, a.to_q_lora)
+                if lp.kind == "v1cat":
+                    ad = None                                   # the q adapter reads h + ctrl: handled by _v1cat_q
+                else:
+                    ad = self._adapter(lp.q, a.to_q_lora)
                 if a is p:
                     lp.ctrl_adapter = ad
                 if not a.key_states_skipped:
@@ -139,6 +146,14 @@ class LoraRuntime:
             lp.out.finalize(self.plan, need_dx=True)
             if lp.kind == "v2":
                 self._v2_tables(lp)
+            if lp.kind == "v1cat":
+                ql = p.to_q_lora
+                lp.cat_ext = torch.zeros(16, C, device=dev, dtype=BF16)                       # hi/lo rows of Aq
+                lp.cat_up = torch.zeros(C, 4, device=dev, dtype=torch.float32)                # Bq
+                lp.cat_down = torch.zeros(C, 4, device=dev, dtype=torch.float32)              # Aq^T
+                self.plan.add_ext(ql.down.weight, lp.cat_ext)
+                self.plan.add_table(ql.up.weight, lp.cat_up)
+                self.plan.add_table(ql.down.weight, lp.cat_down, transposed=True)
         self.signature = self.make_signature(self.W)
 
     # ------------------------------------------------------------------------------------------------ per forward
@@ -147,7 +162,7 @@ class LoraRuntime:
         # (re)group control processors by the tensor that was injected into them
         groups: Dict[int, List[LayerPlan]] = {}
         for lp in self.layers.values():
-            if lp.kind in ("v1", "v2"):
+            if lp.kind in ("v1", "v2", "v1cat"):
                 cs = lp.proc.control_states
                 assert cs is not None, "inject_control_states() must run before the UNet forward (models.py:227)"
                 groups.setdefault(cs.data_ptr(), []).append(lp)
@@ -165,6 +180,9 @@ class LoraRuntime:
             lv.c = c
             T = c.data.shape[0] * c.data.shape[1]
             assert c.data.shape[-1] == lv.cc
+            if lv.nb == 0:                       # concat_hidden levels: every processor runs its own dense control MLP
+                lv.u = lv.du = None
+                continue
             c2 = c.data.view(T, lv.cc)
             u16 = ops.gemm(c2, lv.stack, out_fp32=True)
             lv.u = ops.hilo_combine(u16, lv.nb)
@@ -183,6 +201,11 @@ class LoraRuntime:
             lv = _LevelCtx()
             cvar = control_vars[key]
             lv.cc = cvar.data.shape[-1]
+            if lps[0].kind == "v1cat":
+                for lp in lps:
+                    lp.level = lv
+                self.level_list.append(lv)
+                continue
             v2 = lps[0].kind == "v2"
             lv.nb = len(lps) if v2 else (len(lps) + 1) // 2
             lv.stack = torch.zeros(16 * lv.nb, lv.cc, device=self.device, dtype=BF16)
@@ -249,6 +272,65 @@ class LoraRuntime:
         if lv.du is not None:
             i = lp.col // 4
             ops.rowmat(ea, lp.M, 1, rc, rc, r, s * s, lv.du, 16 * lv.nb, out_mode=1, col_off=16 * (i // 2) + 4 * (i % 2), lo_off=8)
+
+    # ------------------------------------------------------------------------------------------------ v1 + concat_hidden
+    def _v1cat_q(self, ctx: Ctx, lp: LayerPlan, L, hs: Var) -> Var:
+        """q = Wq h + s Bq Aq (h + ctrl),  ctrl = s Bc Ac [h ; c]   (models.py:208-218, 237-238 with concat_hidden)."""
+        p, lv = lp.proc, lp.level
+        s = ctx.scale
+        C = p.hidden_size
+        Ac, Bc = p.to_control.down.weight, p.to_control.up.weight          # [R, C + Cc], [C, R]  (fp32 masters)
+        ql = p.to_q_lora
+        r = ql.down.weight.shape[0]
+        c = lv.c
+        T = hs.data.shape[0] * hs.data.shape[1]
+        h2, c2 = hs.data.view(T, C), c.data.view(T, lv.cc)
+        # bf16 operands of the trainable dense layers, re-derived from the fp32 masters every step
+        Ac_h = Ac[:, :C].to(BF16).contiguous()                             # [R, C]
+        Ac_c = Ac[:, C:].to(BF16).contiguous()                             # [R, Cc]
+        Bc_s = (Bc * s).to(BF16).contiguous()                              # [C, R]   (scale folded)
+        u = ops.gemm(h2, Ac_h)
+        ops.gemm(c2, Ac_c, residual=u, out=u)                              # u = Ac [h ; c]          [T, R]
+        xp = ops.gemm(u, Bc_s, residual=h2)                                # x' = h + s Bc u         [T, C]
+        th16 = ops.gemm(xp, lp.cat_ext, out_fp32=True)                     # hi/lo columns of x' Aq^T
+        q0 = ops.gemm(h2, L.to_q.w, bias=L.to_q.bias)
+        qd, t = ops.v2_inject_fwd(q0, th16, None, r, lp.cat_up, s)         # q = q0 + s t Bq^T,  t = Aq x'
+        out = Var(qd.view(*hs.data.shape[:-1], C), rg=True)
+        if ctx.tape is not None:
+            def bwd():
+                dq = out.grad
+                out.grad = None
+                if dq is None:
+                    return
+                dq2 = dq.contiguous().view(T, C)
+                dt, _ = ops.v2_inject_bwd(dq2, lp.cat_up, None, s, need_dh=False)           # dt = dq Bq  (unscaled)
+                ops.SKINNY.add(t, r, dq2, self.grad_of(ql.up.weight), 1, r, s)             # dBq
+                ops.SKINNY.add(dt, r, xp, self.grad_of(ql.down.weight), C, 1, s)           # dAq += s dt^T x'
+                dxp = ops.rank_update(torch.zeros_like(xp), dt, lp.cat_down, s)            # dL/dx' = s dt Aq   [T, C]
+                # control MLP:  x' = h + (s Bc) u,  u = Ac_h h + Ac_c c
+                du = ops.gemm(dxp, Bc_s.t().contiguous())                                   # [T, R] = dx' (s Bc)
+                R = Ac.shape[0]
+                ops.conv_wgrad(dxp.view(1, 1, T, C), u.view(1, 1, T, R), self.grad_of(Bc).view(C, R, 1, 1), 1, 1, 0, s)   # dBc += s dx'^T u
+                gAc = self.grad_of(Ac)
+                tmp_h = torch.zeros(R, C, 1, 1, device=self.device, dtype=torch.float32)
+                tmp_c = torch.zeros(R, lv.cc, 1, 1, device=self.device, dtype=torch.float32)
+                ops.conv_wgrad(du.view(1, 1, T, R), h2.view(1, 1, T, C), tmp_h, 1, 1, 0, 1.0)                         # dAc_h = du^T h
+                ops.conv_wgrad(du.view(1, 1, T, R), c2.view(1, 1, T, lv.cc), tmp_c, 1, 1, 0, 1.0)                     # dAc_c = du^T c
+                gAc[:, :C].add_(tmp_h.view(R, C))
+                gAc[:, C:].add_(tmp_c.view(R, lv.cc))
+                if hs.rg:
+                    def prod(buf, acc):
+                        b2 = buf.view(T, C)
+                        ops.gemm(dq2, L.to_q.wt, out=b2, residual=b2 if acc else None)      # dq Wq
+                        ops.add(b2, dxp, out=b2)                                            # + dL/dx'
+                        ops.gemm(du, Ac_h.t().contiguous(), out=b2, residual=b2)            # + du Ac_h
+                    E.give_produce(hs, prod)
+                if c.rg:
+                    E.give_produce(c, lambda buf, acc: ops.gemm(du, Ac_c.t().contiguous(), out=buf.view(T, lv.cc),
+                                                                residual=buf.view(T, lv.cc) if acc else None))
+
+            ctx.tape.record(bwd)
+        return out
 
     # ------------------------------------------------------------------------------------------------ V2
     def _v2_inject(self, ctx: Ctx, lp: LayerPlan, h: Var, which: int) -> Var:
@@ -321,7 +403,10 @@ class LoraRuntime:
         on_q = None
         if lp.kind == "v1":
             on_q = lambda e, t_out, dy2: self._v1_q_bwd(ctx, lp, e, t_out, dy2)
-        q = E.linear(ctx, hs, L.to_q, slot=lp.q, t_add=getattr(lp, "t_add", None), on_slot_bwd=on_q)
+        if lp.kind == "v1cat":
+            q = self._v1cat_q(ctx, lp, L, hs)
+        else:
+            q = E.linear(ctx, hs, L.to_q, slot=lp.q, t_add=getattr(lp, "t_add", None), on_slot_bwd=on_q)
         k = E.linear(ctx, kv_in, L.to_k, slot=lp.k)
         v = E.linear(ctx, kv_in, L.to_v, slot=lp.v)
         o = E.attention(ctx, q, k, v, L.heads)

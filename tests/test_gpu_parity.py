@@ -73,7 +73,7 @@ def test_lora_and_optimizer(case):
 
 
 # ------------------------------------------------------------------------------------------------ assembled hot path
-@pytest.mark.parametrize("variant", ["none", "plain", "v1", "v1_stacked", "v2", "v1_post_add"])
+@pytest.mark.parametrize("variant", ["none", "plain", "v1", "v1_stacked", "v2", "v1_post_add", "v1_concat"])
 def test_unet_fwd_bwd_matches_oracle(variant):
     """Noise prediction and every LoRA / control-state gradient vs the fp32 oracle (tiny SD-style config).
     Tolerance: bf16 activations through ~40 layers => <= 2e-2 relative on the prediction, <= 8e-2 on single gradients."""

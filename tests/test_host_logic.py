@@ -137,8 +137,11 @@ def test_unsupported_variants_fail_loudly():
     from controllora_b200.unet_module import GradStore
 
     mu = _tiny_unet()
-    mcl = cb.ControlLoRA(lora_concat_hidden=True, **TINY_LORA)          # configs/danbooru-sketch.json flavour
-    wire_processors(mu, mcl)
+    mcl = cb.ControlLoRA(lora_concat_hidden=True, **TINY_LORA)          # configs/danbooru-sketch.json flavour ...
+    procs = wire_processors(mu, mcl)
+    LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)       # ... builds on its own,
+    for p in procs.values():                                            # but not with another adapter stacked on it
+        p.inject_pre_lora(cb.LoRACrossAttnProcessor(p.hidden_size, p.cross_attention_dim, rank=4))
     with pytest.raises(NotImplementedError):
         LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)
     # post_add stacked with a pre-LoRA is outside the supported set as well

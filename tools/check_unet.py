@@ -56,6 +56,9 @@ def build_pair(variant, B=2, HW=16, seed=0):
         kw.update(lora_control_version=2, lora_pre_conv_skipped=True)
     if variant == "v1_post_add":
         kw.update(lora_post_add=True)            # configs/post-add.json: every adapter reads its projection's output
+    if variant == "v1_concat":
+        # configs/danbooru-sketch.json flavour: to_control = MLP over [h ; c] with a control rank well above the LoRA rank
+        kw.update(lora_concat_hidden=True, lora_control_rank=32, lora_pre_conv_skipped=True, lora_control_self_add=False)
     ocl = MR.ControlLoRA(**kw) if variant != "none" else None
     mcl = cb.ControlLoRA(**kw) if variant != "none" else None
     if ocl is not None:
@@ -116,8 +119,8 @@ def run(variant):
     target = torch.randn(B, 4, HW, HW, generator=g)
     ch = TINY["block_out_channels"]
     ctrl_o, ctrl_m = [], []
-    if variant in ("v1", "v1_stacked", "v2", "v1_post_add"):
-        cc = [256] * 4 if variant == "v2" else list(ch)
+    if variant in ("v1", "v1_stacked", "v2", "v1_post_add", "v1_concat"):
+        cc = [256] * 4 if variant in ("v2", "v1_concat") else list(ch)
         for lvl in range(4):
             s = HW >> lvl
             c = (0.5 * torch.randn(B, cc[lvl], s, s, generator=g)).to(torch.bfloat16).float()
