@@ -374,10 +374,13 @@ v2_inject_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
 // backward (one warp per row, the row stays in registers between the two phases):
 //   dt[m, j] = sum_c dy[m, c] * up[c*4 + j]                       (== cl_rowdot)
 //   dh[m, c] = dy[m, c] + alpha * sum_j dt[m, j] * down[c*4 + j]   (== cl_rank_update), dh optional
+// The same kernel serves the forward as "project, add control, update":  t = x U (+ uc);  y = x + alpha t D^T  with
+// U = Ac_h^T, D = Bc  - no separate skinny GEMM for x Ac_h^T is needed, x is read exactly once.
 template <int IT>
 __global__ void __launch_bounds__(256)
 v2_inject_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ up, const float* __restrict__ down, float alpha,
-                     float* __restrict__ dt_out, __nv_bfloat16* __restrict__ dh, int M, int C) {
+                     float* __restrict__ dt_out, __nv_bfloat16* __restrict__ dh, int M, int C, const float* __restrict__ uc, int ldu,
+                     int rc) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ float s_tab[];                // [4][C] up (transposed) | [4][C] down (transposed)
@@ -419,6 +422,11 @@ v2_inject_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
+        if (uc != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < rc) acc[j] += uc[(long long)m * ldu + j];
+        }
         if (lane == 0) *reinterpret_cast<float4*>(dt_out + (long long)m * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         if (dh != nullptr) {
 #pragma unroll
@@ -671,9 +679,25 @@ extern "C" int cl_v2_inject_bwd(const void* dy, const float* up, const float* do
     if (blocks > num_sms() * 6) blocks = num_sms() * 6;
     const __nv_bfloat16* dd = reinterpret_cast<const __nv_bfloat16*>(dy);
     __nv_bfloat16* hh = reinterpret_cast<__nv_bfloat16*>(dh);
-    if (Ccols <= 512) launch_k(v2_inject_bwd_kernel<2>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols);
-    else if (Ccols <= 768) launch_k(v2_inject_bwd_kernel<3>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols);
-    else launch_k(v2_inject_bwd_kernel<5>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols);
+    if (Ccols <= 512) launch_k(v2_inject_bwd_kernel<2>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols, nullptr, 0, 0);
+    else if (Ccols <= 768) launch_k(v2_inject_bwd_kernel<3>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols, nullptr, 0, 0);
+    else launch_k(v2_inject_bwd_kernel<5>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols, nullptr, 0, 0);
+    DONE();
+}
+
+extern "C" int cl_rank4_project_update(const void* x, const float* proj, const float* upd, const float* uc, int ldu, int rc, float alpha,
+                                       float* t_out, void* y, int M, int Ccols, void* stream_) {
+    STREAM;
+    if (!x || !proj || !upd || !t_out || !y || Ccols % 8 || rc < 0 || rc > 4) return set_error(CL_ERR_INVALID, "cl_rank4_project_update: bad args");
+    if (Ccols > 1280) return set_error(CL_ERR_UNSUPPORTED, "cl_rank4_project_update: C <= 1280");
+    const size_t smem = (size_t)Ccols * 8 * sizeof(float);
+    int blocks = (M + 7) / 8;
+    if (blocks > num_sms() * 6) blocks = num_sms() * 6;
+    const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+    __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
+    if (Ccols <= 512) launch_k(v2_inject_bwd_kernel<2>, blocks, 256, smem, stream, xx, proj, upd, alpha, t_out, yy, M, Ccols, uc, ldu, rc);
+    else if (Ccols <= 768) launch_k(v2_inject_bwd_kernel<3>, blocks, 256, smem, stream, xx, proj, upd, alpha, t_out, yy, M, Ccols, uc, ldu, rc);
+    else launch_k(v2_inject_bwd_kernel<5>, blocks, 256, smem, stream, xx, proj, upd, alpha, t_out, yy, M, Ccols, uc, ldu, rc);
     DONE();
 }
 

@@ -343,12 +343,9 @@ class LoraRuntime:
         rc = down.shape[0]
         T = h.data.shape[0] * h.data.shape[1]
         h2 = h.data.view(T, C)
-        ext = lp.v2_ext[which]
-        # t = h Ac_h^T (tensor core, N = 16 hi/lo columns) + u_c
-        th16 = ops.gemm(h2, ext, out_fp32=True)
         uc = lv.u[:, lp.col + 4 * which:]
-        # one pass: t = hi+lo of th16 (+ u_c), h' = h + s * t Bc^T   ([T, 8] t, cols 0..rc-1 valid, kept for the backward)
-        out_data, t = ops.v2_inject_fwd(h.data, th16, uc, rc, lp.v2_up[which], s)
+        # one pass over h: t = h Ac_h^T + u_c (fp32 row dots), h' = h + s * t Bc^T   (t [T, 4] kept for the backward)
+        out_data, t = ops.rank4_project_update(h.data, lp.v2_down_tab[which], lp.v2_up[which], uc, rc, s)
         out = Var(out_data, rg=True)
         if ctx.tape is not None:
             def bwd():

@@ -548,6 +548,18 @@ def v2_inject_bwd(dy, up_tab, down_tab, alpha: float, need_dh: bool):
     return dt, dh
 
 
+def rank4_project_update(x, proj_tab, upd_tab, uc, rc: int, alpha: float):
+    """t [M, 4] = x @ proj_tab (+ uc[:, :rc]);  y = x + alpha * t @ upd_tab^T.  Tables fp32 [C, 4].  Returns (y, t)."""
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    assert x.is_contiguous()
+    t = torch.empty(M, 4, device=x.device, dtype=torch.float32)
+    y = torch.empty_like(x)
+    ldu = 0 if uc is None else uc.stride(0)
+    _call("cl_rank4_project_update", _p(x), _p(proj_tab), _p(upd_tab), _p(uc), ldu, rc, C.c_float(alpha), _p(t), _p(y), M, Cc)
+    return y, t
+
+
 def conv_wgrad(dy, x, dw, ksize: int, stride: int = 1, pad_lo: int = 1, alpha: float = 1.0):
     """dw (fp32 [Cout, Cin, k, k], accumulated) += alpha * dY^T (*) X ; dy NHWC [n,Ho,Wo,Cout], x NHWC [n,H,W,Cin]"""
     n, H, W, Cin = x.shape

@@ -234,7 +234,11 @@ int cl_rank_update(const void* x, const float* t, int ldt, const float* tab, int
 int cl_v2_inject_fwd(const void* x, const float* th16, const float* uc /* nullable */, int ldu, int rc, const float* tab,
                      float alpha, void* out, float* t_out, int64_t M, int C, void* stream);
 int cl_v2_inject_bwd(const void* dy, const float* up, const float* down, float alpha, float* dt_out, void* dh /* nullable */,
-                     int M, int C, void* stream);                                            /* out = x + alpha * t * tab^T */
+                     int M, int C, void* stream);
+/* One pass "project, add, update" (the V2 forward without a separate skinny GEMM):
+ *   t [M, 4] = x * proj (fp32 [C, 4]) (+ uc [M, rc]);   y = x + alpha * t * upd^T (fp32 [C, 4]).                            */
+int cl_rank4_project_update(const void* x, const float* proj, const float* upd, const float* uc /* nullable */, int ldu, int rc,
+                            float alpha, float* t_out, void* y, int M, int C, void* stream);                                            /* out = x + alpha * t * tab^T */
 int cl_skinny_small(const float* a, int lda, int I, const float* b, int ldb, int J, float* out, float alpha, int M,
                     void* stream);
 int cl_small_matmul(const float* a, int64_t sa_i, int64_t sa_j, const float* b, int64_t sb_j, int64_t sb_k, float* out,
