@@ -373,22 +373,21 @@ class LoraRuntime:
         return out
 
     def _v2_tables(self, lp: LayerPlan):
-        """Per-processor packed operands for the V2 hidden-state update (built lazily, packed every step)."""
-        if getattr(lp, "v2_ext", None) is not None:
+        """Per-processor fp32 tables of the V2 hidden-state update (built once, re-packed from the parameters every step):
+        v2_down_tab[w][c, j] = Ac_h[j, c] (projection h -> t, and dt -> dh in the backward), v2_up[w][c, j] = Bc[c, j]."""
+        if getattr(lp, "v2_up", None) is not None:
             return
         p = lp.proc
         C = p.hidden_size
         dev = self.device
-        lp.v2_ext, lp.v2_up, lp.v2_down_tab = [], [], []
+        lp.v2_up, lp.v2_down_tab = [], []
         for layer in (p.to_control, p.to_control_out):
             down, up = layer.down.weight, layer.up.weight
-            ext = torch.zeros(16, C, device=dev, dtype=BF16)
             upt = torch.zeros(C, 4, device=dev, dtype=torch.float32)
             dnt = torch.zeros(C, 4, device=dev, dtype=torch.float32)
-            self.v2_plan.add_ext(down[:, :C], ext)
             self.v2_plan.add_table(up, upt)
             self.v2_plan.add_table(down[:, :C], dnt, transposed=True)
-            lp.v2_ext.append(ext); lp.v2_up.append(upt); lp.v2_down_tab.append(dnt)
+            lp.v2_up.append(upt); lp.v2_down_tab.append(dnt)
         lp.v2_eye = torch.eye(4, device=dev, dtype=torch.float32)
 
     # ------------------------------------------------------------------------------------------------ attention layer
