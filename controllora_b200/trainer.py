@@ -92,8 +92,20 @@ class Trainer:
         if self._graph is None:
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                self._static_loss = self._forward_backward(*self._static)
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    self._static_loss = self._forward_backward(*self._static)
+            except Exception as ex:      # capture is an optimisation of the launch path only: say so and keep training eagerly
+                import sys
+
+                print(f"controllora_b200.Trainer: CUDA-graph capture failed ({type(ex).__name__}: {ex}); "
+                      f"continuing with per-kernel launches", file=sys.stderr, flush=True)
+                torch.cuda.synchronize()
+                self.cuda_graph = False
+                self._static_loss = None
+                loss = self._forward_backward(*self._static)
+                self._optimizer_tail()
+                return loss
             self.launches_per_step = int(_lib.launch_count() - n0) + 2   # + sumsq + adamw outside the graph
             self._graph = graph
         self._graph.replay()
