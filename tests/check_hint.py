@@ -1,5 +1,5 @@
 """GPU parity of the hint encoder (fwd + all parameter grads) and of one fused Trainer step against the fp32 oracle.
-usage: python tools/check_hint.py [hint_v1|hint_v2|train_v1|train_v2]"""
+usage: python tests/check_hint.py [hint_v1|hint_v2|train_v1|train_v2]"""
 import os
 import subprocess
 import sys
@@ -20,7 +20,7 @@ if DEV == "cpu":
     ops._req = lambda *a, **k: None
     ops._stream = lambda: None
 
-from tools.check_unet import TINY, TINY_LORA, rel  # noqa: E402
+from tests.check_unet import TINY, TINY_LORA, rel  # noqa: E402
 
 
 def hint_case(v2: bool, size=64, B=2):
