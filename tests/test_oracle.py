@@ -160,3 +160,28 @@ def test_oracle_matches_committed_golden_vectors(variant):
     now = run_variant(variant)
     for k in gold:
         assert torch.allclose(now[k], gold[k], atol=2e-5, rtol=2e-4), k
+
+
+GOLDEN_EXTRA = ROOT / "tests" / "golden" / "oracle_extra.pt"
+
+
+@pytest.mark.parametrize("variant", ["v1_post_add", "v1_concat"])
+def test_oracle_variants_match_committed_golden_vectors(variant):
+    """post_add (configs/post-add.json) and concat_hidden (configs/danbooru-sketch.json) flavours of the oracle."""
+    from tests.golden.make_golden import run_variant
+
+    gold = torch.load(GOLDEN_EXTRA)[variant]
+    now = run_variant(variant)
+    for k in gold:
+        assert torch.allclose(now[k], gold[k], atol=2e-5, rtol=2e-4), k
+
+
+def test_oracle_samplers_match_committed_golden_trajectories():
+    """DDIM and DPM-Solver++(2M) restatements: 10- / 12-step trajectories and the 30-step timestep table."""
+    from tests.golden.make_golden import run_samplers
+
+    gold = torch.load(GOLDEN_EXTRA)["samplers"]
+    now = run_samplers()
+    assert torch.equal(now["dpm_timesteps_30"], gold["dpm_timesteps_30"])
+    for k in ("ddim10", "dpmpp12"):
+        assert torch.allclose(now[k], gold[k], atol=1e-5, rtol=1e-5), k
