@@ -8,8 +8,12 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libcontrollora_b200.so"
+# CLB_LIB selects an instrumented build of the same sources (e.g. the CLB_TIMELINE debug library that
+# `python -m controllora_b200.build --timeline` writes next to the product library); never a different implementation.
+LIB_PATH = Path(os.environ["CLB_LIB"]) if os.environ.get("CLB_LIB") else _PKG / "libcontrollora_b200.so"
 
 
 class CLError(RuntimeError):
@@ -114,6 +118,8 @@ class PackDesc(C.Structure):
         ("s_j", C.c_int64), ("s_k", C.c_int64),
         ("ld", C.c_int32),
         ("row_off", C.c_int32),
+        ("mul", C.c_float),
+        ("pad_", C.c_int32),
     ]
 
 

@@ -33,6 +33,11 @@ class ParamArena:
                 p.data = view
                 self._gviews[id(p)] = self.flat_g[off:off + k].view(p.shape)
                 off += k
+        # the reference wraps control_lora in DDP (accelerator.prepare, train_text_to_image_control_lora.py:513), which
+        # broadcasts rank 0's weights at construction: ranks that were seeded differently must not train different replicas
+        if self.world > 1:
+            torch.distributed.broadcast(self.flat_p, src=torch.distributed.get_global_rank(process_group, 0)
+                                        if process_group is not None else 0, group=process_group)
 
     @property
     def grad_scale(self) -> float:

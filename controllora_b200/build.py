@@ -30,7 +30,12 @@ def _newer(a: Path, b: Path) -> bool:
     return (not b.exists()) or a.stat().st_mtime > b.stat().st_mtime
 
 
-def build(verbose: bool = False, force: bool = False) -> Path:
+def build(verbose: bool = False, force: bool = False, timeline: bool = False) -> Path:
+    """timeline=True: debug variant with the in-kernel clock64 event log (-DCLB_TIMELINE) -> libcontrollora_b200_tl.so,
+    objects under build_tl/ (select it with CLB_LIB=...; tools/gemm_timeline.py)."""
+    global OBJ, LIB, FLAGS
+    if timeline:
+        OBJ, LIB, FLAGS = PKG / "build_tl", PKG / "libcontrollora_b200_tl.so", FLAGS + ["-DCLB_TIMELINE"]
     OBJ.mkdir(exist_ok=True)
     sources = sorted(CSRC.glob("*.cu"))
     headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((PKG.parent / "include").glob("*.h"))
@@ -65,5 +70,5 @@ def build(verbose: bool = False, force: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    p = build(verbose="-v" in sys.argv, force="-f" in sys.argv)
+    p = build(verbose="-v" in sys.argv, force="-f" in sys.argv, timeline="--timeline" in sys.argv)
     print(p)

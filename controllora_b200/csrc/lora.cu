@@ -13,7 +13,7 @@ namespace clb {
 // One launch prepares every LoRA operand of a step from the fp32 master weights (descriptor table in device memory):
 //   kind 0: ext[16, K] bf16   rows row_off+j <- hi(src(j, k)), rows 8+row_off+j <- lo(src(j, k)), j < r
 //   kind 1: table[N, rp] fp32  table[n*rp + row_off + j] <- src(j, n), j < r
-// with src(j, k) = src[j*s_j + k*s_k].  Rows / columns not covered by any descriptor must be pre-zeroed once.
+// with src(j, k) = mul * src[j*s_j + k*s_k].  Rows / columns not covered by any descriptor must be pre-zeroed once.
 __global__ void __launch_bounds__(256)
 lora_pack_kernel(const cl_pack_desc* __restrict__ descs, int n_desc) {
     pdl_launch_dependents();
@@ -26,7 +26,7 @@ lora_pack_kernel(const cl_pack_desc* __restrict__ descs, int n_desc) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(i / d.K);
         const int k = (int)(i % d.K);
-        const float v = src[(long long)j * d.s_j + (long long)k * d.s_k];
+        const float v = d.mul * src[(long long)j * d.s_j + (long long)k * d.s_k];
         if (d.kind == 0) {
             __nv_bfloat16* ext = reinterpret_cast<__nv_bfloat16*>(d.dst);
             const __nv_bfloat16 hi = __float2bfloat16(v);

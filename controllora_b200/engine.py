@@ -126,7 +126,8 @@ class Adapter:
     col: int                      # first column of this adapter inside the slot's rank-rp space
     down_grad: Optional[torch.Tensor] = None   # fp32 accumulators (views into the gradient arena)
     up_grad: Optional[torch.Tensor] = None
-    mult: float = 1.0             # extra factor on this adapter's delta (1/scale for the unscaled-value quirk)
+    unscaled: bool = False        # the reference adds this adapter's delta WITHOUT `scale` (stacked value adapters,
+                                  # models.py:260,265,397,402): its up-table is packed with 1/scale (PackPlan.set_unscaled_mul)
 
 
 class LoraSlot:
@@ -142,10 +143,10 @@ class LoraSlot:
         self.ext = self.up_tab = self.ext_t = self.down_tab = None
         self.post_add = False     # models.py:125,132,135,147: the adapter reads the base projection's OUTPUT (then K == N)
 
-    def add(self, down: torch.Tensor, up: torch.Tensor, mult: float = 1.0) -> Adapter:
+    def add(self, down: torch.Tensor, up: torch.Tensor, unscaled: bool = False) -> Adapter:
         r = down.shape[0]
         assert down.shape == (r, self.K) and up.shape == (self.N, r)
-        a = Adapter(down, up, self.rank, mult=mult)
+        a = Adapter(down, up, self.rank, unscaled=unscaled)
         self.adapters.append(a)
         self.rank += r
         if self.rank > 8:
@@ -160,10 +161,10 @@ class LoraSlot:
         self.ext_t = torch.zeros(16, self.N, device=dev, dtype=BF16)
         self.down_tab = torch.zeros(self.K, self.rp, device=dev, dtype=torch.float32) if need_dx else None
         for a in self.adapters:
-            assert a.mult == 1.0, "per-adapter multipliers are folded by the caller"
+            # forward: y += s * t_j (m B_j)^T ; backward: e_j = dy (m B_j), dX += s e_j A_j, dA_j += s e_j^T x, dB_j += s m dy^T t_j
             plan.add_ext(a.down, self.ext, row_off=a.col)
-            plan.add_table(a.up, self.up_tab, col_off=a.col)
-            plan.add_ext(a.up, self.ext_t, row_off=a.col, transposed=True)
+            plan.add_table(a.up, self.up_tab, col_off=a.col, unscaled=a.unscaled)
+            plan.add_ext(a.up, self.ext_t, row_off=a.col, transposed=True, unscaled=a.unscaled)
             if need_dx:
                 plan.add_table(a.down, self.down_tab, col_off=a.col, transposed=True)
 
@@ -195,6 +196,7 @@ def linear(ctx: Ctx, x: Var, lw: LinearW, *, residual: Optional[Var] = None, slo
     out = Var(y, rg=x.rg or trainable or (residual is not None and residual.rg))
     if ctx.tape is not None and out.rg:
         scale = ctx.scale
+        inv_scale = 1.0 / scale if scale != 0.0 else 0.0
 
         def bwd():
             dy = out.grad
@@ -222,7 +224,7 @@ def linear(ctx: Ctx, x: Var, lw: LinearW, *, residual: Optional[Var] = None, slo
                 for a in slot.adapters:
                     r = a.down.shape[0]
                     # dB[n, j] += s * sum_m dy[m, n] * t[m, j] ; dA[j, k] += s * sum_m e[m, j] * x[m, k]
-                    ops.SKINNY.add(t_out[:, a.col:], r, dy2, a.up_grad, 1, r, scale)
+                    ops.SKINNY.add(t_out[:, a.col:], r, dy2, a.up_grad, 1, r, scale * inv_scale if a.unscaled else scale)
                     ops.SKINNY.add(e[:, a.col:], r, x2, a.down_grad, K, 1, scale)
                 if on_slot_bwd is not None:
                     on_slot_bwd(e, t_out, dy2)

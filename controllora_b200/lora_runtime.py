@@ -15,6 +15,7 @@ V2 control (models.py:369, 415):  h' = h + s Bc Ac [h ; c]  is a rank-r update o
 """
 from __future__ import annotations
 
+from types import SimpleNamespace
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -44,10 +45,7 @@ class _LevelCtx:
         self.stack = None               # bf16 [16*nb, Cc]   (hi/lo rows of the control-down matrices)
         self.stack_t = None             # bf16 [Cc, 16*nb]   (transposed, hi duplicated) for the d-control GEMM
         self.nb = 0
-        # per forward
-        self.c: Optional[Var] = None    # [B, HW, Cc] bf16
-        self.u = None                   # fp32 [T, 8*nb]
-        self.du = None                  # bf16 [T, 16*nb]
+        # per-forward products (c Var [B, HW, Cc] bf16, u fp32 [T, 8*nb], du bf16 [T, 16*nb]) live in Ctx.stash
 
 
 class LayerPlan:
@@ -90,8 +88,8 @@ class LoraRuntime:
             sig.append(tuple((id(a), a.key_states_skipped, a.value_states_skipped, a.output_states_skipped) for a in chain))
         return tuple(sig)
 
-    def _adapter(self, slot: LoraSlot, layer) -> E.Adapter:
-        a = slot.add(layer.down.weight, layer.up.weight)
+    def _adapter(self, slot: LoraSlot, layer, unscaled: bool = False) -> E.Adapter:
+        a = slot.add(layer.down.weight, layer.up.weight, unscaled=unscaled)
         a.down_grad = self.grad_of(layer.down.weight)
         a.up_grad = self.grad_of(layer.up.weight)
         return a
@@ -117,6 +115,11 @@ class LoraRuntime:
             if cat and (len(chain) > 1 or any(post_add) or p.to_q_lora.down.weight.shape[0] > 4):
                 raise NotImplementedError("lora_concat_hidden=True is supported for single (unstacked, non-post_add, rank <= 4) processors only")
             lp.kind = "v1cat" if cat else ("v1" if _is_v1(p) else ("v2" if _is_v2(p) else "plain"))
+            if lp.kind in ("v1", "v2"):
+                ctrl = [p.to_control] + ([p.to_control_out] if lp.kind == "v2" else [])
+                if any(c.down.weight.shape[0] > 4 for c in ctrl):
+                    raise NotImplementedError("control rank > 4 is supported only with lora_concat_hidden=True on v1 processors "
+                                              "(dense control MLP path); the rank-4 control tables hold 4 rows per processor")
             C = L.to_q.w.shape[0]
             kv_in = L.to_k.w.shape[1]
             lp.post_add = any(post_add)
@@ -137,7 +140,8 @@ class LoraRuntime:
                 if not a.key_states_skipped:
                     self._adapter(lp.k, a.to_k_lora)
                 if not a.value_states_skipped:
-                    self._adapter(lp.v, a.to_v_lora)
+                    # quirk kept from the reference: stacked adapters' VALUE deltas carry no `scale` (models.py:260,265,397,402)
+                    self._adapter(lp.v, a.to_v_lora, unscaled=a is not p)
                 if a is p or not a.output_states_skipped:
                     self._adapter(lp.out, a.to_out_lora)
             lp.q.finalize(self.plan, need_dx=True)
@@ -171,28 +175,40 @@ class LoraRuntime:
         if getattr(self, "_level_key", None) != key:
             self._build_levels(groups, control_vars)
             self._level_key = key
+        s = ctx.scale
+        if self.plan._unscaled:
+            if s == 0.0:
+                raise NotImplementedError("scale == 0 with stacked value adapters (their deltas are unscaled in the reference)")
+            self.plan.set_unscaled_mul(1.0 / s)
         self.plan.run()
         self.v2_plan.run()
         self.level_plan.run()
-        s = ctx.scale
+        # per-forward products live in ctx.stash (keyed by level / layer plan), never on the shared runtime objects: two
+        # forwards may be in flight before the first backward (gradient accumulation, several UNet calls per loss)
         for (k, lps), lv in zip(groups.items(), self.level_list):
             c = control_vars[k]
-            lv.c = c
+            st = self._fs(ctx, lv)
+            st.c, st.u, st.du = c, None, None
             T = c.data.shape[0] * c.data.shape[1]
             assert c.data.shape[-1] == lv.cc
             if lv.nb == 0:                       # concat_hidden levels: every processor runs its own dense control MLP
-                lv.u = lv.du = None
                 continue
             c2 = c.data.view(T, lv.cc)
             u16 = ops.gemm(c2, lv.stack, out_fp32=True)
-            lv.u = ops.hilo_combine(u16, lv.nb)
-            lv.du = None
+            st.u = ops.hilo_combine(u16, lv.nb)
             if ctx.tape is not None and c.rg:
-                lv.du = torch.zeros(T, 16 * lv.nb, device=self.device, dtype=BF16)
+                st.du = torch.zeros(T, 16 * lv.nb, device=self.device, dtype=BF16)
         for lp in self.layers.values():
-            lp.t_add = None
             if lp.kind == "v1":
                 self._v1_prepare(ctx, lp)
+
+    @staticmethod
+    def _fs(ctx: Ctx, obj) -> SimpleNamespace:
+        """Per-forward state of a level / layer plan inside this forward's Ctx."""
+        st = ctx.stash.get(id(obj))
+        if st is None:
+            st = ctx.stash[id(obj)] = SimpleNamespace(c=None, u=None, du=None, t_add=None, M=None)
+        return st
 
     def _build_levels(self, groups, control_vars):
         self.level_list = []
@@ -242,14 +258,16 @@ class LoraRuntime:
         C = Aq.shape[1]
         M = torch.empty(r, rc, device=self.device, dtype=torch.float32)
         ops.small_matmul(Aq, C, 1, Bc, rc, 1, M, rc, 1, r, C, rc)                  # M = Aq Bc
-        T = lv.u.shape[0]
+        lvs = self._fs(ctx, lv)
+        T = lvs.u.shape[0]
         rp = lp.q.rp
         t_add = torch.zeros(T, rp, device=self.device, dtype=torch.float32) if lp.q.rank != r else \
             torch.empty(T, rp, device=self.device, dtype=torch.float32)
-        u = lv.u[:, lp.col:]
+        u = lvs.u[:, lp.col:]
         # t_add[:, col_a + i] = s * sum_j u[:, j] * M[i, j]
         ops.rowmat(u, M, rc, 1, r, rc, s, t_add[:, ad.col:], rp)
-        lp.t_add, lp.M = t_add, M
+        st = self._fs(ctx, lp)
+        st.t_add, st.M = t_add, M
 
     def _v1_q_bwd(self, ctx: Ctx, lp: LayerPlan, e, t_out, dy2):
         """Gradients of the control branch of a v1 q-projection (see module docstring)."""
@@ -259,7 +277,8 @@ class LoraRuntime:
         Aq, Bc, Ac = ad.down, p.to_control.up.weight, p.to_control.down.weight
         rc = Bc.shape[1]
         C = Aq.shape[1]
-        u = lv.u[:, lp.col:]
+        lvs, lps = self._fs(ctx, lv), self._fs(ctx, lp)
+        u = lvs.u[:, lp.col:]
         ea = e[:, ad.col:]
         G = torch.zeros(r, rc, device=self.device, dtype=torch.float32)
         ops.skinny_small(ea, r, u, rc, G, 1.0)                                     # G = e^T u
@@ -267,11 +286,11 @@ class LoraRuntime:
         ops.small_matmul(Aq, 1, C, G, rc, 1, self.grad_of(Bc), rc, 1, C, r, rc, alpha=s * s, accumulate=True)  # dBc += s^2 Aq^T G
         T = u.shape[0]
         du = torch.empty(T, rc, device=self.device, dtype=torch.float32)
-        ops.rowmat(ea, lp.M, 1, rc, rc, r, s * s, du, rc)                           # du = s^2 e M
-        ops.SKINNY.add(du, rc, lv.c.data.view(T, lv.cc), self.grad_of(Ac), lv.cc, 1, 1.0)   # dAc += du^T c
-        if lv.du is not None:
+        ops.rowmat(ea, lps.M, 1, rc, rc, r, s * s, du, rc)                          # du = s^2 e M
+        ops.SKINNY.add(du, rc, lvs.c.data.view(T, lv.cc), self.grad_of(Ac), lv.cc, 1, 1.0)   # dAc += du^T c
+        if lvs.du is not None:
             i = lp.col // 4
-            ops.rowmat(ea, lp.M, 1, rc, rc, r, s * s, lv.du, 16 * lv.nb, out_mode=1, col_off=16 * (i // 2) + 4 * (i % 2), lo_off=8)
+            ops.rowmat(ea, lps.M, 1, rc, rc, r, s * s, lvs.du, 16 * lv.nb, out_mode=1, col_off=16 * (i // 2) + 4 * (i % 2), lo_off=8)
 
     # ------------------------------------------------------------------------------------------------ v1 + concat_hidden
     def _v1cat_q(self, ctx: Ctx, lp: LayerPlan, L, hs: Var) -> Var:
@@ -282,7 +301,7 @@ class LoraRuntime:
         Ac, Bc = p.to_control.down.weight, p.to_control.up.weight          # [R, C + Cc], [C, R]  (fp32 masters)
         ql = p.to_q_lora
         r = ql.down.weight.shape[0]
-        c = lv.c
+        c = self._fs(ctx, lv).c
         T = hs.data.shape[0] * hs.data.shape[1]
         h2, c2 = hs.data.view(T, C), c.data.view(T, lv.cc)
         # bf16 operands of the trainable dense layers, re-derived from the fp32 masters every step
@@ -343,7 +362,8 @@ class LoraRuntime:
         rc = down.shape[0]
         T = h.data.shape[0] * h.data.shape[1]
         h2 = h.data.view(T, C)
-        uc = lv.u[:, lp.col + 4 * which:]
+        lvs = self._fs(ctx, lv)
+        uc = lvs.u[:, lp.col + 4 * which:]
         # one pass over h: t = h Ac_h^T + u_c (fp32 row dots), h' = h + s * t Bc^T   (t [T, 4] kept for the backward)
         out_data, t = ops.rank4_project_update(h.data, lp.v2_down_tab[which], lp.v2_up[which], uc, rc, s)
         out = Var(out_data, rg=True)
@@ -361,13 +381,13 @@ class LoraRuntime:
                 # dAc_h[j, k] += s * sum_m dt[m, j] h[m, k] ; dAc_c likewise with c
                 gdown = self.grad_of(down)
                 ops.SKINNY.add(dt, rc, h2, gdown, C + lv.cc, 1, s)
-                ops.SKINNY.add(dt, rc, lv.c.data.view(T, lv.cc), gdown[:, C:], C + lv.cc, 1, s)
+                ops.SKINNY.add(dt, rc, lvs.c.data.view(T, lv.cc), gdown[:, C:], C + lv.cc, 1, s)
                 # dh = dy + s * dt Ac_h
                 if h.rg:
                     E.give_tensor(h, dh)
-                if lv.du is not None:
+                if lvs.du is not None:
                     i = lp.col // 8
-                    ops.rowmat(dt, lp.v2_eye, 4, 1, rc, rc, s, lv.du, 16 * lv.nb, out_mode=1, col_off=16 * i + 4 * which, lo_off=8)
+                    ops.rowmat(dt, lp.v2_eye, 4, 1, rc, rc, s, lvs.du, 16 * lv.nb, out_mode=1, col_off=16 * i + 4 * which, lo_off=8)
 
             ctx.tape.record(bwd)
         return out
@@ -402,7 +422,7 @@ class LoraRuntime:
         if lp.kind == "v1cat":
             q = self._v1cat_q(ctx, lp, L, hs)
         else:
-            q = E.linear(ctx, hs, L.to_q, slot=lp.q, t_add=getattr(lp, "t_add", None), on_slot_bwd=on_q)
+            q = E.linear(ctx, hs, L.to_q, slot=lp.q, t_add=self._fs(ctx, lp).t_add, on_slot_bwd=on_q)
         k = E.linear(ctx, kv_in, L.to_k, slot=lp.k)
         v = E.linear(ctx, kv_in, L.to_v, slot=lp.v)
         o = E.attention(ctx, q, k, v, L.heads)
@@ -413,9 +433,10 @@ class LoraRuntime:
     def finish_backward(self, ctx: Ctx):
         """After the tape ran: one GEMM per level turns the collected du blocks into d(control state)."""
         for lv in getattr(self, "level_list", []):
-            if lv.du is None or lv.c is None or not lv.c.rg:
+            st = self._fs(ctx, lv)
+            if st.du is None or st.c is None or not st.c.rg:
                 continue
-            T = lv.du.shape[0]
-            E.give_produce(lv.c, lambda buf, acc, lv=lv, T=T: ops.gemm(lv.du, lv.stack_t, out=buf.view(T, lv.cc),
-                                                                     residual=buf.view(T, lv.cc) if acc else None))
-            lv.du = None
+            T = st.du.shape[0]
+            E.give_produce(st.c, lambda buf, acc, lv=lv, st=st, T=T: ops.gemm(st.du, lv.stack_t, out=buf.view(T, lv.cc),
+                                                                             residual=buf.view(T, lv.cc) if acc else None))
+            st.du = None

@@ -128,12 +128,16 @@ def gemm(
 
 
 _SPLIT_WS = {}
+_WS_GRAVEYARD = []   # outgrown scratch buffers: a captured CUDA graph may have their addresses baked in, so they are kept
+                     # alive for the process lifetime instead of going back to the caching allocator (a few MB each)
 
 
 def _split_ws(numel: int, device) -> torch.Tensor:
     """fp32 scratch for split-K partial tiles, one growing buffer per device (stream-ordered re-use)."""
     buf = _SPLIT_WS.get(device)
     if buf is None or buf.numel() < numel:
+        if buf is not None:
+            _WS_GRAVEYARD.append(buf)
         buf = torch.empty(max(numel, 1 << 22), device=device, dtype=torch.float32)
         _SPLIT_WS[device] = buf
     return buf
@@ -172,6 +176,8 @@ def _gn_ws(device, n, G, Cc):
     key = (device, "gn")
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() * 8 < nbytes:
+        if buf is not None:
+            _WS_GRAVEYARD.append(buf)
         buf = torch.empty((nbytes + 7) // 8 + 1024, device=device, dtype=torch.float64)
         _ws_cache[key] = buf
     return buf
@@ -381,6 +387,21 @@ def mse_loss(pred, target, gscale: float = 1.0, need_grad=True):
     return loss, dpred
 
 
+def add_noise(x0, sqrt_ac, sqrt_1mac, step_counter, seed: int, v_prediction: bool = False, out=None):
+    """Device-side `randn_like` + `randint` + `add_noise` + target selection (train_text_to_image_control_lora.py:757-779).
+    x0 [B, ...] fp32; sqrt_ac / sqrt_1mac fp32 [T] device tables; step_counter: int64 [1] device tensor (advanced by one).
+    Returns (noisy, target, timesteps fp32 [B])."""
+    _req(x0, torch.float32, "x0")
+    assert x0.is_contiguous() and step_counter.dtype == torch.int64 and step_counter.is_cuda
+    B = x0.shape[0]
+    per = x0.numel() // B
+    noisy, target, ts = out if out is not None else (torch.empty_like(x0), torch.empty_like(x0),
+                                                     torch.empty(B, device=x0.device, dtype=torch.float32))
+    _call("cl_add_noise", _p(x0), _p(sqrt_ac), _p(sqrt_1mac), _p(step_counter), C.c_uint64(seed & (2**64 - 1)), sqrt_ac.numel(),
+          int(v_prediction), _p(noisy), _p(target), _p(ts), B, per)
+    return noisy, target, ts
+
+
 def attention_bwd(q, k, v, o, d_o, lse, heads: int, scale: float, need_dq=True, need_dkv=True, dq=None, dk=None, dv=None):
     from ._lib import AttnBwdArgs
 
@@ -422,35 +443,58 @@ class PackPlan:
         self.max_elems = 1
         self._dev = None
         self._keep = []
+        self._unscaled = []      # descriptor indices whose `mul` follows 1/scale (set_unscaled_mul)
+        self._unscaled_mul = 1.0
 
-    def add(self, src: torch.Tensor, dst: torch.Tensor, kind: int, r: int, K: int, s_j: int, s_k: int, ld: int, row_off: int):
+    def add(self, src: torch.Tensor, dst: torch.Tensor, kind: int, r: int, K: int, s_j: int, s_k: int, ld: int, row_off: int,
+            unscaled: bool = False):
         from ._lib import PackDesc
 
+        # bounds of the packed operand (an out-of-range descriptor would be a silent out-of-bounds device write)
+        if kind == 0 and not (0 <= row_off and row_off + r <= 8 and dst.shape[0] == 16 and K <= dst.shape[1]):
+            raise ValueError(f"PackPlan: ext rows [{row_off}, {row_off + r}) x {K} do not fit the 8+8 hi/lo rows of {tuple(dst.shape)}")
+        if kind == 1 and not (0 <= row_off and row_off + r <= dst.shape[1] and K <= dst.shape[0]):
+            raise ValueError(f"PackPlan: table columns [{row_off}, {row_off + r}) do not fit {tuple(dst.shape)}")
+        if kind == 2 and not (0 <= row_off and row_off + r <= 8 and 8 + row_off + r <= dst.shape[1] and K <= dst.shape[0]):
+            raise ValueError(f"PackPlan: transposed hi/lo columns [{row_off}, {row_off + r}) do not fit {tuple(dst.shape)}")
         d = PackDesc()
         d.src, d.dst = src.data_ptr(), dst.data_ptr()
         d.kind, d.r, d.K, d.s_j, d.s_k, d.ld, d.row_off = kind, r, K, s_j, s_k, ld, row_off
+        d.mul = self._unscaled_mul if unscaled else 1.0
+        if unscaled:
+            self._unscaled.append(len(self.descs))
         self.descs.append(d)
         self._keep.append((src, dst))
         self.max_elems = max(self.max_elems, r * K)
         self._dev = None
 
-    def add_ext(self, down_like: torch.Tensor, ext: torch.Tensor, row_off: int = 0, transposed: bool = False):
+    def set_unscaled_mul(self, mul: float) -> None:
+        """Adapters flagged `unscaled` (stacked pre/post value adapters, models.py:260,265,397,402: their delta is added
+        WITHOUT `scale`) are packed with mul = 1/scale so that the fused epilogue's common `scale` cancels."""
+        if mul != self._unscaled_mul:
+            self._unscaled_mul = mul
+            for i in self._unscaled:
+                self.descs[i].mul = mul
+            if self._unscaled:
+                self._dev = None
+
+    def add_ext(self, down_like: torch.Tensor, ext: torch.Tensor, row_off: int = 0, transposed: bool = False, unscaled: bool = False):
         """ext rows <- rows of `down_like` ([r, K]); transposed=True reads a [K, r] matrix (e.g. up.weight) instead."""
         if transposed:
             K, r = down_like.shape
-            self.add(down_like, ext, 0, r, K, down_like.stride(1), down_like.stride(0), ext.stride(0), row_off)
+            self.add(down_like, ext, 0, r, K, down_like.stride(1), down_like.stride(0), ext.stride(0), row_off, unscaled)
         else:
             r, K = down_like.shape
-            self.add(down_like, ext, 0, r, K, down_like.stride(0), down_like.stride(1), ext.stride(0), row_off)
+            self.add(down_like, ext, 0, r, K, down_like.stride(0), down_like.stride(1), ext.stride(0), row_off, unscaled)
 
-    def add_table(self, up_like: torch.Tensor, table: torch.Tensor, col_off: int = 0, transposed: bool = False):
+    def add_table(self, up_like: torch.Tensor, table: torch.Tensor, col_off: int = 0, transposed: bool = False, unscaled: bool = False):
         """table[n, col_off + j] <- up_like[n, j] ([N, r]); transposed=True reads a [r, N] matrix (down.weight)."""
         if transposed:
             r, N = up_like.shape
-            self.add(up_like, table, 1, r, N, up_like.stride(0), up_like.stride(1), table.stride(0), col_off)
+            self.add(up_like, table, 1, r, N, up_like.stride(0), up_like.stride(1), table.stride(0), col_off, unscaled)
         else:
             N, r = up_like.shape
-            self.add(up_like, table, 1, r, N, up_like.stride(1), up_like.stride(0), table.stride(0), col_off)
+            self.add(up_like, table, 1, r, N, up_like.stride(1), up_like.stride(0), table.stride(0), col_off, unscaled)
 
     def run(self):
         from ._lib import PackDesc

@@ -22,7 +22,8 @@ BF16 = torch.bfloat16
 
 class Trainer:
     def __init__(self, unet, control_lora, lr: float = 1e-4, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,
-                 max_grad_norm: float = 1.0, process_group=None, cuda_graph: bool = False, graph_warmup: int = 2):
+                 max_grad_norm: float = 1.0, process_group=None, cuda_graph: bool = False, graph_warmup: int = 2,
+                 noise_seed: int = 0, prediction_type: str = "epsilon", num_train_timesteps: int = 1000):
         self.unet, self.cl = unet, control_lora
         self.lr, self.betas, self.wd, self.eps, self.max_norm = lr, betas, weight_decay, eps, max_grad_norm
         self.pg = process_group
@@ -57,6 +58,20 @@ class Trainer:
         self._static_loss = None
         self._eager_calls = 0
         self.launches_per_step = None    # kernel launches of one step (counted while capturing / running eagerly)
+        # device-side step glue (train_text_to_image_control_lora.py:757-765,774-779): Philox noise, timesteps, add_noise, target
+        if prediction_type not in ("epsilon", "v_prediction"):
+            raise ValueError(f"Unknown prediction type {prediction_type}")        # train_...:779
+        self.prediction_type = prediction_type
+        self.noise_seed = int(noise_seed)
+        from .sampler import sd15_alphas_cumprod
+        ac = torch.tensor(sd15_alphas_cumprod(num_train_timesteps), dtype=torch.float64)
+        self.sqrt_ac = ac.sqrt().float().to(dev)
+        self.sqrt_1mac = (1.0 - ac).sqrt().float().to(dev)
+        rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
+        # every rank draws its own noise / timesteps: the rank is folded into the Philox key, the step counter is shared
+        self.rng_counter = torch.zeros(1, device=dev, dtype=torch.int64)
+        self._rank_seed = (self.noise_seed + 0x9E3779B97F4A7C15 * rank) & (2**64 - 1)
+        self._mode = None                # "noised" (step) or "latents" (step_from_latents): one captured graph per Trainer
 
     def step(self, noisy_latents: torch.Tensor, timesteps: torch.Tensor, ehs: torch.Tensor, guide: torch.Tensor,
              target: torch.Tensor, eager: bool = False) -> torch.Tensor:
@@ -67,15 +82,34 @@ class Trainer:
         into a CUDA graph (inputs are copied into static buffers first) and every later call replays it; the gradient
         all-reduce and the optimizer kernels stay outside the graph (NCCL's watchdog thread must not meet a global
         capture, and the AdamW bias correction is a host scalar).  eager=True forces the uncaptured path."""
+        return self._run("noised", self._forward_backward, (noisy_latents, timesteps, ehs, guide, target), eager)
+
+    def step_from_latents(self, latents: torch.Tensor, ehs: torch.Tensor, guide: torch.Tensor, eager: bool = False) -> torch.Tensor:
+        """The whole body of train_text_to_image_control_lora.py:757-796 after the VAE / text encoder: draws the noise and
+        one timestep per image on the device (`cl_add_noise`, counter-based Philox: fresh numbers on every CUDA-graph
+        replay), forms noisy latents and the epsilon / v-prediction target, then runs the fused step.  latents: the scaled
+        VAE latents [B,4,h,w] fp32."""
+        return self._run("latents", self._forward_backward_latents, (latents, ehs, guide), eager)
+
+    def _forward_backward_latents(self, latents, ehs, guide) -> torch.Tensor:
+        noisy, target, ts = ops.add_noise(latents, self.sqrt_ac, self.sqrt_1mac, self.rng_counter, self._rank_seed,
+                                          v_prediction=self.prediction_type == "v_prediction")
+        self.last_noise_draw = (noisy, target, ts)       # kept for inspection / tests (graph mode: static buffers)
+        return self._forward_backward(noisy, ts, ehs, guide, target)
+
+    def _run(self, mode: str, fb, args, eager: bool) -> torch.Tensor:
         from . import _lib
 
         if not self.cuda_graph or eager:
             n0 = _lib.launch_count()
-            loss = self._forward_backward(noisy_latents, timesteps, ehs, guide, target)
+            loss = fb(*args)
             self._optimizer_tail()
             self.launches_per_step = int(_lib.launch_count() - n0)
             return loss
-        args = (noisy_latents, timesteps, ehs, guide, target)
+        if self._mode is None:
+            self._mode = mode
+        elif self._mode != mode:
+            raise ValueError("Trainer(cuda_graph=True): step() and step_from_latents() cannot be mixed on one Trainer")
         if self._static is None:
             self._static = [torch.empty_like(a_).copy_(a_) for a_ in args]
         else:
@@ -86,7 +120,7 @@ class Trainer:
                     st.copy_(a_, non_blocking=True)
         if self._graph is None and self._eager_calls < self.graph_warmup:
             self._eager_calls += 1
-            loss = self._forward_backward(*self._static)
+            loss = fb(*self._static)
             self._optimizer_tail()
             return loss
         if self._graph is None:
@@ -94,7 +128,7 @@ class Trainer:
             n0 = _lib.launch_count()
             try:
                 with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                    self._static_loss = self._forward_backward(*self._static)
+                    self._static_loss = fb(*self._static)
             except Exception as ex:      # capture is an optimisation of the launch path only: say so and keep training eagerly
                 import sys
 
@@ -103,7 +137,7 @@ class Trainer:
                 torch.cuda.synchronize()
                 self.cuda_graph = False
                 self._static_loss = None
-                loss = self._forward_backward(*self._static)
+                loss = fb(*self._static)
                 self._optimizer_tail()
                 return loss
             self.launches_per_step = int(_lib.launch_count() - n0) + 2   # + sumsq + adamw outside the graph
@@ -149,19 +183,54 @@ class Trainer:
     # `checkpointing_steps` (train_text_to_image_control_lora.py:805-809) and resumes from the highest `checkpoint-N`
     # (:713-735).  Same directory convention here: the ControlLoRA weights in the reference's own format
     # (config.json + diffusion_pytorch_model.safetensors, the files of :927-929) plus the optimizer state of the flat arenas.
+    def _named_arena_params(self):
+        """(name, parameter) of every tensor in the arena: ControlLoRA parameters under their state-dict names, parameters
+        that live outside control_lora (e.g. stacked pre_loras from unet.trainable_parameters()) as `extra.<index>`."""
+        names = {id(p): n for n, p in self.cl.named_parameters()}
+        out, k = [], 0
+        for p in self.params:
+            if id(p) in names:
+                out.append((names[id(p)], p))
+            else:
+                out.append((f"extra.{k}", p))
+                k += 1
+        return out
+
     def save_checkpoint(self, output_dir, global_step: Optional[int] = None) -> str:
+        """`checkpoint-N/` = what `accelerator.save_state` keeps (train_text_to_image_control_lora.py:805-809: model, optimizer,
+        LR scheduler, RNG), in this framework's own file layout (NOT interchangeable with accelerate's pickles):
+          config.json + diffusion_pytorch_model.safetensors   the ControlLoRA in the reference's save_pretrained format (:927-929)
+          optimizer.bin    flat AdamW moments + hyper-parameters + the ordered parameter-name list + arena-only parameters
+          scheduler.bin    LR schedule state (the reference's default `constant` schedule: base lr and last_epoch)
+          random_states_<rank>.pkl   device Philox (seed, step counter) of the noise / timestep draws + torch / numpy / python RNG"""
         import os
+        import pickle
+        import random
 
         step = self.step_idx if global_step is None else int(global_step)
         path = os.path.join(str(output_dir), f"checkpoint-{step}")
         os.makedirs(path, exist_ok=True)
-        self.cl.save_config(path)
-        self.cl.save_pretrained(path, safe_serialization=True)
-        torch.save({"step_idx": self.step_idx, "global_step": step, "numel": self.numel, "lr": self.lr, "betas": self.betas,
-                    "weight_decay": self.wd, "eps": self.eps, "max_grad_norm": self.max_norm,
-                    "exp_avg": self.flat_m[:self.numel].detach().cpu(), "exp_avg_sq": self.flat_v[:self.numel].detach().cpu(),
-                    "param_names": [n for n, _ in self.cl.named_parameters()]},
-                   os.path.join(path, "optimizer.bin"))
+        rank = torch.distributed.get_rank(self.pg) if self.world > 1 else 0
+        named = self._named_arena_params()
+        if rank == 0:
+            self.cl.save_config(path)
+            self.cl.save_pretrained(path, safe_serialization=True)
+            torch.save({"step_idx": self.step_idx, "global_step": step, "numel": self.numel, "lr": self.lr, "betas": self.betas,
+                        "weight_decay": self.wd, "eps": self.eps, "max_grad_norm": self.max_norm,
+                        "exp_avg": self.flat_m[:self.numel].detach().cpu(), "exp_avg_sq": self.flat_v[:self.numel].detach().cpu(),
+                        "param_names": [n for n, _ in named], "param_numels": [p.numel() for _, p in named],
+                        "extra_params": {n: p.detach().cpu() for n, p in named if n.startswith("extra.")}},
+                       os.path.join(path, "optimizer.bin"))
+            torch.save({"schedule": "constant", "base_lr": self.lr, "last_epoch": self.step_idx}, os.path.join(path, "scheduler.bin"))
+        try:
+            import numpy as np
+            np_state = np.random.get_state()
+        except Exception:
+            np_state = None
+        with open(os.path.join(path, f"random_states_{rank}.pkl"), "wb") as f:
+            pickle.dump({"noise_seed": self.noise_seed, "rank_seed": self._rank_seed, "rng_counter": int(self.rng_counter.item()),
+                         "torch_cpu": torch.get_rng_state(), "torch_cuda": torch.cuda.get_rng_state(self.flat_p.device)
+                         if self.flat_p.is_cuda else None, "numpy": np_state, "python": random.getstate()}, f)
         return path
 
     @staticmethod
@@ -178,9 +247,11 @@ class Trainer:
         return None if best is None else os.path.join(str(output_dir), best)
 
     def load_checkpoint(self, path) -> int:
-        """Restore parameters (into the flat arena the kernels read) and AdamW moments; returns the stored global step.
-        A captured CUDA graph stays valid: it reads the same arena addresses."""
+        """Restore parameters (into the flat arena the kernels read), AdamW moments, the step count and the RNG state;
+        returns the stored global step.  A captured CUDA graph stays valid: it reads the same arena / counter addresses."""
         import os
+        import pickle
+        import random
 
         st = os.path.join(str(path), "diffusion_pytorch_model.safetensors")
         if os.path.isfile(st):
@@ -189,19 +260,37 @@ class Trainer:
             sd = load_file(st)
         else:
             sd = torch.load(os.path.join(str(path), "diffusion_pytorch_model.bin"), map_location="cpu")
-        own = dict(self.cl.named_parameters())
-        missing = [k for k in own if k not in sd]
+        opt = torch.load(os.path.join(str(path), "optimizer.bin"), map_location="cpu", weights_only=False)
+        named = self._named_arena_params()
+        if int(opt["numel"]) != self.numel:
+            raise ValueError("optimizer state does not match this Trainer's parameter count")
+        if "param_names" in opt and (list(opt["param_names"]) != [n for n, _ in named]
+                                     or list(opt.get("param_numels", [p.numel() for _, p in named])) != [p.numel() for _, p in named]):
+            raise ValueError("checkpoint parameter order / names do not match this Trainer's arena (different wiring or config)")
+        extra = opt.get("extra_params", {})
+        missing = [n for n, _ in named if (n not in sd and n not in extra)]
         if missing:
             raise KeyError(f"checkpoint {path} lacks parameters: {missing[:4]}...")
         with torch.no_grad():
-            for k, p in own.items():
-                p.data.copy_(sd[k].to(p.data.device, p.data.dtype))      # p.data is a view into flat_p
-        opt = torch.load(os.path.join(str(path), "optimizer.bin"), map_location="cpu")
-        if int(opt["numel"]) != self.numel:
-            raise ValueError("optimizer state does not match this ControlLoRA's parameter count")
-        with torch.no_grad():
+            for n, p in named:
+                src = sd[n] if n in sd else extra[n]
+                p.data.copy_(src.to(p.data.device, p.data.dtype))      # p.data is a view into flat_p
             self.flat_m[:self.numel].copy_(opt["exp_avg"].to(self.flat_m.device))
             self.flat_v[:self.numel].copy_(opt["exp_avg_sq"].to(self.flat_v.device))
             self.flat_g.zero_()
         self.step_idx = int(opt["step_idx"])
+        rank = torch.distributed.get_rank(self.pg) if self.world > 1 else 0
+        rs = os.path.join(str(path), f"random_states_{rank}.pkl")
+        if os.path.isfile(rs):
+            with open(rs, "rb") as f:
+                r = pickle.load(f)
+            self.noise_seed, self._rank_seed = int(r["noise_seed"]), int(r["rank_seed"])
+            self.rng_counter.fill_(int(r["rng_counter"]))
+            torch.set_rng_state(r["torch_cpu"])
+            if r.get("torch_cuda") is not None and self.flat_p.is_cuda:
+                torch.cuda.set_rng_state(r["torch_cuda"], self.flat_p.device)
+            if r.get("numpy") is not None:
+                import numpy as np
+                np.random.set_state(r["numpy"])
+            random.setstate(r["python"])
         return int(opt.get("global_step", self.step_idx))

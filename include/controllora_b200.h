@@ -180,6 +180,13 @@ int cl_timestep_embedding(const float* t, float* out, int B, int dim, void* stre
 int cl_small_linear(const float* x, const void* w, const float* bias, float* out, int Bt, int N, int K, int silu_in,
                     int silu_out, void* stream);
 int cl_mse_loss(const float* pred, const float* target, float* loss, float* dpred, int64_t n, float gscale, void* stream);
+/* Step glue in front of the UNet (replaces train_text_to_image_control_lora.py:757-765 `torch.randn_like` / `torch.randint` /
+ * `noise_scheduler.add_noise` and :774-779 target selection): Philox4x32-10 noise + one timestep per image, counter-based
+ * on (seed, *step_counter); *step_counter is advanced by one on the stream (CUDA-graph safe).  x0 / noisy / target:
+ * [B, per_image] fp32 (per_image % 4 == 0); sqrt_ac / sqrt_1mac: device tables [num_train_timesteps]; timesteps: [B] fp32. */
+int cl_add_noise(const float* x0, const float* sqrt_ac, const float* sqrt_1mac, unsigned long long* step_counter,
+                 unsigned long long seed, int num_train_timesteps, int v_prediction, float* noisy, float* target,
+                 float* timesteps, int B, int per_image, void* stream);
 /* classifier-free-guidance combine + DDIM (eta = 0) update of the denoise loop, one fused elementwise kernel:
  * eps2 = [uncond | cond] noise predictions (each n_half floats), latents updated in place. */
 int cl_cfg_ddim_step(const float* eps2, float* latents, int64_t n_half, float guidance, float sqrt_at, float sqrt_1m_at,
@@ -208,6 +215,8 @@ typedef struct {
     int64_t s_j, s_k;  /* element strides of src */
     int32_t ld;        /* dst leading dimension (elements) */
     int32_t row_off;   /* first ext row / table column written */
+    float mul;         /* factor applied to every packed value (1/scale for the unscaled stacked-value quirk, models.py:260,265,397,402) */
+    int32_t pad_;
 } cl_pack_desc;
 
 int cl_lora_pack_batch(const cl_pack_desc* descs_dev, int n_desc, int max_elems, void* stream);

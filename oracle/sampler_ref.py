@@ -78,3 +78,70 @@ class DPMSolverPP2M:
 
 def cfg_combine(eps_uncond, eps_cond, guidance):
     return eps_uncond + guidance * (eps_cond - eps_uncond)
+
+
+# ---------------------------------------------------------------------------------------------- training-step glue
+def add_noise(x0, noise, t, ac=None):
+    """diffusers DDPMScheduler.add_noise (train_text_to_image_control_lora.py:765): sqrt(ac[t]) x0 + sqrt(1 - ac[t]) noise."""
+    ac = alphas_cumprod() if ac is None else ac
+    shape = (-1,) + (1,) * (x0.dim() - 1)
+    sa = ac[t.long()].sqrt().to(x0.dtype).view(shape)
+    sb = (1 - ac[t.long()]).sqrt().to(x0.dtype).view(shape)
+    return sa * x0 + sb * noise
+
+
+def get_velocity(x0, noise, t, ac=None):
+    """diffusers DDPMScheduler.get_velocity (train_text_to_image_control_lora.py:777): sqrt(ac) noise - sqrt(1 - ac) x0."""
+    ac = alphas_cumprod() if ac is None else ac
+    shape = (-1,) + (1,) * (x0.dim() - 1)
+    sa = ac[t.long()].sqrt().to(x0.dtype).view(shape)
+    sb = (1 - ac[t.long()]).sqrt().to(x0.dtype).view(shape)
+    return sa * noise - sb * x0
+
+
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123).
+    ctr: uint32 array [..., 4], key: (k0, k1).  Returns uint32 [..., 4].  Pinned by Random123's known-answer vectors
+    (tests/test_oracle.py)."""
+    import numpy as np
+
+    c = [np.asarray(ctr[..., i], dtype=np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & MASK
+        k1 = (k1 + np.uint64(0xBB67AE85)) & MASK
+    return np.stack([v.astype(np.uint32) for v in c], -1)
+
+
+def device_noise(seed, step, B, per_image, num_train_timesteps=1000):
+    """Restatement of the counter layout of csrc/noise.cu: returns (noise float32 [B, per_image], timesteps int [B])."""
+    import numpy as np
+
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    hi = ((step >> 32) & 0xFFFFFFFF) << 8
+    cb = np.zeros((B, 4), dtype=np.uint32)
+    cb[:, 0] = np.arange(B, dtype=np.uint32)
+    cb[:, 2] = np.uint32((1 + hi) & 0xFFFFFFFF)
+    cb[:, 3] = np.uint32(step & 0xFFFFFFFF)
+    rt = philox4x32_10(cb, key)[:, 0].astype(np.uint64)
+    ts = ((rt * np.uint64(num_train_timesteps)) >> np.uint64(32)).astype(np.int64)
+    groups = B * per_image // 4
+    cg = np.zeros((groups, 4), dtype=np.uint32)
+    gi = np.arange(groups, dtype=np.uint64)
+    cg[:, 0] = (gi & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    cg[:, 1] = (gi >> np.uint64(32)).astype(np.uint32)
+    cg[:, 2] = np.uint32(hi & 0xFFFFFFFF)
+    cg[:, 3] = np.uint32(step & 0xFFFFFFFF)
+    r = philox4x32_10(cg, key)
+    u = ((r >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * np.float32(1.0 / 16777216.0)
+    out = np.empty((groups, 4), dtype=np.float32)
+    for h in range(2):
+        rad = np.sqrt(np.float32(-2.0) * np.log(u[:, 2 * h]))
+        ang = np.float32(2.0) * u[:, 2 * h + 1].astype(np.float64) * np.pi
+        out[:, 2 * h] = (rad * np.cos(ang)).astype(np.float32)
+        out[:, 2 * h + 1] = (rad * np.sin(ang)).astype(np.float32)
+    return out.reshape(B, per_image), ts

@@ -59,28 +59,51 @@ def hint_case(v2: bool, size=64, B=2):
         worst = max(worst, e)
         print(f"  control_state[{i}] {tuple(b.shape)} rel={e:.3e}")
     rows = []
+    zero_b = _zero_grad_biases(ocl)
+    oparams = dict(ocl.named_parameters())
+    cat_o, cat_m = [], []
     for (n1, p1), (n2, p2) in zip(ocl.named_parameters(), mcl.named_parameters()):
         if n1.startswith("lora_layers"):
             continue
         assert p2.grad is not None, n2
-        # a conv bias that feeds a GroupNorm with one channel per group has an exactly-zero true gradient (the oracle
-        # shows fp32 noise ~1e-4 there): measure such tensors against the scale of their layer's weight gradient
-        scale = float(p1.grad.norm())
-        if n1.endswith("bias"):
-            wname = n1[:-4] + "weight"
-            scale = max(scale, 1e-2 * float(dict(ocl.named_parameters())[wname].grad.norm()))
-        err = float((p2.grad.detach().float().cpu() - p1.grad).norm()) / (scale + 1e-30)
-        rows.append((err, n1, float(p1.grad.norm())))
+        g2 = p2.grad.detach().float().cpu()
+        if n1 in zero_b:
+            # exactly-zero true gradient: ours must stay at noise level next to the layer's weight gradient
+            wn = float(oparams[n1[:-4] + "weight"].grad.norm())
+            assert float(g2.norm()) < 2e-2 * wn, (n1, float(g2.norm()), wn)
+            continue
+        rows.append((rel(g2, p1.grad), n1, float(p1.grad.norm())))
+        cat_o.append(p1.grad.flatten()); cat_m.append(g2.flatten())
     rows.sort(reverse=True)
     for e, n, nrm in rows[:10]:
         print(f"  grad rel={e:.3e} |g|={nrm:.3e} {n}")
-    ok = worst < 3e-2 and rows[0][0] < 0.12
+    e_all = rel(torch.cat(cat_m), torch.cat(cat_o))
+    print(f"  all hint-encoder gradients (concatenated, {len(rows)} tensors) rel={e_all:.3e}; worst tensor rel={rows[0][0]:.3e}")
+    ok = worst < 3e-2 and e_all < 5e-2 and rows[0][0] < 8e-2
     print("CASE_OK" if ok else "CASE_FAIL")
     return ok
 
 
+def _zero_grad_biases(cl):
+    """Conv biases whose TRUE gradient is exactly zero: the conv feeds a GroupNorm with one channel per group (the
+    32-channel first pyramid level, models.py:690-748), which removes any per-channel constant.  The oracle shows fp32
+    noise there (|g| ~ 1e-9 x the weight gradient); Adam turns that noise into +-lr updates in ANY implementation, so
+    these tensors carry no parity information and are excluded from the update / gradient metrics."""
+    groups = cl.config["norm_num_groups"] if isinstance(cl.config, dict) else cl.config.norm_num_groups
+    return {n for n, p in cl.named_parameters()
+            if n.endswith("bias") and p.dim() == 1 and p.numel() == groups and ("conv1" in n or "downsamplers" in n or n == "conv_in.bias")}
+
+
 def train_case(v2: bool, B=2, HW=16):
-    """Two fused Trainer steps vs the oracle driven by torch.optim.AdamW + clip_grad_norm_ (the reference's step glue)."""
+    """Two fused Trainer steps vs the oracle driven by torch.optim.AdamW + clip_grad_norm_ (the reference's step glue,
+    train_text_to_image_control_lora.py:783-796).  Three separate checks, each with its own tolerance:
+      (1) gradient parity: the gradient arena after the fused backward vs the oracle's autograd gradients
+          (bf16 pipeline vs fp32: <= 5e-2 relative on the concatenated gradient, tiny config);
+      (2) optimizer parity: clip_grad_norm_ + torch.optim.AdamW applied to OUR gradients on the host must reproduce the
+          fused clip + AdamW kernel's parameter update (fp32 arithmetic on both sides: <= 2e-3 relative);
+      (3) end-to-end parameter update vs the oracle trajectory, provably-zero-gradient biases excluded.  Adam's first
+          updates are +-lr * sign(g), so every gradient element whose sign differs costs 2 lr: this number measures the
+          fraction of near-zero gradient elements, it is capped loosely (<= 0.25) and reported."""
     import torch
     from oracle import models_ref as MR
     from oracle import unet_ref as UR
@@ -103,13 +126,20 @@ def train_case(v2: bool, B=2, HW=16):
     mcl = cb.ControlLoRA(**kw)
     mcl.load_state_dict(ocl.state_dict())
     mcl.to(DEV)
+    import copy
+    hcl = copy.deepcopy(ocl)                      # host twin that receives OUR gradients (check 2)
     MR.wire_processors(ounet, ocl)
     MR.wire_processors(munet, mcl)
-    opt = torch.optim.AdamW(ocl.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    adam = dict(lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    opt = torch.optim.AdamW(ocl.parameters(), **adam)
+    hopt = torch.optim.AdamW(hcl.parameters(), **adam)
     tr = Trainer(munet, mcl, lr=1e-4)
     g = torch.Generator().manual_seed(5)
     size = HW * 8
+    zero_b = _zero_grad_biases(ocl)
+    names = [n for n, _ in ocl.named_parameters()]
     p0 = {n: p.detach().clone() for n, p in ocl.named_parameters()}
+    worst_grad = worst_opt = 0.0
     for step in range(2):
         x = torch.randn(B, 4, HW, HW, generator=g).to(torch.bfloat16).float()
         t = torch.randint(0, 1000, (B,), generator=g)
@@ -119,18 +149,41 @@ def train_case(v2: bool, B=2, HW=16):
         ocl(guide)
         lo = torch.nn.functional.mse_loss(ounet(x, t, e).sample, tgt)
         lo.backward()
+        go = {n: p.grad.detach().clone() for n, p in ocl.named_parameters()}
         gn = torch.nn.utils.clip_grad_norm_(ocl.parameters(), 1.0)
         opt.step()
         opt.zero_grad()
-        lm = tr.step(x.to(DEV), t.to(DEV).float(), e.to(DEV).to(torch.bfloat16), guide.to(DEV), tgt.to(DEV))
+        # ours, split at the gradient: fused forward/backward, read the arena, then the fused clip + AdamW tail
+        before = {n: p.detach().cpu().clone() for n, p in mcl.named_parameters()}
+        lm = tr._forward_backward(x.to(DEV), t.to(DEV).float(), e.to(DEV).to(torch.bfloat16), guide.to(DEV), tgt.to(DEV))
+        gm = {n: tr.arena.grad_of(p).detach().cpu().clone() for n, p in mcl.named_parameters()}
+        tr._optimizer_tail()
         if DEV == "cuda":
             torch.cuda.synchronize()
+        after = {n: p.detach().cpu().clone() for n, p in mcl.named_parameters()}
+        # (1) gradient parity
+        sel = [n for n in names if n not in zero_b]
+        e_grad = rel(torch.cat([gm[n].flatten() for n in sel]), torch.cat([go[n].flatten() for n in sel]))
+        worst_grad = max(worst_grad, e_grad)
+        # (2) optimizer parity on our own gradients
+        with torch.no_grad():
+            for (n, p) in hcl.named_parameters():
+                p.copy_(before[n])
+                p.grad = gm[n].clone()
+        torch.nn.utils.clip_grad_norm_(hcl.parameters(), 1.0)
+        hopt.step()
+        num = sum(float(((after[n] - before[n]) - (p.detach() - before[n])).pow(2).sum()) for n, p in hcl.named_parameters())
+        den = sum(float((p.detach() - before[n]).pow(2).sum()) for n, p in hcl.named_parameters())
+        e_opt = (num / max(den, 1e-30)) ** 0.5
+        worst_opt = max(worst_opt, e_opt)
         print(f"  step {step}: loss oracle={float(lo):.6f} ours={float(lm):.6f}  oracle grad-norm={float(gn):.4f} "
-              f"ours={float(tr.gnorm_sq.sqrt()):.4f}")
-    # compare parameter UPDATES (Adam normalises gradients, so the update direction is a sharp test)
+              f"ours={float(tr.gnorm_sq.sqrt()):.4f}  grad rel={e_grad:.3e}  clip+AdamW rel (same grads)={e_opt:.3e}")
+    # (3) end-to-end parameter updates
     num = den = 0.0
     worst = (0.0, "")
     for (n, po), (_, pm) in zip(ocl.named_parameters(), mcl.named_parameters()):
+        if n in zero_b:
+            continue
         do = po.detach() - p0[n]
         dm = pm.detach().cpu() - p0[n]
         num += float((dm - do).pow(2).sum())
@@ -139,8 +192,10 @@ def train_case(v2: bool, B=2, HW=16):
         if e > worst[0] and float(do.norm()) > 1e-6:
             worst = (e, n)
     tot = (num / den) ** 0.5
-    print(f"  parameter-update rel (all params) = {tot:.3e}; worst tensor {worst[1]} rel={worst[0]:.3e}")
-    ok = tot < 0.35
+    print(f"  gradient rel (worst step) = {worst_grad:.3e}; clip+AdamW on identical gradients rel = {worst_opt:.3e}")
+    print(f"  parameter-update rel vs the oracle trajectory (zero-gradient biases {sorted(zero_b)} excluded) = {tot:.3e}; "
+          f"worst tensor {worst[1]} rel={worst[0]:.3e}")
+    ok = worst_grad < 5e-2 and worst_opt < 2e-3 and tot < 0.25
     print("CASE_OK" if ok else "CASE_FAIL")
     return ok
 

@@ -106,11 +106,18 @@ def build_pair(variant, B=2, HW=16, seed=0):
 
 
 def run(variant):
+    """variant[@scale]: e.g. "v1_stacked@0.5" runs with cross_attention_kwargs={"scale": 0.5} (models.py:118-120: the
+    processors' `scale` argument; stacked value adapters stay unscaled, models.py:260,265,397,402)."""
     import torch
     from oracle import models_ref as MR
 
     torch.backends.cuda.matmul.allow_tf32 = False
     B, HW = 2, 16
+    scale = 1.0
+    if "@" in variant:
+        variant, sc = variant.split("@")
+        scale = float(sc)
+    cak = None if scale == 1.0 else {"scale": scale}
     ounet, munet, ocl, mcl = build_pair(variant, B, HW)
     g = torch.Generator().manual_seed(5)
     sample = torch.randn(B, 4, HW, HW, generator=g).to(torch.bfloat16).float()
@@ -134,21 +141,22 @@ def run(variant):
                 p.inject_control_states(cm)
     # ---- oracle (CPU, fp32)
     t0 = time.time()
-    po = ounet(sample, t, ehs).sample
+    po = ounet(sample, t, ehs, cross_attention_kwargs=cak).sample
     lo = torch.nn.functional.mse_loss(po, target)
     oparams = {}
     if variant != "none":
         lo.backward()
-    print(f"[{variant}] oracle fwd+bwd {time.time()-t0:.1f}s  loss={float(lo):.6f}")
+    label = variant if scale == 1.0 else f"{variant}@{scale}"
+    print(f"[{label}] oracle fwd+bwd {time.time()-t0:.1f}s  loss={float(lo):.6f}")
     # ---- ours
-    pm = munet(sample.to(DEV), t.to(DEV), ehs.to(DEV).to(torch.bfloat16)).sample
+    pm = munet(sample.to(DEV), t.to(DEV), ehs.to(DEV).to(torch.bfloat16), cross_attention_kwargs=cak).sample
     lm = torch.nn.functional.mse_loss(pm, target.to(DEV))
     if variant != "none":
         lm.backward()
     if DEV == "cuda":
         torch.cuda.synchronize()
     e_pred = rel(pm, po)
-    print(f"[{variant}] noise-pred rel={e_pred:.3e}  loss ours={float(lm):.6f}")
+    print(f"[{label}] noise-pred rel={e_pred:.3e}  loss ours={float(lm):.6f}")
     worst = 0.0
     if variant != "none":
         # parameters: match by traversal order of the processors
@@ -177,7 +185,7 @@ def run(variant):
         allg_m = torch.cat([munet.attn_processors[n].get_parameter(k).grad.flatten().cpu() for n in onames
                             for k, _ in munet.attn_processors[n].named_parameters()
                             if ounet.attn_processors[n].get_parameter(k).grad is not None])
-        print(f"[{variant}] all LoRA grads (concatenated) rel={rel(allg_m, allg_o):.3e}  worst tensor rel={worst:.3e}  n={len(rows)}")
+        print(f"[{label}] all LoRA grads (concatenated) rel={rel(allg_m, allg_o):.3e}  worst tensor rel={worst:.3e}  n={len(rows)}")
         for lvl, (co, cm) in enumerate(zip(ctrl_o, ctrl_m)):
             print(f"    d control[{lvl}] rel={rel(cm.grad, co.grad):.3e} |g|={float(co.grad.norm()):.3e}")
     ok = e_pred < 2e-2 and worst < 8e-2

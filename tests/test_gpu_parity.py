@@ -74,11 +74,36 @@ def test_lora_and_optimizer(case):
 
 
 # ------------------------------------------------------------------------------------------------ assembled hot path
-@pytest.mark.parametrize("variant", ["none", "plain", "v1", "v1_stacked", "v2", "v1_post_add", "v1_concat"])
+@pytest.mark.parametrize("variant", ["none", "plain", "v1", "v1_stacked", "v2", "v1_post_add", "v1_concat",
+                                     "v1_stacked@0.5", "v2@0.5", "plain@2.0"])
 def test_unet_fwd_bwd_matches_oracle(variant):
     """Noise prediction and every LoRA / control-state gradient vs the fp32 oracle (tiny SD-style config).
     Tolerance: bf16 activations through ~40 layers => <= 2e-2 relative on the prediction, <= 8e-2 on single gradients."""
     assert check_unet.run(variant)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs, real shapes
+@pytest.mark.parametrize("config,batch", [("diffusiondb-canny-v2", 1), ("diffusiondb-canny", 1)])
+def test_fullsize_parity_and_precision_contract(config, batch):
+    """BASELINE C4 (`diffusiondb-canny-v2`, V2 processors) and C2 (`diffusiondb-canny`, v1 + pre-convs) on the real SD-1.5
+    shapes through the drop-in classes: noise prediction, loss and every ControlLoRA / hint-encoder gradient against the
+    fp32 CPU oracle, and the precision contract ours-vs-fp32 <= 1.25 x (eager bf16 autocast)-vs-fp32 (tests/check_fullsize.py
+    states the tolerances)."""
+    from tests import check_fullsize
+
+    log = None
+    try:
+        import pathlib
+        d = pathlib.Path(check_fullsize.ROOT) / "gpurun_out"
+        d.mkdir(exist_ok=True)
+        log = open(d / f"parity_fullsize_{config}_b{batch}.log", "w")
+    except OSError:
+        pass
+    try:
+        assert check_fullsize.run(config, batch, log)
+    finally:
+        if log is not None:
+            log.close()
 
 
 @pytest.mark.parametrize("case", ["hint_v1", "hint_v2"])
@@ -213,3 +238,73 @@ def test_ddim_loop_tracks_oracle_on_tiny_unet():
     err = float((out.cpu() - x).norm() / x.norm())
     print("ddim 3-step latent rel err", err)
     assert err < 6e-2
+
+
+# ------------------------------------------------------------------------------------------------ step glue (noise, timesteps, add_noise)
+def test_add_noise_matches_oracle_restatement():
+    """cl_add_noise against the numpy restatement of its Philox4x32-10 counter layout (oracle/sampler_ref.device_noise,
+    itself pinned by Random123's known-answer vectors in tests/test_oracle.py) and the restated DDPMScheduler.add_noise /
+    get_velocity: timesteps bit-exact, normals to fp32 libm precision, fresh draws per call, epsilon and v-prediction."""
+    import numpy as np
+    from controllora_b200 import ops
+    from controllora_b200.sampler import sd15_alphas_cumprod
+    from oracle import sampler_ref as SR
+
+    B, per = 8, 4 * 64 * 64
+    ac = torch.tensor(sd15_alphas_cumprod(), dtype=torch.float64)
+    sa, sb = ac.sqrt().float().cuda(), (1 - ac).sqrt().float().cuda()
+    x0 = torch.randn(B, 4, 64, 64, generator=torch.Generator().manual_seed(0))
+    ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    seed = 0x1234_5678_9ABC_DEF0
+    prev_ts = None
+    for step, vpred in ((0, False), (1, True), (2, False)):
+        noisy, target, ts = ops.add_noise(x0.cuda(), sa, sb, ctr, seed, v_prediction=vpred)
+        torch.cuda.synchronize()
+        assert int(ctr) == step + 1                                   # the counter advanced on the stream
+        n_ref, t_ref = SR.device_noise(seed, step, B, per)
+        assert np.array_equal(ts.cpu().numpy().astype(np.int64), t_ref)
+        n_ref = torch.from_numpy(n_ref).view(B, 4, 64, 64)
+        t_t = torch.from_numpy(t_ref)
+        ref_noisy = SR.add_noise(x0, n_ref, t_t)
+        ref_target = SR.get_velocity(x0, n_ref, t_t) if vpred else n_ref
+        assert torch.allclose(noisy.cpu(), ref_noisy, atol=2e-5, rtol=1e-5)
+        assert torch.allclose(target.cpu(), ref_target, atol=2e-5, rtol=1e-5)
+        if prev_ts is not None:
+            assert not torch.equal(prev_ts, ts.cpu())
+        prev_ts = ts.cpu()
+    # distribution sanity at full size
+    noisy, target, ts = ops.add_noise(torch.zeros(64, 4, 64, 64, device="cuda"), sa, sb, ctr, seed)
+    assert abs(float(target.mean())) < 5e-3 and abs(float(target.std()) - 1.0) < 5e-3
+    assert 0 <= float(ts.min()) and float(ts.max()) <= 999
+
+
+def test_train_step_from_latents_graph_draws_fresh_noise():
+    """Trainer.step_from_latents under CUDA-graph replay: every replay draws new timesteps / noise (device step counter)
+    and the loss stays finite; the draw of step k equals the oracle restatement for counter k."""
+    import numpy as np
+    import controllora_b200 as cb
+    from controllora_b200.configs import wire_processors
+    from controllora_b200.trainer import Trainer
+    from controllora_b200.unet import synthetic_state_dict
+    from oracle import sampler_ref as SR
+
+    TINY, TINY_LORA = check_unet.TINY, check_unet.TINY_LORA
+    unet = cb.UNet2DConditionModel.from_state_dict(synthetic_state_dict(TINY, 0), "cuda", TINY)
+    cl = cb.ControlLoRA(**TINY_LORA).cuda()
+    wire_processors(unet, cl)
+    tr = Trainer(unet, cl, lr=1e-4, cuda_graph=True, noise_seed=77)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(2, 4, 16, 16, generator=g).cuda()
+    e = torch.randn(2, 77, 64, generator=g).cuda().to(torch.bfloat16)
+    guide = (torch.rand(2, 3, 128, 128, generator=g) * 2 - 1).cuda()
+    seen = []
+    for k in range(5):
+        loss = tr.step_from_latents(lat, e, guide)
+        torch.cuda.synchronize()
+        assert torch.isfinite(loss).all()
+        _, target, ts = tr.last_noise_draw
+        n_ref, t_ref = SR.device_noise(77, k, 2, 4 * 16 * 16)
+        assert np.array_equal(ts.cpu().numpy().astype(np.int64), t_ref), k
+        assert torch.allclose(target.cpu().view(2, -1), torch.from_numpy(n_ref), atol=2e-5, rtol=1e-5)
+        seen.append(tuple(t_ref.tolist()))
+    assert tr._graph is not None and len(set(seen)) == 5

@@ -237,13 +237,19 @@ def test_trainer_checkpoint_roundtrip(tmp_path):
         tr.flat_m[:tr.numel].copy_(torch.randn(tr.numel, generator=g))
         tr.flat_v[:tr.numel].copy_(torch.rand(tr.numel, generator=g))
     tr.step_idx = 37
+    tr.rng_counter.fill_(9)                       # 9 noise draws so far (device Philox step counter)
     assert Trainer.latest_checkpoint(tmp_path) is None
     tr.save_checkpoint(tmp_path, global_step=30)
     p37 = tr.save_checkpoint(tmp_path)
+    expected_next = torch.rand(3)                 # what the host RNG yields right after the save
     assert Trainer.latest_checkpoint(tmp_path) == p37 and p37.endswith("checkpoint-37")
+    import os
+    assert {"config.json", "diffusion_pytorch_model.safetensors", "optimizer.bin", "scheduler.bin", "random_states_0.pkl"} <= set(os.listdir(p37))
     tr2, cl2 = make(5)
     assert not torch.equal(tr2.flat_p, tr.flat_p)
     assert tr2.load_checkpoint(p37) == 37 and tr2.step_idx == 37
+    assert int(tr2.rng_counter) == 9 and tr2.noise_seed == tr.noise_seed        # RNG state resumes (train_...:805-809 save_state)
+    assert torch.equal(torch.rand(3), expected_next)
     assert torch.equal(tr2.flat_p[:tr.numel], tr.flat_p[:tr.numel])
     assert torch.equal(tr2.flat_m, tr.flat_m) and torch.equal(tr2.flat_v, tr.flat_v)
     for (n1, a), (n2, b) in zip(cl.named_parameters(), cl2.named_parameters()):
@@ -251,3 +257,36 @@ def test_trainer_checkpoint_roundtrip(tmp_path):
     # the ControlLoRA part of the checkpoint is a plain reference-format model directory
     cl3 = cb.ControlLoRA.from_pretrained(p37)
     assert all(torch.equal(a, b.cpu()) for a, b in zip(cl3.state_dict().values(), cl.state_dict().values()))
+
+
+def test_trainer_checkpoint_keeps_arena_only_parameters_and_checks_names(tmp_path):
+    """Stacked pre_loras are trained through the arena but are not part of control_lora's state dict (models.py:189-190):
+    the checkpoint stores them by arena name and refuses to load into a differently wired Trainer."""
+    from controllora_b200.trainer import Trainer
+
+    def make(stacked):
+        torch.manual_seed(0)
+        mu = _tiny_unet()
+        mcl = cb.ControlLoRA(**TINY_LORA)
+        procs = wire_processors(mu, mcl)
+        extra = []
+        if stacked:
+            for name, p in procs.items():
+                pre = cb.LoRACrossAttnProcessor(p.hidden_size, p.cross_attention_dim, rank=4)
+                p.inject_pre_lora(pre)
+                extra.append(pre)
+        return Trainer(mu, mcl, lr=1e-4), extra
+
+    tr, extra = make(True)
+    assert tr.numel > sum(p.numel() for p in tr.cl.parameters())
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        tr.flat_p[:tr.numel].copy_(torch.randn(tr.numel, generator=g))
+    path = tr.save_checkpoint(tmp_path, global_step=3)
+    tr2, extra2 = make(True)
+    tr2.load_checkpoint(path)
+    assert torch.equal(tr2.flat_p[:tr.numel], tr.flat_p[:tr.numel])
+    assert all(torch.equal(a, b) for ea, eb in zip(extra, extra2) for a, b in zip(ea.parameters(), eb.parameters()))
+    tr3, _ = make(False)
+    with pytest.raises(ValueError):
+        tr3.load_checkpoint(path)

@@ -185,3 +185,37 @@ def test_oracle_samplers_match_committed_golden_trajectories():
     assert torch.equal(now["dpm_timesteps_30"], gold["dpm_timesteps_30"])
     for k in ("ddim10", "dpmpp12"):
         assert torch.allclose(now[k], gold[k], atol=1e-5, rtol=1e-5), k
+
+
+def test_philox_restatement_matches_random123_known_answers():
+    """oracle/sampler_ref.philox4x32_10 (the checker of csrc/noise.cu) against the known-answer vectors shipped with
+    Random123 (kat_vectors, philox4x32 10 rounds)."""
+    import numpy as np
+    from oracle import sampler_ref as SR
+
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        got = SR.philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0]
+        assert tuple(int(v) for v in got) == want
+
+
+def test_device_noise_restatement_statistics_and_add_noise():
+    import numpy as np
+    import torch
+    from oracle import sampler_ref as SR
+
+    n, t = SR.device_noise(5, 3, 16, 4096)
+    assert abs(float(n.mean())) < 2e-2 and abs(float(n.std()) - 1) < 2e-2 and t.min() >= 0 and t.max() < 1000
+    n2, t2 = SR.device_noise(5, 4, 16, 4096)
+    assert not np.array_equal(t, t2) and not np.array_equal(n, n2)
+    x0 = torch.randn(16, 4, 32, 32)
+    nz = torch.from_numpy(n).view(16, 4, 32, 32)
+    tt = torch.from_numpy(t)
+    ac = SR.alphas_cumprod()
+    y = SR.add_noise(x0, nz, tt)
+    b = 3
+    assert torch.allclose(y[b], (ac[t[b]].sqrt() * x0[b] + (1 - ac[t[b]]).sqrt() * nz[b]).float(), atol=1e-6)
+    v = SR.get_velocity(x0, nz, tt)
+    assert torch.allclose(v[b], (ac[t[b]].sqrt() * nz[b] - (1 - ac[t[b]]).sqrt() * x0[b]).float(), atol=1e-6)
