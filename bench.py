@@ -34,7 +34,9 @@ def gemm_traffic_per_launch():
     """DRAM bytes per gemm_tc_kernel launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the GEMM launches of
     one training step) from the committed ncu capture profiles/r01_gemm_traffic.json; None when the file is missing."""
     try:
-        d = json.loads((Path(__file__).resolve().parent / "profiles" / "r01_gemm_traffic.json").read_text())
+        root = Path(__file__).resolve().parent / "profiles"
+        f = root / "r02_gemm_traffic.json"
+        d = json.loads((f if f.exists() else root / "r01_gemm_traffic.json").read_text())
         return float(d["bytes_per_launch"])
     except Exception:
         return None
@@ -51,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary numbers (denoise C3/C5, drop-in path, per-shape GEMM table)")
     return ap.parse_args()
 
 
@@ -228,6 +231,161 @@ def run_reference(a):
     print(json.dumps(out), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------ auxiliary GPU numbers
+def _randomize_up(torch, module, dev, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n_, p_ in module.named_parameters():
+            if n_.endswith("up.weight"):
+                p_.copy_((0.02 * torch.randn(p_.shape, generator=g)).to(p_.device))
+
+
+def aux_denoise(torch, cb, unet, which):
+    """BASELINE.json configs 3 and 5 through controllora_b200.sampler.GraphedSampler (one captured step replayed):
+    c3 = configs/mpii-pose.json (v1), 512x512, batch 8 (UNet batch 16), 50-step DDIM, CFG 7.5   (train_...:829-843)
+    c5 = mix_lora_and_control_lora.py: v1 ControlLoRA + rank-4 plain LoRA stacked as pre_lora on every processor (:94-121),
+         768x768 (96x96 latents), batch 4 (UNet batch 8), 30 steps of DPMSolverMultistepScheduler (:80,153-164)."""
+    from controllora_b200.configs import NAMED, wire_processors
+    from controllora_b200.sampler import GraphedSampler
+
+    dev = unet.device_
+    cl = cb.ControlLoRA.from_config(NAMED["mpii-pose"]).to(dev)
+    _randomize_up(torch, cl, dev, 3)
+    procs = wire_processors(unet, cl)
+    if which == "c5":
+        for name, p in procs.items():
+            pre = cb.LoRACrossAttnProcessor(p.hidden_size, p.cross_attention_dim, rank=4).to(dev)
+            _randomize_up(torch, pre, dev, 5)
+            p.inject_pre_lora(pre)
+        Bn, size, steps, sched = 4, 768, 30, "dpmpp"
+    else:
+        Bn, size, steps, sched = 8, 512, 50, "ddim"
+    g = torch.Generator().manual_seed(11)
+    guide = (torch.rand(Bn, 3, size, size, generator=g) * 2 - 1).to(dev)
+    cond = torch.randn(Bn, 77, 768, generator=g).to(dev).to(torch.bfloat16)
+    unc = torch.randn(Bn, 77, 768, generator=g).to(dev).to(torch.bfloat16)
+    gs = GraphedSampler(unet, cl, Bn, size, size, scheduler=sched, num_inference_steps=steps, guidance_scale=7.5)
+    gs(guide, cond, unc, seed=0)                               # warm-up call: hint encoder, capture, full loop
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lat = gs(guide, cond, unc, seed=1)                         # timed: hint encoder + invariant products + `steps` replays
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"value": steps / ms * 1e3, "unit": "denoise steps/s", "ms_total": ms, "steps": steps, "image": size, "batch": Bn,
+            "unet_batch": 2 * Bn, "scheduler": sched, "launches_per_step": gs.launches_per_step,
+            "latents_finite": bool(torch.isfinite(lat).all()),
+            "what": ("configs/mpii-pose.json v1 ControlLoRA, 50-step DDIM + CFG 7.5" if which == "c3" else
+                     "mix_lora_and_control_lora.py: v1 ControlLoRA + stacked rank-4 pre-LoRA, 30-step DPM-Solver++(2M) + CFG 7.5") +
+                    "; whole call timed (hint encoder + timestep-invariant products once, then one CUDA-graph replay per step)"}
+
+
+def aux_dropin(torch, cb, unet, config_name, B, steps=4):
+    """The path a reference maintainer gets from the import swap alone: train_...:771-796 verbatim -
+    control_lora(guide), unet(...).sample, F.mse_loss, loss.backward() through the autograd bridge, clip_grad_norm_,
+    torch.optim.AdamW - no fused Trainer, no CUDA graph."""
+    from controllora_b200.configs import NAMED, wire_processors
+
+    dev = unet.device_
+    cl = cb.ControlLoRA.from_config(NAMED[config_name]).to(dev)
+    _randomize_up(torch, cl, dev, 3)
+    wire_processors(unet, cl)
+    opt = torch.optim.AdamW(cl.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    x, t, e, guide, tgt = (h.to(dev) for h in synth_inputs(torch, B))
+    e = e.to(torch.bfloat16)
+
+    def step():
+        cl(guide)
+        pred = unet(x, t, e).sample
+        loss = torch.nn.functional.mse_loss(pred.float(), tgt.float(), reduction="mean")
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(cl.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps * 1e3
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "wall_ms_per_step": wall, "steps": steps,
+            "final_loss": float(loss), "what": "drop-in classes under torch autograd + torch.optim.AdamW (train_...:771-796 verbatim), "
+                                                "per-kernel launches from Python (no fused Trainer, no CUDA graph)"}
+
+
+def aux_gemm_table(torch, ops):
+    """Per-shape throughput of the tcgen05 GEMM family at the SD-1.5 shapes (SURVEY 8a census), each timed ALONE with CUDA
+    events over operand sets that rotate through > 126 MB (so L2 does not hold them), against the burst bf16 peak of
+    MEASURED_PEAKS.json; cuBLAS (torch.matmul) on the same shape is printed beside it for context only."""
+    peak = 1667.1
+    pth = ROOT / "MEASURED_PEAKS.json"
+    if pth.exists():
+        peak = json.loads(pth.read_text()).get("bf16_tflops", peak)
+    dev = "cuda"
+    shapes = [("attn proj + LoRA r4 (north_star)", 32768, 320, 320, True), ("attn proj", 32768, 320, 320, False),
+              ("attn proj + LoRA r4", 8192, 640, 640, True), ("attn proj + LoRA r4", 2048, 1280, 1280, True),
+              ("ff1", 32768, 2560, 320, False), ("ff2", 32768, 320, 1280, False), ("ff1", 8192, 5120, 640, False),
+              ("ff2", 8192, 640, 2560, False), ("ff1", 2048, 10240, 1280, False), ("ff2", 2048, 1280, 5120, False)]
+    convs = [(8, 64, 320, 320), (8, 32, 640, 640), (8, 16, 1280, 1280), (8, 64, 640, 320)]
+    rows = []
+
+    def timed(fn, nsets, iters=6):
+        for i in range(nsets):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            for i in range(nsets):
+                fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (iters * nsets)
+
+    for name, M, N, K, lora in shapes:
+        per = 2 * (M * K + M * N)
+        nsets = max(2, min(16, int(200e6 // per) + 1))
+        As = [torch.randn(M, K, device=dev).to(torch.bfloat16) for _ in range(nsets)]
+        Ds = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(nsets)]
+        Wt = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+        kw = {}
+        if lora:
+            down = torch.randn(4, K, device=dev) / 4
+            kw = dict(ext=ops.split_bf16_ext(down, K), lora_up=torch.randn(N, 4, device=dev) * 0.1, lora_scale=1.0,
+                      t_out=torch.empty(M, 4, device=dev))
+        ms = timed(lambda i: ops.gemm(As[i], Wt, out=Ds[i], **kw), nsets)
+        ms_ref = timed(lambda i: torch.matmul(As[i], Wt.t(), out=Ds[i]), nsets)
+        fl = 2.0 * M * N * K + (2.0 * M * 16 * K if lora else 0.0)
+        rows.append({"op": name, "M": M, "N": N, "K": K, "lora": lora, "us": ms * 1e3, "tflops": fl / ms / 1e9,
+                     "frac_of_burst_peak": fl / ms / 1e9 / peak, "hbm_gbs": (per + 2 * N * K) / ms / 1e6,
+                     "cublas_us_no_lora": ms_ref * 1e3, "vs_cublas": ms_ref / ms})
+        del As, Ds
+    for n, H, Cc, N in convs:
+        M, K = n * H * H, 9 * Cc
+        per = 2 * (n * H * H * Cc + M * N)
+        nsets = max(2, min(16, int(200e6 // per) + 1))
+        Xs = [torch.randn(n, H, H, Cc, device=dev).to(torch.bfloat16) for _ in range(nsets)]
+        Ds = [torch.empty(n, H, H, N, device=dev, dtype=torch.bfloat16) for _ in range(nsets)]
+        Wt = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+        ms = timed(lambda i: ops.gemm(Xs[i], Wt, out=Ds[i], conv_stride=1), nsets)
+        fl = 2.0 * M * N * K
+        rows.append({"op": "conv3x3 (implicit GEMM)", "M": M, "N": N, "K": K, "lora": False, "us": ms * 1e3, "tflops": fl / ms / 1e9,
+                     "frac_of_burst_peak": fl / ms / 1e9 / peak, "hbm_gbs": (per + 2 * N * K) / ms / 1e6,
+                     "cublas_us_no_lora": None, "vs_cublas": None})
+        del Xs, Ds
+    return {"rows": rows, "peak_tflops_burst": peak,
+            "what": "each shape timed alone (CUDA events, operands rotated through >126 MB); frac = TFLOP/s / measured burst bf16 peak"}
+
+
 # ------------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(a):
     import torch
@@ -365,7 +523,9 @@ def run_ours(a):
             M = A_.shape[0] if not conv else A_.shape[0] * A_.shape[1] * A_.shape[2] // (conv * conv)
             N, K = B_.shape
             fl = 2.0 * M * N * K + (2.0 * M * 16 * K if kw.get("lora_up") is not None else 0.0)
-            rec.append((fl, s0, s1))
+            # algorithmic bytes of the launch: A, W and D once each in their storage type (+ the residual read when fused)
+            by = 2.0 * (A_.numel() + N * K) + (4.0 if kw.get("out_fp32") else 2.0) * M * N + (2.0 * M * N if kw.get("residual") is not None else 0.0)
+            rec.append((fl, s0, s1, by))
             return r
 
         ops.gemm = timed_gemm
@@ -380,43 +540,31 @@ def run_ours(a):
         ops.gemm = orig
         fl = sum(r[0] for r in rec)
         tm = sum(r[1].elapsed_time(r[2]) for r in rec)
+        alg_bytes = sum(r[3] for r in rec)
         ach = fl / (tm * 1e-3) / 1e12
     if rank == 0 and not a.no_roofline:
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN,EXT,BK> (all fused linear / LoRA / implicit-GEMM conv launches of one step)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": gemm_traffic_per_launch(),
-                "launches_per_step": len(rec), "gemm_ms_per_step": tm, "algorithmic_gflop_per_step": fl / 1e9, "peak_source": which,
+                "launches_per_step": len(rec), "gemm_ms_per_step": tm, "algorithmic_gflop_per_step": fl / 1e9,
+                "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_per_launch": alg_bytes / max(len(rec), 1),
+                "peak_source": which,
                 "step_model_flops_utilisation": (GFLOP_PER_IMAGE_STEP * 1e9 * B / (ms_step * 1e-3)) / (peak_tf * 1e12)}
-    # ---------------- secondary metric of BASELINE.json: denoise steps/s = UNet evaluations at the CFG batch (2B) + fused
-    #                  CFG/DDIM update per second (control injected once per image batch)
-    trace("denoise")
-    denoise = None
-    if rank == 0:
-        try:
-            from controllora_b200.sampler import ddim_coeffs, ddim_timesteps, sd15_alphas_cumprod
-            with torch.no_grad():
-                cl(torch.cat([guide, guide], 0))
-                x2t = torch.full((2 * B,), 500.0, device=dev)
-                e2 = torch.cat([e, e], 0)
-                lat = x.clone()
-                ac = sd15_alphas_cumprod()
-                ts = ddim_timesteps(50)
-                def dstep(t):
-                    eps2 = unet(torch.cat([lat, lat], 0), x2t.fill_(float(t)), e2).sample
-                    a_t, a_p = ddim_coeffs(t, 50, ac)
-                    ops.cfg_ddim_step(eps2, lat, 7.5, a_t, a_p)
-                for t in ts[:3]:
-                    dstep(t)
-                torch.cuda.synchronize()
-                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                d0.record()
-                for t in ts[3:13]:
-                    dstep(t)
-                d1.record()
-                torch.cuda.synchronize()
-                denoise = {"value": 10.0 / (d0.elapsed_time(d1) * 1e-3), "unit": "denoise steps/s",
-                           "what": f"50-step DDIM + CFG 7.5, batch {B} (UNet batch {2 * B}), 10 timed steps, {a.config} processors"}
-        except Exception as ex:
-            denoise = {"value": None, "unit": "denoise steps/s", "what": f"failed: {ex}"}
+    # ---------------- auxiliary numbers (rank 0, after every measurement of the headline): BASELINE configs C3 / C5 denoise
+    #                  steps/s, the drop-in (autograd + torch.optim.AdamW) path, and the per-shape GEMM table
+    trace("aux")
+    aux = {}
+    graph_used = bool(tr.cuda_graph and tr._graph is not None)
+    if rank == 0 and not a.no_aux:
+        del tr
+        torch.cuda.empty_cache()
+        for key, fn in (("denoise_c3", lambda: aux_denoise(torch, cb, unet, "c3")), ("denoise_c5", lambda: aux_denoise(torch, cb, unet, "c5")),
+                        ("dropin_train_step", lambda: aux_dropin(torch, cb, unet, a.config, B)),
+                        ("gemm_per_shape", lambda: aux_gemm_table(torch, ops))):
+            try:
+                aux[key] = fn()
+            except Exception as ex:      # an auxiliary number must never take the headline down
+                aux[key] = {"value": None, "what": f"failed: {type(ex).__name__}: {ex}"}
+            torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
     trace("report")
@@ -435,7 +583,7 @@ def run_ours(a):
             "config": {"workload": f"{a.config} ControlLoRA train step on the SD-1.5 UNet, 512x512 (64x64 latents, 77x768 text states), "
                                    f"batch {B}/GPU, hint encoder + UNet fwd/bwd + clip + AdamW" + (" + NCCL all-reduce of the flat grad arena" if world > 1 else ""),
                        "global_batch": world * B, "parallelism": f"dp{world}",
-                       "cuda_graph": bool(tr.cuda_graph and tr._graph is not None),
+                       "cuda_graph": graph_used,
                        "l2_policy": "no explicit flush: each step streams 1.7 GB of frozen weights plus >5 GB of activations, far beyond the 126 MB L2",
                        "weights": "random-init (seeded), SD-1.5 / ControlLoRA shapes", "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -444,8 +592,10 @@ def run_ours(a):
         }
         if roof is not None:
             out["roofline"] = roof
-        if denoise is not None:
-            out["aux"] = {"denoise": denoise}
+        if aux:
+            out["aux"] = aux
+            if roof is not None and isinstance(aux.get("gemm_per_shape"), dict) and aux["gemm_per_shape"].get("rows"):
+                roof["per_shape"] = aux["gemm_per_shape"]["rows"]
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out), flush=True)

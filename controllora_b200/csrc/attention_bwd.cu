@@ -7,10 +7,16 @@
 // Two kernels, no atomics:
 //   attn_bwd_dkv: CTA = (batch, head, 128-key block), loops over query blocks.  Works on the transposed problem so
 //       that TMEM lane == key row:   S^T = K Q^T,  dP^T = V dO^T  (both operands K-major smem tiles);  the softmax
-//       warps turn them into bf16 P^T and dS^T tiles in smem (K-major over queries);  dV += P^T dO and
-//       dK += dS^T Q then consume the *same* dO / Q smem tiles again, this time as MN-major B operands.
+//       warps turn them into bf16 P^T and dS^T and write them back INTO TENSOR MEMORY (tcgen05.st, packed two bf16 per
+//       32-bit column, over the S^T / dP^T columns each warp has already consumed);  dV += P^T dO and dK += dS^T Q then
+//       take their A operand from TMEM (tcgen05.mma with a TMEM A operand) and the *same* dO / Q smem tiles again as
+//       MN-major B operands.
 //   attn_bwd_dq:  CTA = (batch, head, 128-query block), loops over key blocks:  S = Q K^T, dP = dO V^T,
-//       dS -> smem,  dQ += dS K (K tile as MN-major B operand).
+//       dS -> TMEM,  dQ += dS K (dS as TMEM A operand, K tile as MN-major B operand).
+// Why TMEM operands: ncu (profiles/r02_attn_bwd_ncu.md) showed both kernels bound by SHARED-MEMORY bandwidth - the
+// P^T / dS^T tiles cost 16-byte st.shared wavefronts on the way in and 16 KB of operand fetch per MMA group on the way
+// out (dkv: 116 M LSU wavefronts + 96 KB of MMA operand reads per query block against 128 B/clk/SM).  Through TMEM they
+// cost neither.
 // Warp roles as in the forward kernel: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 4-7 softmax/epilogue.
 #include <stdio.h>
 #include <string.h>
@@ -92,8 +98,11 @@ struct DkvCfg {
     static constexpr int KV_BYTES = DCH * BK * 128;             // K tile (and V tile)
     static constexpr int QD_TILE = DCH * BQ * 128;              // Q_j tile (and dO_j tile)
     static constexpr int STAGE_BYTES = 2 * QD_TILE;
-    static constexpr int PT_BYTES = (BQ / 64) * BK * 128;       // P^T tile (and dS^T tile)
-    static constexpr int SMEM_BYTES = 1024 + 2 * KV_BYTES + STAGES * STAGE_BYTES + 2 * PT_BYTES + 2 * 2 * BQ * 4 + 256;
+    static constexpr int SMEM_BYTES = 1024 + 2 * KV_BYTES + STAGES * STAGE_BYTES + 2 * 2 * BQ * 4 + 256;
+    // P^T / dS^T live in TMEM over the S^T / dP^T columns: the softmax warp of column half h owns S^T columns
+    // [h*BQ/2, (h+1)*BQ/2) and packs the bf16 result of its chunk c (16 queries -> 8 columns) at the start of that range
+    static constexpr int CH_PER_HALF = BQ / 32;                 // 16-query chunks per softmax warp
+    __host__ __device__ static constexpr int a_col(int chunk) { return (chunk / CH_PER_HALF) * (BQ / 2) + (chunk % CH_PER_HALF) * 8; }
     static constexpr int TM_ST = 0, TM_DPT = BQ, TM_DK = 2 * BQ, TM_DV = 2 * BQ + DP;
     static constexpr int TMEM_NEED = 2 * BQ + 2 * DP;
     static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
@@ -119,9 +128,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint8_t* smem_k = smem;
     uint8_t* smem_v = smem_k + Cfg::KV_BYTES;
     uint8_t* smem_st = smem_v + Cfg::KV_BYTES;                       // stages: [Q_j | dO_j]
-    uint8_t* smem_pt = smem_st + STAGES * Cfg::STAGE_BYTES;
-    uint8_t* smem_dst = smem_pt + Cfg::PT_BYTES;
-    float* smem_lse = reinterpret_cast<float*>(smem_dst + Cfg::PT_BYTES);   // [2][BQ]
+    float* smem_lse = reinterpret_cast<float*>(smem_st + STAGES * Cfg::STAGE_BYTES);   // [2][BQ]
     float* smem_delta = smem_lse + 2 * BQ;                                  // [2][BQ]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_delta + 2 * BQ);
     uint64_t* kv_full = bars;
@@ -183,7 +190,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             constexpr uint32_t idesc_g = make_idesc_bf16(128, DP, 0, 1);    // [keys x d], B MN-major
             mbar_wait(kv_full, 0);
             const uint32_t sk = smem_u32(smem_k), sv = smem_u32(smem_v);
-            const uint32_t spt = smem_u32(smem_pt), sdst = smem_u32(smem_dst);
             int stage = 0; uint32_t phase = 0;
             for (int j = 0; j < num_q; ++j) {
                 mbar_wait(&st_full[stage], phase);
@@ -209,11 +215,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < BQ / 16; ++kk) {
-                    const uint32_t offa = (kk / 4) * (BK * 128) + (kk % 4) * 32;
-                    // dV += P^T dO_j ;  dK += dS^T Q_j   (B tiles [queries][64 d]: MN-major, LBO = chunk stride)
-                    tc_mma_ss(tmem_base + Cfg::TM_DV, make_smem_desc(spt + offa, 16, 1024, 2),
+                    // dV += P^T dO_j ;  dK += dS^T Q_j   (A: bf16 P^T / dS^T of query chunk kk in TMEM; B tiles [queries][64 d]:
+                    // MN-major, LBO = chunk stride)
+                    tc_mma_ts(tmem_base + Cfg::TM_DV, tmem_base + Cfg::TM_ST + Cfg::a_col(kk),
                               make_smem_desc(sdo + kk * 2048, BQ * 128, 1024, 2), idesc_g, (j | kk) != 0);
-                    tc_mma_ss(tmem_base + Cfg::TM_DK, make_smem_desc(sdst + offa, 16, 1024, 2),
+                    tc_mma_ts(tmem_base + Cfg::TM_DK, tmem_base + Cfg::TM_DPT + Cfg::a_col(kk),
                               make_smem_desc(sq + kk * 2048, BQ * 128, 1024, 2), idesc_g, (j | kk) != 0);
                 }
                 tc_commit(&st_empty[stage]);
@@ -266,11 +272,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     pk[i >> 1] = pack_bf16x2(p0, p1);
                     dk_[i >> 1] = pack_bf16x2(d0, d1);
                 }
-                store_row16_swz(smem_pt, BK * 128, r, c, pk);
-                store_row16_swz(smem_dst, BK * 128, r, c, dk_);
+                // bf16 P^T / dS^T of this chunk -> TMEM, over S^T / dP^T columns this warp has already read
+                tmem_st_32x8(tmem_base + Cfg::TM_ST + lane_off + Cfg::a_col(c), pk);
+                tmem_st_32x8(tmem_base + Cfg::TM_DPT + lane_off + Cfg::a_col(c), dk_);
             }
+            tc_wait_st();
             tc_fence_before();
-            fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
         }
@@ -293,8 +300,9 @@ struct DqCfg {
     static constexpr int QD_BYTES = DCH * BM * 128;             // Q tile (and dO tile)
     static constexpr int KV_TILE = DCH * BKB * 128;
     static constexpr int STAGE_BYTES = 2 * KV_TILE;
-    static constexpr int DS_BYTES = (BKB / 64) * BM * 128;
-    static constexpr int SMEM_BYTES = 1024 + 2 * QD_BYTES + STAGES * STAGE_BYTES + DS_BYTES + 256;
+    static constexpr int SMEM_BYTES = 1024 + 2 * QD_BYTES + STAGES * STAGE_BYTES + 256;
+    static constexpr int CH_PER_HALF = BKB / 32;                // dS (bf16, TMEM) over the S columns: see DkvCfg::a_col
+    __host__ __device__ static constexpr int a_col(int chunk) { return (chunk / CH_PER_HALF) * (BKB / 2) + (chunk % CH_PER_HALF) * 8; }
     static constexpr int TM_S = 0, TM_DP = BKB, TM_DQ = 2 * BKB;
     static constexpr int TMEM_NEED = 2 * BKB + DP;
     static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
@@ -315,8 +323,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint8_t* smem_q = smem;
     uint8_t* smem_do = smem_q + Cfg::QD_BYTES;
     uint8_t* smem_kv = smem_do + Cfg::QD_BYTES;
-    uint8_t* smem_ds = smem_kv + STAGES * Cfg::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ds + Cfg::DS_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + STAGES * Cfg::STAGE_BYTES);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;
     uint64_t* kv_empty = kv_full + STAGES;
@@ -375,7 +382,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             constexpr uint32_t idesc_s = make_idesc_bf16(128, BKB, 0, 0);
             constexpr uint32_t idesc_g = make_idesc_bf16(128, DP, 0, 1);
             mbar_wait(q_full, 0);
-            const uint32_t sq = smem_u32(smem_q), sdo = smem_u32(smem_do), sds = smem_u32(smem_ds);
+            const uint32_t sq = smem_u32(smem_q), sdo = smem_u32(smem_do);
             int stage = 0; uint32_t phase = 0;
             for (int i = 0; i < num_kv; ++i) {
                 mbar_wait(&kv_full[stage], phase);
@@ -401,8 +408,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < BKB / 16; ++kk) {
-                    const uint32_t offa = (kk / 4) * (BM * 128) + (kk % 4) * 32;
-                    tc_mma_ss(tmem_base + Cfg::TM_DQ, make_smem_desc(sds + offa, 16, 1024, 2),
+                    tc_mma_ts(tmem_base + Cfg::TM_DQ, tmem_base + Cfg::TM_S + Cfg::a_col(kk),
                               make_smem_desc(sk + kk * 2048, BKB * 128, 1024, 2), idesc_g, (i | kk) != 0);
                 }
                 tc_commit(&kv_empty[stage]);
@@ -444,10 +450,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     const float d1 = p1 * (__uint_as_float(g[j + 1]) - delta) * p.scale;
                     dk_[j >> 1] = pack_bf16x2(d0, d1);
                 }
-                store_row16_swz(smem_ds, BM * 128, r, c, dk_);
+                tmem_st_32x8(tmem_base + Cfg::TM_S + lane_off + Cfg::a_col(c), dk_);    // bf16 dS chunk -> TMEM (A operand of dQ)
             }
+            tc_wait_st();
             tc_fence_before();
-            fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
         }

@@ -331,3 +331,46 @@ extern "C" int cl_bf16_to_f32(const void* x, float* y, int64_t n, void* stream_)
     launch_k(bf16_to_f32_kernel, ew_blocks(n), 256, 0, stream, BF(x), y, n);
     DONE();
 }
+
+// ------------------------------------------------------------------------------------------ strided weight-space helpers
+// (trainable dense operands of the concat_hidden control MLP, models.py:208-214: bf16 views / transposes of the fp32 masters
+//  and strided accumulation of their fp32 weight gradients)
+namespace clb {
+// dst[i*ld + j] = bf16(alpha * src[i*s_i + j*s_j])
+__global__ void cast_matrix_kernel(const float* __restrict__ src, long long s_i, long long s_j, __nv_bfloat16* __restrict__ dst,
+                                   long long ld, int I, int J, float alpha) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long total = (long long)I * J;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / J), j = (int)(k % J);
+        dst[i * ld + j] = __float2bfloat16(alpha * src[i * s_i + j * s_j]);
+    }
+}
+// dst[i*ld + j] += alpha * src[i*J + j]   (fp32)
+__global__ void axpy_matrix_kernel(const float* __restrict__ src, float* __restrict__ dst, long long ld, int I, int J, float alpha) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long total = (long long)I * J;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k / J), j = (int)(k % J);
+        dst[i * ld + j] += alpha * src[k];
+    }
+}
+}  // namespace clb
+
+extern "C" int cl_cast_matrix_bf16(const float* src, int64_t s_i, int64_t s_j, void* dst, int64_t ld, int I, int J, float alpha,
+                                   void* stream_) {
+    STREAM;
+    if (!src || !dst || I <= 0 || J <= 0) return set_error(CL_ERR_INVALID, "cl_cast_matrix_bf16: bad args");
+    launch_k(clb::cast_matrix_kernel, ew_blocks((long long)I * J), 256, 0, stream, src, (long long)s_i, (long long)s_j, BFW(dst),
+             (long long)ld, I, J, alpha);
+    DONE();
+}
+
+extern "C" int cl_axpy_matrix_f32(const float* src, float* dst, int64_t ld, int I, int J, float alpha, void* stream_) {
+    STREAM;
+    if (!src || !dst || I <= 0 || J <= 0) return set_error(CL_ERR_INVALID, "cl_axpy_matrix_f32: bad args");
+    launch_k(clb::axpy_matrix_kernel, ew_blocks((long long)I * J), 256, 0, stream, src, dst, (long long)ld, I, J, alpha);
+    DONE();
+}

@@ -58,6 +58,8 @@ struct GemmParams {
     void* out;
     long long ldd;
     int out_fp32;
+    int tma_store;    // bf16 output through per-warp TMA stores of 32x32 sub-tiles (new epilogue); 0 = per-lane global stores
+    int ew, eh, en;   // conv: the 32 rows of a TMEM lane quadrant as a box of the output image (ew * eh * en == 32)
     int b_resident;   // B (weights) tile of this CTA's n-block stays in smem for the CTA lifetime (small K)
     // split-K (streaming mode only): tile space is (m, n, split); split s covers k-blocks [s*kb_per_split, ...) and stores
     // its fp32 partial tile to split_ws[s][M][N]; splitk_finish_kernel sums the partials and applies the epilogue.
@@ -158,7 +160,8 @@ __device__ __forceinline__ void decode_row(const GemmParams& p, int m_blk, int r
 template <int BN, int EXT, int BK, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmE, const GemmParams p, const int num_stages) {
+               const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD, const GemmParams p,
+               const int num_stages) {
     pdl_launch_dependents();
     using Cfg = GemmCfg<BN, EXT, BK, CG>;
     const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;      // 0 = leader of the pair
@@ -191,6 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (EXT) tma_prefetch_desc(&tmE);
+        if (p.tma_store) tma_prefetch_desc(&tmD);
     }
     if (warp_idx == 1 && lane == 0) {
         for (int i = 0; i < num_stages; ++i) {
@@ -339,6 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int rp = p.lora_rp;
         const uint32_t up_addr = smem_u32(smem_up);
         int it = 0;
+        int epi_gran = 0;                          // granules this warp has stored through TMA (staging buffer = parity)
         for (TileIter ti(p, sched_cta, sched_n, sched_m); ti.valid(); ti.next(), ++it) {
             const int m_blk = (CG == 2) ? ti.m_blk * 2 + cta_rank : ti.m_blk;
             const int n_blk = ti.n_blk;
@@ -379,6 +384,100 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 8; ++j) tl[j] *= p.lora_scale;
             }
 
+            if (p.tma_store) {
+                // ---- bf16 output, thread == output row: accumulator (+ LoRA + bias + row bias + residual) in registers,
+                //      packed to bf16, staged as a 32 x 64 B sub-tile (64B-swizzled, 4 conflict-free 16-byte stores per lane)
+                //      and written by ONE TMA store per granule; two staging buffers per warp keep a store in flight while
+                //      the next granule is produced.  Row-wise operands (residual) are fetched before the TMEM load is
+                //      waited on, so their latency overlaps it.
+                int sc1 = 0, sc2 = 0, sc3 = 0;            // store coordinates of this warp's 32 rows
+                if (p.a_mode == 0) {
+                    sc1 = m_blk * BLOCK_M + quad * 32;
+                } else {
+                    const int r0 = quad * 32;
+                    const int tw = m_blk % p.tiles_w, th = (m_blk / p.tiles_w) % p.tiles_h, tn = m_blk / (p.tiles_w * p.tiles_h);
+                    sc1 = tw * p.bw + r0 % p.bw;
+                    sc2 = th * p.bh + (r0 / p.bw) % p.bh;
+                    sc3 = tn * p.bn + r0 / (p.bw * p.bh);
+                }
+                const bool row_ok = my_m >= 0;
+                const __nv_bfloat16* res_row = (p.residual != nullptr && row_ok) ? p.residual + (long long)my_m * p.ldr : nullptr;
+                const float* rb_row = (p.row_bias != nullptr && row_ok) ? p.row_bias + (long long)my_grp * p.ld_rb : nullptr;
+                for (int g = half; g < BN / 32; g += 2) {
+                    const int col0 = n_blk * BN + g * 32;
+                    if (col0 >= p.N) break;                   // (warp-uniform)
+                    uint4 rr[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        rr[j] = make_uint4(0u, 0u, 0u, 0u);
+                        if (res_row != nullptr && col0 + 8 * j < p.N) rr[j] = *reinterpret_cast<const uint4*>(res_row + col0 + 8 * j);
+                    }
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_base + g * 32, v);
+                    float f[32];
+                    // column-wise operands while the TMEM load is in flight
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (col0 + 4 * j < p.N) {
+                            if (p.bias != nullptr) bz = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+                            if (rb_row != nullptr) {
+                                const float4 rb = *reinterpret_cast<const float4*>(rb_row + col0 + 4 * j);
+                                bz.x += rb.x; bz.y += rb.y; bz.z += rb.z; bz.w += rb.w;
+                            }
+                        }
+                        f[4 * j] = bz.x; f[4 * j + 1] = bz.y; f[4 * j + 2] = bz.z; f[4 * j + 3] = bz.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 a0 = unpack_bf16x2(rr[j].x), a1 = unpack_bf16x2(rr[j].y), a2 = unpack_bf16x2(rr[j].z),
+                                     a3 = unpack_bf16x2(rr[j].w);
+                        f[8 * j] += a0.x; f[8 * j + 1] += a0.y; f[8 * j + 2] += a1.x; f[8 * j + 3] += a1.y;
+                        f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
+                    }
+                    if (EXT) {
+                        if (rp == 4) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                const int n = min(col0 + c, p.N - 1);
+                                const float4 u = ld_shared_f4(up_addr + n * 16);
+                                f[c] += tl[0] * u.x + tl[1] * u.y + tl[2] * u.z + tl[3] * u.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                const int n = min(col0 + c, p.N - 1);
+                                const float4 u0 = ld_shared_f4(up_addr + n * 32);
+                                const float4 u1 = ld_shared_f4(up_addr + n * 32 + 16);
+                                f[c] += tl[0] * u0.x + tl[1] * u0.y + tl[2] * u0.z + tl[3] * u0.w + tl[4] * u1.x +
+                                        tl[5] * u1.y + tl[6] * u1.z + tl[7] * u1.w;
+                            }
+                        }
+                    }
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) f[c] += __uint_as_float(v[c]);
+                    // the store issued two granules ago has finished reading this staging buffer
+                    const uint32_t sbuf = stg_addr + (uint32_t)(epi_gran & 1) * 2048u;
+                    if (lane == 0) bulk_wait_group_read<1>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]); o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                        o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                        st_shared_u4(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), o);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.a_mode == 0) tma_store_2d(&tmD, sbuf, col0, sc1);
+                        else tma_store_4d(&tmD, sbuf, col0, sc1, sc2, sc3);
+                        bulk_commit_group();
+                    }
+                    ++epi_gran;
+                }
+            } else
             for (int g = half; g < BN / 32; g += 2) {
                 const int col0 = n_blk * BN + g * 32;   // first global column of this granule
                 if (col0 >= p.N) break;                   // (warp-uniform) nothing to store
@@ -488,6 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (ew == 0 && lane == 0) TL(32);  // epilogue: tile done
         }
+        if (p.tma_store && lane == 0) bulk_wait_group_read<0>();   // staging smem must outlive the last TMA stores
     }
 
     tc_fence_before();
@@ -548,8 +648,8 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, int M, int N, con
 // =====================================================================================================
 
 template <int BN, int EXT, int BK = 64, int CG = 1>
-static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tE, const GemmParams& p_in,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tE, const CUtensorMap& tD,
+                       const GemmParams& p_in, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, EXT, BK, CG>;
     GemmParams p = p_in;
     const int up_bytes = (p.lora_up != nullptr) ? ((p.N * p.lora_rp * 4 + 15) & ~15) : 0;
@@ -600,9 +700,9 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        CL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EXT, BK, CG>, tA, tB, tE, p, stages));
+        CL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EXT, BK, CG>, tA, tB, tE, tD, p, stages));
     } else {
-        launch_k(gemm_tc_kernel<BN, EXT, BK, CG>, grid, NUM_THREADS, smem_bytes, stream, tA, tB, tE, p, stages);
+        launch_k(gemm_tc_kernel<BN, EXT, BK, CG>, grid, NUM_THREADS, smem_bytes, stream, tA, tB, tE, tD, p, stages);
     }
     count_launch();
     if (p.splits > 1) {
@@ -806,37 +906,66 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     if (p.row_bias && p.rows_per_group <= 0) return set_error(CL_ERR_INVALID, "cl_gemm: rows_per_group");
     if ((p.ldd % 4) || (p.residual && (p.ldr % 4))) return set_error(CL_ERR_INVALID, "cl_gemm: ldd/ldr % 4");
 
+    // bf16 outputs whose rows are 16-byte addressable leave through per-warp TMA stores (thread == row epilogue); fp32
+    // outputs, split-K partial tiles and odd strides keep the per-lane store path.  CLB_GEMM_TMA_STORE=0 disables.
+    CUtensorMap tD;
+    memset(&tD, 0, sizeof(tD));
+    static const int tma_store_enabled = [] { const char* e = getenv("CLB_GEMM_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(a->out) & 15) == 0) && (p.ldd % 8 == 0) && (a->N % 8 == 0) &&
+                           (!p.residual || (((reinterpret_cast<uintptr_t>(a->residual) & 15) == 0) && (p.ldr % 8 == 0)));
+    if (tma_store_enabled && !p.out_fp32 && p.splits == 1 && aligned16) {
+        if (a->a_mode == 0) {
+            uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
+            uint64_t strides[1] = {(uint64_t)p.ldd * 2};
+            uint32_t box[2] = {32, 32};
+            CL_CHECK(get_tensor_map(&tD, a->out, 2, dims, strides, box, 64));
+            p.tma_store = 1;
+        } else if (p.ldd == a->N) {
+            // rows quad*32 .. quad*32+31 of a (bn x bh x bw) output tile, w fastest, form the box (en x eh x ew)
+            p.ew = p.bw < 32 ? p.bw : 32;
+            p.eh = (32 / p.ew) < p.bh ? (32 / p.ew) : p.bh;
+            p.en = 32 / (p.ew * p.eh);
+            if (p.en <= p.bn && p.ew * p.eh * p.en == 32) {
+                uint64_t dims[4] = {(uint64_t)a->N, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.n_img};
+                uint64_t strides[3] = {(uint64_t)a->N * 2, (uint64_t)p.Wo * a->N * 2, (uint64_t)p.Ho * p.Wo * a->N * 2};
+                uint32_t box[4] = {32, (uint32_t)p.ew, (uint32_t)p.eh, (uint32_t)p.en};
+                CL_CHECK(get_tensor_map(&tD, a->out, 4, dims, strides, box, 64));
+                p.tma_store = 1;
+            }
+        }
+    }
+
     if (BK == 32) {
         if (lora) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: LoRA epilogue is not instantiated for 32-channel convs");
         switch (bn_sel) {
-            case 32: return launch_gemm<32, 0, 32>(tA, tB, tE, p, stream);
-            case 64: return launch_gemm<64, 0, 32>(tA, tB, tE, p, stream);
-            case 128: return launch_gemm<128, 0, 32>(tA, tB, tE, p, stream);
+            case 32: return launch_gemm<32, 0, 32>(tA, tB, tE, tD, p, stream);
+            case 64: return launch_gemm<64, 0, 32>(tA, tB, tE, tD, p, stream);
+            case 128: return launch_gemm<128, 0, 32>(tA, tB, tE, tD, p, stream);
             default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n for 32-channel convs must be 32/64/128");
         }
     }
     if (lora) {
         switch (bn_sel) {
-            case 64: return launch_gemm<64, 16>(tA, tB, tE, p, stream);
-            case 128: return launch_gemm<128, 16>(tA, tB, tE, p, stream);
-            case 160: return launch_gemm<160, 16>(tA, tB, tE, p, stream);
+            case 64: return launch_gemm<64, 16>(tA, tB, tE, tD, p, stream);
+            case 128: return launch_gemm<128, 16>(tA, tB, tE, tD, p, stream);
+            case 160: return launch_gemm<160, 16>(tA, tB, tE, tD, p, stream);
             default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n for LoRA must be 64/128/160");
         }
     }
     if (cg == 2) {
         switch (bn_sel) {
-            case 64: return launch_gemm<64, 0, 64, 2>(tA, tB, tE, p, stream);
-            case 128: return launch_gemm<128, 0, 64, 2>(tA, tB, tE, p, stream);
-            case 160: return launch_gemm<160, 0, 64, 2>(tA, tB, tE, p, stream);
-            case 256: return launch_gemm<256, 0, 64, 2>(tA, tB, tE, p, stream);
+            case 64: return launch_gemm<64, 0, 64, 2>(tA, tB, tE, tD, p, stream);
+            case 128: return launch_gemm<128, 0, 64, 2>(tA, tB, tE, tD, p, stream);
+            case 160: return launch_gemm<160, 0, 64, 2>(tA, tB, tE, tD, p, stream);
+            case 256: return launch_gemm<256, 0, 64, 2>(tA, tB, tE, tD, p, stream);
             default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n must be 64/128/160/256");
         }
     }
     switch (bn_sel) {
-        case 64: return launch_gemm<64, 0>(tA, tB, tE, p, stream);
-        case 128: return launch_gemm<128, 0>(tA, tB, tE, p, stream);
-        case 160: return launch_gemm<160, 0>(tA, tB, tE, p, stream);
-        case 256: return launch_gemm<256, 0>(tA, tB, tE, p, stream);
+        case 64: return launch_gemm<64, 0>(tA, tB, tE, tD, p, stream);
+        case 128: return launch_gemm<128, 0>(tA, tB, tE, tD, p, stream);
+        case 160: return launch_gemm<160, 0>(tA, tB, tE, tD, p, stream);
+        case 256: return launch_gemm<256, 0>(tA, tB, tE, tD, p, stream);
         default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n must be 64/128/160/256");
     }
 }

@@ -408,3 +408,80 @@ extern "C" int cl_cfg_dpmpp_step(const float* eps2, float* latents, float* x0_pr
     launch_k(clb::cfg_dpmpp_kernel, blocks, 256, 0, stream, eps2, latents, x0_prev, n_half, guidance, alpha_s, sigma_s, c_x, c_m0, c_m1);
     DONE();
 }
+
+// ------------------------------------------------------------------------------------------ denoise loop as ONE replayed CUDA graph
+// The per-step scalars of the loop (timestep, solver coefficients) come from device tables indexed by a device step
+// counter, so the captured {prep -> UNet -> CFG + solver update -> counter + 1} sequence can be replayed num_steps times
+// without host work (StableDiffusionPipeline.__call__'s loop, train_text_to_image_control_lora.py:829-843).
+namespace clb {
+// x2 = [latents | latents] (the CFG batch), tt[0 .. B2) = timestep_table[*step]
+__global__ void sampler_prep_kernel(const float* __restrict__ latents, float* __restrict__ x2, float* __restrict__ tt,
+                                    const float* __restrict__ ts_table, const unsigned long long* __restrict__ step_ctr,
+                                    long long n_half, int B2) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const unsigned long long step = *step_ctr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_half; i += (long long)gridDim.x * blockDim.x) {
+        const float v = latents[i];
+        x2[i] = v;
+        x2[n_half + i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < B2) tt[threadIdx.x] = ts_table[step];
+}
+
+// kind 0: DDIM (coef = sqrt_at, sqrt_1m_at, sqrt_aprev, sqrt_1m_aprev), kind 1: DPM-Solver++(2M) (coef = alpha_s, sigma_s,
+// c_x, c_m0, c_m1); same arithmetic as cfg_ddim_kernel / cfg_dpmpp_kernel, coefficients read from coef[*step][8].
+__global__ void cfg_solver_dev_kernel(const float* __restrict__ eps2, float* __restrict__ x, float* __restrict__ x0_prev,
+                                      const float* __restrict__ coef, const unsigned long long* __restrict__ step_ctr,
+                                      long long n_half, float g, int kind) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const float* c = coef + 8 * (*step_ctr);
+    const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
+    const float inv_a = 1.f / c0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_half; i += (long long)gridDim.x * blockDim.x) {
+        const float eu = eps2[i], ec = eps2[n_half + i];
+        const float e = eu + g * (ec - eu);
+        const float xv = x[i];
+        if (kind == 0) {
+            const float x0 = (xv - c1 * e) / c0;
+            x[i] = c2 * x0 + c3 * e;
+        } else {
+            const float x0 = (xv - c1 * e) * inv_a;
+            x[i] = c2 * xv + c3 * x0 + c4 * x0_prev[i];
+            x0_prev[i] = x0;
+        }
+    }
+}
+
+__global__ void counter_advance_kernel(unsigned long long* ctr) {
+    pdl_launch_dependents();
+    pdl_wait();
+    *ctr += 1ull;
+}
+}  // namespace clb
+
+extern "C" int cl_sampler_prep(const float* latents, float* x2, float* tt, const float* ts_table, const unsigned long long* step_ctr,
+                               int64_t n_half, int B2, void* stream_) {
+    STREAM;
+    if (!latents || !x2 || !tt || !ts_table || !step_ctr || B2 <= 0 || B2 > 256)
+        return set_error(CL_ERR_INVALID, "cl_sampler_prep: bad arguments (CFG batch <= 256)");
+    int blocks = (int)((n_half + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    launch_k(clb::sampler_prep_kernel, blocks, 256, 0, stream, latents, x2, tt, ts_table, step_ctr, (long long)n_half, B2);
+    DONE();
+}
+
+extern "C" int cl_cfg_solver_step_dev(const float* eps2, float* latents, float* x0_prev, const float* coef,
+                                      unsigned long long* step_ctr, int64_t n_half, float guidance, int kind, void* stream_) {
+    STREAM;
+    if (!eps2 || !latents || !coef || !step_ctr || (kind == 1 && !x0_prev) || (kind != 0 && kind != 1))
+        return set_error(CL_ERR_INVALID, "cl_cfg_solver_step_dev: bad arguments");
+    int blocks = (int)((n_half + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    launch_k(clb::cfg_solver_dev_kernel, blocks, 256, 0, stream, eps2, latents, x0_prev, coef, (const unsigned long long*)step_ctr,
+             (long long)n_half, guidance, kind);
+    count_launch();
+    launch_k(clb::counter_advance_kernel, 1, 1, 0, stream, step_ctr);
+    DONE();
+}

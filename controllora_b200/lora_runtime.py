@@ -304,10 +304,12 @@ class LoraRuntime:
         c = self._fs(ctx, lv).c
         T = hs.data.shape[0] * hs.data.shape[1]
         h2, c2 = hs.data.view(T, C), c.data.view(T, lv.cc)
-        # bf16 operands of the trainable dense layers, re-derived from the fp32 masters every step
-        Ac_h = Ac[:, :C].to(BF16).contiguous()                             # [R, C]
-        Ac_c = Ac[:, C:].to(BF16).contiguous()                             # [R, Cc]
-        Bc_s = (Bc * s).to(BF16).contiguous()                              # [C, R]   (scale folded)
+        # bf16 operands of the trainable dense layers (and their transposes for the backward), re-derived from the fp32 masters
+        # every step by strided cast kernels: Ac = [Ac_h | Ac_c] is [R, C + Cc] row-major, Bc is [C, R]
+        R, ldA = Ac.shape[0], Ac.stride(0)
+        Ac_h = ops.cast_matrix(Ac, R, C, ldA, 1)                           # [R, C]
+        Ac_c = ops.cast_matrix(Ac[:, C:], R, lv.cc, ldA, 1)                # [R, Cc]
+        Bc_s = ops.cast_matrix(Bc, C, R, Bc.stride(0), 1, alpha=s)         # [C, R]   (scale folded)
         u = ops.gemm(h2, Ac_h)
         ops.gemm(c2, Ac_c, residual=u, out=u)                              # u = Ac [h ; c]          [T, R]
         xp = ops.gemm(u, Bc_s, residual=h2)                                # x' = h + s Bc u         [T, C]
@@ -325,27 +327,29 @@ class LoraRuntime:
                 dt, _ = ops.v2_inject_bwd(dq2, lp.cat_up, None, s, need_dh=False)           # dt = dq Bq  (unscaled)
                 ops.SKINNY.add(t, r, dq2, self.grad_of(ql.up.weight), 1, r, s)             # dBq
                 ops.SKINNY.add(dt, r, xp, self.grad_of(ql.down.weight), C, 1, s)           # dAq += s dt^T x'
-                dxp = ops.rank_update(torch.zeros_like(xp), dt, lp.cat_down, s)            # dL/dx' = s dt Aq   [T, C]
+                zero = torch.empty_like(xp)
+                zero.zero_()                                                                # allocator-level memset
+                dxp = ops.rank_update(zero, dt, lp.cat_down, s, out=zero)                   # dL/dx' = s dt Aq   [T, C]
                 # control MLP:  x' = h + (s Bc) u,  u = Ac_h h + Ac_c c
-                du = ops.gemm(dxp, Bc_s.t().contiguous())                                   # [T, R] = dx' (s Bc)
-                R = Ac.shape[0]
+                Bc_st = ops.cast_matrix(Bc, R, C, 1, Bc.stride(0), alpha=s)                 # (s Bc)^T  [R, C]
+                du = ops.gemm(dxp, Bc_st)                                                   # [T, R] = dx' (s Bc)
                 ops.conv_wgrad(dxp.view(1, 1, T, C), u.view(1, 1, T, R), self.grad_of(Bc).view(C, R, 1, 1), 1, 1, 0, s)   # dBc += s dx'^T u
                 gAc = self.grad_of(Ac)
                 tmp_h = torch.zeros(R, C, 1, 1, device=self.device, dtype=torch.float32)
                 tmp_c = torch.zeros(R, lv.cc, 1, 1, device=self.device, dtype=torch.float32)
                 ops.conv_wgrad(du.view(1, 1, T, R), h2.view(1, 1, T, C), tmp_h, 1, 1, 0, 1.0)                         # dAc_h = du^T h
                 ops.conv_wgrad(du.view(1, 1, T, R), c2.view(1, 1, T, lv.cc), tmp_c, 1, 1, 0, 1.0)                     # dAc_c = du^T c
-                gAc[:, :C].add_(tmp_h.view(R, C))
-                gAc[:, C:].add_(tmp_c.view(R, lv.cc))
+                ops.axpy_matrix(tmp_h.view(R, C), gAc[:, :C])
+                ops.axpy_matrix(tmp_c.view(R, lv.cc), gAc[:, C:])
                 if hs.rg:
                     def prod(buf, acc):
                         b2 = buf.view(T, C)
                         ops.gemm(dq2, L.to_q.wt, out=b2, residual=b2 if acc else None)      # dq Wq
                         ops.add(b2, dxp, out=b2)                                            # + dL/dx'
-                        ops.gemm(du, Ac_h.t().contiguous(), out=b2, residual=b2)            # + du Ac_h
+                        ops.gemm(du, ops.cast_matrix(Ac, C, R, 1, ldA), out=b2, residual=b2)  # + du Ac_h   (operand = Ac_h^T [C, R])
                     E.give_produce(hs, prod)
                 if c.rg:
-                    E.give_produce(c, lambda buf, acc: ops.gemm(du, Ac_c.t().contiguous(), out=buf.view(T, lv.cc),
+                    E.give_produce(c, lambda buf, acc: ops.gemm(du, ops.cast_matrix(Ac[:, C:], lv.cc, R, 1, ldA), out=buf.view(T, lv.cc),
                                                                 residual=buf.view(T, lv.cc) if acc else None))
 
             ctx.tape.record(bwd)
@@ -423,8 +427,14 @@ class LoraRuntime:
             q = self._v1cat_q(ctx, lp, L, hs)
         else:
             q = E.linear(ctx, hs, L.to_q, slot=lp.q, t_add=self._fs(ctx, lp).t_add, on_slot_bwd=on_q)
-        k = E.linear(ctx, kv_in, L.to_k, slot=lp.k)
-        v = E.linear(ctx, kv_in, L.to_v, slot=lp.v)
+        kvc = ctx.stash.get("kv_cache") if (ehs is not None and ctx.tape is None) else None
+        if kvc is not None and L.name in kvc:
+            k, v = kvc[L.name]                # text-state projections are timestep-invariant inside a denoise loop
+        else:
+            k = E.linear(ctx, kv_in, L.to_k, slot=lp.k)
+            v = E.linear(ctx, kv_in, L.to_v, slot=lp.v)
+            if kvc is not None:
+                kvc[L.name] = (k, v)
         o = E.attention(ctx, q, k, v, L.heads)
         if lp.kind == "v2":
             o = self._v2_inject(ctx, lp, o, 1)

@@ -647,6 +647,40 @@ def cfg_dpmpp_step(eps2, latents, x0_prev, guidance, alpha_s, sigma_s, c_x, c_m0
           C.c_float(alpha_s), C.c_float(sigma_s), C.c_float(c_x), C.c_float(c_m0), C.c_float(c_m1))
 
 
+def cast_matrix(src, I: int, J: int, s_i: int, s_j: int, alpha: float = 1.0, out=None):
+    """out[i, j] = bf16(alpha * src.flat[i*s_i + j*s_j]) for a strided (sliced / transposed) view of an fp32 master weight."""
+    _req(src, torch.float32, "src")
+    out = torch.empty(I, J, device=src.device, dtype=BF16) if out is None else out
+    _call("cl_cast_matrix_bf16", _p(src), C.c_int64(s_i), C.c_int64(s_j), _p(out), C.c_int64(out.stride(0)), I, J, C.c_float(alpha))
+    return out
+
+
+def axpy_matrix(src, dst, alpha: float = 1.0):
+    """dst[i, j] += alpha * src[i, j]; src fp32 contiguous [I, J], dst fp32 with row stride dst.stride(0), unit column stride."""
+    _req(src, torch.float32, "src")
+    _req(dst, torch.float32, "dst")
+    I, J = src.shape[0], src.numel() // src.shape[0]
+    assert src.is_contiguous() and dst.stride(-1) == 1 and dst.shape[0] == I
+    _call("cl_axpy_matrix_f32", _p(src), _p(dst), C.c_int64(dst.stride(0)), I, J, C.c_float(alpha))
+
+
+def sampler_prep(latents, x2, tt, ts_table, step_ctr):
+    n_half = latents.numel()
+    assert x2.numel() == 2 * n_half and latents.is_contiguous() and x2.is_contiguous() and step_ctr.dtype == torch.int64
+    _call("cl_sampler_prep", _p(latents), _p(x2), _p(tt), _p(ts_table), _p(step_ctr), C.c_int64(n_half), tt.numel())
+
+
+def cfg_solver_step_dev(eps2, latents, x0_prev, coef, step_ctr, guidance: float, kind: int):
+    """CFG + (kind 0: DDIM | kind 1: DPM-Solver++(2M)) update with the step's coefficients read from coef[*step_ctr]; advances
+    the device step counter.  eps2 [2B, ...] fp32 = [uncond | cond]."""
+    _req(eps2, torch.float32, "eps2")
+    _req(latents, torch.float32, "latents")
+    assert eps2.is_contiguous() and latents.is_contiguous() and eps2.numel() == 2 * latents.numel()
+    assert coef.dtype == torch.float32 and coef.is_contiguous() and coef.shape[1] == 8 and step_ctr.dtype == torch.int64
+    _call("cl_cfg_solver_step_dev", _p(eps2), _p(latents), _p(x0_prev), _p(coef), _p(step_ctr), C.c_int64(latents.numel()),
+          C.c_float(guidance), int(kind))
+
+
 class SkinnyQueue:
     """Collects the rank-r gradient reductions (dA / dB of every LoRA adapter) and issues them CL_SKINNY_MAX at a time
     through cl_skinny_atb_batch.  The queue keeps the operand tensors alive until the launch is enqueued."""

@@ -120,3 +120,128 @@ def dpmpp_sample(unet, control_lora, guide: torch.Tensor, cond: torch.Tensor, un
         a_s, sg_s, c_x, c_m0, c_m1 = dpmpp_2m_coeffs(i, ts, ac)
         ops.cfg_dpmpp_step(eps2, latents, x0_prev, guidance_scale, a_s, sg_s, c_x, c_m0, c_m1)
     return latents
+
+
+# ---------------------------------------------------------------------------------------------- whole loop as one replayed graph
+class GraphedSampler:
+    """The denoise loop of the reference's pipelines (train_text_to_image_control_lora.py:829-843, apps/gradio_canny2image.py:
+    81-89, mix_lora_and_control_lora.py:153-164) as ONE captured CUDA graph that is replayed once per step:
+
+        prep (x2 = [latents | latents], timestep from a device table)  ->  UNet on the CFG batch 2B
+        ->  fused CFG + solver update (coefficients from a device table)  ->  device step counter + 1
+
+    Everything that does not depend on the timestep runs once per image batch, outside the graph: the hint
+    encoder, LoRA operand packing, the per-level control products `u = Ac c` / v1 `t_add` tables, and the k / v projections
+    of the text states.  scheduler: "ddim" (eta = 0, config C3) or "dpmpp" (DPM-Solver++(2M), the reference's validation /
+    app scheduler, config C5)."""
+
+    def __init__(self, unet, control_lora, batch: int, height: int = 512, width: int = 512, scheduler: str = "ddim",
+                 num_inference_steps: int = 50, guidance_scale: float = 7.5, scale: float = 1.0, text_dim: Optional[int] = None):
+        if scheduler not in ("ddim", "dpmpp"):
+            raise ValueError(f"unknown scheduler {scheduler}")
+        self.unet, self.cl = unet, control_lora
+        self.B, self.h, self.w = batch, height // 8, width // 8
+        self.kind = 0 if scheduler == "ddim" else 1
+        self.steps, self.guidance, self.scale = int(num_inference_steps), float(guidance_scale), float(scale)
+        dev = unet.device_
+        ac = sd15_alphas_cumprod()
+        if self.kind == 0:
+            ts = ddim_timesteps(self.steps)
+            rows = []
+            for t in ts:
+                a_t, a_p = ddim_coeffs(t, self.steps, ac)
+                rows.append([a_t ** 0.5, (1 - a_t) ** 0.5, a_p ** 0.5, (1 - a_p) ** 0.5, 0, 0, 0, 0])
+        else:
+            ts = dpm_timesteps(self.steps)
+            rows = [list(dpmpp_2m_coeffs(i, ts, ac)) + [0, 0, 0] for i in range(self.steps)]
+        self.timesteps = ts
+        self.ts_table = torch.tensor([float(t) for t in ts], dtype=torch.float32, device=dev)
+        self.coef = torch.tensor(rows, dtype=torch.float32, device=dev).contiguous()
+        B2 = 2 * batch
+        td = text_dim if text_dim is not None else unet.config.cross_attention_dim
+        self.latents = torch.zeros(batch, 4, self.h, self.w, device=dev, dtype=torch.float32)
+        self.x0_prev = torch.zeros_like(self.latents)
+        self.x2 = torch.zeros(B2, 4, self.h, self.w, device=dev, dtype=torch.float32)
+        self.tt = torch.zeros(B2, device=dev, dtype=torch.float32)
+        self.ehs = torch.zeros(B2, 77, td, device=dev, dtype=torch.bfloat16)
+        self.guide2 = torch.zeros(B2, 3, height, width, device=dev, dtype=torch.float32)
+        self.step_ctr = torch.zeros(1, device=dev, dtype=torch.int64)
+        self._graph = None
+        self._ctx = None
+        self.launches_per_step = None
+
+    def _one_step(self):
+        ops.sampler_prep(self.latents, self.x2, self.tt, self.ts_table, self.step_ctr)
+        ctx = self._ctx
+        pred, _, _ = self.unet.run_engine(self.x2, self.tt, self.ehs, {}, tape=None, scale=self.scale, prepared=ctx)
+        ops.cfg_solver_step_dev(pred.data, self.latents, self.x0_prev, self.coef, self.step_ctr, self.guidance, self.kind)
+
+    @torch.no_grad()
+    def __call__(self, guide: torch.Tensor, cond: torch.Tensor, uncond: torch.Tensor, latents: Optional[torch.Tensor] = None,
+                 seed: int = 0, use_graph: bool = True) -> torch.Tensor:
+        """guide [B,3,H,W] in [-1,1]; cond / uncond [B,77,D].  Returns the final latents [B,4,H/8,W/8] fp32 (a view of the
+        sampler's static buffer: clone it before the next call)."""
+        from . import _lib
+
+        B = self.B
+        assert guide.shape[0] == B
+        if latents is None:
+            g = torch.Generator(device="cpu").manual_seed(seed)
+            latents = torch.randn(B, 4, self.h, self.w, generator=g)
+        self.latents.copy_(latents.to(self.latents.device, torch.float32))
+        self.x0_prev.zero_()
+        self.step_ctr.zero_()
+        self.guide2[:B].copy_(guide)
+        self.guide2[B:].copy_(guide)
+        self.ehs[:B].copy_(uncond.to(torch.bfloat16))
+        self.ehs[B:].copy_(cond.to(torch.bfloat16))
+        # once per image batch: hint encoder (control states into static memory), packing, u = Ac c, t_add tables
+        self.cl(self.guide2)
+        if self._graph is None or not use_graph:
+            self._ctx = self.unet.prepare_inference(self.scale)
+        else:
+            # the captured kernels read the addresses held by the prepared context: refresh its contents in place
+            self._refresh_prepared()
+        if not use_graph:
+            for _ in range(self.steps):
+                self._one_step()
+            return self.latents
+        first = 0
+        if self._graph is None:
+            self._one_step()                      # eager warm-up step (fills the text k / v cache, allocator warm-up)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                self._one_step()
+            self.launches_per_step = int(_lib.launch_count() - n0)
+            self._graph = graph
+            # the capture itself does not execute: state is after ONE eager step
+            first = 1
+        for _ in range(first, self.steps):
+            self._graph.replay()
+        return self.latents
+
+    def _refresh_prepared(self):
+        """A later call with a new guide / prompt: recompute the timestep-invariant products INTO the buffers the captured
+        graph reads (control states, u, t_add, cached text k / v)."""
+        old = self._ctx
+        new = self.unet.prepare_inference(self.scale)
+        # first evaluation with the new context fills its k / v cache; then copy every product into the old buffers
+        ops.sampler_prep(self.latents, self.x2, self.tt, self.ts_table, self.step_ctr)
+        self.unet.run_engine(self.x2, self.tt, self.ehs, {}, tape=None, scale=self.scale, prepared=new)
+        for key, st_old in old.stash.items():
+            st_new = new.stash.get(key)
+            if key == "kv_cache":
+                for name, (k_old, v_old) in st_old.items():
+                    k_new, v_new = st_new[name]
+                    k_old.data.copy_(k_new.data)
+                    v_old.data.copy_(v_new.data)
+                continue
+            for f in ("u", "t_add", "M"):
+                a, b = getattr(st_old, f, None), getattr(st_new, f, None)
+                if a is not None and b is not None:
+                    a.copy_(b)
+            if getattr(st_old, "c", None) is not None and getattr(st_new, "c", None) is not None:
+                if st_old.c.data.data_ptr() != st_new.c.data.data_ptr():
+                    st_old.c.data.copy_(st_new.c.data)

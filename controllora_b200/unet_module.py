@@ -155,12 +155,28 @@ class UNet2DConditionModel(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------------------ engine entry
+    def prepare_inference(self, scale: float = 1.0) -> Ctx:
+        """Timestep-invariant part of a forward, run ONCE per denoise loop: LoRA operand packing, the per-level
+        control products u = Ac c, the v1 `t_add` tables, and (filled lazily on the first evaluation) the k / v
+        projections of the text states.  The returned Ctx is passed to `run_engine(..., prepared=ctx)` for every step;
+        the injected control states and `encoder_hidden_states` must stay the same tensors for its lifetime."""
+        rt = self._get_runtime()
+        ctx = Ctx(tape=None, scale=scale)
+        control, _ = self.collect_control(False)
+        rt.begin(ctx, control)
+        ctx.stash["kv_cache"] = {}
+        return ctx
+
     def run_engine(self, sample: torch.Tensor, timesteps: torch.Tensor, ehs: torch.Tensor, control: Dict[int, Var],
-                   tape: Optional[Tape], scale: float = 1.0):
+                   tape: Optional[Tape], scale: float = 1.0, prepared: Optional[Ctx] = None):
         """Low-level entry (also used by the fused Trainer): returns (pred Var [B,4,H,W] fp32, ctx, runtime)."""
         rt = self._get_runtime()
-        ctx = Ctx(tape=tape, scale=scale)
-        rt.begin(ctx, control)
+        if prepared is not None:
+            assert tape is None, "a prepared (inference) context carries no tape"
+            ctx = prepared
+        else:
+            ctx = Ctx(tape=tape, scale=scale)
+            rt.begin(ctx, control)
         if tape is not None:
             # recorded before any UNet op => runs after all of them in the backward sweep
             tape.record(lambda: rt.finish_backward(ctx))

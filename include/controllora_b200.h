@@ -189,12 +189,24 @@ int cl_add_noise(const float* x0, const float* sqrt_ac, const float* sqrt_1mac, 
                  float* timesteps, int B, int per_image, void* stream);
 /* classifier-free-guidance combine + DDIM (eta = 0) update of the denoise loop, one fused elementwise kernel:
  * eps2 = [uncond | cond] noise predictions (each n_half floats), latents updated in place. */
+/* strided weight-space helpers of the dense (concat_hidden, models.py:208-214) control MLP: bf16 view / transpose of an fp32
+ * master (dst[i*ld + j] = bf16(alpha * src[i*s_i + j*s_j])) and strided fp32 accumulation (dst[i*ld + j] += alpha * src[i*J + j]) */
+int cl_cast_matrix_bf16(const float* src, int64_t s_i, int64_t s_j, void* dst, int64_t ld, int I, int J, float alpha, void* stream);
+int cl_axpy_matrix_f32(const float* src, float* dst, int64_t ld, int I, int J, float alpha, void* stream);
 int cl_cfg_ddim_step(const float* eps2, float* latents, int64_t n_half, float guidance, float sqrt_at, float sqrt_1m_at,
                      float sqrt_aprev, float sqrt_1m_aprev, void* stream);
 /* CFG + DPM-Solver++(2M) update (diffusers DPMSolverMultistepScheduler defaults; the scheduler of the reference's
  * validation loop / apps): x0 = (x - sigma_s eps)/alpha_s; x <- c_x x + c_m0 x0 + c_m1 x0_prev; x0_prev <- x0.        */
 int cl_cfg_dpmpp_step(const float* eps2 /* [2B,...] = [uncond | cond] */, float* latents, float* x0_prev, int64_t n_half,
                       float guidance, float alpha_s, float sigma_s, float c_x, float c_m0, float c_m1, void* stream);
+/* Graph-replayable form of the two loops above: per-step scalars come from device tables indexed by *step_ctr.
+ * cl_sampler_prep: x2 = [latents | latents], tt[0..B2) = ts_table[*step_ctr].
+ * cl_cfg_solver_step_dev: kind 0 = DDIM (coef row: sqrt_at, sqrt_1m_at, sqrt_aprev, sqrt_1m_aprev), kind 1 =
+ *   DPM-Solver++(2M) (alpha_s, sigma_s, c_x, c_m0, c_m1); coef is [num_steps][8] fp32; then *step_ctr += 1 on the stream. */
+int cl_sampler_prep(const float* latents, float* x2, float* tt, const float* ts_table, const unsigned long long* step_ctr,
+                    int64_t n_half, int B2, void* stream);
+int cl_cfg_solver_step_dev(const float* eps2, float* latents, float* x0_prev, const float* coef, unsigned long long* step_ctr,
+                           int64_t n_half, float guidance, int kind, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * LoRA side path (diffusers LoRALinearLayer instances created at models.py:89-97,185,316-323).

@@ -26,8 +26,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 # err(ours) <= MARGIN * err(eager bf16): both are bf16 pipelines with different rounding points, so they are compared
-# with a small allowance for seed-to-seed scatter; the absolute caps are the tolerance contract written into the test.
-MARGIN = 1.25
+# directly (measured round 2: ours 0.31-0.78 of the eager-bf16 error, profiles/r02_parity_fullsize.log); the absolute caps are the tolerance contract written into the test.
+MARGIN = 1.0
 CAP_PRED = 1.5e-2        # relative L2 of the noise prediction vs the fp32 oracle
 CAP_GRAD_ALL = 5e-2      # relative L2 of the concatenated gradient of every trainable parameter
 CAP_LOSS = 2e-3
@@ -76,6 +76,8 @@ def run(config_name="diffusiondb-canny-v2", B=1, log=None):
         for n, p in ocl.named_parameters():
             if "norm" in n:
                 p.add_(0.1 * torch.randn(p.shape, generator=g))
+    import copy
+    bunet_cpu, bcl_cpu = copy.deepcopy(ounet), copy.deepcopy(ocl)      # arm (b)'s twins, copied before any forward caches state
     MR.wire_processors(ounet, ocl)
     x, t, e, guide, tgt = bench.synth_inputs(torch, B)
     x = x.to(torch.bfloat16).float()
@@ -123,9 +125,8 @@ def run(config_name="diffusiondb-canny-v2", B=1, log=None):
     out["oracle_cpu_s"] = time.time() - t0
 
     # ---------------- (b) the reference's own precision: eager PyTorch, bf16 UNet, fp32 adapters under bf16 autocast
-    import copy
-    bunet = copy.deepcopy(ounet).to(dev).to(torch.bfloat16)
-    bcl = copy.deepcopy(ocl).to(dev)
+    bunet = bunet_cpu.to(dev).to(torch.bfloat16)
+    bcl = bcl_cpu.to(dev)
     MR.wire_processors(bunet, bcl)
     pred_b, loss_b, grads_b = arm_oracle(bunet, bcl, dev, True)
     del bunet, bcl
