@@ -70,7 +70,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* o_full = p_full + 1;           // 1
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 1);
 
-    const int warp_idx = threadIdx.x >> 5;
+    const int warp_idx = uniform_warp_idx();
     const int lane = threadIdx.x & 31;
     const int qb = blockIdx.x % p.num_q_blocks;
     const int bh = blockIdx.x / p.num_q_blocks;
@@ -112,26 +112,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tmem_o = tmem_base + BLOCK_N;
 
     if (warp_idx == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+        {   // whole warp converged; the *_e calls elect one lane for the instruction itself
+            mbar_arrive_expect_tx_e(q_full, Cfg::Q_BYTES);
             for (int c = 0; c < Cfg::DCH; ++c)
-                tma_load_4d(&tmQ, q_full, smem_q + c * BLOCK_M * 128, c * 64, h, q0, b);
+                tma_load_4d_e(&tmQ, q_full, smem_q + c * BLOCK_M * 128, c * 64, h, q0, b);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < num_kv; ++i) {
                 mbar_wait(&kv_empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&kv_full[stage], Cfg::STAGE_BYTES);
+                mbar_arrive_expect_tx_e(&kv_full[stage], Cfg::STAGE_BYTES);
                 uint8_t* sk = smem_kv + stage * Cfg::STAGE_BYTES;
                 uint8_t* sv = sk + Cfg::KV_TILE_BYTES;
                 for (int c = 0; c < Cfg::DCH; ++c) {
-                    tma_load_4d(&tmK, &kv_full[stage], sk + c * BLOCK_N * 128, c * 64, h, i * BLOCK_N, b);
-                    tma_load_4d(&tmV, &kv_full[stage], sv + c * BLOCK_N * 128, c * 64, h, i * BLOCK_N, b);
+                    tma_load_4d_e(&tmK, &kv_full[stage], sk + c * BLOCK_N * 128, c * 64, h, i * BLOCK_N, b);
+                    tma_load_4d_e(&tmV, &kv_full[stage], sv + c * BLOCK_N * 128, c * 64, h, i * BLOCK_N, b);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
+        {   // whole warp converged; the *_e calls elect one lane for the instruction itself
             constexpr uint32_t idesc_s = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
             constexpr uint32_t idesc_o = make_idesc_bf16(BLOCK_M, DP, 0, 1);  // B = V is MN-major
             mbar_wait(q_full, 0);
@@ -149,10 +149,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int kk = 0; kk < DP / 16; ++kk) {
                     const uint32_t off = (kk / 4) * (BLOCK_M * 128) + (kk % 4) * 32;
                     const uint32_t offk = (kk / 4) * (BLOCK_N * 128) + (kk % 4) * 32;
-                    tc_mma_ss(tmem_s, make_smem_desc(sq + off, 16, 1024, 2), make_smem_desc(sk + offk, 16, 1024, 2),
+                    tc_mma_ss_e(tmem_s, make_smem_desc(sq + off, 16, 1024, 2), make_smem_desc(sk + offk, 16, 1024, 2),
                               idesc_s, kk != 0 ? 1u : 0u);
                 }
-                tc_commit(s_full);
+                tc_commit_e(s_full);
                 // O += P V  (K loop over the keys of this block)
                 mbar_wait(p_full, i & 1);
                 tc_fence_after();
@@ -162,12 +162,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     const uint64_t adesc = make_smem_desc(sp + offp, 16, 1024, 2);
                     // V tile: [keys][64 d] rows of 128 B; MN-major: LBO = next 64-d chunk, SBO = next 8 keys
                     const uint64_t bdesc = make_smem_desc(sv + kk * 2048, BLOCK_N * 128, 1024, 2);
-                    tc_mma_ss(tmem_o, adesc, bdesc, idesc_o, (i | kk) != 0 ? 1u : 0u);
+                    tc_mma_ss_e(tmem_o, adesc, bdesc, idesc_o, (i | kk) != 0 ? 1u : 0u);
                 }
-                tc_commit(&kv_empty[stage]);
+                tc_commit_e(&kv_empty[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            tc_commit(o_full);
+            tc_commit_e(o_full);
         }
     } else if (warp_idx >= 4) {
         const int quad = warp_idx & 3;
@@ -338,7 +338,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint64_t* o_full = p_full + 2;           // 1
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 1);
 
-    const int warp_idx = threadIdx.x >> 5;
+    const int warp_idx = uniform_warp_idx();
     const int lane = threadIdx.x & 31;
     const int qb = blockIdx.x % p.num_q_blocks;   // 256-query blocks
     const int bh = blockIdx.x / p.num_q_blocks;
@@ -381,24 +381,24 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // 384 threads x 168 registers at launch; the softmax warpgroups hold a 128-column S row per thread
     if (warp_idx == 0) {
         setmaxnreg_dec<88>();
-        if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
-            tma_load_4d(&tmQ, q_full, smem_q, 0, h, q0, b);
-            tma_load_4d(&tmQ, q_full, smem_q + BLOCK_M * 128, 0, h, q0 + BLOCK_M, b);
+        {   // whole warp converged; the *_e calls elect one lane for the instruction itself
+            mbar_arrive_expect_tx_e(q_full, Cfg::Q_BYTES);
+            tma_load_4d_e(&tmQ, q_full, smem_q, 0, h, q0, b);
+            tma_load_4d_e(&tmQ, q_full, smem_q + BLOCK_M * 128, 0, h, q0 + BLOCK_M, b);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < num_kv; ++i) {
                 mbar_wait(&kv_empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&kv_full[stage], Cfg::STAGE_BYTES);
+                mbar_arrive_expect_tx_e(&kv_full[stage], Cfg::STAGE_BYTES);
                 uint8_t* sk = smem_kv + stage * Cfg::STAGE_BYTES;
-                tma_load_4d(&tmK, &kv_full[stage], sk, 0, h, i * BLOCK_N, b);
-                tma_load_4d(&tmV, &kv_full[stage], sk + Cfg::KV_TILE_BYTES, 0, h, i * BLOCK_N, b);
+                tma_load_4d_e(&tmK, &kv_full[stage], sk, 0, h, i * BLOCK_N, b);
+                tma_load_4d_e(&tmV, &kv_full[stage], sk + Cfg::KV_TILE_BYTES, 0, h, i * BLOCK_N, b);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp_idx == 1) {
         setmaxnreg_dec<88>();
-        if (lane == 0) {
+        {   // whole warp converged; the *_e calls elect one lane for the instruction itself
             constexpr uint32_t idesc_s = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
             constexpr uint32_t idesc_o = make_idesc_bf16(BLOCK_M, DP, 0, 1);  // B = V is MN-major
             const uint32_t sq = smem_u32(smem_q);
@@ -406,9 +406,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             auto issue_s = [&](int t, uint32_t sk) {
 #pragma unroll
                 for (int kk = 0; kk < DP / 16; ++kk)
-                    tc_mma_ss(tmem_base + t * BLOCK_N, make_smem_desc(sq + t * (BLOCK_M * 128) + kk * 32, 16, 1024, 2),
+                    tc_mma_ss_e(tmem_base + t * BLOCK_N, make_smem_desc(sq + t * (BLOCK_M * 128) + kk * 32, 16, 1024, 2),
                               make_smem_desc(sk + kk * 32, 16, 1024, 2), idesc_s, kk != 0 ? 1u : 0u);
-                tc_commit(&s_full[t]);
+                tc_commit_e(&s_full[t]);
             };
             mbar_wait(q_full, 0);
             mbar_wait(&kv_full[0], 0);
@@ -436,18 +436,18 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                     for (int kk = 0; kk < BLOCK_N / 16; ++kk) {
                         const uint32_t offp = t * Cfg::P_TILE_BYTES + (kk / 4) * (BLOCK_M * 128) + (kk % 4) * 32;
-                        tc_mma_ss(tmem_base + 2 * BLOCK_N + t * DP, make_smem_desc(sp + offp, 16, 1024, 2),
+                        tc_mma_ss_e(tmem_base + 2 * BLOCK_N + t * DP, make_smem_desc(sp + offp, 16, 1024, 2),
                                   make_smem_desc(sv + kk * 2048, BLOCK_N * 128, 1024, 2), idesc_o,
                                   (i | kk) != 0 ? 1u : 0u);
                     }
                     // S_t of the next key block: its softmax starts while the other tile's PV runs
                     if (more) issue_s(t, sk_next);
                 }
-                tc_commit(&kv_empty[stage]);
+                tc_commit_e(&kv_empty[stage]);
                 stage = nstage;
                 phase = nphase;
             }
-            tc_commit(o_full);
+            tc_commit_e(o_full);
         }
     } else if (warp_idx < 4) {
         setmaxnreg_dec<88>();

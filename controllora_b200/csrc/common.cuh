@@ -110,6 +110,12 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar,
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (both 16-byte aligned, size a multiple of 16), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // TMA stores (smem tile -> global tensor, bulk async group); out-of-bounds parts of the box are clipped by the hardware
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -321,6 +327,23 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
         : "r"(taddr)
         : "memory");
 }
+
+// ---------------------------------------------------------------- warp-converged issue ("_e" = elected)
+// The producer / MMA warps run their loops with all 32 lanes converged and call these: every lane evaluates the (warp-
+// uniform) operands, elect.sync picks one lane - always the same one for the full mask, which tcgen05.commit relies on -
+// and only that lane executes the instruction.  Because nothing depends on the lane id, ptxas keeps addresses, descriptors
+// and coordinates in uniform registers and feeds UTMALDG / UTCHMMA directly, instead of the ELECT + R2UR.BROADCAST
+// "waterfall" it has to emit for a per-thread value under `if (lane == 0)` (~150 clk per tcgen05.mma, round-2 probe).
+__device__ __forceinline__ void mbar_arrive_expect_tx_e(uint64_t* bar, uint32_t bytes) { if (elect_one_sync()) mbar_arrive_expect_tx(bar, bytes); }
+__device__ __forceinline__ void tma_load_2d_e(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) { if (elect_one_sync()) tma_load_2d(m, bar, dst, c0, c1); }
+__device__ __forceinline__ void tma_load_3d_e(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) { if (elect_one_sync()) tma_load_3d(m, bar, dst, c0, c1, c2); }
+__device__ __forceinline__ void tma_load_4d_e(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) { if (elect_one_sync()) tma_load_4d(m, bar, dst, c0, c1, c2, c3); }
+__device__ __forceinline__ void tma_load_5d_e(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) { if (elect_one_sync()) tma_load_5d(m, bar, dst, c0, c1, c2, c3, c4); }
+__device__ __forceinline__ void bulk_copy_g2s_e(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) { if (elect_one_sync()) bulk_copy_g2s(dst_smem, src, bytes, bar); }
+__device__ __forceinline__ void tc_commit_e(uint64_t* bar) { if (elect_one_sync()) tc_commit(bar); }
+__device__ __forceinline__ void tc_mma_ss_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) { if (elect_one_sync()) tc_mma_ss(d_tmem, adesc, bdesc, idesc, accumulate); }
+__device__ __forceinline__ void tc_mma_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) { if (elect_one_sync()) tc_mma_ts(d_tmem, a_tmem, bdesc, idesc, accumulate); }
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);

@@ -65,19 +65,28 @@ struct GemmParams {
     // its fp32 partial tile to split_ws[s][M][N]; splitk_finish_kernel sums the partials and applies the epilogue.
     int splits, kb_per_split;
     float* split_ws;
+    int dbg_reps;     // CLB_TIMELINE builds only: every k-step's MMAs are issued 1 + dbg_reps times (tensor-pipe rate probe)
 };
 
 #ifdef CLB_TIMELINE
 // debug: per-SM event log  [sm][slot] = (clock64, tag)  -- tools/gemm_timeline.py prints it
+// three roles per SM (producer / MMA / first epilogue warp), 80 slots each; the slot counter is a register of the calling
+// thread, so an event costs one clock read and two plain stores (the first version used a global atomic per event, ~1000
+// cycles each, which distorted the very thing it measured)
 __device__ unsigned long long g_tl[160 * 256 * 2];
 __device__ unsigned int g_tl_n[160];
-__device__ __forceinline__ void tl_rec(int tag) {
+__device__ __forceinline__ void tl_rec(int tag, int& slot) {
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    const unsigned int i = atomicAdd(&g_tl_n[smid], 1u);
-    if (i < 256) { g_tl[(smid * 256 + i) * 2] = clock64(); g_tl[(smid * 256 + i) * 2 + 1] = (unsigned long long)tag; }
+    const int role = tag < 20 ? 0 : (tag < 30 ? 1 : 2);
+    if (slot < 80) {
+        const unsigned int i = role * 80 + slot;
+        g_tl[(smid * 256 + i) * 2] = clock64();
+        g_tl[(smid * 256 + i) * 2 + 1] = (unsigned long long)tag;
+        ++slot;
+    }
 }
-#define TL(tag) tl_rec(tag)
+#define TL(tag) tl_rec(tag, tl_slot)
 #else
 #define TL(tag)
 #endif
@@ -117,21 +126,29 @@ struct TileIter {
 // each CTA ends up with its 128 x BN accumulator rows in its own TMEM -> 1.5x less L2->SM traffic per flop at BN = 256.
 template <int BN, int EXT, int BK, int CG = 1>
 struct GemmCfg {
-    static constexpr int UMMA_N = BN + EXT;
+    // BN > 256 (the 256 x 320 CTA-pair tile): the tile's columns are produced by NSPLIT MMAs of MMA_N columns each that share
+    // the A stage - per k-block a CTA then moves 128 A rows + BN/2 B rows for BN columns of work, 1.45x fewer L2->SM bytes per
+    // flop than the 256 x 160 tile (the deep-K N = 320 / 640 GEMMs sat at ~37 B/clk/SM of operand traffic = the L2 limit)
+    static constexpr int NSPLIT = (BN > 256) ? 2 : 1;
+    static constexpr int MMA_N = BN / NSPLIT + EXT;           // N of one tcgen05.mma
+    static constexpr int UMMA_N = MMA_N;
     static constexpr int ROW_BYTES = BK * 2;
     static constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
-    static constexpr int B_ROWS = UMMA_N / CG;                 // B rows staged by one CTA
+    static constexpr int MMA_B_ROWS = MMA_N / CG;             // B rows one CTA stages for one MMA
+    static constexpr int B_ROWS = NSPLIT * MMA_B_ROWS;        // B rows staged by one CTA per k-block
     static constexpr int B_STAGE_BYTES = B_ROWS * ROW_BYTES;
-    static_assert(CG == 1 || (CG == 2 && EXT == 0 && (BN / 2) % 8 == 0), "CTA-pair variant: no LoRA rows, BN/2 % 8 == 0");
+    static_assert(CG == 1 || (CG == 2 && EXT == 0 && (BN / NSPLIT / 2) % 8 == 0), "CTA-pair variant: no LoRA rows, B half % 8 == 0");
+    static_assert(NSPLIT == 1 || (CG == 2 && EXT == 0), "split-N tiles are CTA-pair, no-LoRA only");
     static constexpr int SBO = 8 * ROW_BYTES;                  // 8-row swizzle atom
     static constexpr int LAYOUT = (BK == 64) ? 2 : 4;          // UMMA layout type: 128B / 64B swizzle
     static_assert(BK == 64 || BK == 32, "BK");
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int BUF_COLS = (UMMA_N + 31) / 32 * 32;
-    static constexpr int TMEM_COLS = (2 * BUF_COLS <= 32) ? 32 : (2 * BUF_COLS <= 64) ? 64 : (2 * BUF_COLS <= 128) ? 128
-                                   : (2 * BUF_COLS <= 256) ? 256 : 512;
-    static_assert(2 * BUF_COLS <= 512, "TMEM overflow");
-    static_assert(UMMA_N % 16 == 0 && UMMA_N >= 16 && UMMA_N <= 256, "invalid UMMA N");
+    static constexpr int BUF_COLS = (BN + EXT + 31) / 32 * 32;
+    static constexpr int NBUF = (2 * BUF_COLS <= 512) ? 2 : 1; // accumulator buffers (epilogue of tile i overlaps tile i+1 when 2)
+    static constexpr int TMEM_COLS = (NBUF * BUF_COLS <= 32) ? 32 : (NBUF * BUF_COLS <= 64) ? 64 : (NBUF * BUF_COLS <= 128) ? 128
+                                   : (NBUF * BUF_COLS <= 256) ? 256 : 512;
+    static_assert(NBUF * BUF_COLS <= 512, "TMEM overflow");
+    static_assert(MMA_N % 16 == 0 && MMA_N >= 16 && MMA_N <= 256, "invalid UMMA N");
     static_assert(BN % 32 == 0, "BN must be a multiple of the 32-column epilogue granule");
 };
 
@@ -186,8 +203,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* b_full = tmem_empty + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full + 1);
 
-    const int warp_idx = threadIdx.x >> 5;
+    // warp index made provably warp-uniform (shuffle from lane 0): the producer / MMA warps below run their loops with
+    // all 32 lanes converged and elect one lane only around the TMA / tcgen05 instructions, so that ptxas keeps addresses,
+    // descriptors and coordinates in UNIFORM registers.  (With the whole loop under `if (lane == 0)` every tcgen05.mma was
+    // preceded by an ELECT + 5 x R2UR.BROADCAST "waterfall" that paced the tensor pipe at ~150 clk per MMA - round 2 probe,
+    // profiles/r02_mma_rate.log - against a 72-128 clk floor.)
+    const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+#ifdef CLB_TIMELINE
+    int tl_slot = 0;
+#endif
 
     if (warp_idx == 0 && lane == 0) {
         TL(1);   // kernel entry
@@ -214,7 +239,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     pdl_wait();   // prologue above touched only smem / TMEM / kernel params
     // LoRA-up table -> smem (persistent for the CTA lifetime)
-    for (int i = threadIdx.x; i < up_floats; i += NUM_THREADS) smem_up[i] = p.lora_up[i];
+    // (16-byte loads: the scalar version of this copy was three dependent global-load round trips per thread, ~1.2 us)
+    for (int i = threadIdx.x; i < up_floats / 4; i += NUM_THREADS)
+        reinterpret_cast<float4*>(smem_up)[i] = __ldg(reinterpret_cast<const float4*>(p.lora_up) + i);
     tc_fence_before();
     if (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / TMA credit
     else __syncthreads();
@@ -222,18 +249,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp_idx == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
+        // ===================================================== TMA producer (whole warp converged, one elected lane issues)
+        {
             int stage = 0;
             uint32_t phase = 0;
             TileIter ti(p, sched_cta, sched_n, sched_m);
             if (p.b_resident && ti.valid()) {
-                mbar_arrive_expect_tx(b_full, p.num_k_blocks * Cfg::B_STAGE_BYTES);
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                    uint8_t* sb = smem_b + kb * Cfg::B_STAGE_BYTES;
-                    tma_load_2d(&tmB, b_full, sb, kb * BK, ti.n_blk * BN);
-                    if (EXT) tma_load_2d(&tmE, b_full, sb + BN * Cfg::ROW_BYTES, kb * BK, 0);
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(b_full, p.num_k_blocks * Cfg::B_STAGE_BYTES);
+                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        uint8_t* sb = smem_b + kb * Cfg::B_STAGE_BYTES;
+                        tma_load_2d(&tmB, b_full, sb, kb * BK, ti.n_blk * BN);
+                        if (EXT) tma_load_2d(&tmE, b_full, sb + BN * Cfg::ROW_BYTES, kb * BK, 0);
+                    }
                 }
+                __syncwarp();
             }
             for (; ti.valid(); ti.next()) {
                 const int m_blk = (CG == 2) ? ti.m_blk * 2 + cta_rank : ti.m_blk;
@@ -244,59 +274,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     th = (m_blk / p.tiles_w) % p.tiles_h;
                     tn = m_blk / (p.tiles_w * p.tiles_h);
                 }
-                TL(10);  // producer: tile start
+                if (lane == 0) TL(10);  // producer: tile start
                 const int kb1 = ti.kb_end();
                 for (int kb = ti.kb_begin(); kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (lane == 0 && kb < 10) TL(11);   // producer: ring slot acquired
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-                    if (CG == 2) {
-                        // both CTAs' bytes are credited to the LEADER's full barrier (one arrival: the leader's producer)
-                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                        const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
-                        if (p.a_mode == 0) {
-                            tma_load_2d_cg2(&tmA, fb, sa, kb * BK, m_blk * BLOCK_M);
-                        } else {
-                            const int tap = kb / p.cblocks, cb = kb % p.cblocks;
-                            const int ky = tap / 3, kx = tap % 3;
-                            if (p.a_mode == 1) {
-                                tma_load_4d_cg2(&tmA, fb, sa, cb * BK, tw * p.bw + kx - 1, th * p.bh + ky - 1, tn * p.bn);
-                            } else {
-                                const int iy = ky - p.pad_lo, ix = kx - p.pad_lo;
-                                tma_load_5d_cg2(&tmA, fb, sa, (ix & 1) * p.C + cb * BK, tw * p.bw + (ix >> 1), iy & 1,
-                                                th * p.bh + (iy >> 1), tn * p.bn);
-                            }
-                        }
-                        tma_load_2d_cg2(&tmB, fb, sb, kb * BK, n_blk * BN + cta_rank * Cfg::B_ROWS);
-                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
-                        continue;
-                    }
-                    mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES);
-                    if (p.a_mode == 0) {
-                        tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BLOCK_M);
-                    } else {
+                    // A-operand coordinates of this k-block (conv: the 3x3 tap and channel block)
+                    int ca0 = kb * BK, ca1 = m_blk * BLOCK_M, ca2 = 0, ca3 = 0, ca4 = 0;
+                    if (p.a_mode != 0) {
                         const int tap = kb / p.cblocks, cb = kb % p.cblocks;
                         const int ky = tap / 3, kx = tap % 3;
                         if (p.a_mode == 1) {
-                            tma_load_4d(&tmA, &full_bar[stage], sa, cb * BK, tw * p.bw + kx - 1,
-                                        th * p.bh + ky - 1, tn * p.bn);
+                            ca0 = cb * BK; ca1 = tw * p.bw + kx - 1; ca2 = th * p.bh + ky - 1; ca3 = tn * p.bn;
                         } else {
                             const int iy = ky - p.pad_lo, ix = kx - p.pad_lo;
-                            tma_load_5d(&tmA, &full_bar[stage], sa, (ix & 1) * p.C + cb * BK,
-                                        tw * p.bw + (ix >> 1), iy & 1, th * p.bh + (iy >> 1), tn * p.bn);
+                            ca0 = (ix & 1) * p.C + cb * BK; ca1 = tw * p.bw + (ix >> 1); ca2 = iy & 1; ca3 = th * p.bh + (iy >> 1);
+                            ca4 = tn * p.bn;
                         }
                     }
-                    if (!p.b_resident) {
-                        tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * BN);
-                        if (EXT) tma_load_2d(&tmE, &full_bar[stage], sb + BN * Cfg::ROW_BYTES, kb * BK, 0);
+                    if (elect_one_sync()) {
+                        if (CG == 2) {
+                            // both CTAs' bytes are credited to the LEADER's full barrier (one arrival: the leader's producer)
+                            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                            if (p.a_mode == 0) tma_load_2d_cg2(&tmA, fb, sa, ca0, ca1);
+                            else if (p.a_mode == 1) tma_load_4d_cg2(&tmA, fb, sa, ca0, ca1, ca2, ca3);
+                            else tma_load_5d_cg2(&tmA, fb, sa, ca0, ca1, ca2, ca3, ca4);
+#pragma unroll
+                            for (int hh = 0; hh < Cfg::NSPLIT; ++hh)
+                                tma_load_2d_cg2(&tmB, fb, sb + hh * Cfg::MMA_B_ROWS * Cfg::ROW_BYTES, kb * BK,
+                                                n_blk * BN + hh * (BN / Cfg::NSPLIT) + cta_rank * Cfg::MMA_B_ROWS);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES);
+                            if (p.a_mode == 0) tma_load_2d(&tmA, &full_bar[stage], sa, ca0, ca1);
+                            else if (p.a_mode == 1) tma_load_4d(&tmA, &full_bar[stage], sa, ca0, ca1, ca2, ca3);
+                            else tma_load_5d(&tmA, &full_bar[stage], sa, ca0, ca1, ca2, ca3, ca4);
+                            if (!p.b_resident) {
+                                tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * BN);
+                                if (EXT) tma_load_2d(&tmE, &full_bar[stage], sb + BN * Cfg::ROW_BYTES, kb * BK, 0);
+                            }
+                        }
                     }
+                    __syncwarp();
+                    if (lane == 0 && kb < 10) TL(12);   // producer: loads of this k-block issued
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp_idx == 1) {
         // ===================================================== MMA issuer
-        if (lane == 0 && cta_rank == 0) {
+        if (cta_rank == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, Cfg::UMMA_N, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -304,34 +333,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             TileIter ti(p, sched_cta, sched_n, sched_m);
             if (p.b_resident && ti.valid()) mbar_wait(b_full, 0);
             for (; ti.valid(); ti.next(), ++it) {
-                const int buf = it & 1;
-                const uint32_t buf_phase = (it >> 1) & 1;
-                TL(20);  // mma: waiting for a free accumulator
+                const int buf = it % Cfg::NBUF;
+                const uint32_t buf_phase = (it / Cfg::NBUF) & 1;
+                if (lane == 0) TL(20);  // mma: waiting for a free accumulator
                 mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
                 tc_fence_after();
-                TL(21);  // mma: accumulator free
+                if (lane == 0) TL(21);  // mma: accumulator free
                 const uint32_t d_tmem = tmem_base + buf * Cfg::BUF_COLS;
                 const int kb0 = ti.kb_begin(), kb1 = ti.kb_end();
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait(&full_bar[stage], phase);      // all 32 lanes poll: keeps the loop convergent
                     tc_fence_after();
-                    if (kb == kb0) TL(22);  // mma: first stage landed
+                    if (lane == 0) { if (kb == kb0) TL(22); else if (kb < kb0 + 10) TL(24); }
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                     const uint32_t sb = smem_u32(smem_b + (p.b_resident ? kb : stage) * Cfg::B_STAGE_BYTES);
+                    const uint32_t first = (kb != kb0) ? 1u : 0u;
+                    if (elect_one_sync()) {
+#ifdef CLB_TIMELINE
+                        for (int rep = 0; rep < p.dbg_reps; ++rep) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t adesc = make_smem_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                        const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                        if (CG == 2) tc_mma_ss_cg2(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-                        else tc_mma_ss(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint64_t adesc = make_smem_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+#pragma unroll
+                                for (int hh = 0; hh < Cfg::NSPLIT; ++hh) {
+                                    const uint64_t bdesc = make_smem_desc(sb + hh * Cfg::MMA_B_ROWS * Cfg::ROW_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                                    if (CG == 2) tc_mma_ss_cg2(d_tmem + hh * Cfg::MMA_N, adesc, bdesc, idesc, 1u);
+                                    else tc_mma_ss(d_tmem + hh * Cfg::MMA_N, adesc, bdesc, idesc, 1u);
+                                }
+                            }
+                        }
+#endif
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t adesc = make_smem_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+#pragma unroll
+                            for (int hh = 0; hh < Cfg::NSPLIT; ++hh) {
+                                const uint64_t bdesc = make_smem_desc(sb + hh * Cfg::MMA_B_ROWS * Cfg::ROW_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                                if (CG == 2) tc_mma_ss_cg2(d_tmem + hh * Cfg::MMA_N, adesc, bdesc, idesc, (k != 0) ? 1u : first);
+                                else tc_mma_ss(d_tmem + hh * Cfg::MMA_N, adesc, bdesc, idesc, (k != 0) ? 1u : first);
+                            }
+                        }
+                        // smem slot is free once these MMAs retire (pair: in both CTAs)
+                        if (CG == 2) tc_commit_cg2(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
                     }
-                    // smem slot is free once these MMAs retire (pair: in both CTAs)
-                    if (CG == 2) tc_commit_cg2(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
+                    __syncwarp();
+                    if (lane == 0 && kb < kb0 + 10) TL(25);   // mma: k-block issued + committed
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
                 // accumulator complete -> epilogue (pair: each CTA drains its own 128 rows)
-                if (CG == 2) tc_commit_cg2(&tmem_full[buf], 3); else tc_commit(&tmem_full[buf]);
-                TL(23);  // mma: all MMAs of the tile issued
+                if (elect_one_sync()) {
+                    if (CG == 2) tc_commit_cg2(&tmem_full[buf], 3); else tc_commit(&tmem_full[buf]);
+                }
+                __syncwarp();
+                if (lane == 0) TL(23);  // mma: all MMAs of the tile issued
             }
         }
     } else if (warp_idx >= 4) {
@@ -347,8 +401,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (TileIter ti(p, sched_cta, sched_n, sched_m); ti.valid(); ti.next(), ++it) {
             const int m_blk = (CG == 2) ? ti.m_blk * 2 + cta_rank : ti.m_blk;
             const int n_blk = ti.n_blk;
-            const int buf = it & 1;
-            const uint32_t buf_phase = (it >> 1) & 1;
+            const int buf = it % Cfg::NBUF;
+            const uint32_t buf_phase = (it / Cfg::NBUF) & 1;
             // rows: phase-1 thread owns row (quad*32 + lane); phase-2 lane handles rows (lane>>3) + 4*i
             int my_m, my_grp;
             decode_row(p, m_blk, quad * 32 + lane, my_m, my_grp);
@@ -384,7 +438,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 8; ++j) tl[j] *= p.lora_scale;
             }
 
-            if (p.tma_store) {
+            if (p.tma_store == 4) {
+                // timing experiment only (CLB_GEMM_EPI_DEBUG=4): no epilogue work at all, the accumulator is dropped
+            } else if (p.tma_store) {
                 // ---- bf16 output, thread == output row: accumulator (+ LoRA + bias + row bias + residual) in registers,
                 //      packed to bf16, staged as a 32 x 64 B sub-tile (64B-swizzled, 4 conflict-free 16-byte stores per lane)
                 //      and written by ONE TMA store per granule; two staging buffers per warp keep a store in flight while
@@ -457,6 +513,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_wait_ld();
 #pragma unroll
                     for (int c = 0; c < 32; ++c) f[c] += __uint_as_float(v[c]);
+                    if (p.tma_store >= 2) {
+                        // thread == row, four 16-byte global stores per granule straight from registers
+                        if (row_ok && p.tma_store == 2) {
+                            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)my_m * p.ldd + col0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (col0 + 8 * j < p.N) {
+                                    uint4 o;
+                                    o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]); o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                                    o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                                    *reinterpret_cast<uint4*>(orow + 8 * j) = o;
+                                }
+                            }
+                        } else if (p.tma_store == 3 && f[0] == 12345.678f) {
+                            *reinterpret_cast<float*>(p.out) = f[1] + f[31];      // timing experiment: compute, never store
+                        }
+                        ++epi_gran;
+                        continue;
+                    }
                     // the store issued two granules ago has finished reading this staging buffer
                     const uint32_t sbuf = stg_addr + (uint32_t)(epi_gran & 1) * 2048u;
                     if (lane == 0) bulk_wait_group_read<1>();
@@ -663,6 +738,10 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     if (CG == 1 && p.splits == 1 && p.a_mode == 0 && a_room >= 3 * Cfg::A_STAGE_BYTES && grid_res > 0 && grid_res * 10 >= grid * 9 &&
         p.num_m_blocks >= 3 * (grid_res / p.num_n_blocks)) {
         p.b_resident = 1;
+        // short-K resident tiles hand a finished accumulator to the epilogue every ~2 k cycles: measured (round 2) the
+        // per-lane store epilogue keeps up with that better than two TMA stores in flight per warp (18.5 vs 20.1 us at
+        // 32768 x 320 x 320), while the TMA epilogue wins wherever the epilogue is exposed (convs, 256 x 320 tiles)
+        if (p.tma_store == 1) p.tma_store = 0;
         stages = a_room / Cfg::A_STAGE_BYTES;
         if (stages > 8) stages = 8;
         smem_bytes = fixed + b_res_bytes + stages * Cfg::A_STAGE_BYTES;
@@ -723,13 +802,14 @@ using namespace clb;
 #ifdef CLB_TIMELINE
 extern "C" int cl_debug_timeline(unsigned long long* host_buf, unsigned int* host_n, int reset) {
     if (reset) {
-        unsigned int z[160] = {0};
-        cudaMemcpyToSymbol(clb::g_tl_n, z, sizeof(z));
+        static unsigned long long z[160 * 256 * 2];
+        memset(z, 0, sizeof(z));
+        cudaMemcpyToSymbol(clb::g_tl, z, sizeof(z));
         return 0;
     }
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(host_buf, clb::g_tl, sizeof(unsigned long long) * 160 * 256 * 2);
-    cudaMemcpyFromSymbol(host_n, clb::g_tl_n, sizeof(unsigned int) * 160);
+    for (int i = 0; i < 160; ++i) host_n[i] = 240;       // fixed slots; unused ones have tag 0
     return 0;
 }
 #endif
@@ -759,13 +839,18 @@ static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool
     const int cg = gemm_cta_group(a, BK, num_m_blocks);
     const int sms = num_sms() / cg;                        // scheduling units: CTAs or CTA pairs
     TilePlan best = {0, 1};
+#ifdef CLB_TIMELINE
+    if (a->block_n != 0) return TilePlan{a->block_n, 1};     // probe builds: any instantiated width, as given
+#endif
     if (a->block_n != 0) best.bn = a->block_n;
     else if (!lora && a->a_mode == 0 && a->K <= 320 && a->N % 160 == 0 && a->M >= 8192) best.bn = 160;  // weights stay smem-resident
     long long best_cost = -1;
-    static const int cands[5] = {256, 160, 128, 64, 32};
-    for (int ci = 0; ci < 5; ++ci) {
+    static const int wide_enabled = [] { const char* e = getenv("CLB_GEMM_BN320"); return (e && e[0] == '0') ? 0 : 1; }();
+    static const int cands[6] = {320, 256, 160, 128, 64, 32};
+    for (int ci = 0; ci < 6; ++ci) {
         const int bn = cands[ci];
         if (best.bn != 0 && bn != best.bn) continue;           // fixed by the caller / the resident rule
+        if (bn == 320 && (cg != 2 || lora || !wide_enabled || a->N % 320 != 0)) continue;   // CTA-pair, no-LoRA tile
         if (best.bn == 0) {
             if (a->N % bn != 0) continue;
             if (lora && bn > 160) continue;
@@ -783,7 +868,9 @@ static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool
         const int kbps = (nkb + splits - 1) / splits;
         splits = (nkb + kbps - 1) / kbps;
         const long long waves = ((long long)tiles * splits + sms - 1) / sms;
-        const long long cost = waves * (128 + bn / cg + 32) * kbps;   // rows a CTA pulls from L2 per k-block
+        // rows a CTA pulls from L2 per k-block; the 320-column tile has ONE accumulator buffer, so its epilogue (~ 5 k-blocks
+        // worth of time) is not hidden behind the next tile's main loop
+        const long long cost = waves * ((128 + bn / cg + 32) * (long long)kbps + (bn == 320 ? 5 * (128 + 160 + 32) : 0));
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = {bn, splits}; }
     }
     if (best_cost < 0) {   // no candidate divides N: tail tiles
@@ -885,7 +972,8 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     {
         uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
         uint64_t strides[1] = {(uint64_t)a->ldb * 2};
-        uint32_t box[2] = {(uint32_t)BK, (uint32_t)(bn_sel / cg)};     // a CTA of a pair stages half of the B rows
+        // a CTA of a pair stages half of the B rows of each MMA (the 320-column tile issues two 160-column MMAs per k-step)
+        uint32_t box[2] = {(uint32_t)BK, (uint32_t)((bn_sel > 256 ? bn_sel / 2 : bn_sel) / cg)};
         CL_CHECK(get_tensor_map(&tB, a->b, 2, dims, strides, box, swz));
     }
     if (lora) {
@@ -896,6 +984,9 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
         CL_CHECK(get_tensor_map(&tE, a->ext, 2, dims, strides, box, swz));
     }
 
+#ifdef CLB_TIMELINE
+    { const char* e = getenv("CLB_TL_MMA_REPS"); p.dbg_reps = e ? atoi(e) : 0; }
+#endif
     p.bias = a->bias; p.row_bias = a->row_bias; p.rows_per_group = a->rows_per_group;
     p.ld_rb = a->ld_row_bias > 0 ? a->ld_row_bias : a->N;
     if (p.row_bias && (p.ld_rb % 4)) return set_error(CL_ERR_INVALID, "cl_gemm: ld_row_bias must be a multiple of 4");
@@ -913,7 +1004,12 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     static const int tma_store_enabled = [] { const char* e = getenv("CLB_GEMM_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(a->out) & 15) == 0) && (p.ldd % 8 == 0) && (a->N % 8 == 0) &&
                            (!p.residual || (((reinterpret_cast<uintptr_t>(a->residual) & 15) == 0) && (p.ldr % 8 == 0)));
-    if (tma_store_enabled && !p.out_fp32 && p.splits == 1 && aligned16) {
+    // CLB_GEMM_EPI: 1 = TMA stores (default), 2 = per-thread 16-byte global stores; 3 / 4 = timing experiments that produce
+    // WRONG results (no stores / no epilogue) and exist only to attribute the kernel's time
+    static const int epi_mode = [] { const char* e = getenv("CLB_GEMM_EPI"); return (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 1; }();
+    if (tma_store_enabled && !p.out_fp32 && p.splits == 1 && aligned16 && epi_mode >= 2) {
+        p.tma_store = epi_mode;
+    } else if (tma_store_enabled && !p.out_fp32 && p.splits == 1 && aligned16) {
         if (a->a_mode == 0) {
             uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
             uint64_t strides[1] = {(uint64_t)p.ldd * 2};
@@ -958,10 +1054,16 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
             case 128: return launch_gemm<128, 0, 64, 2>(tA, tB, tE, tD, p, stream);
             case 160: return launch_gemm<160, 0, 64, 2>(tA, tB, tE, tD, p, stream);
             case 256: return launch_gemm<256, 0, 64, 2>(tA, tB, tE, tD, p, stream);
-            default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n must be 64/128/160/256");
+            case 320: return launch_gemm<320, 0, 64, 2>(tA, tB, tE, tD, p, stream);
+            default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n must be 64/128/160/256/320");
         }
     }
     switch (bn_sel) {
+#ifdef CLB_TIMELINE
+        case 96: return launch_gemm<96, 0>(tA, tB, tE, tD, p, stream);
+        case 192: return launch_gemm<192, 0>(tA, tB, tE, tD, p, stream);
+        case 224: return launch_gemm<224, 0>(tA, tB, tE, tD, p, stream);
+#endif
         case 64: return launch_gemm<64, 0>(tA, tB, tE, tD, p, stream);
         case 128: return launch_gemm<128, 0>(tA, tB, tE, tD, p, stream);
         case 160: return launch_gemm<160, 0>(tA, tB, tE, tD, p, stream);

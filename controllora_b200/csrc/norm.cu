@@ -323,6 +323,254 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     }
 }
 
+// ---------------------------------------------------------------------------------------------- GroupNorm, one launch
+// One thread-block CLUSTER per image (up to 16 CTAs, each owning a slab of rows of all channels): phase 1 reduces the slab
+// (thread == fixed 8-channel chunk, partial sums in registers), the CTAs exchange their per-group partial sums through
+// distributed shared memory (fp64), every CTA derives the per-channel affine coefficients, and phase 2 streams the slab
+// again - from L2, where phase 1 just left it - to write y (forward) or dx (backward).  Replaces reduce -> memset ->
+// coef -> apply (3 kernels + 1 memset node, fp64 global atomics, a workspace) by ONE kernel and no workspace.
+__device__ __forceinline__ double ld_dsmem_f64(uint32_t cluster_addr) {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
+
+static constexpr int GNC_THREADS = 512;
+
+// BWD = 0: y = act(GN(x)), stats out.   BWD = 1: dx (+)= dGN(x, dy), stats in, optional dgamma / dbeta accumulation.
+template <int BWD>
+__global__ void __launch_bounds__(GNC_THREADS, 2)
+gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* gamma,
+                  const float* beta, float* stats, __nv_bfloat16* __restrict__ out, float* dgamma, float* dbeta, int HW, int C, int G,
+                  float eps, double inv_m, int silu, int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
+    // grid (CL, n_img, CS): the cluster of CL CTAs shares the rows of image blockIdx.y; blockIdx.z selects one of CS
+    // contiguous channel ranges (whole groups - GroupNorm statistics never cross a group), so that n_img * CL * CS CTAs
+    // cover the machine about twice even at batch 8.  Inside the kernel C / G / pointers are made LOCAL to that range.
+    const int n = blockIdx.y;
+    const int CL = gridDim.x;                          // cluster == the gridDim.x CTAs of one (image, channel range)
+    const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+    const int Cfull = C, Gfull = G;
+    const int cpg = C / G;
+    G = Gfull / (int)gridDim.z;                        // groups of this CTA
+    C = G * cpg;                                       // channels of this CTA
+    const int cbase = (int)blockIdx.z * C;             // first channel
+    const int gbase = (int)blockIdx.z * G;             // first group
+    gamma += cbase; beta += cbase;
+    if (dgamma != nullptr) { dgamma += cbase; dbeta += cbase; }
+    stats += ((long long)n * Gfull + gbase) * 2;       // stats[(g_local) * 2 + {0,1}] below
+    const int chunks = C / 8;
+    const int rows_par = blockDim.x / chunks;
+    const int chunk = threadIdx.x % chunks;
+    const int rsub = threadIdx.x / chunks;
+    const bool active = rsub < rows_par;
+    const int c0 = chunk * 8;
+    const int rows_cta = (HW + CL - 1) / CL;
+    const int row0 = crank * rows_cta;
+    const int row1 = min(HW, row0 + rows_cta);
+    const __nv_bfloat16* xp = x + (long long)n * HW * Cfull + cbase + c0;
+    const __nv_bfloat16* dp = BWD ? dy + (long long)n * HW * Cfull + cbase + c0 : nullptr;
+
+    extern __shared__ __align__(16) unsigned char gnc_raw[];
+    double* gpart = reinterpret_cast<double*>(gnc_raw);                    // [G][2]  this CTA's partial group sums
+    float* coef = reinterpret_cast<float*>(gpart + 2 * G);                 // [4][C]  per-channel coefficients
+    float* part0 = coef + 4 * C;                                           // [rows_par][C]
+    float* part1 = part0 + (size_t)rows_par * C;                           // [rows_par][C]
+
+    // ---------------- phase 1
+    float a0[8], a1[8], sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a0[j] = a1[j] = 0.f; sc[j] = sh[j] = 0.f; }
+    if (BWD && active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c0 + j) / cpg;
+            const float mu = stats[g * 2], rs = stats[g * 2 + 1];
+            sc[j] = rs * gamma[c0 + j];
+            sh[j] = fmaf(-mu, sc[j], beta[c0 + j]);
+        }
+    }
+    if (active) {
+        if (!BWD) {
+            for (int r = row0 + rsub; r < row1; r += 4 * rows_par) {       // 4 rows (64 B) in flight per thread
+                uint4 u[4];
+                bool ok[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rq = r + q * rows_par;
+                    ok[q] = rq < row1;
+                    u[q] = ldg16(xp + (long long)(ok[q] ? rq : r) * Cfull);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (!ok[q]) continue;
+                    float xv[8];
+                    unpack8(u[q], xv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
+                }
+            }
+        } else {
+            for (int r = row0 + rsub; r < row1; r += 2 * rows_par) {
+                const int r1 = r + rows_par;
+                const bool ok1 = r1 < row1;
+                const long long o0 = (long long)r * Cfull, o1 = (long long)(ok1 ? r1 : r) * Cfull;
+                const uint4 ux0 = ldg16(xp + o0), ud0 = ldg16(dp + o0), ux1 = ldg16(xp + o1), ud1 = ldg16(dp + o1);
+                float xv[8], dv[8];
+                unpack8(ux0, xv);
+                unpack8(ud0, dv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float dz = dv[j];
+                    if (silu) dz *= silu_grad_fast(fmaf(xv[j], sc[j], sh[j]));
+                    a0[j] = fmaf(dz, xv[j], a0[j]);
+                    a1[j] += dz;
+                }
+                if (ok1) {
+                    unpack8(ux1, xv);
+                    unpack8(ud1, dv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float dz = dv[j];
+                        if (silu) dz *= silu_grad_fast(fmaf(xv[j], sc[j], sh[j]));
+                        a0[j] = fmaf(dz, xv[j], a0[j]);
+                        a1[j] += dz;
+                    }
+                }
+            }
+        }
+        float* d0 = part0 + (size_t)rsub * C + c0;
+        float* d1 = part1 + (size_t)rsub * C + c0;
+        *reinterpret_cast<float4*>(d0) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+        *reinterpret_cast<float4*>(d0 + 4) = make_float4(a0[4], a0[5], a0[6], a0[7]);
+        *reinterpret_cast<float4*>(d1) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+        *reinterpret_cast<float4*>(d1 + 4) = make_float4(a1[4], a1[5], a1[6], a1[7]);
+    }
+    __syncthreads();
+    // per-channel totals of this CTA -> coef planes 0 / 1 (scratch until the coefficients are written)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int g = 0; g < rows_par; ++g) { s0 += part0[(size_t)g * C + c]; s1 += part1[(size_t)g * C + c]; }
+        if (BWD) {
+            const int g = c / cpg;
+            const float mu = stats[g * 2], rs = stats[g * 2 + 1];
+            const float dzxh = rs * fmaf(-mu, s1, s0);              // this slab's share of sum dz*xhat of the channel
+            if (dgamma != nullptr) { atomicAdd(&dgamma[c], dzxh); atomicAdd(&dbeta[c], s1); }
+            const float gm = gamma[c];
+            s0 = gm * s1;                                            // -> group sum of dz*gamma
+            s1 = gm * dzxh;                                          // -> group sum of dz*gamma*xhat
+        }
+        coef[c] = s0;
+        coef[C + c] = s1;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s0 += coef[c]; s1 += coef[C + c]; }
+        gpart[2 * g] = s0;
+        gpart[2 * g + 1] = s1;
+    }
+    // ---------------- exchange: every CTA sums the partials of all CTAs of its image (distributed shared memory)
+    if (CL > 1) cluster_sync_all(); else __syncthreads();
+    double* gtot = reinterpret_cast<double*>(part0);                 // [G][2] (part0 is free now)
+    for (int g = threadIdx.x; g < 2 * G; g += blockDim.x) {
+        double s = 0.0;
+        if (CL > 1) {
+            const uint32_t local = smem_u32(gpart + g);
+            for (int rk = 0; rk < CL; ++rk) s += ld_dsmem_f64(mapa_shared(local, (uint32_t)rk));
+        } else {
+            s = gpart[g];
+        }
+        gtot[g] = s;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        if (!BWD) {
+            const double mu = gtot[2 * g] * inv_m;
+            double var = gtot[2 * g + 1] * inv_m - mu * mu;
+            if (var < 0.0) var = 0.0;
+            const float rs = (float)(1.0 / sqrt(var + (double)eps));
+            const float fmu = (float)mu;
+            if (crank == 0 && c == g * cpg) { stats[g * 2] = fmu; stats[g * 2 + 1] = rs; }
+            const float s_ = rs * gamma[c];
+            coef[2 * C + c] = s_;
+            coef[3 * C + c] = fmaf(-fmu, s_, beta[c]);
+        } else {
+            const float mu = stats[g * 2], rs = stats[g * 2 + 1];
+            const float im = (float)inv_m;
+            const float K2 = rs * rs * (float)gtot[2 * g + 1] * im;
+            coef[2 * C + c] = fmaf(-mu, K2, rs * (float)gtot[2 * g] * im);    // K1
+            coef[3 * C + c] = K2;
+        }
+    }
+    __syncthreads();
+    // ---------------- phase 2 (the slab is L2-resident: phase 1 just streamed it)
+    if (active) {
+        __nv_bfloat16* op = out + (long long)n * HW * Cfull + cbase + c0;
+        if (!BWD) {
+            float s2[8], h2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s2[j] = coef[2 * C + c0 + j]; h2[j] = coef[3 * C + c0 + j]; }
+            for (int r = row0 + rsub; r < row1; r += 4 * rows_par) {
+                uint4 u[4];
+                bool ok[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rq = r + q * rows_par;
+                    ok[q] = rq < row1;
+                    u[q] = ldg16(xp + (long long)(ok[q] ? rq : r) * Cfull);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (!ok[q]) continue;
+                    float xv[8], o[8];
+                    unpack8(u[q], xv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float z = fmaf(xv[j], s2[j], h2[j]);
+                        o[j] = silu ? z * fast_sigmoid(z) : z;
+                    }
+                    store8(op + (long long)(r + q * rows_par) * Cfull, o);
+                }
+            }
+        } else {
+            float k1[8], k2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { k1[j] = coef[2 * C + c0 + j]; k2[j] = coef[3 * C + c0 + j]; }
+            for (int r = row0 + rsub; r < row1; r += 2 * rows_par) {
+                const int r1 = r + rows_par;
+                const bool ok1 = r1 < row1;
+                const long long o0 = (long long)r * Cfull, o1 = (long long)(ok1 ? r1 : r) * Cfull;
+                const uint4 ux0 = ldg16(xp + o0), ud0 = ldg16(dp + o0), ux1 = ldg16(xp + o1), ud1 = ldg16(dp + o1);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (q == 1 && !ok1) continue;
+                    float xv[8], dv[8], o[8];
+                    unpack8(q ? ux1 : ux0, xv);
+                    unpack8(q ? ud1 : ud0, dv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float dz = dv[j];
+                        if (silu) dz *= silu_grad_fast(fmaf(xv[j], sc[j], sh[j]));
+                        o[j] = fmaf(-xv[j], k2[j], fmaf(dz, sc[j], -k1[j]));       // dz*A - K1 - x*K2   (A == sc)
+                    }
+                    __nv_bfloat16* dst = op + (q ? o1 : o0);
+                    if (accumulate) {
+                        float pv[8];
+                        load8(dst, pv);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] += pv[j];
+                    }
+                    store8(dst, o);
+                }
+            }
+        }
+    }
+    if (CL > 1) cluster_sync_all();      // peers may still be reading this CTA's gpart
+}
+
 // ---------------------------------------------------------------------------------------------- LayerNorm
 // One warp per row; the row (C <= 2560) lives in registers.
 static constexpr int LN_MAX_IT = 10;  // 10 * 32 lanes * 8 = 2560 channels
@@ -503,6 +751,67 @@ static int gn_flat_blocks(int HW, int C, int n, int per_thread) {
     return (int)blocks;
 }
 
+
+// One-launch GroupNorm: pick the cluster size (CTAs per image) and launch gn_cluster_kernel<BWD>.  Returns CL_OK, or a
+// positive value when this shape / device has to take the three-kernel path.
+template <int BWD>
+static int gn_cluster_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, const float* gamma, const float* beta, float* stats,
+                             __nv_bfloat16* out, float* dgamma, float* dbeta, int n, int HW, int C, int G, float eps, int silu,
+                             int accumulate, cudaStream_t stream) {
+    static const int enabled = [] { const char* e = getenv("CLB_GN_FUSED"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (!enabled || C % 8 != 0 || C < 8 || C % G != 0) return 1;
+    const int cpg = C / G;
+    // channel ranges per image (whole groups, >= 128 channels = 256 contiguous bytes per row and a multiple of 8 channels)
+    int cs = 1;
+    while (G % (2 * cs) == 0 && (C / (2 * cs)) >= 128 && ((G / (2 * cs)) * cpg) % 8 == 0 && n * 16 * cs < 2 * num_sms()) cs *= 2;
+    const int Cl = C / cs, Gl = G / cs;
+    if (Cl / 8 > GNC_THREADS) return 1;
+    const int chunks = Cl / 8;
+    const int rows_par = GNC_THREADS / chunks;
+    const size_t smem = sizeof(double) * 2 * Gl + sizeof(float) * ((size_t)4 * Cl + (size_t)2 * rows_par * Cl);
+    if (smem > 100 * 1024 || (size_t)2 * rows_par * Cl * sizeof(float) < sizeof(double) * 2 * Gl) return 1;
+    static bool attr_done = false;
+    static int max_cluster = 8;
+    if (!attr_done) {
+        CL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        // clusters of 16 CTAs are "non-portable": opt in, and keep 8 when the device refuses
+        if (cudaFuncSetAttribute(gn_cluster_kernel<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+            cudaFuncSetAttribute(gn_cluster_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)
+            max_cluster = 16;
+        (void)cudaGetLastError();
+        attr_done = true;
+    }
+    // CTAs per image: enough CTAs to fill the machine once, at least ~8 rows per row-slot, a power of two <= max_cluster
+    int cl = max_cluster;
+    while (cl > 1 && (n * cl * cs > 3 * num_sms() || HW / cl < rows_par)) cl >>= 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cl, n, cs);
+    cfg.blockDim = dim3(GNC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cl > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cl; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    const double inv_m = 1.0 / ((double)HW * (C / G));
+    CL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_cluster_kernel<BWD>, x, dy, gamma, beta, stats, out, dgamma, dbeta, HW, C, G, eps, inv_m,
+                                     silu, accumulate));
+    count_launch();
+    return CL_OK;
+}
+
 extern "C" int64_t cl_groupnorm_ws_bytes(int n, int G, int C) { return (int64_t)16 * n * G + (int64_t)24 * n * C; }
 
 extern "C" int cl_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
@@ -511,6 +820,11 @@ extern "C" int cl_groupnorm_fwd(const void* x, const float* gamma, const float* 
     if (!x || !gamma || !beta || !y || !ws) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: null pointer");
     if (stats == nullptr) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: stats buffer is required");
     if (G <= 0 || C % G != 0) return set_error(CL_ERR_INVALID, "cl_groupnorm_fwd: C %% G != 0");
+    {
+        const int st = gn_cluster_launch<0>(reinterpret_cast<const __nv_bfloat16*>(x), nullptr, gamma, beta, stats,
+                                            reinterpret_cast<__nv_bfloat16*>(y), nullptr, nullptr, n, HW, C, G, eps, silu, 0, stream);
+        if (st <= 0) return st;          // launched (CL_OK) or failed; > 0: shape not covered -> three-kernel path below
+    }
     int threads, rows_per_cta, grid_x;
     CL_CHECK(gn_launch_geometry(HW, C, n, threads, rows_per_cta, grid_x));
     double* gsum = ws;
@@ -542,6 +856,12 @@ extern "C" int cl_groupnorm_bwd(const void* x, const void* dy, const float* gamm
     if (!x || !dy || !gamma || !beta || !stats || !dx || !ws) return set_error(CL_ERR_INVALID, "cl_groupnorm_bwd: null pointer");
     if (G <= 0 || C % G != 0) return set_error(CL_ERR_INVALID, "cl_groupnorm_bwd: C %% G != 0");
     if (G > 4096) return set_error(CL_ERR_UNSUPPORTED, "cl_groupnorm_bwd: G <= 4096");
+    {
+        const int st = gn_cluster_launch<1>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), gamma,
+                                            beta, const_cast<float*>(stats), reinterpret_cast<__nv_bfloat16*>(dx), dgamma, dbeta, n, HW,
+                                            C, G, 0.f, silu, accumulate, stream);
+        if (st <= 0) return st;
+    }
     int threads, rows_per_cta, grid_x;
     CL_CHECK(gn_launch_geometry(HW, C, n, threads, rows_per_cta, grid_x));
     float* coef = reinterpret_cast<float*>(ws + (size_t)2 * n * G);

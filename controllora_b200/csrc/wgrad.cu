@@ -48,7 +48,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     uint64_t* empty_bar = bars + WG_STAGES;
     uint64_t* acc_full = empty_bar + WG_STAGES;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_full + 1);
-    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp_idx = uniform_warp_idx(), lane = threadIdx.x & 31;
 
     // work decomposition: blockIdx.y -> (cout tile, cin tile, tap group); blockIdx.x -> pixel split
     int wy = blockIdx.y;
@@ -75,24 +75,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp_idx == 0) {
-        if (lane == 0) {
+        {   // whole warp converged; the *_e calls elect one lane for the instruction itself
             int stage = 0; uint32_t phase = 0;
             for (int pb = pb0; pb < pb1; ++pb) {
                 const int tw = pb % p.tiles_w, th = (pb / p.tiles_w) % p.tiles_h, tn = pb / (p.tiles_w * p.tiles_h);
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full_bar[stage], WG_A_BYTES + ntaps * WG_B_BYTES);
+                mbar_arrive_expect_tx_e(&full_bar[stage], WG_A_BYTES + ntaps * WG_B_BYTES);
                 uint8_t* sa = smem + stage * WG_STAGE_BYTES;
                 for (int c = 0; c < 2; ++c)
-                    tma_load_4d(&tmDY, &full_bar[stage], sa + c * (128 * 128), cot * 128 + c * 64, tw * p.bw, th * p.bh, tn * p.bn);
+                    tma_load_4d_e(&tmDY, &full_bar[stage], sa + c * (128 * 128), cot * 128 + c * 64, tw * p.bw, th * p.bh, tn * p.bn);
                 for (int t = 0; t < ntaps; ++t) {
                     uint8_t* sb = sa + WG_A_BYTES + t * WG_B_BYTES;
                     const int tap = tap0 + t;
                     const int ky = (p.ksize == 3) ? tap / 3 : 1, kx = (p.ksize == 3) ? tap % 3 : 1;
                     if (p.mode != 2) {
-                        tma_load_4d(&tmX, &full_bar[stage], sb, cit * WG_NT, tw * p.bw + kx - 1, th * p.bh + ky - 1, tn * p.bn);
+                        tma_load_4d_e(&tmX, &full_bar[stage], sb, cit * WG_NT, tw * p.bw + kx - 1, th * p.bh + ky - 1, tn * p.bn);
                     } else {
                         const int iy = ky - p.pad_lo, ix = kx - p.pad_lo;
-                        tma_load_5d(&tmX, &full_bar[stage], sb, (ix & 1) * p.C_in_map + cit * WG_NT, tw * p.bw + (ix >> 1), iy & 1,
+                        tma_load_5d_e(&tmX, &full_bar[stage], sb, (ix & 1) * p.C_in_map + cit * WG_NT, tw * p.bw + (ix >> 1), iy & 1,
                                     th * p.bh + (iy >> 1), tn * p.bn);
                     }
                 }
@@ -100,7 +100,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
+        {   // whole warp converged; the *_e calls elect one lane for the instruction itself
             constexpr uint32_t idesc = make_idesc_bf16(128, WG_NT, 1, 1);   // A and B both MN-major
             int stage = 0; uint32_t phase = 0;
             bool first = true;
@@ -112,15 +112,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
                     const uint32_t sb = sa + WG_A_BYTES + t * WG_B_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {   // 128 pixels = 8 x K16
-                        tc_mma_ss(tmem_base + t * WG_NT, make_smem_desc(sa + kk * 2048, 128 * 128, 1024, 2),
+                        tc_mma_ss_e(tmem_base + t * WG_NT, make_smem_desc(sa + kk * 2048, 128 * 128, 1024, 2),
                                   make_smem_desc(sb + kk * 2048, 128 * 128, 1024, 2), idesc, (first && kk == 0) ? 0u : 1u);
                     }
                 }
                 first = false;
-                tc_commit(&empty_bar[stage]);
+                tc_commit_e(&empty_bar[stage]);
                 if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
             }
-            tc_commit(acc_full);
+            tc_commit_e(acc_full);
         }
     } else if (warp_idx >= 4) {
         if (pb1 > pb0) {

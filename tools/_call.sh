@@ -1,14 +1,9 @@
 set -x
-timeout 600 python -m pytest tests -m gpu -q -x -k "gemm or conv or attention" > gpurun_out/r2c3_tests_kernels.log 2>&1; echo tests=$?
-tail -8 gpurun_out/r2c3_tests_kernels.log
-timeout 200 python tools/check_gemm.py perf > gpurun_out/r2c3_gemm_perf.log 2>&1; grep perf gpurun_out/r2c3_gemm_perf.log
-CLB_GEMM_TMA_STORE=0 timeout 200 python tools/check_gemm.py perf > gpurun_out/r2c3_gemm_perf_oldepi.log 2>&1; grep "perf M" gpurun_out/r2c3_gemm_perf_oldepi.log | head -4
-timeout 200 python tools/check_ops.py attn_perf > gpurun_out/r2c3_attn.log 2>&1; cat gpurun_out/r2c3_attn.log | tail -6
-timeout 100 python tools/check_ops2.py attn_perf2 > gpurun_out/r2c3_attn_bwd.log 2>&1; tail -6 gpurun_out/r2c3_attn_bwd.log
-for sh in "32768 320 320" "32768 320 320 lora" "32768 320 320 res"; do
-  echo "=== timeline $sh" >> gpurun_out/r2c3_timeline.log
-  CLB_LIB=$PWD/controllora_b200/libcontrollora_b200_tl.so timeout 120 python tools/gemm_timeline.py $sh >> gpurun_out/r2c3_timeline.log 2>&1
-done
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2c3_tests.log 2>&1; echo tests=$?
-tail -8 gpurun_out/r2c3_tests.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-aux > gpurun_out/r2c3_bench.log 2>&1; tail -1 gpurun_out/r2c3_bench.log | cut -c1-400
+export CLB_LIB=$PWD/controllora_b200/libcontrollora_b200_tl.so
+for bn in 64 256; do echo "=== bn=$bn K=1280 EPI=4"; CLB_GEMM_EPI=4 timeout 100 python tools/gemm_timeline.py 4096 1280 1280 $bn 2>&1 | head -120; done > gpurun_out/r2c6_kb_timeline.log 2>&1
+echo "=== resident K=320 EPI=4" >> gpurun_out/r2c6_kb_timeline.log; CLB_GEMM_EPI=4 timeout 100 python tools/gemm_timeline.py 32768 320 320 2>&1 | head -100 >> gpurun_out/r2c6_kb_timeline.log
+unset CLB_LIB
+timeout 600 python -m pytest tests -m gpu -q -x -k "norm or gemm or conv" > gpurun_out/r2c6_tests.log 2>&1; echo tests=$?; tail -3 gpurun_out/r2c6_tests.log
+echo "=== GN fused split"; timeout 300 python tools/bw_bench.py --iters 5 2>&1 | grep -i "groupnorm" | cut -c1-110
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-aux > gpurun_out/r2c6_bench.log 2>&1; tail -1 gpurun_out/r2c6_bench.log | cut -c1-300
+CLB_GN_FUSED=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-aux > gpurun_out/r2c6_bench_gnold.log 2>&1; tail -1 gpurun_out/r2c6_bench_gnold.log | cut -c1-300

@@ -75,6 +75,14 @@ def plain_bn256():
 
 
 @case
+def plain_bn320():
+    """256 x 320 CTA-pair tiles (two 160-column MMAs per k-step sharing the A stage, one accumulator buffer)."""
+    _run_plain(4096, 640, 2560, 320)
+    _run_plain(32768, 320, 2880, 320)
+    _run_plain(1000, 320, 2048, 320)      # M tail inside a pair
+
+
+@case
 def plain_big():
     _run_plain(32768, 320, 320)
     _run_plain(8192, 640, 2560)
@@ -199,6 +207,14 @@ def conv_s2():
     _conv_case(2, 64, 64, 320, 320, 2, 1, True)
     _conv_case(2, 64, 64, 64, 64, 2, 0, False)
     _conv_case(4, 16, 16, 1280, 1280, 2, 1, False)
+
+
+@case
+def conv_bn320():
+    """deep-K convs whose N is a multiple of 320 take the 256 x 320 pair tile (plan_tiles); with the fused epilogue operands"""
+    _conv_case(8, 64, 64, 320, 320, 1, 1, True)
+    _conv_case(8, 32, 32, 640, 640, 1, 1, True)
+    _conv_case(8, 32, 32, 1280, 640, 1, 1, False)
 
 
 @case

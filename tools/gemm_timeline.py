@@ -31,14 +31,25 @@ ops.gemm(a, b, out=out, block_n=bn, **kw)
 buf = (C.c_ulonglong * (160 * 256 * 2))()
 cnt = (C.c_uint * 160)()
 lib.cl_debug_timeline(buf, cnt, 0)
-names = {1: "entry", 10: "prod:tile", 20: "mma:wait_acc", 21: "mma:acc_free", 22: "mma:stage0", 23: "mma:issued", 30: "epi:wait",
+names = {1: "entry", 10: "prod:tile", 11: "prod:slot", 12: "prod:issued", 24: "mma:kb_ready", 25: "mma:kb_issued", 20: "mma:wait_acc", 21: "mma:acc_free", 22: "mma:stage0", 23: "mma:issued", 30: "epi:wait",
          31: "epi:ready", 32: "epi:done"}
-for sm in (0, 1, 77):
+for sm in (0, 77):
     n = min(cnt[sm], 256)
-    ev = sorted((buf[(sm * 256 + i) * 2], buf[(sm * 256 + i) * 2 + 1]) for i in range(n))
+    ev = sorted((buf[(sm * 256 + i) * 2], buf[(sm * 256 + i) * 2 + 1]) for i in range(n) if buf[(sm * 256 + i) * 2 + 1] != 0)
     if not ev:
         continue
     t0 = ev[0][0]
     print(f"--- SM {sm}: {n} events")
     for t, tag in ev:
         print(f"  {t - t0:8d}  {names.get(tag, tag)}")
+
+# summary: tensor-pipe time per tcgen05.mma dispatch (K = 16) on SM 0, from the MMA thread's stage0 -> issued intervals
+import os
+reps = int(os.environ.get("CLB_TL_MMA_REPS", "0"))
+n = min(cnt[0], 256)
+ev = sorted((buf[i * 2], buf[i * 2 + 1]) for i in range(n) if buf[i * 2 + 1] in (22, 23))
+pairs = [(b[0] - a[0]) for a, b in zip(ev, ev[1:]) if a[1] == 22 and b[1] == 23]
+nkb = (K + 63) // 64
+if pairs:
+    per = [d / (nkb * 4 * (reps + 1)) for d in pairs]
+    print(f"SUMMARY M={M} N={N} K={K} bn={bn} reps={reps}: tiles={len(pairs)} clk/dispatch min={min(per):.1f} avg={sum(per)/len(per):.1f}  (k-blocks/tile {nkb})")
