@@ -6,8 +6,9 @@ drivers use.  Importing the package does not require a GPU; running any op does 
 from .models import (ControlLoRA, ControlLoRACrossAttnProcessor, ControlLoRACrossAttnProcessorV2, ControlLoRAOutput,
                      LoRACrossAttnProcessor, LoRALinearLayer)
 from .unet_module import UNet2DConditionModel
+from .vae import AutoencoderKL
 
 __all__ = [
     "ControlLoRA", "ControlLoRAOutput", "ControlLoRACrossAttnProcessor", "ControlLoRACrossAttnProcessorV2",
-    "LoRACrossAttnProcessor", "LoRALinearLayer", "UNet2DConditionModel",
+    "LoRACrossAttnProcessor", "LoRALinearLayer", "UNet2DConditionModel", "AutoencoderKL",
 ]

@@ -19,6 +19,7 @@
 // cost neither.
 // Warp roles as in the forward kernel: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 4-7 softmax/epilogue.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -38,6 +39,8 @@ struct AttnBwdParams {
     __nv_bfloat16* dv; long long lddv;
     float scale, scale_log2;
     int num_blocks;       // key blocks (dkv) or query blocks (dq) per (b, h)
+    int poly_exp;         // every second exp2 of the softmax recomputation runs on the FMA pipe (exp2_poly) instead of MUFU
+    int stats_all;        // dkv: LSE / delta of ALL query blocks are staged in shared memory once (no per-block CTA barrier)
 };
 
 // write 32 consecutive bf16 values (columns [c32*32, c32*32+32) of row r) into a K-major 128B-swizzled tile whose
@@ -235,16 +238,29 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t lane_off = uint32_t(quad * 32) << 16;
         const bool key_ok = (k0 + r) < p.Nk;
         const long long stat_base = ((long long)b * p.H + h) * p.Nq;
-        for (int j = 0; j < num_q; ++j) {
-            // stage this query block's LSE / delta (double-buffered; the named barrier orders it w.r.t. the reads)
-            float* ls = smem_lse + (j & 1) * BQ;
-            float* de = smem_delta + (j & 1) * BQ;
-            if (st < BQ) {
-                const int q = j * BQ + st;
-                ls[st] = (q < p.Nq) ? p.lse[stat_base + q] : INFINITY;   // +inf -> P = 0 for padded queries
-                de[st] = (q < p.Nq) ? p.delta[stat_base + q] : 0.f;
+        // LSE and delta * scale of every query of this (b, h): staged ONCE when they fit (Nq <= 4096: 32 KB) - the per-block
+        // staging + CTA-wide named barrier of the fallback path was the top stall of this kernel (ncu, round 2)
+        float* all_lse = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+        float* all_del = all_lse + num_q * BQ;
+        if (p.stats_all) {
+            for (int i = st; i < num_q * BQ; i += 256) {
+                all_lse[i] = (i < p.Nq) ? p.lse[stat_base + i] : INFINITY;     // +inf -> P = 0 for padded queries
+                all_del[i] = (i < p.Nq) ? p.delta[stat_base + i] * p.scale : 0.f;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        for (int j = 0; j < num_q; ++j) {
+            float* ls = p.stats_all ? all_lse + j * BQ : smem_lse + (j & 1) * BQ;
+            float* de = p.stats_all ? all_del + j * BQ : smem_delta + (j & 1) * BQ;
+            if (!p.stats_all) {
+                // fallback: stage this query block's LSE / delta (double-buffered; the named barrier orders it w.r.t. the reads)
+                if (st < BQ) {
+                    const int q = j * BQ + st;
+                    ls[st] = (q < p.Nq) ? p.lse[stat_base + q] : INFINITY;
+                    de[st] = (q < p.Nq) ? p.delta[stat_base + q] * p.scale : 0.f;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             mbar_wait(s_full, j & 1);
             tc_fence_after();
 #pragma unroll
@@ -252,9 +268,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 uint32_t s[16], g[16];
                 tmem_ld_32x16(tmem_base + Cfg::TM_ST + lane_off + c * 16, s);
                 tmem_ld_32x16(tmem_base + Cfg::TM_DPT + lane_off + c * 16, g);
-                tc_wait_ld();
                 uint32_t pk[8], dk_[8];
-                float lsv[16], dev[16];     // this chunk's per-query LSE / delta: broadcast 16-byte shared loads
+                float lsv[16], dev[16];     // this chunk's per-query LSE / delta*scale: broadcast 16-byte shared loads
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
                     const float4 l4 = *reinterpret_cast<const float4*>(ls + c * 16 + i);
@@ -262,13 +277,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     lsv[i] = l4.x; lsv[i + 1] = l4.y; lsv[i + 2] = l4.z; lsv[i + 3] = l4.w;
                     dev[i] = d4.x; dev[i + 1] = d4.y; dev[i + 2] = d4.z; dev[i + 3] = d4.w;
                 }
+                tc_wait_ld();
+                // no key mask: row r of P^T / dS^T only feeds row r of dV / dK, and rows beyond Nk are never stored
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lsv[i]));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -lsv[i + 1]));
-                    if (!key_ok) { p0 = 0.f; p1 = 0.f; }
-                    const float d0 = p0 * (__uint_as_float(g[i]) - dev[i]) * p.scale;
-                    const float d1 = p1 * (__uint_as_float(g[i + 1]) - dev[i + 1]) * p.scale;
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lsv[i]));
+                    const float x1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -lsv[i + 1]);
+                    const float p1 = p.poly_exp ? exp2_poly(x1) : fast_exp2(x1);
+                    const float d0 = p0 * fmaf(__uint_as_float(g[i]), p.scale, -dev[i]);
+                    const float d1 = p1 * fmaf(__uint_as_float(g[i + 1]), p.scale, -dev[i + 1]);
                     pk[i >> 1] = pack_bf16x2(p0, p1);
                     dk_[i >> 1] = pack_bf16x2(d0, d1);
                 }
@@ -441,7 +458,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     float p0 = fast_exp2(fmaf(__uint_as_float(s[j]), p.scale_log2, -lse));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -lse));
+                    const float x1 = fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -lse);
+                    float p1 = p.poly_exp ? exp2_poly(x1) : fast_exp2(x1);
                     if (tail) {
                         if (kbase + c * 16 + j >= p.Nk) p0 = 0.f;
                         if (kbase + c * 16 + j + 1 >= p.Nk) p1 = 0.f;
@@ -621,7 +639,8 @@ attn_bwd_dq64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
                 float p0 = fast_exp2(fmaf(__uint_as_float(s[j]), p.scale_log2, -lse));
-                float p1 = fast_exp2(fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -lse));
+                const float x1 = fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -lse);
+                    float p1 = p.poly_exp ? exp2_poly(x1) : fast_exp2(x1);
                 if (kbase + j >= p.Nk) p0 = 0.f;
                 if (kbase + j + 1 >= p.Nk) p1 = 0.f;
                 const float d0 = p0 * fmaf(__uint_as_float(g[j]), p.scale, -delta_s);
@@ -799,7 +818,8 @@ attn_bwd_dkv64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
                 const float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lsv[i]));
-                const float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -lsv[i + 1]));
+                const float x1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -lsv[i + 1]);
+                    const float p1 = p.poly_exp ? exp2_poly(x1) : fast_exp2(x1);
                 const float d0 = p0 * (__uint_as_float(g[i]) - dev[i]) * p.scale;
                 const float d1 = p1 * (__uint_as_float(g[i + 1]) - dev[i + 1]) * p.scale;
                 pk[i >> 1] = pack_bf16x2(p0, p1);
@@ -861,6 +881,8 @@ static int launch_attn_bwd(const cl_attn_bwd_args* a, cudaStream_t stream) {
     p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
     p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.lddv = a->lddv;
     p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+    p.num_blocks = 0; p.stats_all = 0;
+    { static const int pe = [] { const char* e = getenv("CLB_ATTN_POLY_EXP"); return (e && e[0] == '0') ? 0 : 1; }(); p.poly_exp = pe; }
     {
         const long long total = (long long)a->B * a->Nq * a->H;
         int blocks = (int)((total + 255) / 256);
@@ -900,11 +922,15 @@ static int launch_attn_bwd(const cl_attn_bwd_args* a, cudaStream_t stream) {
         static bool done = false;
         if (!done) {
             CL_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<DP, BQ, STAGES_KV>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             done = true;
         }
         p.num_blocks = (a->Nk + 127) / 128;
-        launch_k(attn_bwd_dkv_kernel<DP, BQ, STAGES_KV>, a->B * a->H * p.num_blocks, BWD_THREADS, Cfg::SMEM_BYTES, stream, tq, tk, tv, tdo, p);
+        const int nq_pad = (a->Nq + BQ - 1) / BQ * BQ;
+        const int stats_bytes = nq_pad * 8;
+        p.stats_all = (Cfg::SMEM_BYTES + stats_bytes <= (Cfg::MIN_CTAS == 2 ? 110 * 1024 : 200 * 1024)) ? 1 : 0;
+        launch_k(attn_bwd_dkv_kernel<DP, BQ, STAGES_KV>, a->B * a->H * p.num_blocks, BWD_THREADS,
+                 Cfg::SMEM_BYTES + (p.stats_all ? stats_bytes : 0), stream, tq, tk, tv, tdo, p);
         count_launch();
     }
     if (DP == 64 && v2_enabled && a->dq != nullptr) {

@@ -375,6 +375,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f through the 1.5 * 2^23 magic add, 2^f on
+// [-0.5, 0.5] as a degree-4 polynomial (relative error < 5e-5, far below the bf16 rounding of P), n added to the exponent.
+// The attention softmax loops alternate this with ex2.approx so that the exp work is split between the MUFU pipe (16 / clk / SM)
+// and the FMA pipe (ncu round 2: XU 53-54 % busy in the forward and dQ kernels, the hottest pipe).
+__device__ __forceinline__ float exp2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;               // 0x4B400000: low mantissa bits of t = round(x)
+    const float f = x - (t - 12582912.0f);
+    float r = fmaf(f, 0.0096181291f, 0.0555041087f);
+    r = fmaf(r, f, 0.2402265070f);
+    r = fmaf(r, f, 0.6931471806f);
+    r = fmaf(r, f, 1.0f);
+    return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -374,3 +374,85 @@ extern "C" int cl_axpy_matrix_f32(const float* src, float* dst, int64_t ld, int 
     launch_k(clb::axpy_matrix_kernel, ew_blocks((long long)I * J), 256, 0, stream, src, dst, (long long)ld, I, J, alpha);
     DONE();
 }
+
+// ------------------------------------------------------------------------------------------ VAE helpers
+// Row softmax of the one-head AttentionBlock of the VAE mid block (diffusers AttentionBlock: softmax(q k^T / sqrt(C)) in fp32):
+// p[r, :] = softmax(scale * s[r, :]) written as bf16.  One CTA per row, the row cached in shared memory (cols <= 12288).
+namespace clb {
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int cols, float scale_log2) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float row[];
+    __shared__ float red[8];
+    const float* sr = s + (long long)blockIdx.x * cols;
+    __nv_bfloat16* pr = p + (long long)blockIdx.x * cols;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(sr + c);
+        *reinterpret_cast<float4*>(row + c) = v;
+        mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+        float4 v = *reinterpret_cast<float4*>(row + c);
+        v.x = fast_exp2((v.x - mx) * scale_log2); v.y = fast_exp2((v.y - mx) * scale_log2);
+        v.z = fast_exp2((v.z - mx) * scale_log2); v.w = fast_exp2((v.w - mx) * scale_log2);
+        *reinterpret_cast<float4*>(row + c) = v;
+        sum += v.x + v.y + v.z + v.w;
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += red[i];
+    const float inv = 1.f / sum;
+    for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<float4*>(row + c);
+        uint2 o;
+        o.x = pack_bf16x2(v.x * inv, v.y * inv);
+        o.y = pack_bf16x2(v.z * inv, v.w * inv);
+        *reinterpret_cast<uint2*>(pr + c) = o;
+    }
+}
+
+// y[n, c, :] = mul * x[n, c, :] + shift[c]   (NCHW fp32; the post_quant_conv bias as a shift of the latents)
+__global__ void channel_affine_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ shift,
+                                           float mul, int C, long long hw, long long total) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((i / hw) % C);
+        y[i] = fmaf(mul, x[i], shift[c]);
+    }
+}
+}  // namespace clb
+
+extern "C" int cl_softmax_rows(const float* s, void* p, int rows, int cols, float scale, void* stream_) {
+    STREAM;
+    if (!s || !p || rows <= 0 || cols <= 0 || cols % 4 != 0 || cols > 12288)
+        return set_error(CL_ERR_INVALID, "cl_softmax_rows: cols must be a multiple of 4, <= 12288");
+    static bool done = false;
+    if (!done) {
+        CL_CUDA_CHECK(cudaFuncSetAttribute(clb::softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4));
+        done = true;
+    }
+    launch_k(clb::softmax_rows_kernel, rows, 256, (size_t)cols * 4, stream, s, BFW(p), cols, scale * 1.4426950408889634f);
+    DONE();
+}
+
+extern "C" int cl_channel_affine_nchw(const float* x, float* y, const float* shift, float mul, int n, int C, int64_t hw, void* stream_) {
+    STREAM;
+    if (!x || !y || !shift || n <= 0 || C <= 0 || hw <= 0) return set_error(CL_ERR_INVALID, "cl_channel_affine_nchw: bad args");
+    const long long total = (long long)n * C * hw;
+    launch_k(clb::channel_affine_nchw_kernel, ew_blocks(total), 256, 0, stream, x, y, shift, mul, C, (long long)hw, total);
+    DONE();
+}

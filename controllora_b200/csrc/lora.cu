@@ -112,7 +112,7 @@ struct SkinnyBatch {
 // RT: compile-time bound on the rank (4 or 8); U: rows in flight per thread.  All U row loads (16 B of b, the RT
 // coefficients of a) are issued before the FMAs: with one load in flight per thread the kernel ran at ~25 % of HBM speed.
 template <int RT, int U>
-__global__ void __launch_bounds__(512, (RT <= 4) ? 2 : 1)
+__global__ void __launch_bounds__(512, 1)
 skinny_atb_batch_kernel(const __grid_constant__ SkinnyBatch batch, int slabs) {
     pdl_launch_dependents();
     pdl_wait();
@@ -376,7 +376,10 @@ v2_inject_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
 //   dh[m, c] = dy[m, c] + alpha * sum_j dt[m, j] * down[c*4 + j]   (== cl_rank_update), dh optional
 // The same kernel serves the forward as "project, add control, update":  t = x U (+ uc);  y = x + alpha t D^T  with
 // U = Ac_h^T, D = Bc  - no separate skinny GEMM for x Ac_h^T is needed, x is read exactly once.
-template <int IT>
+// R rows per warp are processed together: every coefficient fetched from the shared-memory tables is used for R rows (the
+// one-row version read 16 KB of table per 1.3 KB row: shared-memory bound, 37 us for a 32768 x 320 pass), and the R x IT
+// 16-byte row loads are all in flight before the first use.
+template <int IT, int R>
 __global__ void __launch_bounds__(256)
 v2_inject_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ up, const float* __restrict__ down, float alpha,
                      float* __restrict__ dt_out, __nv_bfloat16* __restrict__ dh, int M, int C, const float* __restrict__ uc, int ldu,
@@ -394,18 +397,24 @@ v2_inject_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
     const int lane = threadIdx.x & 31;
     const int chunks = C / 8;
     const int warps_total = gridDim.x * (blockDim.x >> 5);
-    for (int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M; m += warps_total) {
-        float v[IT][8];
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int m0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; m0 < M; m0 += warps_total * R) {
+        float v[R][IT][8];
+        float acc[R][4];
 #pragma unroll
-        for (int it = 0; it < IT; ++it) {
-            const int ch = it * 32 + lane;
-            if (ch < chunks) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + (long long)m * C + ch * 8));
-                const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-                v[it][0] = a0.x; v[it][1] = a0.y; v[it][2] = a1.x; v[it][3] = a1.y;
-                v[it][4] = a2.x; v[it][5] = a2.y; v[it][6] = a3.x; v[it][7] = a3.y;
+        for (int r = 0; r < R; ++r) {
+            const int m = min(m0 + r, M - 1);               // clamped rows are computed and dropped
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int ch = it * 32 + lane;
+                if (ch < chunks) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + (long long)m * C + ch * 8));
+                    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+                    v[r][it][0] = a0.x; v[r][it][1] = a0.y; v[r][it][2] = a1.x; v[r][it][3] = a1.y;
+                    v[r][it][4] = a2.x; v[r][it][5] = a2.y; v[r][it][6] = a3.x; v[r][it][7] = a3.y;
+                }
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
         }
 #pragma unroll
         for (int it = 0; it < IT; ++it) {
@@ -415,19 +424,29 @@ v2_inject_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
                 for (int j = 0; j < 4; ++j) {
                     const float4 u0 = *reinterpret_cast<const float4*>(s_up + j * C + ch * 8);
                     const float4 u1 = *reinterpret_cast<const float4*>(s_up + j * C + ch * 8 + 4);
-                    acc[j] += v[it][0] * u0.x + v[it][1] * u0.y + v[it][2] * u0.z + v[it][3] * u0.w + v[it][4] * u1.x +
-                              v[it][5] * u1.y + v[it][6] * u1.z + v[it][7] * u1.w;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        acc[r][j] += v[r][it][0] * u0.x + v[r][it][1] * u0.y + v[r][it][2] * u0.z + v[r][it][3] * u0.w +
+                                     v[r][it][4] * u1.x + v[r][it][5] * u1.y + v[r][it][6] * u1.z + v[r][it][7] * u1.w;
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
-        if (uc != nullptr) {
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < rc) acc[j] += uc[(long long)m * ldu + j];
+            for (int j = 0; j < 4; ++j) acc[r][j] = warp_sum(acc[r][j]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int m = m0 + r;
+            if (m < M) {
+                if (uc != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < rc) acc[r][j] += uc[(long long)m * ldu + j];
+                }
+                if (lane == 0) *reinterpret_cast<float4*>(dt_out + (long long)m * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+            }
         }
-        if (lane == 0) *reinterpret_cast<float4*>(dt_out + (long long)m * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         if (dh != nullptr) {
 #pragma unroll
             for (int it = 0; it < IT; ++it) {
@@ -435,18 +454,26 @@ v2_inject_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
                 if (ch < chunks) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float tj = alpha * acc[j];
                         const float4 d0 = *reinterpret_cast<const float4*>(s_dn + j * C + ch * 8);
                         const float4 d1 = *reinterpret_cast<const float4*>(s_dn + j * C + ch * 8 + 4);
-                        v[it][0] = fmaf(tj, d0.x, v[it][0]); v[it][1] = fmaf(tj, d0.y, v[it][1]);
-                        v[it][2] = fmaf(tj, d0.z, v[it][2]); v[it][3] = fmaf(tj, d0.w, v[it][3]);
-                        v[it][4] = fmaf(tj, d1.x, v[it][4]); v[it][5] = fmaf(tj, d1.y, v[it][5]);
-                        v[it][6] = fmaf(tj, d1.z, v[it][6]); v[it][7] = fmaf(tj, d1.w, v[it][7]);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const float tj = alpha * acc[r][j];
+                            v[r][it][0] = fmaf(tj, d0.x, v[r][it][0]); v[r][it][1] = fmaf(tj, d0.y, v[r][it][1]);
+                            v[r][it][2] = fmaf(tj, d0.z, v[r][it][2]); v[r][it][3] = fmaf(tj, d0.w, v[r][it][3]);
+                            v[r][it][4] = fmaf(tj, d1.x, v[r][it][4]); v[r][it][5] = fmaf(tj, d1.y, v[r][it][5]);
+                            v[r][it][6] = fmaf(tj, d1.z, v[r][it][6]); v[r][it][7] = fmaf(tj, d1.w, v[r][it][7]);
+                        }
                     }
-                    uint4 o;
-                    o.x = pack_bf16x2(v[it][0], v[it][1]); o.y = pack_bf16x2(v[it][2], v[it][3]);
-                    o.z = pack_bf16x2(v[it][4], v[it][5]); o.w = pack_bf16x2(v[it][6], v[it][7]);
-                    *reinterpret_cast<uint4*>(dh + (long long)m * C + ch * 8) = o;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (m0 + r < M) {
+                            uint4 o;
+                            o.x = pack_bf16x2(v[r][it][0], v[r][it][1]); o.y = pack_bf16x2(v[r][it][2], v[r][it][3]);
+                            o.z = pack_bf16x2(v[r][it][4], v[r][it][5]); o.w = pack_bf16x2(v[r][it][6], v[r][it][7]);
+                            *reinterpret_cast<uint4*>(dh + (long long)(m0 + r) * C + ch * 8) = o;
+                        }
+                    }
                 }
             }
         }
@@ -589,18 +616,20 @@ extern "C" int cl_skinny_atb_batch(const cl_skinny_desc* descs, int n, void* str
     if (smem > 200 * 1024) return set_error(CL_ERR_UNSUPPORTED, "cl_skinny_atb_batch: shared memory");
     static bool done = false;
     if (!done) {
-        CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CL_CUDA_CHECK(cudaFuncSetAttribute(skinny_atb_batch_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         done = true;
     }
     int max_r = 0;
     for (int i = 0; i < n; ++i) max_r = descs[i].r > max_r ? descs[i].r : max_r;
     // ~one wave of CTAs in total (two resident per SM for rank <= 4); every problem gets the same number of row slabs
-    int slabs = (num_sms() * (max_r <= 4 ? 2 : 1) + n - 1) / n;
+    // one 512-thread CTA per SM, 8 (rank <= 4) or 4 rows in flight per thread; slabs * n must NOT exceed the SM count: the
+    // round-1 grid (ceil: 304 CTAs on 296 slots) ran a second, almost empty wave and took twice the time (ncu: SMs active 56 %)
+    int slabs = num_sms() / n;
     if (slabs > (max_m + 63) / 64) slabs = (max_m + 63) / 64;
     if (slabs < 1) slabs = 1;
-    if (max_r <= 4) launch_k(skinny_atb_batch_kernel<4, 2>, dim3(slabs, n), 512, smem, stream, batch, slabs);
-    else launch_k(skinny_atb_batch_kernel<8, 2>, dim3(slabs, n), 512, smem, stream, batch, slabs);
+    if (max_r <= 4) launch_k(skinny_atb_batch_kernel<4, 8>, dim3(slabs, n), 512, smem, stream, batch, slabs);
+    else launch_k(skinny_atb_batch_kernel<8, 4>, dim3(slabs, n), 512, smem, stream, batch, slabs);
     DONE();
 }
 
@@ -675,13 +704,13 @@ extern "C" int cl_v2_inject_bwd(const void* dy, const float* up, const float* do
     if (!dy || !up || !dt_out || (dh && !down) || Ccols % 8) return set_error(CL_ERR_INVALID, "cl_v2_inject_bwd: bad args");
     if (Ccols > 1280) return set_error(CL_ERR_UNSUPPORTED, "cl_v2_inject_bwd: C <= 1280");
     const size_t smem = (size_t)Ccols * 8 * sizeof(float);
-    int blocks = (M + 7) / 8;
+    int blocks = (M + 15) / 16;
     if (blocks > num_sms() * 6) blocks = num_sms() * 6;
     const __nv_bfloat16* dd = reinterpret_cast<const __nv_bfloat16*>(dy);
     __nv_bfloat16* hh = reinterpret_cast<__nv_bfloat16*>(dh);
-    if (Ccols <= 512) launch_k(v2_inject_bwd_kernel<2>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols, nullptr, 0, 0);
-    else if (Ccols <= 768) launch_k(v2_inject_bwd_kernel<3>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols, nullptr, 0, 0);
-    else launch_k(v2_inject_bwd_kernel<5>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols, nullptr, 0, 0);
+    if (Ccols <= 512) launch_k(v2_inject_bwd_kernel<2, 4>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols, nullptr, 0, 0);
+    else if (Ccols <= 768) launch_k(v2_inject_bwd_kernel<3, 2>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols, nullptr, 0, 0);
+    else launch_k(v2_inject_bwd_kernel<5, 2>, blocks, 256, smem, stream, dd, up, down, alpha, dt_out, hh, M, Ccols, nullptr, 0, 0);
     DONE();
 }
 
@@ -691,13 +720,13 @@ extern "C" int cl_rank4_project_update(const void* x, const float* proj, const f
     if (!x || !proj || !upd || !t_out || !y || Ccols % 8 || rc < 0 || rc > 4) return set_error(CL_ERR_INVALID, "cl_rank4_project_update: bad args");
     if (Ccols > 1280) return set_error(CL_ERR_UNSUPPORTED, "cl_rank4_project_update: C <= 1280");
     const size_t smem = (size_t)Ccols * 8 * sizeof(float);
-    int blocks = (M + 7) / 8;
+    int blocks = (M + 15) / 16;
     if (blocks > num_sms() * 6) blocks = num_sms() * 6;
     const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
-    if (Ccols <= 512) launch_k(v2_inject_bwd_kernel<2>, blocks, 256, smem, stream, xx, proj, upd, alpha, t_out, yy, M, Ccols, uc, ldu, rc);
-    else if (Ccols <= 768) launch_k(v2_inject_bwd_kernel<3>, blocks, 256, smem, stream, xx, proj, upd, alpha, t_out, yy, M, Ccols, uc, ldu, rc);
-    else launch_k(v2_inject_bwd_kernel<5>, blocks, 256, smem, stream, xx, proj, upd, alpha, t_out, yy, M, Ccols, uc, ldu, rc);
+    if (Ccols <= 512) launch_k(v2_inject_bwd_kernel<2, 4>, blocks, 256, smem, stream, xx, proj, upd, alpha, t_out, yy, M, Ccols, uc, ldu, rc);
+    else if (Ccols <= 768) launch_k(v2_inject_bwd_kernel<3, 2>, blocks, 256, smem, stream, xx, proj, upd, alpha, t_out, yy, M, Ccols, uc, ldu, rc);
+    else launch_k(v2_inject_bwd_kernel<5, 2>, blocks, 256, smem, stream, xx, proj, upd, alpha, t_out, yy, M, Ccols, uc, ldu, rc);
     DONE();
 }
 

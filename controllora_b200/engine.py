@@ -145,7 +145,8 @@ class LoraSlot:
 
     def add(self, down: torch.Tensor, up: torch.Tensor, unscaled: bool = False) -> Adapter:
         r = down.shape[0]
-        assert down.shape == (r, self.K) and up.shape == (self.N, r)
+        # up may cover only the FIRST rows of a fused projection (q of a fused q|k|v weight): the other rows stay zero
+        assert down.shape == (r, self.K) and up.shape[1] == r and up.shape[0] <= self.N
         a = Adapter(down, up, self.rank, unscaled=unscaled)
         self.adapters.append(a)
         self.rank += r
@@ -224,7 +225,8 @@ def linear(ctx: Ctx, x: Var, lw: LinearW, *, residual: Optional[Var] = None, slo
                 for a in slot.adapters:
                     r = a.down.shape[0]
                     # dB[n, j] += s * sum_m dy[m, n] * t[m, j] ; dA[j, k] += s * sum_m e[m, j] * x[m, k]
-                    ops.SKINNY.add(t_out[:, a.col:], r, dy2, a.up_grad, 1, r, scale * inv_scale if a.unscaled else scale)
+                    dyu = dy2 if a.up.shape[0] == N else dy2[:, :a.up.shape[0]]     # fused q|k|v weight: the adapter owns the q columns
+                    ops.SKINNY.add(t_out[:, a.col:], r, dyu, a.up_grad, 1, r, scale * inv_scale if a.unscaled else scale)
                     ops.SKINNY.add(e[:, a.col:], r, x2, a.down_grad, K, 1, scale)
                 if on_slot_bwd is not None:
                     on_slot_bwd(e, t_out, dy2)
@@ -362,6 +364,33 @@ def attention(ctx: Ctx, q: Var, k: Var, v: Var, heads: int) -> Var:
                 give_tensor(k, dk)
             if v.rg:
                 give_tensor(v, dv)
+
+        ctx.tape.record(bwd)
+    return out
+
+
+def attention_qkv(ctx: Ctx, qkv: Var, heads: int) -> Var:
+    """Self-attention on a fused projection output qkv [B, N, 3C] = [q | k | v] (one GEMM, models.py:231,248,257 as a single
+    N = 3C launch): q / k / v are strided views, and the backward writes dq | dk | dv straight into ONE [B, N, 3C] buffer so
+    that the projection's dX is one K = 3C GEMM instead of three accumulating ones."""
+    B, Nt, C3 = qkv.data.shape
+    Cc = C3 // 3
+    d = Cc // heads
+    scale = d ** -0.5
+    q, k, v = qkv.data[..., :Cc], qkv.data[..., Cc:2 * Cc], qkv.data[..., 2 * Cc:]
+    need = ctx.tape is not None and qkv.rg
+    o, lse = ops.attention_fwd(q, k, v, heads, scale, need_lse=need)
+    out = Var(o, rg=qkv.rg)
+    if need:
+        def bwd():
+            do = out.grad
+            out.grad = None
+            if do is None:
+                return
+            g = torch.empty_like(qkv.data)
+            ops.attention_bwd(q, k, v, o, do, lse, heads, scale, need_dq=True, need_dkv=True,
+                              dq=g[..., :Cc], dk=g[..., Cc:2 * Cc], dv=g[..., 2 * Cc:])
+            give_tensor(qkv, g)
 
         ctx.tape.record(bwd)
     return out

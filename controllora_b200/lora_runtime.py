@@ -15,6 +15,7 @@ V2 control (models.py:369, 415):  h' = h + s Bc Ac [h ; c]  is a rank-r update o
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 from typing import Callable, Dict, List, Optional
 
@@ -25,6 +26,7 @@ from . import ops
 from .engine import Ctx, LoraSlot, Var
 
 BF16 = torch.bfloat16
+_FUSE_QKV = os.environ.get("CLB_FUSE_QKV", "1") != "0"
 
 
 def _is_v1(p) -> bool:
@@ -123,7 +125,11 @@ class LoraRuntime:
             C = L.to_q.w.shape[0]
             kv_in = L.to_k.w.shape[1]
             lp.post_add = any(post_add)
-            lp.q = LoraSlot(C, C, dev)
+            # V2 self-attention: k / v carry no LoRA (models.py:306-307) and read the same h' as q -> ONE fused q|k|v projection
+            # (N = 3C, the q adapter owns the first C output rows); CLB_FUSE_QKV=0 keeps three launches
+            # (the fused epilogue keeps the [3C, 4] up-table in shared memory: 3C * 16 B <= 48 KB, i.e. the 320 / 640-wide levels)
+            lp.fuse_qkv = bool(_FUSE_QKV and _is_v2(p) and not L.is_cross and len(chain) == 1 and not any(post_add) and 3 * C * 16 <= 49152)
+            lp.q = LoraSlot(3 * C if lp.fuse_qkv else C, C, dev)
             # post_add adapters read the projection's output: their `down` has C input features even for the text k / v
             lp.k = LoraSlot(C, C if lp.post_add else kv_in, dev)
             lp.v = LoraSlot(C, C if lp.post_add else kv_in, dev)
@@ -423,6 +429,15 @@ class LoraRuntime:
         on_q = None
         if lp.kind == "v1":
             on_q = lambda e, t_out, dy2: self._v1_q_bwd(ctx, lp, e, t_out, dy2)
+        if lp.kind == "v2" and ehs is None and lp.fuse_qkv:
+            # q | k | v of V2 self-attention as ONE GEMM over h' and ONE attention op on the fused buffer
+            if getattr(L, "w_qkv", None) is None:
+                w = torch.cat([L.to_q.w, L.to_k.w, L.to_v.w], 0).contiguous()                  # [3C, C]
+                L.w_qkv = E.LinearW(w, None, w.t().contiguous())
+            qkv = E.linear(ctx, hs, L.w_qkv, slot=lp.q)
+            o = E.attention_qkv(ctx, qkv, L.heads)
+            o = self._v2_inject(ctx, lp, o, 1)
+            return E.linear(ctx, o, L.to_out, slot=lp.out, residual=residual)
         if lp.kind == "v1cat":
             q = self._v1cat_q(ctx, lp, L, hs)
         else:
@@ -430,6 +445,15 @@ class LoraRuntime:
         kvc = ctx.stash.get("kv_cache") if (ehs is not None and ctx.tape is None) else None
         if kvc is not None and L.name in kvc:
             k, v = kvc[L.name]                # text-state projections are timestep-invariant inside a denoise loop
+        elif _FUSE_QKV and ehs is not None and (lp.k is None or lp.k.rank == 0) and (lp.v is None or lp.v.rank == 0) and not kv_in.rg:
+            # no adapters on k / v (V2, or plain attention) and nothing to differentiate: k | v of the text states as ONE GEMM
+            if getattr(L, "w_kv", None) is None:
+                L.w_kv = E.LinearW(torch.cat([L.to_k.w, L.to_v.w], 0).contiguous(), None, None)
+            kv = E.linear(ctx, kv_in, L.w_kv)
+            Cc = L.to_k.w.shape[0]
+            k, v = Var(kv.data[..., :Cc]), Var(kv.data[..., Cc:])
+            if kvc is not None:
+                kvc[L.name] = (k, v)
         else:
             k = E.linear(ctx, kv_in, L.to_k, slot=lp.k)
             v = E.linear(ctx, kv_in, L.to_v, slot=lp.v)

@@ -647,6 +647,25 @@ def cfg_dpmpp_step(eps2, latents, x0_prev, guidance, alpha_s, sigma_s, c_x, c_m0
           C.c_float(alpha_s), C.c_float(sigma_s), C.c_float(c_x), C.c_float(c_m0), C.c_float(c_m1))
 
 
+def softmax_rows(s, scale: float):
+    """p = softmax(scale * s, dim=-1) as bf16; s fp32 [R, C] contiguous (the VAE's one-head attention scores)."""
+    _req(s, torch.float32, "s")
+    assert s.dim() == 2 and s.is_contiguous()
+    p = torch.empty(s.shape, device=s.device, dtype=BF16)
+    _call("cl_softmax_rows", _p(s), _p(p), s.shape[0], s.shape[1], C.c_float(scale))
+    return p
+
+
+def channel_affine_nchw(x, mul: float, shift):
+    """y[n, c] = mul * x[n, c] + shift[c] on NCHW fp32."""
+    _req(x, torch.float32, "x")
+    _req(shift, torch.float32, "shift")
+    n, Cc = x.shape[0], x.shape[1]
+    y = torch.empty_like(x)
+    _call("cl_channel_affine_nchw", _p(x), _p(y), _p(shift), C.c_float(mul), n, Cc, C.c_int64(x.numel() // (n * Cc)))
+    return y
+
+
 def cast_matrix(src, I: int, J: int, s_i: int, s_j: int, alpha: float = 1.0, out=None):
     """out[i, j] = bf16(alpha * src.flat[i*s_i + j*s_j]) for a strided (sliced / transposed) view of an fp32 master weight."""
     _req(src, torch.float32, "src")

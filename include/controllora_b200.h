@@ -189,6 +189,11 @@ int cl_add_noise(const float* x0, const float* sqrt_ac, const float* sqrt_1mac, 
                  float* timesteps, int B, int per_image, void* stream);
 /* classifier-free-guidance combine + DDIM (eta = 0) update of the denoise loop, one fused elementwise kernel:
  * eps2 = [uncond | cond] noise predictions (each n_half floats), latents updated in place. */
+/* VAE (train_text_to_image_control_lora.py:753-754, pipeline decode): row softmax of the one-head AttentionBlock
+ * (p = softmax(scale * s) per row, fp32 in, bf16 out, cols % 4 == 0, <= 12288) and the post_quant_conv bias as a per-channel
+ * shift of NCHW fp32 latents (y = mul * x + shift[c]). */
+int cl_softmax_rows(const float* s, void* p, int rows, int cols, float scale, void* stream);
+int cl_channel_affine_nchw(const float* x, float* y, const float* shift, float mul, int n, int C, int64_t hw, void* stream);
 /* strided weight-space helpers of the dense (concat_hidden, models.py:208-214) control MLP: bf16 view / transpose of an fp32
  * master (dst[i*ld + j] = bf16(alpha * src[i*s_i + j*s_j])) and strided fp32 accumulation (dst[i*ld + j] += alpha * src[i*J + j]) */
 int cl_cast_matrix_bf16(const float* src, int64_t s_i, int64_t s_j, void* dst, int64_t ld, int I, int J, float alpha, void* stream);

@@ -336,3 +336,14 @@ def test_graphed_sampler_matches_eager_loop(scheduler, variant):
         print(f"graphed {scheduler}/{variant} call {call}: rel diff vs per-step loop {err:.3e}; launches/step {gs.launches_per_step}")
         assert err < 2e-3, (call, err)
     assert gs._graph is not None
+
+
+# ------------------------------------------------------------------------------------------------ VAE either side of the step
+@pytest.mark.parametrize("which", ["tiny", "full"])
+def test_vae_encode_decode_matches_oracle(which):
+    """`vae.encode(x).latent_dist` moments / sample and `vae.decode(z).sample` (train_...:753-754, pipeline decode) against the
+    fp32 oracle restatement of diffusers' AutoencoderKL: a small config and the SD-1.5 VAE shapes (128/256/512/512 channels,
+    one-head 512-wide mid attention) at 256x256.  bf16 activations through ~25 conv / norm layers: <= 2e-2 relative."""
+    from tests import check_vae
+
+    assert check_vae.run(which)

@@ -219,3 +219,26 @@ def test_device_noise_restatement_statistics_and_add_noise():
     assert torch.allclose(y[b], (ac[t[b]].sqrt() * x0[b] + (1 - ac[t[b]]).sqrt() * nz[b]).float(), atol=1e-6)
     v = SR.get_velocity(x0, nz, tt)
     assert torch.allclose(v[b], (ac[t[b]].sqrt() * nz[b] - (1 - ac[t[b]]).sqrt() * x0[b]).float(), atol=1e-6)
+
+
+def test_vae_oracle_matches_sd15_anchors():
+    """oracle/vae_ref.AutoencoderKL: exact parameter count of the SD-1.5 VAE (83 653 863) and the diffusers-0.13 key names the
+    published vae/diffusion_pytorch_model.* files use; encode -> decode round-trips shapes."""
+    import torch
+    from oracle import vae_ref as VR
+
+    m = VR.AutoencoderKL()
+    assert sum(p.numel() for p in m.parameters()) == 83_653_863
+    keys = set(m.state_dict().keys())
+    for k in ("encoder.conv_in.weight", "encoder.down_blocks.0.resnets.1.conv2.bias", "encoder.down_blocks.2.downsamplers.0.conv.weight",
+              "encoder.down_blocks.1.resnets.0.conv_shortcut.weight", "encoder.mid_block.attentions.0.query.weight",
+              "encoder.mid_block.attentions.0.proj_attn.bias", "encoder.conv_norm_out.weight", "quant_conv.weight", "post_quant_conv.bias",
+              "decoder.up_blocks.3.resnets.2.norm1.weight", "decoder.up_blocks.0.upsamplers.0.conv.weight", "decoder.conv_out.bias"):
+        assert k in keys, k
+    assert "encoder.down_blocks.3.downsamplers.0.conv.weight" not in keys and "decoder.up_blocks.3.upsamplers.0.conv.weight" not in keys
+    t = VR.init_synthetic_(VR.AutoencoderKL(block_out_channels=(32, 64), layers_per_block=1), 0)
+    with torch.no_grad():
+        z = t.encode_sample(torch.rand(1, 3, 32, 32) * 2 - 1, torch.zeros(1, 4, 16, 16))
+        assert z.shape == (1, 4, 16, 16) and t.decode(z).shape == (1, 3, 32, 32)
+        mean, logvar = t.encode_moments(torch.zeros(1, 3, 32, 32))
+        assert float(logvar.max()) <= 20.0 and float(logvar.min()) >= -30.0
