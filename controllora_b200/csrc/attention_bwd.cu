@@ -39,7 +39,6 @@ struct AttnBwdParams {
     __nv_bfloat16* dv; long long lddv;
     float scale, scale_log2;
     int num_blocks;       // key blocks (dkv) or query blocks (dq) per (b, h)
-    int poly_exp;         // every second exp2 of the softmax recomputation runs on the FMA pipe (exp2_poly) instead of MUFU
     int stats_all;        // dkv: LSE / delta of ALL query blocks are staged in shared memory once (no per-block CTA barrier)
 };
 
@@ -282,8 +281,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     const float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lsv[i]));
-                    const float x1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -lsv[i + 1]);
-                    const float p1 = p.poly_exp ? exp2_poly(x1) : fast_exp2(x1);
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -lsv[i + 1]));
                     const float d0 = p0 * fmaf(__uint_as_float(g[i]), p.scale, -dev[i]);
                     const float d1 = p1 * fmaf(__uint_as_float(g[i + 1]), p.scale, -dev[i + 1]);
                     pk[i >> 1] = pack_bf16x2(p0, p1);
@@ -458,8 +456,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     float p0 = fast_exp2(fmaf(__uint_as_float(s[j]), p.scale_log2, -lse));
-                    const float x1 = fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -lse);
-                    float p1 = p.poly_exp ? exp2_poly(x1) : fast_exp2(x1);
+                    float p1 = fast_exp2(fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -lse));
                     if (tail) {
                         if (kbase + c * 16 + j >= p.Nk) p0 = 0.f;
                         if (kbase + c * 16 + j + 1 >= p.Nk) p1 = 0.f;
@@ -639,8 +636,7 @@ attn_bwd_dq64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
                 float p0 = fast_exp2(fmaf(__uint_as_float(s[j]), p.scale_log2, -lse));
-                const float x1 = fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -lse);
-                    float p1 = p.poly_exp ? exp2_poly(x1) : fast_exp2(x1);
+                float p1 = fast_exp2(fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -lse));
                 if (kbase + j >= p.Nk) p0 = 0.f;
                 if (kbase + j + 1 >= p.Nk) p1 = 0.f;
                 const float d0 = p0 * fmaf(__uint_as_float(g[j]), p.scale, -delta_s);
@@ -818,8 +814,7 @@ attn_bwd_dkv64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
                 const float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lsv[i]));
-                const float x1 = fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -lsv[i + 1]);
-                    const float p1 = p.poly_exp ? exp2_poly(x1) : fast_exp2(x1);
+                const float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -lsv[i + 1]));
                 const float d0 = p0 * (__uint_as_float(g[i]) - dev[i]) * p.scale;
                 const float d1 = p1 * (__uint_as_float(g[i + 1]) - dev[i + 1]) * p.scale;
                 pk[i >> 1] = pack_bf16x2(p0, p1);
@@ -882,7 +877,6 @@ static int launch_attn_bwd(const cl_attn_bwd_args* a, cudaStream_t stream) {
     p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv); p.lddv = a->lddv;
     p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
     p.num_blocks = 0; p.stats_all = 0;
-    { static const int pe = [] { const char* e = getenv("CLB_ATTN_POLY_EXP"); return (e && e[0] == '0') ? 0 : 1; }(); p.poly_exp = pe; }
     {
         const long long total = (long long)a->B * a->Nq * a->H;
         int blocks = (int)((total + 255) / 256);

@@ -31,7 +31,6 @@ struct AttnFwdParams {
     float* lse;
     float scale_log2;
     int num_q_blocks;
-    int poly_exp;         // every second exp2 on the FMA pipe (exp2_poly) instead of MUFU
 };
 
 template <int DP, int BLOCK_N, int STAGES>
@@ -238,8 +237,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -m_new));
-                    const float x1 = fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -m_new);
-                    float p1 = p.poly_exp ? exp2_poly(x1) : fast_exp2(x1);
+                    float p1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -m_new));
                     if (tail) {
                         if (kbase + c * 32 + j >= p.Nk) p0 = 0.f;
                         if (kbase + c * 32 + j + 1 >= p.Nk) p1 = 0.f;
@@ -515,8 +513,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     float p0 = fast_exp2(fmaf(__uint_as_float(s[c][j]), p.scale_log2, -m_use));
-                    const float x1 = fmaf(__uint_as_float(s[c][j + 1]), p.scale_log2, -m_use);
-                    float p1 = p.poly_exp ? exp2_poly(x1) : fast_exp2(x1);
+                    float p1 = fast_exp2(fmaf(__uint_as_float(s[c][j + 1]), p.scale_log2, -m_use));
                     if (tail) {
                         if (kbase + c * 32 + j >= p.Nk) p0 = 0.f;
                         if (kbase + c * 32 + j + 1 >= p.Nk) p1 = 0.f;
@@ -594,7 +591,6 @@ static int launch_attn_fwd(const cl_attn_fwd_args* a, cudaStream_t stream) {
     p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.ldo = a->ldo; p.lse = a->lse;
     p.scale_log2 = a->scale * 1.4426950408889634f;
     p.num_q_blocks = (a->Nq + 127) / 128;
-    { static const int pe = [] { const char* e = getenv("CLB_ATTN_POLY_EXP"); return (e && e[0] == '0') ? 0 : 1; }(); p.poly_exp = pe; }
     static bool attr_done = false;
     if (!attr_done) {
         CL_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<DP, BLOCK_N, STAGES>,
@@ -619,7 +615,6 @@ static int launch_attn_fwd2(const cl_attn_fwd_args* a, cudaStream_t stream) {
     p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.ldo = a->ldo; p.lse = a->lse;
     p.scale_log2 = a->scale * 1.4426950408889634f;
     p.num_q_blocks = (a->Nq + 255) / 256;
-    { static const int pe = [] { const char* e = getenv("CLB_ATTN_POLY_EXP"); return (e && e[0] == '0') ? 0 : 1; }(); p.poly_exp = pe; }
     static bool attr_done = false;
     if (!attr_done) {
         CL_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));

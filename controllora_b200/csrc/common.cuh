@@ -377,8 +377,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f through the 1.5 * 2^23 magic add, 2^f on
 // [-0.5, 0.5] as a degree-4 polynomial (relative error < 5e-5, far below the bf16 rounding of P), n added to the exponent.
-// The attention softmax loops alternate this with ex2.approx so that the exp work is split between the MUFU pipe (16 / clk / SM)
-// and the FMA pipe (ncu round 2: XU 53-54 % busy in the forward and dQ kernels, the hottest pipe).
+// NOT used by the attention kernels: measured on B200 (round 2), alternating it with ex2.approx in the softmax loops made the
+// forward 1.7x SLOWER (494 -> 849 us at 4096^2, d = 40): the ~10 extra FMA / ALU instructions per element cost more issue
+// slots than the MUFU slot they free (the loops are issue-bound: ncu IPC 1.3-1.8 of 4 with XU at 53 %).  Kept for reference.
 __device__ __forceinline__ float exp2_poly(float x) {
     x = fmaxf(x, -125.0f);
     const float t = x + 12582912.0f;               // 0x4B400000: low mantissa bits of t = round(x)

@@ -827,10 +827,12 @@ static inline int gemm_block_k(const cl_gemm_args* a) { return (a->a_mode != 0 &
 // case; CLB_GEMM_2CTA=0 falls back to single-CTA tiles.
 static int gemm_cta_group(const cl_gemm_args* a, int BK, int num_m_blocks) {
     static const int pair_enabled = [] { const char* e = getenv("CLB_GEMM_2CTA"); return (e && e[0] == '0') ? 0 : 1; }();
+    // smallest K that runs as CTA pairs.  Round-2 measurement: a CTA ingests ~64 B/clk through TMA (about one 128-byte row per
+    // 2 clk), so a 1-CTA 128 x BN tile needs (128 + BN) rows per k-block against 2*BN clk of MMA work and is load-bound by 1.5x or
+    // more, while a pair stages 128 + BN/2 rows per CTA - balanced from BN = 256 up.  CLB_GEMM_PAIR_MINK overrides.
+    static const int pair_min_k = [] { const char* e = getenv("CLB_GEMM_PAIR_MINK"); return e ? atoi(e) : 2048; }();
     const bool small_k_resident = a->a_mode == 0 && a->K <= 320 && a->N % 160 == 0 && a->M >= 8192;
-    // K >= 2048: measured on B200, pairs cut the L2->SM traffic by 1.3-1.5x everywhere but only pay for their cluster
-    // launch / cross-CTA signalling on deep-K tiles (convs, FFN-down); short-K GEMMs stay on single CTAs.
-    return (pair_enabled && a->lora_up == nullptr && BK == 64 && !small_k_resident && num_m_blocks >= 2 && a->K >= 2048) ? 2 : 1;
+    return (pair_enabled && a->lora_up == nullptr && BK == 64 && !small_k_resident && num_m_blocks >= 2 && a->K >= pair_min_k) ? 2 : 1;
 }
 
 static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool allow_split) {
@@ -842,16 +844,17 @@ static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool
 #ifdef CLB_TIMELINE
     if (a->block_n != 0) return TilePlan{a->block_n, 1};     // probe builds: any instantiated width, as given
 #endif
-    if (a->block_n != 0) best.bn = a->block_n;
-    else if (!lora && a->a_mode == 0 && a->K <= 320 && a->N % 160 == 0 && a->M >= 8192) best.bn = 160;  // weights stay smem-resident
+    int fixed_bn = 0;                                         // tile width imposed by the caller / the resident rule
+    if (a->block_n != 0) fixed_bn = a->block_n;
+    else if (!lora && a->a_mode == 0 && a->K <= 320 && a->N % 160 == 0 && a->M >= 8192) fixed_bn = 160;  // weights stay smem-resident
     long long best_cost = -1;
     static const int wide_enabled = [] { const char* e = getenv("CLB_GEMM_BN320"); return (e && e[0] == '0') ? 0 : 1; }();
     static const int cands[6] = {320, 256, 160, 128, 64, 32};
     for (int ci = 0; ci < 6; ++ci) {
         const int bn = cands[ci];
-        if (best.bn != 0 && bn != best.bn) continue;           // fixed by the caller / the resident rule
+        if (fixed_bn != 0 && bn != fixed_bn) continue;
         if (bn == 320 && (cg != 2 || lora || !wide_enabled || a->N % 320 != 0)) continue;   // CTA-pair, no-LoRA tile
-        if (best.bn == 0) {
+        if (fixed_bn == 0) {
             if (a->N % bn != 0) continue;
             if (lora && bn > 160) continue;
             if (BK == 32 ? (bn > 128) : (bn < 64)) continue;   // instantiated variants
@@ -868,9 +871,13 @@ static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool
         const int kbps = (nkb + splits - 1) / splits;
         splits = (nkb + kbps - 1) / kbps;
         const long long waves = ((long long)tiles * splits + sms - 1) / sms;
-        // rows a CTA pulls from L2 per k-block; the 320-column tile has ONE accumulator buffer, so its epilogue (~ 5 k-blocks
-        // worth of time) is not hidden behind the next tile's main loop
-        const long long cost = waves * ((128 + bn / cg + 32) * (long long)kbps + (bn == 320 ? 5 * (128 + 160 + 32) : 0));
+        // Cost in clocks (round-2 measurements): a CTA ingests ~one 128-byte operand row per 2 clk through TMA, so a k-block costs
+        // max(2 * rows staged by the CTA, MMA time = 2 * bn) + ~100; a tile additionally pays its exposed epilogue (the 320-column
+        // tile has ONE accumulator buffer: ~3000 clk, otherwise ~300), and a split-K plan its finishing launch (~12000 clk).
+        // (Round 1 compared only the staged rows - and, through a bookkeeping bug, never looked past the first valid width.)
+        const long long t_load = 2LL * (128 + bn / cg), t_mma = 2LL * bn;
+        const long long t_kb = (t_load > t_mma ? t_load : t_mma) + 100;
+        const long long cost = waves * (t_kb * kbps + (bn == 320 ? 3000 : 300)) + (splits > 1 ? 12000 : 0);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = {bn, splits}; }
     }
     if (best_cost < 0) {   // no candidate divides N: tail tiles
@@ -960,6 +967,11 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     const TilePlan plan = plan_tiles(a, BK, p.num_m_blocks, a->split_k > 1);
     const int bn_sel = plan.bn;
     const int cg = (bn_sel >= 64) ? gemm_cta_group(a, BK, p.num_m_blocks) : 1;
+    {
+        static const int dbg = [] { const char* e = getenv("CLB_GEMM_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
+        if (dbg) fprintf(stderr, "cl_gemm M=%d N=%d K=%d mode=%d lora=%d -> bn=%d cg=%d splits=%d (asked bn=%d split_k=%d)\n", a->M, a->N, a->K,
+                         a->a_mode, lora ? 1 : 0, bn_sel, cg, plan.splits, a->block_n, a->split_k);
+    }
     p.num_n_blocks = (a->N + bn_sel - 1) / bn_sel;
     p.splits = 1;
     p.kb_per_split = p.num_k_blocks;

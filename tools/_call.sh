@@ -1,7 +1,6 @@
 set -x
-timeout 600 python -m pytest tests -m gpu -q -x -k "attention or lora or train or unet" > gpurun_out/r2c10_tests.log 2>&1; echo tests=$?; tail -3 gpurun_out/r2c10_tests.log | cut -c1-200
-timeout 100 python tools/check_ops2.py attn_perf2 2>&1 | tail -5
-CLB_ATTN_POLY_EXP=0 timeout 100 python tools/check_ops2.py attn_perf2 2>&1 | tail -5
-timeout 300 python tools/bw_bench.py --iters 5 2>&1 | grep -i "skinny" | cut -c1-110
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-aux > gpurun_out/r2c10_bench.log 2>&1; tail -1 gpurun_out/r2c10_bench.log | cut -c1-300
-CLB_ATTN_POLY_EXP=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-aux > gpurun_out/r2c10_bench_nopoly.log 2>&1; tail -1 gpurun_out/r2c10_bench_nopoly.log | cut -c1-300
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2c13_tests.log 2>&1; echo tests=$?; tail -4 gpurun_out/r2c13_tests.log | cut -c1-200
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2c13_smoke.log 2>&1; tail -2 gpurun_out/r2c13_smoke.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2c13_bench.log 2>&1; tail -1 gpurun_out/r2c13_bench.log | cut -c1-400
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_tc_kernel --launch-skip 1500 -c 480 --csv --log-file gpurun_out/r2c13_gemm_dram.csv python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-roofline --no-aux > gpurun_out/r2c13_ncu_dram.log 2>&1; tail -1 gpurun_out/r2c13_ncu_dram.log | cut -c1-120
+timeout 200 python tools/check_gemm.py perf 2>&1 | grep perf > gpurun_out/r2c13_gemm_perf.log; cat gpurun_out/r2c13_gemm_perf.log
