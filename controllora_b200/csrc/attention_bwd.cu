@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#define CLB_FAMILY 2      // CLB_PDL_MASK bit of this file's kernels
 #include "host_common.h"
 #include "../../include/controllora_b200.h"
 

@@ -296,6 +296,9 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v
 
 // Per-warpgroup register re-budgeting (all 4 warps of the warpgroup execute it): producer warps give registers back,
 // math warps take them.
+// named CTA barriers (id 1..15): arrive = announce and continue, sync = wait for `count` threads
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -354,6 +357,13 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     return __bfloat1622float2(t);
 }
 
+// (a, b) -> bf16x2 of the rounded values and bf16x2 of the rounding residuals: a ~= hi.x + lo.x to ~2^-17 relative
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(a, b);
+    const float2 h = unpack_bf16x2(hi);
+    lo = pack_bf16x2(a - h.x, b - h.y);
+}
+
 // explicit shared-space vector accesses (a generic pointer derived through integer casts makes nvcc emit the slower
 // generic LD/ST; these take the 32-bit shared address)
 __device__ __forceinline__ void st_shared_f4(uint32_t addr, float4 v) {
@@ -366,6 +376,12 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 }
 __device__ __forceinline__ void st_shared_u4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // 2^x on the MUFU pipe (ex2.approx.ftz: one instruction; exp2(-inf) = +0)

@@ -6,9 +6,13 @@
 //   warp 0      TMA producer   (A tile 128x64, B tile BNx64 [+16 LoRA-down rows], 128B swizzle, mbarrier ring)
 //   warp 1      MMA issuer     (one elected thread, tcgen05.mma cta_group::1, M=128, N=BN[+16], K=16)
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue       (tcgen05.ld -> LoRA rank-r update in fp32 -> smem transpose -> bias/residual ->
-//                               coalesced global stores); two TMEM accumulator buffers so the epilogue of tile i
-//                               overlaps the main loop of tile i+1.
+//   warps 4-11  epilogue       (tcgen05.ld -> smem transpose / TMA store -> bias/residual -> coalesced global stores); two
+//                               TMEM accumulator buffers so the epilogue of tile i overlaps the main loop of tile i+1.
+// LoRA (EXT = 16): the 16 extra B rows (bf16 hi / lo halves of the rank-r down matrix) make the main loop produce
+// t = x A^T in 16 extra accumulator columns; four epilogue warps read them (+ t_add, -> t_out, * scale), split t into bf16
+// hi / lo and write it as a 128 x 32 K-major operand into shared memory, next to the same split of the up matrix, and the MMA
+// warp adds  t B^T  to the accumulator with one (rank <= 4) or two (rank <= 8) more tcgen05.mma (K = 16): the rank-r update
+// costs the tensor pipe ~100 clk per tile instead of 128 FMAs + 32 broadcast shared loads per thread and granule.
 // The A operand is either a plain row-major matrix or an NHWC image read as 3x3 windows (implicit GEMM: the
 // "im2col" is done by TMA box loads with shifted coordinates, out-of-bounds zero fill == conv zero padding).
 //
@@ -22,11 +26,16 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#define CLB_FAMILY 1      // CLB_PDL_MASK bit of this file's kernels
 #include "host_common.h"
 #include "../../include/controllora_b200.h"
 
 namespace clb {
 
+#ifndef CLB_REGS_CTRL
+#define CLB_REGS_CTRL 56     // setmaxnreg of the producer / MMA / allocator warpgroup
+#define CLB_REGS_EPI 224     // ... and of the two epilogue warpgroups (128 * 56 + 256 * 224 = 64512 = 384 * 168, the launch allocation)
+#endif
 static constexpr int BLOCK_M = 128;
 // BLOCK_K (template BK): 64 bf16 = 128 B rows with the 128B swizzle, or 32 bf16 = 64 B rows with the 64B swizzle
 // (used for the 32-channel layers of the hint encoder, where a 3x3 tap only offers 32 contiguous K elements).
@@ -60,12 +69,14 @@ struct GemmParams {
     int out_fp32;
     int tma_store;    // bf16 output through per-warp TMA stores of 32x32 sub-tiles (new epilogue); 0 = per-lane global stores
     int ew, eh, en;   // conv: the 32 rows of a TMEM lane quadrant as a box of the output image (ew * eh * en == 32)
+    int epi_bf16;     // per-lane store epilogue: nothing is added to the accumulator -> transpose in bf16 (host-checked alignment)
     int b_resident;   // B (weights) tile of this CTA's n-block stays in smem for the CTA lifetime (small K)
     // split-K (streaming mode only): tile space is (m, n, split); split s covers k-blocks [s*kb_per_split, ...) and stores
     // its fp32 partial tile to split_ws[s][M][N]; splitk_finish_kernel sums the partials and applies the epilogue.
     int splits, kb_per_split;
     float* split_ws;
     int dbg_reps;     // CLB_TIMELINE builds only: every k-step's MMAs are issued 1 + dbg_reps times (tensor-pipe rate probe)
+    int dbg_id;       // CLB_TIMELINE builds only: launch ordinal (mod 64) for the globaltimer entry / exit record
 };
 
 #ifdef CLB_TIMELINE
@@ -75,6 +86,13 @@ struct GemmParams {
 // cycles each, which distorted the very thing it measured)
 __device__ unsigned long long g_tl[160 * 256 * 2];
 __device__ unsigned int g_tl_n[160];
+// globaltimer (ns) per launch ordinal: [id][0] = first CTA entry, [1] = last CTA entry, [2] = first CTA exit, [3] = last CTA exit
+__device__ unsigned long long g_gt[64 * 4];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void tl_rec(int tag, int& slot) {
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -87,8 +105,14 @@ __device__ __forceinline__ void tl_rec(int tag, int& slot) {
     }
 }
 #define TL(tag) tl_rec(tag, tl_slot)
+#if CLB_TIMELINE >= 2
+#define TLK(tag) tl_rec(tag, tl_slot)      // per-k-block events (perturb the producer / MMA cadence: level 2 only)
+#else
+#define TLK(tag)
+#endif
 #else
 #define TL(tag)
+#define TLK(tag)
 #endif
 
 // tile -> (m_blk, n_blk).  Streaming mode: n fastest (CTAs that run concurrently share the A rows through L2).
@@ -193,15 +217,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* smem_b = smem_a + num_stages * A_STAGE_BYTES;
     const int b_slots = p.b_resident ? p.num_k_blocks : num_stages;
     uint8_t* smem_stage = smem_b + b_slots * Cfg::B_STAGE_BYTES;             // epilogue staging
-    float* smem_up = reinterpret_cast<float*>(smem_stage + EPI_STAGING_BYTES);  // [N][rp] when LoRA is on
-    const int up_floats = (p.lora_up != nullptr) ? p.N * p.lora_rp : 0;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_up) + ((up_floats * 4 + 15) & ~15));
+    // LoRA: t (128 x 32 bf16, 64-byte rows, 64B swizzle) and the up matrix of the tile's n-block (BN x 32 bf16, same layout)
+    uint8_t* smem_text = smem_stage + EPI_STAGING_BYTES;
+    uint8_t* smem_bext = smem_text + (EXT ? BLOCK_M * 64 : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bext + (EXT ? BN * 64 : 0));
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + num_stages;
     uint64_t* tmem_full = bars + 2 * num_stages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* b_full = tmem_empty + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full + 1);
+    uint64_t* ext_ready = b_full + 1;       // [2] t operand of the buffer's tile is in shared memory (4 converting warps)
+    uint64_t* tmem_full2 = ext_ready + 2;   // [2] accumulator incl. the rank-r update is complete
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full2 + 2);
 
     // warp index made provably warp-uniform (shuffle from lane 0): the producer / MMA warps below run their loops with
     // all 32 lanes converged and elect one lane only around the TMA / tcgen05 instructions, so that ptxas keeps addresses,
@@ -214,40 +241,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int tl_slot = 0;
 #endif
 
-    if (warp_idx == 0 && lane == 0) {
-        TL(1);   // kernel entry
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        if (EXT) tma_prefetch_desc(&tmE);
-        if (p.tma_store) tma_prefetch_desc(&tmD);
-    }
-    if (warp_idx == 1 && lane == 0) {
-        for (int i = 0; i < num_stages; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+    // Prologue.  The producer warp initialises the barriers and (single-CTA tiles) does not wait for the rest of the CTA: it
+    // announces itself on a named barrier and starts streaming operands while warp 2 allocates TMEM, so the first TMA round trip (~1 k clk) overlaps the ~1.5 k clk of set-up instead of following it.
+    if (warp_idx == 0) {
+        if (lane == 0) {
+#ifdef CLB_TIMELINE
+            { const unsigned long long t = gtime(); atomicMin(&g_gt[p.dbg_id * 4], t); atomicMax(&g_gt[p.dbg_id * 4 + 1], t); }
+#endif
+            TL(1);   // kernel entry
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            if (EXT) tma_prefetch_desc(&tmE);
+            if (p.tma_store) tma_prefetch_desc(&tmD);
+            for (int i = 0; i < num_stages; ++i) {
+                mbar_init(&full_bar[i], 1);
+                mbar_init(&empty_bar[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&tmem_full[i], 1);
+                mbar_init(&tmem_empty[i], CG * NUM_EPI_WARPS);   // pair: both CTAs' epilogues release the leader's barrier
+                mbar_init(&ext_ready[i], 4);
+                mbar_init(&tmem_full2[i], 1);
+            }
+            mbar_init(b_full, 1);
+            fence_barrier_init();
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], CG * NUM_EPI_WARPS);   // pair: both CTAs' epilogues release the leader's barrier
-        }
-        mbar_init(b_full, 1);
-        fence_barrier_init();
+        __syncwarp();
     }
     if (warp_idx == 2) {
         if (CG == 2) { tmem_alloc_cg2(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
         else { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     pdl_wait();   // prologue above touched only smem / TMEM / kernel params
-    // LoRA-up table -> smem (persistent for the CTA lifetime)
-    // (16-byte loads: the scalar version of this copy was three dependent global-load round trips per thread, ~1.2 us)
-    for (int i = threadIdx.x; i < up_floats / 4; i += NUM_THREADS)
-        reinterpret_cast<float4*>(smem_up)[i] = __ldg(reinterpret_cast<const float4*>(p.lora_up) + i);
-    tc_fence_before();
-    if (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / TMA credit
-    else __syncthreads();
-    tc_fence_after();
+#ifdef CLB_NO_EARLY_PRODUCER
+    constexpr bool kEarlyProducer = false;
+#else
+    constexpr bool kEarlyProducer = true;
+#endif
+    if (CG == 2 || !kEarlyProducer) {
+        tc_fence_before();
+        if (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / TMA credit
+        else __syncthreads();
+        tc_fence_after();
+    } else if (warp_idx == 0) {
+        __threadfence_block();
+        named_bar_arrive(1, NUM_THREADS);   // barriers are initialised; the producer runs ahead
+    } else {
+        tc_fence_before();
+        named_bar_sync(1, NUM_THREADS);
+        tc_fence_after();
+    }
     const uint32_t tmem_base = *tmem_ptr_smem;
-
+    // register re-balancing between the warpgroups: the producer / MMA / allocator warps need few registers, the epilogue
+    // warps hold two 32-column granules plus their row operands (128 x 56 + 256 x 224 <= 64 K registers)
+    if (warp_idx < 4) {
+#ifndef CLB_NO_SETMAXNREG
+    setmaxnreg_dec<CLB_REGS_CTRL>();
+#endif
     if (warp_idx == 0) {
         // ===================================================== TMA producer (whole warp converged, one elected lane issues)
         {
@@ -278,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int kb1 = ti.kb_end();
                 for (int kb = ti.kb_begin(); kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (lane == 0 && kb < 10) TL(11);   // producer: ring slot acquired
+                    if (lane == 0 && kb < 10) TLK(11);   // producer: ring slot acquired
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
                     // A-operand coordinates of this k-block (conv: the 3x3 tap and channel block)
@@ -318,7 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     __syncwarp();
-                    if (lane == 0 && kb < 10) TL(12);   // producer: loads of this k-block issued
+                    if (lane == 0 && kb < 10) TLK(12);   // producer: loads of this k-block issued
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -344,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);      // all 32 lanes poll: keeps the loop convergent
                     tc_fence_after();
-                    if (lane == 0) { if (kb == kb0) TL(22); else if (kb < kb0 + 10) TL(24); }
+                    if (lane == 0) { if (kb == kb0) TL(22); else if (kb < kb0 + 10) TLK(24); }
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
                     const uint32_t sb = smem_u32(smem_b + (p.b_resident ? kb : stage) * Cfg::B_STAGE_BYTES);
                     const uint32_t first = (kb != kb0) ? 1u : 0u;
@@ -377,7 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (CG == 2) tc_commit_cg2(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
                     }
                     __syncwarp();
-                    if (lane == 0 && kb < kb0 + 10) TL(25);   // mma: k-block issued + committed
+                    if (lane == 0 && kb < kb0 + 10) TLK(25);   // mma: k-block issued + committed
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
                 // accumulator complete -> epilogue (pair: each CTA drains its own 128 rows)
@@ -385,19 +435,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (CG == 2) tc_commit_cg2(&tmem_full[buf], 3); else tc_commit(&tmem_full[buf]);
                 }
                 __syncwarp();
+                if (EXT) {
+                    // rank-r update on the tensor core: the epilogue turned the 16 extra accumulator columns into the K-major
+                    // operand t (bf16 hi | lo); D[:, 0:BN] += t * up^T with K = 16 per instruction
+                    mbar_wait(&ext_ready[buf], buf_phase);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        constexpr uint32_t idesc_x = make_idesc_bf16(BLOCK_M, BN, 0, 0);
+                        const uint32_t ta = smem_u32(smem_text), tb = smem_u32(smem_bext);
+                        const int nk = (p.lora_rp > 4) ? 2 : 1;
+                        for (int k = 0; k < nk; ++k)
+                            tc_mma_ss(d_tmem, make_smem_desc(ta + k * 32, 16, 512, 4), make_smem_desc(tb + k * 32, 16, 512, 4), idesc_x, 1u);
+                        tc_commit(&tmem_full2[buf]);
+                    }
+                    __syncwarp();
+                }
                 if (lane == 0) TL(23);  // mma: all MMAs of the tile issued
             }
         }
-    } else if (warp_idx >= 4) {
+    }
+    } else {
+#ifndef CLB_NO_SETMAXNREG
+        setmaxnreg_inc<CLB_REGS_EPI>();
+#endif
         // ===================================================== epilogue
         const int ew = warp_idx - 4;              // 0..7
         const int quad = warp_idx & 3;            // TMEM lane quadrant this warp may access
         const int half = ew >> 2;                 // the two warps of a quadrant split the column granules
         const uint32_t stg_addr = smem_u32(smem_stage + ew * 32 * STAGE_ROW_BYTES);
         const int rp = p.lora_rp;
-        const uint32_t up_addr = smem_u32(smem_up);
         int it = 0;
         int epi_gran = 0;                          // granules this warp has stored through TMA (staging buffer = parity)
+        int bext_n_blk = -1;                       // n-block whose up matrix is in smem_bext
         for (TileIter ti(p, sched_cta, sched_n, sched_m); ti.valid(); ti.next(), ++it) {
             const int m_blk = (CG == 2) ? ti.m_blk * 2 + cta_rank : ti.m_blk;
             const int n_blk = ti.n_blk;
@@ -406,36 +475,105 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // rows: phase-1 thread owns row (quad*32 + lane); phase-2 lane handles rows (lane>>3) + 4*i
             int my_m, my_grp;
             decode_row(p, m_blk, quad * 32 + lane, my_m, my_grp);
-
-            if (ew == 0 && lane == 0) TL(30);  // epilogue: waiting for the accumulator
-            mbar_wait(&tmem_full[buf], buf_phase);
-            tc_fence_after();
-            if (ew == 0 && lane == 0) TL(31);  // epilogue: accumulator ready
             const uint32_t t_base = tmem_base + (uint32_t(quad * 32) << 16) + buf * Cfg::BUF_COLS;
 
-            float tl[8];
+            if (EXT && half == 0) {
+                // ---- LoRA: the four half-0 warps (one per TMEM lane quadrant, 128 threads) prepare the operands of the rank-r MMA
+                // up matrix of this n-block -> smem_bext (only when the n-block changed; the previous tile's rank-r MMA has
+                // retired: its commit preceded this tile's main-loop commit).  Row n: 64 bytes = 4 chunks of 8 bf16,
+                // rank <= 4: [hi hi | lo lo | 0 | 0], rank <= 8: [hi | hi | lo | lo]; chunk c of row n sits at c ^ ((n >> 1) & 3).
+                if (n_blk != bext_n_blk) {
+                    bext_n_blk = n_blk;
+                    for (int n = quad * 32 + lane; n < BN; n += 128) {
+                        const int ng = n_blk * BN + n;
+                        float u[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tl[j] = 0.f;
-            if (EXT) {
-                uint32_t e[16];
-                tmem_ld_32x16(t_base + BN, e);
-                tc_wait_ld();
+                        for (int j = 0; j < 8; ++j) u[j] = 0.f;
+                        if (ng < p.N) {
+                            const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.lora_up + (long long)ng * rp));
+                            u[0] = a4.x; u[1] = a4.y; u[2] = a4.z; u[3] = a4.w;
+                            if (rp > 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.lora_up + (long long)ng * rp + 4));
+                                u[4] = b4.x; u[5] = b4.y; u[6] = b4.z; u[7] = b4.w;
+                            }
+                        }
+                        uint32_t hi[4], lo[4];     // bf16x2 pairs (j, j+1)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) tl[j] = __uint_as_float(e[j]) + __uint_as_float(e[j + 8]);
+                        for (int j = 0; j < 4; ++j) split_bf16x2(u[2 * j], u[2 * j + 1], hi[j], lo[j]);
+                        uint4 c0, c1, c2, c3;
+                        if (rp <= 4) {
+                            c0 = make_uint4(hi[0], hi[1], hi[0], hi[1]); c1 = make_uint4(lo[0], lo[1], lo[0], lo[1]);
+                            c2 = make_uint4(0u, 0u, 0u, 0u); c3 = c2;
+                        } else {
+                            c0 = make_uint4(hi[0], hi[1], hi[2], hi[3]); c1 = c0;
+                            c2 = make_uint4(lo[0], lo[1], lo[2], lo[3]); c3 = c2;
+                        }
+                        const uint32_t row = smem_u32(smem_bext) + n * 64;
+                        const int sw = (n >> 1) & 3;
+                        st_shared_u4(row + ((0 ^ sw) << 4), c0); st_shared_u4(row + ((1 ^ sw) << 4), c1);
+                        st_shared_u4(row + ((2 ^ sw) << 4), c2); st_shared_u4(row + ((3 ^ sw) << 4), c3);
+                    }
+                }
+                if (ew == 0 && lane == 0) TL(30);  // epilogue: waiting for the accumulator
+                mbar_wait(&tmem_full[buf], buf_phase);
+                tc_fence_after();
+                if (ew == 0 && lane == 0) TL(31);  // epilogue: accumulator ready
+                // t = x A^T from the 16 extra columns (hi + lo halves of the down matrix), + t_add, -> t_out, * scale
+                float tl[8];
+                {
+                    uint32_t e[16];
+                    tmem_ld_32x16(t_base + BN, e);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) tl[j] = __uint_as_float(e[j]) + __uint_as_float(e[j + 8]);
+                }
                 if (my_m >= 0) {
                     if (p.t_add != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             if (j < rp) tl[j] += p.t_add[(long long)my_m * rp + j];
                     }
-                    if (p.t_out != nullptr && n_blk == 0 && half == 0) {
+                    if (p.t_out != nullptr && n_blk == 0) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             if (j < rp) p.t_out[(long long)my_m * rp + j] = tl[j];
                     }
                 }
+                {
+                    uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) tl[j] *= p.lora_scale;
+                    for (int j = 0; j < 4; ++j) split_bf16x2(tl[2 * j] * p.lora_scale, tl[2 * j + 1] * p.lora_scale, hi[j], lo[j]);
+                    // row r = quad*32 + lane of the K-major t operand: rank <= 4: [hi lo | hi lo | 0 | 0]  (k 0-3 t_hi, 4-7 t_lo, 8-11 t_hi,
+                    // 12-15 t_lo against up [hi hi | lo lo]), rank <= 8: [hi | lo | hi | lo] against up [hi | hi | lo | lo]
+                    uint4 c0, c1, c2, c3;
+                    if (rp <= 4) {
+                        c0 = make_uint4(hi[0], hi[1], lo[0], lo[1]); c1 = c0;
+                        c2 = make_uint4(0u, 0u, 0u, 0u); c3 = c2;
+                    } else {
+                        c0 = make_uint4(hi[0], hi[1], hi[2], hi[3]); c1 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        c2 = c0; c3 = c1;
+                    }
+                    const int r = quad * 32 + lane;
+                    const uint32_t row = smem_u32(smem_text) + r * 64;
+                    const int sw = (r >> 1) & 3;
+                    st_shared_u4(row + ((0 ^ sw) << 4), c0); st_shared_u4(row + ((1 ^ sw) << 4), c1);
+                    st_shared_u4(row + ((2 ^ sw) << 4), c2); st_shared_u4(row + ((3 ^ sw) << 4), c3);
+                }
+                fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ext_ready[buf]);
+                if (ew == 0 && lane == 0) TL(38);  // epilogue: LoRA operands handed to the MMA warp
+            }
+            if (!EXT) {
+                if (ew == 0 && lane == 0) TL(30);  // epilogue: waiting for the accumulator
+                mbar_wait(&tmem_full[buf], buf_phase);
+                tc_fence_after();
+                if (ew == 0 && lane == 0) TL(31);  // epilogue: accumulator ready
+            } else {
+                mbar_wait(&tmem_full2[buf], buf_phase);
+                tc_fence_after();
+                if (ew == 0 && lane == 0) TL(39);  // epilogue: accumulator incl. rank-r update ready
             }
 
             if (p.tma_store == 4) {
@@ -491,25 +629,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         f[8 * j] += a0.x; f[8 * j + 1] += a0.y; f[8 * j + 2] += a1.x; f[8 * j + 3] += a1.y;
                         f[8 * j + 4] += a2.x; f[8 * j + 5] += a2.y; f[8 * j + 6] += a3.x; f[8 * j + 7] += a3.y;
                     }
-                    if (EXT) {
-                        if (rp == 4) {
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) {
-                                const int n = min(col0 + c, p.N - 1);
-                                const float4 u = ld_shared_f4(up_addr + n * 16);
-                                f[c] += tl[0] * u.x + tl[1] * u.y + tl[2] * u.z + tl[3] * u.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) {
-                                const int n = min(col0 + c, p.N - 1);
-                                const float4 u0 = ld_shared_f4(up_addr + n * 32);
-                                const float4 u1 = ld_shared_f4(up_addr + n * 32 + 16);
-                                f[c] += tl[0] * u0.x + tl[1] * u0.y + tl[2] * u0.z + tl[3] * u0.w + tl[4] * u1.x +
-                                        tl[5] * u1.y + tl[6] * u1.z + tl[7] * u1.w;
-                            }
-                        }
-                    }
                     tc_wait_ld();
 #pragma unroll
                     for (int c = 0; c < 32; ++c) f[c] += __uint_as_float(v[c]);
@@ -552,107 +671,157 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     ++epi_gran;
                 }
-            } else
-            for (int g = half; g < BN / 32; g += 2) {
-                const int col0 = n_blk * BN + g * 32;   // first global column of this granule
-                if (col0 >= p.N) break;                   // (warp-uniform) nothing to store
-                uint32_t v[32];
-                tmem_ld_32x32(t_base + g * 32, v);
-                tc_wait_ld();
-                float f[32];
+            } else {
+                // ---- per-lane store epilogue (fp32 outputs, split-K partials, smem-resident short-K tiles).  The warp's granules
+                //      (g = half, half + 2, ...) are software-pipelined: the TMEM load of the next granule and the global loads of
+                //      this one (residual, row bias) are in flight while the LoRA update / transpose / stores of this one run -
+                //      with two epilogue warps per scheduler the old load -> wait -> use chain ran at ~0.3 IPC.
+                auto gran_ok = [&](int g) { return g < BN / 32 && n_blk * BN + g * 32 < p.N; };   // warp-uniform
+                const bool bf16_stage = p.epi_bf16 != 0;
+                auto process = [&](uint32_t (&v)[32], const int g) {
+                    const int col0 = n_blk * BN + g * 32;   // first global column of this granule
+                    // phase-2 coordinates and operands first (lane -> row (lane>>3) + 4*i, chunk lane&7): loads issued before use
+                    const int ch = lane & 7;
+                    const int n0 = col0 + ch * 4;
+                    const bool col_ok = n0 < p.N;  // N % 4 == 0 is enforced on the host
+                    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (col_ok && p.bias != nullptr && p.splits == 1) bz = *reinterpret_cast<const float4*>(p.bias + n0);
+                    int mrow[8];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]);
-                if (EXT) {
-                    if (rp == 4) {
+                    for (int i = 0; i < 8; ++i) {
+                        const int m_r = __shfl_sync(0xffffffffu, my_m, (lane >> 3) + 4 * i);   // every lane takes part in the shuffle
+                        mrow[i] = col_ok ? m_r : -1;
+                    }
+                    uint2 rr[8];
+                    const bool has_rb = p.row_bias != nullptr, has_res = p.residual != nullptr;
+                    if (has_res) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const int n = min(col0 + c, p.N - 1);
-                            const float4 u = ld_shared_f4(up_addr + n * 16);
-                            f[c] += tl[0] * u.x + tl[1] * u.y + tl[2] * u.z + tl[3] * u.w;
+                        for (int i = 0; i < 8; ++i) {
+                            rr[i] = make_uint2(0u, 0u);
+                            if (mrow[i] >= 0) rr[i] = *reinterpret_cast<const uint2*>(p.residual + (long long)mrow[i] * p.ldr + n0);
+                        }
+                    }
+                    if (ew == 0 && lane == 0) TL(33);  // epilogue: granule in registers, phase-2 loads issued
+                    float f[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]);
+                    // ---- phase 1 -> smem (row = lane, 8 chunks of 16 B, XOR swizzle keeps both phases conflict-free)
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_f4(stg_addr + lane * STAGE_ROW_BYTES + ((j ^ (lane & 7)) << 4),
+                                     make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                    __syncwarp();
+                    if (ew == 0 && lane == 0) TL(35);  // epilogue: staged
+                    // ---- phase 2: coalesced bias / residual / store
+                    float4 q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = (lane >> 3) + 4 * i;
+                        q[i] = ld_shared_f4(stg_addr + r * STAGE_ROW_BYTES + ((ch ^ (r & 7)) << 4));
+                    }
+                    if (has_rb) {      // (conv time-embedding bias: rare, loaded late to keep the register budget of the pipelined loop)
+                        float4 rb[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int grp = __shfl_sync(0xffffffffu, my_grp, (lane >> 3) + 4 * i);
+                            rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (mrow[i] >= 0) rb[i] = *reinterpret_cast<const float4*>(p.row_bias + (long long)grp * p.ld_rb + n0);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { q[i].x += rb[i].x; q[i].y += rb[i].y; q[i].z += rb[i].z; q[i].w += rb[i].w; }
+                    }
+                    if (has_res) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 a = unpack_bf16x2(rr[i].x), b = unpack_bf16x2(rr[i].y);
+                            q[i].x += a.x; q[i].y += a.y; q[i].z += b.x; q[i].w += b.y;
+                        }
+                    }
+                    if (ew == 0 && lane == 0) TL(36);  // epilogue: phase-2 operands applied
+                    if (p.splits > 1) {
+                        float* part = p.split_ws + (long long)ti.split * p.M * p.N;   // host cleared bias/row_bias/residual
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (mrow[i] >= 0) *reinterpret_cast<float4*>(part + (long long)mrow[i] * p.N + n0) = q[i];
+                    } else if (p.out_fp32) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (mrow[i] >= 0) {
+                                float4 o = make_float4(q[i].x + bz.x, q[i].y + bz.y, q[i].z + bz.z, q[i].w + bz.w);
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)mrow[i] * p.ldd + n0) = o;
+                            }
                         }
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const int n = min(col0 + c, p.N - 1);
-                            const float4 u0 = ld_shared_f4(up_addr + n * 32);
-                            const float4 u1 = ld_shared_f4(up_addr + n * 32 + 16);
-                            f[c] += tl[0] * u0.x + tl[1] * u0.y + tl[2] * u0.z + tl[3] * u0.w + tl[4] * u1.x +
-                                    tl[5] * u1.y + tl[6] * u1.z + tl[7] * u1.w;
+                        for (int i = 0; i < 8; ++i) {
+                            if (mrow[i] >= 0) {
+                                uint2 o;
+                                o.x = pack_bf16x2(q[i].x + bz.x, q[i].y + bz.y);
+                                o.y = pack_bf16x2(q[i].z + bz.z, q[i].w + bz.w);
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)mrow[i] * p.ldd + n0) = o;
+                            }
                         }
                     }
-                }
-                // ---- phase 1 -> smem (row = lane, 8 chunks of 16 B, XOR swizzle keeps both phases conflict-free)
-                __syncwarp();
+                };
+                uint32_t va[32], vb[32];
+                int g = half;
+                if (bf16_stage) {
+                    // ---- nothing to add after the accumulator (no bias / residual / LoRA): round to bf16 first, transpose 64-byte
+                    //      rows through the staging buffer (half the shared-memory traffic of the fp32 transpose) and store 16 bytes
+                    //      per lane (8 rows x 64 B per instruction)
+                    auto process16 = [&](uint32_t (&v)[32], const int gg) {
+                        const int col0 = n_blk * BN + gg * 32;
+                        __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    st_shared_f4(stg_addr + lane * STAGE_ROW_BYTES + ((j ^ (lane & 7)) << 4),
-                                 make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
-                __syncwarp();
-                // ---- phase 2: lane -> (row = (lane>>3) + 4*i, chunk = lane&7): coalesced bias / residual / store.
-                //      All loads of the 8 row-iterations are issued before any use (predicated, no branches in between).
-                const int ch = lane & 7;
-                const int n0 = col0 + ch * 4;
-                const bool col_ok = n0 < p.N;  // N % 4 == 0 is enforced on the host
-                float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (col_ok && p.bias != nullptr) bz = *reinterpret_cast<const float4*>(p.bias + n0);
-                int mrow[8];
-                float4 q[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = (lane >> 3) + 4 * i;
-                    const int m_r = __shfl_sync(0xffffffffu, my_m, r);   // every lane takes part in the shuffle
-                    mrow[i] = col_ok ? m_r : -1;
-                    q[i] = ld_shared_f4(stg_addr + r * STAGE_ROW_BYTES + ((ch ^ (r & 7)) << 4));
-                }
-                if (p.row_bias != nullptr) {
-                    float4 rb[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int grp = __shfl_sync(0xffffffffu, my_grp, (lane >> 3) + 4 * i);
-                        rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (mrow[i] >= 0) rb[i] = *reinterpret_cast<const float4*>(p.row_bias + (long long)grp * p.ld_rb + n0);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { q[i].x += rb[i].x; q[i].y += rb[i].y; q[i].z += rb[i].z; q[i].w += rb[i].w; }
-                }
-                if (p.residual != nullptr) {
-                    uint2 rr[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        rr[i] = make_uint2(0u, 0u);
-                        if (mrow[i] >= 0) rr[i] = *reinterpret_cast<const uint2*>(p.residual + (long long)mrow[i] * p.ldr + n0);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 a = unpack_bf16x2(rr[i].x), b = unpack_bf16x2(rr[i].y);
-                        q[i].x += a.x; q[i].y += a.y; q[i].z += b.x; q[i].w += b.y;
-                    }
-                }
-                if (p.splits > 1) {
-                    float* part = p.split_ws + (long long)ti.split * p.M * p.N;   // host cleared bias/row_bias/residual
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (mrow[i] >= 0) *reinterpret_cast<float4*>(part + (long long)mrow[i] * p.N + n0) = q[i];
-                } else if (p.out_fp32) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (mrow[i] >= 0) {
-                            float4 o = make_float4(q[i].x + bz.x, q[i].y + bz.y, q[i].z + bz.z, q[i].w + bz.w);
-                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)mrow[i] * p.ldd + n0) = o;
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 o;
+                            o.x = pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]));
+                            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                            st_shared_u4(stg_addr + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), o);
                         }
+                        __syncwarp();
+                        const int cq = lane & 3;
+                        const int n0 = col0 + cq * 8;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = (lane >> 2) + 8 * i;
+                            const uint4 o = ld_shared_u4(stg_addr + r * 64 + ((cq ^ ((r >> 1) & 3)) << 4));
+                            const int m_r = __shfl_sync(0xffffffffu, my_m, r);
+                            if (m_r >= 0 && n0 < p.N)
+                                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m_r * p.ldd + n0) = o;
+                        }
+                    };
+                    if (gran_ok(g)) tmem_ld_32x32(t_base + g * 32, va);
+                    while (gran_ok(g)) {
+                        tc_wait_ld();
+                        if (gran_ok(g + 2)) tmem_ld_32x32(t_base + (g + 2) * 32, vb);
+                        process16(va, g);
+                        g += 2;
+                        if (!gran_ok(g)) break;
+                        tc_wait_ld();
+                        if (gran_ok(g + 2)) tmem_ld_32x32(t_base + (g + 2) * 32, va);
+                        process16(vb, g);
+                        g += 2;
                     }
                 } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (mrow[i] >= 0) {
-                            uint2 o;
-                            o.x = pack_bf16x2(q[i].x + bz.x, q[i].y + bz.y);
-                            o.y = pack_bf16x2(q[i].z + bz.z, q[i].w + bz.w);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)mrow[i] * p.ldd + n0) = o;
-                        }
-                    }
+                if (gran_ok(g)) tmem_ld_32x32(t_base + g * 32, va);
+                while (gran_ok(g)) {
+                    tc_wait_ld();
+                    if (gran_ok(g + 2)) tmem_ld_32x32(t_base + (g + 2) * 32, vb);
+                    process(va, g);
+                    g += 2;
+                    if (!gran_ok(g)) break;
+                    tc_wait_ld();
+                    if (gran_ok(g + 2)) tmem_ld_32x32(t_base + (g + 2) * 32, va);
+                    process(vb, g);
+                    g += 2;
+                }
                 }
             }
+            if (ew == 0 && lane == 0) TL(37);  // epilogue: all stores issued
             // all TMEM reads of this buffer are complete (tc_wait_ld above) -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -672,6 +841,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
         else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+#ifdef CLB_TIMELINE
+        if (lane == 0) { const unsigned long long t = gtime(); atomicMin(&g_gt[p.dbg_id * 4 + 2], t); atomicMax(&g_gt[p.dbg_id * 4 + 3], t); }
+#endif
     }
 }
 
@@ -727,8 +899,8 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
                        const GemmParams& p_in, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, EXT, BK, CG>;
     GemmParams p = p_in;
-    const int up_bytes = (p.lora_up != nullptr) ? ((p.N * p.lora_rp * 4 + 15) & ~15) : 0;
-    const int fixed = 1024 /*align slack*/ + EPI_STAGING_BYTES + up_bytes + 512 /*barriers: 2 * stages + 5 words*/;
+    const int ext_bytes = EXT ? (BLOCK_M + BN) * 64 : 0;      // LoRA: t and up operands of the rank-r MMA
+    const int fixed = 1024 /*align slack*/ + EPI_STAGING_BYTES + ext_bytes + 512 /*barriers: 2 * stages + 9 words*/;
     int stages, smem_bytes;
     int grid = num_sms();
     // B-resident mode: the weight tile of one n-block fits next to >= 3 A stages and every CTA re-uses it >= 3 times
@@ -778,7 +950,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        cfg.numAttrs = pdl_enabled(CLB_FAMILY) ? 2 : 1;
         CL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EXT, BK, CG>, tA, tB, tE, tD, p, stages));
     } else {
         launch_k(gemm_tc_kernel<BN, EXT, BK, CG>, grid, NUM_THREADS, smem_bytes, stream, tA, tB, tE, tD, p, stages);
@@ -805,11 +977,19 @@ extern "C" int cl_debug_timeline(unsigned long long* host_buf, unsigned int* hos
         static unsigned long long z[160 * 256 * 2];
         memset(z, 0, sizeof(z));
         cudaMemcpyToSymbol(clb::g_tl, z, sizeof(z));
+        unsigned long long g[64 * 4];
+        for (int i = 0; i < 64; ++i) { g[i * 4] = ~0ull; g[i * 4 + 1] = 0; g[i * 4 + 2] = ~0ull; g[i * 4 + 3] = 0; }
+        cudaMemcpyToSymbol(clb::g_gt, g, sizeof(g));
         return 0;
     }
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(host_buf, clb::g_tl, sizeof(unsigned long long) * 160 * 256 * 2);
     for (int i = 0; i < 160; ++i) host_n[i] = 240;       // fixed slots; unused ones have tag 0
+    return 0;
+}
+extern "C" int cl_debug_gtimes(unsigned long long* host_buf) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_buf, clb::g_gt, sizeof(unsigned long long) * 64 * 4);
     return 0;
 }
 #endif
@@ -907,7 +1087,6 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     const bool lora = a->lora_up != nullptr;
     if (lora && (a->ext == nullptr || (a->lora_rp != 4 && a->lora_rp != 8)))
         return set_error(CL_ERR_INVALID, "cl_gemm: LoRA epilogue needs ext and lora_rp in {4,8}");
-    if (lora && a->N * a->lora_rp * 4 > 49152) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: LoRA N too large");
     if ((a->t_add || a->t_out) && !lora) return set_error(CL_ERR_INVALID, "cl_gemm: t_add/t_out need the LoRA epilogue");
 
     GemmParams p;
@@ -998,6 +1177,7 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
 
 #ifdef CLB_TIMELINE
     { const char* e = getenv("CLB_TL_MMA_REPS"); p.dbg_reps = e ? atoi(e) : 0; }
+    { static int ordinal = 0; p.dbg_id = (ordinal++) & 63; }
 #endif
     p.bias = a->bias; p.row_bias = a->row_bias; p.rows_per_group = a->rows_per_group;
     p.ld_rb = a->ld_row_bias > 0 ? a->ld_row_bias : a->N;
@@ -1043,6 +1223,7 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
         }
     }
 
+    p.epi_bf16 = (!p.out_fp32 && p.splits == 1 && aligned16 && p.bias == nullptr && p.row_bias == nullptr && p.residual == nullptr) ? 1 : 0;
     if (BK == 32) {
         if (lora) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: LoRA epilogue is not instantiated for 32-channel convs");
         switch (bn_sel) {

@@ -18,8 +18,13 @@ int num_sms();
 int get_tensor_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, int swizzle_bytes /* 0, 64 or 128 */);
 
-// Programmatic dependent launch (opt-in: CLB_PDL=1): see pdl_launch_dependents / pdl_wait in common.cuh.
-bool pdl_enabled();
+// Programmatic dependent launch (default: GEMM family only; CLB_PDL=0 disables): see pdl_launch_dependents / pdl_wait in common.cuh.
+// family: the CLB_FAMILY bit of the launching file (gemm 1, attention 2, norm 4, lora 8, elementwise 16, smallops 32, wgrad 64,
+// noise / optim 128); CLB_PDL_MASK (default: 1 = gemm, see host_common.cu) selects which families' kernels may start early.
+bool pdl_enabled(int family);
+#ifndef CLB_FAMILY
+#define CLB_FAMILY 128
+#endif
 
 // Launch `kernel` with the programmatic-stream-serialization attribute: inside a stream (or a captured CUDA graph) the
 // grid may start while the previous kernel drains; every kernel of this library executes griddepcontrol.wait before its
@@ -36,7 +41,7 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = pdl_enabled(CLB_FAMILY) ? 1 : 0;
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

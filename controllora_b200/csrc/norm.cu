@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "common.cuh"
+#define CLB_FAMILY 4      // CLB_PDL_MASK bit of this file's kernels
 #include "host_common.h"
 #include "../../include/controllora_b200.h"
 
@@ -798,7 +799,7 @@ static int gn_cluster_launch(const __nv_bfloat16* x, const __nv_bfloat16* dy, co
         attr[na].val.clusterDim.x = cl; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
         ++na;
     }
-    if (pdl_enabled()) {
+    if (pdl_enabled(CLB_FAMILY)) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;

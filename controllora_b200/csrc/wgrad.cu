@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#define CLB_FAMILY 64      // CLB_PDL_MASK bit of this file's kernels
 #include "host_common.h"
 #include "../../include/controllora_b200.h"
 

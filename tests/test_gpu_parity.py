@@ -21,7 +21,7 @@ from tools import check_gemm, check_ops, check_ops2  # noqa: E402
 
 @pytest.mark.parametrize("case", ["plain_1tile", "plain_k320", "plain_bn64", "plain_bn160_tail", "plain_bn256", "plain_big",
                                   "epilogue_all", "lora_r4", "lora_r4_tadd", "lora_r8_cross", "conv_s1_64", "conv_s1_small",
-                                  "conv_s2", "conv_96", "split_k", "plain_bn320", "conv_bn320"])
+                                  "conv_s2", "conv_96", "split_k", "plain_bn320", "conv_bn320", "resident_short_k"])
 def test_gemm(case):
     check_gemm.CASES[case]()
 

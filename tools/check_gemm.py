@@ -161,6 +161,41 @@ def lora_r8_cross():
     _run_lora(616, 1280, 768, 8, 8, False)
 
 
+@case
+def resident_short_k():
+    """M large enough for the smem-resident-weights mode (per-lane store epilogue): the bf16 transpose path (nothing added to the
+    accumulator), the fp32 transpose path with bias + residual, and the LoRA epilogue (rank 4 and stacked rank 8) with bf16 output."""
+    torch = _setup()
+    from controllora_b200 import ops
+
+    _run_plain(32768, 320, 320)
+    _run_plain(16384 + 64, 640, 320)
+    M, N, K = 32768, 320, 320
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = (torch.randn(N, K, device="cuda") / K**0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    base = _gemm_ref(a, b)
+    out = ops.gemm(a, b, bias=bias, residual=res)
+    torch.cuda.synchronize()
+    e = _rel(out, base + bias + res.float())
+    print(f"resident bias+residual: rel={e:.3e}")
+    assert e < 4e-3
+    for r, rp in ((4, 4), (8, 8)):
+        down = torch.randn(r, K, device="cuda") / r
+        up = torch.randn(N, rp, device="cuda") * 0.5
+        t_add = torch.randn(M, rp, device="cuda")
+        t_out = torch.empty(M, rp, device="cuda")
+        out = ops.gemm(a, b, ext=ops.split_bf16_ext(down, K), lora_up=up, lora_scale=0.7, t_add=t_add, t_out=t_out, bias=bias, residual=res)
+        torch.cuda.synchronize()
+        t_ref = a.float() @ down.t() + t_add[:, :r]
+        ref = base + 0.7 * (t_ref @ up[:, :r].t()) + bias + res.float()
+        e, e_t = _rel(out, ref), _rel(t_out[:, :r], t_ref)
+        lora_only = _rel(out.float() - base - bias - res.float(), 0.7 * (t_ref @ up[:, :r].t()))
+        print(f"resident lora r={r}: rel={e:.3e} lora-term rel={lora_only:.3e} t rel={e_t:.3e}")
+        assert e < 4e-3 and e_t < 1e-4 and lora_only < 3e-2
+
+
 def _conv_case(n, H, W, Cc, N, stride, pad_lo, with_epi):
     torch = _setup()
     import torch.nn.functional as F

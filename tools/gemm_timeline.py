@@ -32,7 +32,8 @@ buf = (C.c_ulonglong * (160 * 256 * 2))()
 cnt = (C.c_uint * 160)()
 lib.cl_debug_timeline(buf, cnt, 0)
 names = {1: "entry", 10: "prod:tile", 11: "prod:slot", 12: "prod:issued", 24: "mma:kb_ready", 25: "mma:kb_issued", 20: "mma:wait_acc", 21: "mma:acc_free", 22: "mma:stage0", 23: "mma:issued", 30: "epi:wait",
-         31: "epi:ready", 32: "epi:done"}
+         31: "epi:ready", 32: "epi:done", 33: "epi:gran_regs", 34: "epi:lora_done", 35: "epi:staged", 36: "epi:p2_loaded", 37: "epi:stores_issued",
+         38: "epi:t_ready", 39: "epi:acc2_ready"}
 for sm in (0, 77):
     n = min(cnt[sm], 256)
     ev = sorted((buf[(sm * 256 + i) * 2], buf[(sm * 256 + i) * 2 + 1]) for i in range(n) if buf[(sm * 256 + i) * 2 + 1] != 0)
