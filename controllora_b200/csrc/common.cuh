@@ -262,8 +262,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 //   [0,14) start address >> 4   [16,30) leading-dim byte offset >> 4   [32,46) stride-dim byte offset >> 4
 //   [46,48) version = 1         [61,64) swizzle: 0 none, 2 = 128B, 4 = 64B, 6 = 32B
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-    uint64_t d = 0;
+                                                   uint32_t layout_type, uint32_t base_offset = 0) {
+    uint64_t d = uint64_t(base_offset & 7u) << 49;     // start address not aligned to the swizzle repeat (shifted-row operands)
     d |= uint64_t((saddr & 0x3FFFFu) >> 4);
     d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32;

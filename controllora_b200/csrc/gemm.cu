@@ -39,6 +39,9 @@ namespace clb {
 static constexpr int BLOCK_M = 128;
 // BLOCK_K (template BK): 64 bf16 = 128 B rows with the 128B swizzle, or 32 bf16 = 64 B rows with the 64B swizzle
 // (used for the 32-channel layers of the hint encoder, where a 3x3 tap only offers 32 contiguous K elements).
+static constexpr int STRIP_ROWS = 130;                    // 128 output pixels + one halo pixel either side
+static constexpr int STRIP_SLOT = 8704;                   // 130 x 64 B rounded up to the 512-byte period of the 64B swizzle
+static constexpr int STRIP_STAGE = 26624;                 // three halo rows, 1024-aligned
 static constexpr int NUM_EPI_WARPS = 8;
 static constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 static constexpr int STAGE_ROW_BYTES = 128;              // epilogue staging: 32 fp32 columns per row
@@ -69,6 +72,9 @@ struct GemmParams {
     int out_fp32;
     int tma_store;    // bf16 output through per-warp TMA stores of 32x32 sub-tiles (new epilogue); 0 = per-lane global stores
     int ew, eh, en;   // conv: the 32 rows of a TMEM lane quadrant as a box of the output image (ew * eh * en == 32)
+    int strip;        // 32-channel stride-1 conv, 128-pixel row tiles: a stage = the three 130-pixel halo rows of the tile, the nine taps
+                      // are shared-memory descriptors shifted by 0 / 1 / 2 pixels (3 TMA loads of 130 rows instead of 9 of 128)
+    int strip_bo;     // debug: how the descriptor base offset of a shifted tap is formed (0: none, 1: (addr >> 7) & 3, 2: (addr >> 7) & 7)
     int epi_bf16;     // per-lane store epilogue: nothing is added to the accumulator -> transpose in bf16 (host-checked alignment)
     int b_resident;   // B (weights) tile of this CTA's n-block stays in smem for the CTA lifetime (small K)
     // split-K (streaming mode only): tile space is (m, n, split); split s covers k-blocks [s*kb_per_split, ...) and stores
@@ -157,10 +163,16 @@ struct GemmCfg {
     static constexpr int MMA_N = BN / NSPLIT + EXT;           // N of one tcgen05.mma
     static constexpr int UMMA_N = MMA_N;
     static constexpr int ROW_BYTES = BK * 2;
-    static constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
+    // k-blocks per pipeline stage: the 32-channel convs (64-byte rows) move only 8 KB of A per k-block, so the per-k-block costs
+    // of the two single-thread loops (barrier round trip, coordinate math, commit: ~400 clk) dominated; three k-blocks (the
+    // three horizontal taps of one filter row when C = 32) share a stage, a barrier and a commit.  9 * C / 32 k-blocks: always % 3.
+    static constexpr int KPS = (BK == 32) ? 3 : 1;
+    static constexpr int A_SUB_BYTES = BLOCK_M * ROW_BYTES;
+    static constexpr int A_STAGE_BYTES = KPS * A_SUB_BYTES;
     static constexpr int MMA_B_ROWS = MMA_N / CG;             // B rows one CTA stages for one MMA
     static constexpr int B_ROWS = NSPLIT * MMA_B_ROWS;        // B rows staged by one CTA per k-block
-    static constexpr int B_STAGE_BYTES = B_ROWS * ROW_BYTES;
+    static constexpr int B_SUB_BYTES = B_ROWS * ROW_BYTES;
+    static constexpr int B_STAGE_BYTES = KPS * B_SUB_BYTES;
     static_assert(CG == 1 || (CG == 2 && EXT == 0 && (BN / NSPLIT / 2) % 8 == 0), "CTA-pair variant: no LoRA rows, B half % 8 == 0");
     static_assert(NSPLIT == 1 || (CG == 2 && EXT == 0), "split-N tiles are CTA-pair, no-LoRA only");
     static constexpr int SBO = 8 * ROW_BYTES;                  // 8-row swizzle atom
@@ -209,14 +221,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int sched_cta = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int sched_n = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int sched_m = (CG == 2) ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;
-    constexpr int A_STAGE_BYTES = Cfg::A_STAGE_BYTES;
+    const bool strip = (BK == 32) && p.strip != 0;
+    const int A_STAGE_BYTES = strip ? STRIP_STAGE : Cfg::A_STAGE_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve (base is 1024-aligned by the runtime for dynamic smem declared __align__(1024); re-align anyway)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem_a + num_stages * A_STAGE_BYTES;
-    const int b_slots = p.b_resident ? p.num_k_blocks : num_stages;
-    uint8_t* smem_stage = smem_b + b_slots * Cfg::B_STAGE_BYTES;             // epilogue staging
+    const int b_bytes = p.b_resident ? p.num_k_blocks * Cfg::B_SUB_BYTES : num_stages * Cfg::B_STAGE_BYTES;
+    uint8_t* smem_stage = smem_b + ((b_bytes + 1023) & ~1023);               // epilogue staging
     // LoRA: t (128 x 32 bf16, 64-byte rows, 64B swizzle) and the up matrix of the tile's n-block (BN x 32 bf16, same layout)
     uint8_t* smem_text = smem_stage + EPI_STAGING_BYTES;
     uint8_t* smem_bext = smem_text + (EXT ? BLOCK_M * 64 : 0);
@@ -306,9 +319,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             TileIter ti(p, sched_cta, sched_n, sched_m);
             if (p.b_resident && ti.valid()) {
                 if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(b_full, p.num_k_blocks * Cfg::B_STAGE_BYTES);
+                    mbar_arrive_expect_tx(b_full, p.num_k_blocks * Cfg::B_SUB_BYTES);
                     for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                        uint8_t* sb = smem_b + kb * Cfg::B_STAGE_BYTES;
+                        uint8_t* sb = smem_b + kb * Cfg::B_SUB_BYTES;
                         tma_load_2d(&tmB, b_full, sb, kb * BK, ti.n_blk * BN);
                         if (EXT) tma_load_2d(&tmE, b_full, sb + BN * Cfg::ROW_BYTES, kb * BK, 0);
                     }
@@ -326,44 +339,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (lane == 0) TL(10);  // producer: tile start
                 const int kb1 = ti.kb_end();
-                for (int kb = ti.kb_begin(); kb < kb1; ++kb) {
+                if (strip) {
+                    // one stage per tile: the halo rows h-1, h, h+1 of the tile's 128-pixel run (out-of-bounds pixels / rows read zero)
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(&full_bar[stage], 3 * STRIP_ROWS * 64);
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+                            tma_load_4d(&tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES + ky * STRIP_SLOT, 0, tw * p.bw - 1, th * p.bh + ky - 1,
+                                        tn * p.bn);
+                    }
+                    __syncwarp();
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                    continue;
+                }
+                for (int kb = ti.kb_begin(); kb < kb1; kb += Cfg::KPS) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (lane == 0 && kb < 10) TLK(11);   // producer: ring slot acquired
-                    uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-                    uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-                    // A-operand coordinates of this k-block (conv: the 3x3 tap and channel block)
-                    int ca0 = kb * BK, ca1 = m_blk * BLOCK_M, ca2 = 0, ca3 = 0, ca4 = 0;
-                    if (p.a_mode != 0) {
-                        const int tap = kb / p.cblocks, cb = kb % p.cblocks;
-                        const int ky = tap / 3, kx = tap % 3;
-                        if (p.a_mode == 1) {
-                            ca0 = cb * BK; ca1 = tw * p.bw + kx - 1; ca2 = th * p.bh + ky - 1; ca3 = tn * p.bn;
-                        } else {
-                            const int iy = ky - p.pad_lo, ix = kx - p.pad_lo;
-                            ca0 = (ix & 1) * p.C + cb * BK; ca1 = tw * p.bw + (ix >> 1); ca2 = iy & 1; ca3 = th * p.bh + (iy >> 1);
-                            ca4 = tn * p.bn;
-                        }
-                    }
                     if (elect_one_sync()) {
                         if (CG == 2) {
                             // both CTAs' bytes are credited to the LEADER's full barrier (one arrival: the leader's producer)
                             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
-                            if (p.a_mode == 0) tma_load_2d_cg2(&tmA, fb, sa, ca0, ca1);
-                            else if (p.a_mode == 1) tma_load_4d_cg2(&tmA, fb, sa, ca0, ca1, ca2, ca3);
-                            else tma_load_5d_cg2(&tmA, fb, sa, ca0, ca1, ca2, ca3, ca4);
-#pragma unroll
-                            for (int hh = 0; hh < Cfg::NSPLIT; ++hh)
-                                tma_load_2d_cg2(&tmB, fb, sb + hh * Cfg::MMA_B_ROWS * Cfg::ROW_BYTES, kb * BK,
-                                                n_blk * BN + hh * (BN / Cfg::NSPLIT) + cta_rank * Cfg::MMA_B_ROWS);
                         } else {
                             mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES);
-                            if (p.a_mode == 0) tma_load_2d(&tmA, &full_bar[stage], sa, ca0, ca1);
-                            else if (p.a_mode == 1) tma_load_4d(&tmA, &full_bar[stage], sa, ca0, ca1, ca2, ca3);
-                            else tma_load_5d(&tmA, &full_bar[stage], sa, ca0, ca1, ca2, ca3, ca4);
-                            if (!p.b_resident) {
-                                tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * BN);
-                                if (EXT) tma_load_2d(&tmE, &full_bar[stage], sb + BN * Cfg::ROW_BYTES, kb * BK, 0);
+                        }
+                        // conv: 3x3 tap and channel block of the stage's first k-block (one division per stage, then counted up)
+                        int tap = 0, cb = 0;
+                        if (p.a_mode != 0) { tap = kb / p.cblocks; cb = kb - tap * p.cblocks; }
+#pragma unroll
+                        for (int sub = 0; sub < Cfg::KPS; ++sub) {
+                            const int kbs = kb + sub;
+                            uint8_t* sa = smem_a + stage * A_STAGE_BYTES + sub * Cfg::A_SUB_BYTES;
+                            uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES + sub * Cfg::B_SUB_BYTES;
+                            // A-operand coordinates of this k-block
+                            int ca0 = kbs * BK, ca1 = m_blk * BLOCK_M, ca2 = 0, ca3 = 0, ca4 = 0;
+                            if (p.a_mode != 0) {
+                                const int ky = tap / 3, kx = tap - ky * 3;
+                                if (p.a_mode == 1) {
+                                    ca0 = cb * BK; ca1 = tw * p.bw + kx - 1; ca2 = th * p.bh + ky - 1; ca3 = tn * p.bn;
+                                } else {
+                                    const int iy = ky - p.pad_lo, ix = kx - p.pad_lo;
+                                    ca0 = (ix & 1) * p.C + cb * BK; ca1 = tw * p.bw + (ix >> 1); ca2 = iy & 1; ca3 = th * p.bh + (iy >> 1);
+                                    ca4 = tn * p.bn;
+                                }
+                                if (++cb == p.cblocks) { cb = 0; ++tap; }
+                            }
+                            if (CG == 2) {
+                                const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                                if (p.a_mode == 0) tma_load_2d_cg2(&tmA, fb, sa, ca0, ca1);
+                                else if (p.a_mode == 1) tma_load_4d_cg2(&tmA, fb, sa, ca0, ca1, ca2, ca3);
+                                else tma_load_5d_cg2(&tmA, fb, sa, ca0, ca1, ca2, ca3, ca4);
+#pragma unroll
+                                for (int hh = 0; hh < Cfg::NSPLIT; ++hh)
+                                    tma_load_2d_cg2(&tmB, fb, sb + hh * Cfg::MMA_B_ROWS * Cfg::ROW_BYTES, kbs * BK,
+                                                    n_blk * BN + hh * (BN / Cfg::NSPLIT) + cta_rank * Cfg::MMA_B_ROWS);
+                            } else {
+                                if (p.a_mode == 0) tma_load_2d(&tmA, &full_bar[stage], sa, ca0, ca1);
+                                else if (p.a_mode == 1) tma_load_4d(&tmA, &full_bar[stage], sa, ca0, ca1, ca2, ca3);
+                                else tma_load_5d(&tmA, &full_bar[stage], sa, ca0, ca1, ca2, ca3, ca4);
+                                if (!p.b_resident) {
+                                    tma_load_2d(&tmB, &full_bar[stage], sb, kbs * BK, n_blk * BN);
+                                    if (EXT) tma_load_2d(&tmE, &full_bar[stage], sb + BN * Cfg::ROW_BYTES, kbs * BK, 0);
+                                }
                             }
                         }
                     }
@@ -391,12 +428,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) TL(21);  // mma: accumulator free
                 const uint32_t d_tmem = tmem_base + buf * Cfg::BUF_COLS;
                 const int kb0 = ti.kb_begin(), kb1 = ti.kb_end();
-                for (int kb = kb0; kb < kb1; ++kb) {
+                if (strip) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) TL(22);
+                    const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(smem_b);
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            // tap (ky, kx): rows kx .. kx + 127 of halo row ky - the operand starts kx pixels (64-byte rows) into the strip
+                            const uint32_t a0 = sa + (tap / 3) * STRIP_SLOT + (tap % 3) * 64;
+                            const uint32_t bo = (p.strip_bo == 0) ? 0u : ((a0 >> 7) & (p.strip_bo == 1 ? 3u : 7u));
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                tc_mma_ss(d_tmem, make_smem_desc(a0 + k * 32, 16, Cfg::SBO, Cfg::LAYOUT, bo),
+                                          make_smem_desc(sb + tap * Cfg::B_SUB_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT), idesc, (tap | k) ? 1u : 0u);
+                        }
+                        tc_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                } else
+                for (int kb = kb0; kb < kb1; kb += Cfg::KPS) {
                     mbar_wait(&full_bar[stage], phase);      // all 32 lanes poll: keeps the loop convergent
                     tc_fence_after();
                     if (lane == 0) { if (kb == kb0) TL(22); else if (kb < kb0 + 10) TLK(24); }
                     const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
-                    const uint32_t sb = smem_u32(smem_b + (p.b_resident ? kb : stage) * Cfg::B_STAGE_BYTES);
+                    const uint32_t sb = smem_u32(smem_b) + (p.b_resident ? kb * Cfg::B_SUB_BYTES : stage * Cfg::B_STAGE_BYTES);
                     const uint32_t first = (kb != kb0) ? 1u : 0u;
                     if (elect_one_sync()) {
 #ifdef CLB_TIMELINE
@@ -414,13 +473,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
 #endif
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t adesc = make_smem_desc(sa + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+                        for (int sub = 0; sub < Cfg::KPS; ++sub) {
 #pragma unroll
-                            for (int hh = 0; hh < Cfg::NSPLIT; ++hh) {
-                                const uint64_t bdesc = make_smem_desc(sb + hh * Cfg::MMA_B_ROWS * Cfg::ROW_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-                                if (CG == 2) tc_mma_ss_cg2(d_tmem + hh * Cfg::MMA_N, adesc, bdesc, idesc, (k != 0) ? 1u : first);
-                                else tc_mma_ss(d_tmem + hh * Cfg::MMA_N, adesc, bdesc, idesc, (k != 0) ? 1u : first);
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint64_t adesc = make_smem_desc(sa + sub * Cfg::A_SUB_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
+#pragma unroll
+                                for (int hh = 0; hh < Cfg::NSPLIT; ++hh) {
+                                    const uint64_t bdesc = make_smem_desc(sb + sub * Cfg::B_SUB_BYTES + hh * Cfg::MMA_B_ROWS * Cfg::ROW_BYTES + k * 32, 16,
+                                                                          Cfg::SBO, Cfg::LAYOUT);
+                                    const uint32_t acc = (sub != 0 || k != 0) ? 1u : first;
+                                    if (CG == 2) tc_mma_ss_cg2(d_tmem + hh * Cfg::MMA_N, adesc, bdesc, idesc, acc);
+                                    else tc_mma_ss(d_tmem + hh * Cfg::MMA_N, adesc, bdesc, idesc, acc);
+                                }
                             }
                         }
                         // smem slot is free once these MMAs retire (pair: in both CTAs)
@@ -895,8 +959,9 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, int M, int N, con
 // =====================================================================================================
 
 template <int BN, int EXT, int BK = 64, int CG = 1>
-static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tE, const CUtensorMap& tD,
-                       const GemmParams& p_in, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tA_in, const CUtensorMap& tB, const CUtensorMap& tE, const CUtensorMap& tD,
+                       const GemmParams& p_in, cudaStream_t stream, const CUtensorMap* tA_strip = nullptr) {
+    const CUtensorMap* tA_sel = &tA_in;
     using Cfg = GemmCfg<BN, EXT, BK, CG>;
     GemmParams p = p_in;
     const int ext_bytes = EXT ? (BLOCK_M + BN) * 64 : 0;      // LoRA: t and up operands of the rank-r MMA
@@ -904,19 +969,24 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     int stages, smem_bytes;
     int grid = num_sms();
     // B-resident mode: the weight tile of one n-block fits next to >= 3 A stages and every CTA re-uses it >= 3 times
-    const int b_res_bytes = p.num_k_blocks * Cfg::B_STAGE_BYTES;
+    const int b_res_bytes = (p.num_k_blocks * Cfg::B_SUB_BYTES + 1023) & ~1023;
     const int a_room = 232448 - fixed - b_res_bytes;
     const int grid_res = (grid / p.num_n_blocks) * p.num_n_blocks;
-    if (CG == 1 && p.splits == 1 && p.a_mode == 0 && a_room >= 3 * Cfg::A_STAGE_BYTES && grid_res > 0 && grid_res * 10 >= grid * 9 &&
+    // (the 32-channel convs of the hint encoder qualify too: all nine taps of a 32 x 32 filter are 18 KB)
+    if (CG == 1 && p.splits == 1 && (p.a_mode == 0 || BK == 32) && a_room >= 3 * Cfg::A_STAGE_BYTES && grid_res > 0 && grid_res * 10 >= grid * 9 &&
         p.num_m_blocks >= 3 * (grid_res / p.num_n_blocks)) {
         p.b_resident = 1;
         // short-K resident tiles hand a finished accumulator to the epilogue every ~2 k cycles: measured (round 2) the
         // per-lane store epilogue keeps up with that better than two TMA stores in flight per warp (18.5 vs 20.1 us at
         // 32768 x 320 x 320), while the TMA epilogue wins wherever the epilogue is exposed (convs, 256 x 320 tiles)
         if (p.tma_store == 1) p.tma_store = 0;
-        stages = a_room / Cfg::A_STAGE_BYTES;
+        int a_stage = Cfg::A_STAGE_BYTES;
+        if (BK == 32 && tA_strip != nullptr && p.num_n_blocks == 1 && a_room >= 3 * STRIP_STAGE) {
+            p.strip = 1; a_stage = STRIP_STAGE; tA_sel = tA_strip;
+        }
+        stages = a_room / a_stage;
         if (stages > 8) stages = 8;
-        smem_bytes = fixed + b_res_bytes + stages * Cfg::A_STAGE_BYTES;
+        smem_bytes = fixed + b_res_bytes + stages * a_stage;
         grid = grid_res;
     } else {
         p.b_resident = 0;
@@ -932,6 +1002,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     }
     const GemmParams full = p;
     if (p.splits > 1) { p.bias = nullptr; p.row_bias = nullptr; p.residual = nullptr; }
+    const CUtensorMap& tA = *tA_sel;
     static bool attr_done = false;
     if (!attr_done) {
         CL_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT, BK, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -1048,7 +1119,8 @@ static TilePlan plan_tiles(const cl_gemm_args* a, int BK, int num_m_blocks, bool
             if (splits > 16) splits = 16;
             if (splits < 2) splits = 1;
         }
-        const int kbps = (nkb + splits - 1) / splits;
+        int kbps = (nkb + splits - 1) / splits;
+        if (BK == 32) kbps = (kbps + 2) / 3 * 3;       // three k-blocks share a pipeline stage in the 32-channel variant
         splits = (nkb + kbps - 1) / kbps;
         const long long waves = ((long long)tiles * splits + sms - 1) / sms;
         // Cost in clocks (round-2 measurements): a CTA ingests ~one 128-byte operand row per 2 clk through TMA, so a k-block costs
@@ -1157,6 +1229,7 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     if (plan.splits > 1) {
         const int want = plan.splits < a->split_k ? plan.splits : a->split_k;   // split_ws holds a->split_k partials
         p.kb_per_split = (p.num_k_blocks + want - 1) / want;
+        if (BK == 32) p.kb_per_split = (p.kb_per_split + 2) / 3 * 3;
         p.splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;     // no empty split
         p.split_ws = reinterpret_cast<float*>(a->split_ws);
     }
@@ -1226,10 +1299,23 @@ extern "C" int cl_gemm(const cl_gemm_args* a, void* stream_) {
     p.epi_bf16 = (!p.out_fp32 && p.splits == 1 && aligned16 && p.bias == nullptr && p.row_bias == nullptr && p.residual == nullptr) ? 1 : 0;
     if (BK == 32) {
         if (lora) return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: LoRA epilogue is not instantiated for 32-channel convs");
+        // halo-strip operand (stride-1 conv, C = 32, tiles = 128-pixel runs of one image row): box = 130 pixels of one row
+        CUtensorMap tS;
+        const CUtensorMap* tSp = nullptr;
+        static const int strip_mode = [] { const char* e = getenv("CLB_GEMM_STRIP"); return e ? atoi(e) : 1; }();   // 0 off, 1..3: base-offset rule + 1
+        if (strip_mode > 0 && a->a_mode == 1 && a->C == 32 && p.bw == 128 && p.bh == 1 && p.bn == 1 && p.splits == 1) {
+            const uint64_t C = a->C, W = a->W, H = a->H, NI = a->n_img;
+            uint64_t dims[4] = {C, W, H, NI};
+            uint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+            uint32_t box[4] = {32, STRIP_ROWS, 1, 1};
+            CL_CHECK(get_tensor_map(&tS, a->a, 4, dims, strides, box, 64));
+            tSp = &tS;
+            p.strip_bo = strip_mode - 1;
+        }
         switch (bn_sel) {
-            case 32: return launch_gemm<32, 0, 32>(tA, tB, tE, tD, p, stream);
-            case 64: return launch_gemm<64, 0, 32>(tA, tB, tE, tD, p, stream);
-            case 128: return launch_gemm<128, 0, 32>(tA, tB, tE, tD, p, stream);
+            case 32: return launch_gemm<32, 0, 32>(tA, tB, tE, tD, p, stream, tSp);
+            case 64: return launch_gemm<64, 0, 32>(tA, tB, tE, tD, p, stream, tSp);
+            case 128: return launch_gemm<128, 0, 32>(tA, tB, tE, tD, p, stream, tSp);
             default: return set_error(CL_ERR_UNSUPPORTED, "cl_gemm: block_n for 32-channel convs must be 32/64/128");
         }
     }

@@ -127,8 +127,7 @@ class LoraRuntime:
             lp.post_add = any(post_add)
             # V2 self-attention: k / v carry no LoRA (models.py:306-307) and read the same h' as q -> ONE fused q|k|v projection
             # (N = 3C, the q adapter owns the first C output rows); CLB_FUSE_QKV=0 keeps three launches
-            # (the fused epilogue keeps the [3C, 4] up-table in shared memory: 3C * 16 B <= 48 KB, i.e. the 320 / 640-wide levels)
-            lp.fuse_qkv = bool(_FUSE_QKV and _is_v2(p) and not L.is_cross and len(chain) == 1 and not any(post_add) and 3 * C * 16 <= 49152)
+            lp.fuse_qkv = bool(_FUSE_QKV and _is_v2(p) and not L.is_cross and len(chain) == 1 and not any(post_add))
             lp.q = LoraSlot(3 * C if lp.fuse_qkv else C, C, dev)
             # post_add adapters read the projection's output: their `down` has C input features even for the text k / v
             lp.k = LoraSlot(C, C if lp.post_add else kv_in, dev)

@@ -31,6 +31,10 @@ def test_conv_32_channels_uses_bk32_path():
     check_gemm._conv_case(2, 64, 64, 32, 32, 1, 1, True)
     check_gemm._conv_case(2, 64, 64, 32, 64, 1, 1, False)
     check_gemm._conv_case(2, 64, 64, 32, 32, 2, 0, False)
+    # enough tiles for the resident-weights mode of the 32-channel variant (3 k-blocks per stage, per-lane store epilogue)
+    check_gemm._conv_case(1, 256, 256, 32, 32, 1, 1, True)
+    check_gemm._conv_case(1, 256, 256, 32, 32, 1, 1, False)
+    check_gemm._conv_case(1, 512, 256, 32, 32, 2, 0, False)
 
 
 # ------------------------------------------------------------------------------------------------ K2: attention

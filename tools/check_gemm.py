@@ -322,8 +322,8 @@ def perf():
         fl = 2.0 * M * N * K
         by = 2.0 * (M * K + N * K + M * N)
         print(f"perf M={M:6d} N={N:6d} K={K:5d}: {ms*1e3:8.1f} us {fl/ms/1e9:8.1f} TFLOP/s {by/ms/1e6:7.1f} GB/s | cuBLAS {ms_ref*1e3:8.1f} us {fl/ms_ref/1e9:8.1f} TFLOP/s")
-    # conv perf
-    for (n, H, Cc, N) in [(8, 64, 320, 320), (8, 32, 640, 640), (8, 16, 1280, 1280), (8, 8, 1280, 1280)]:
+    # conv perf (last row: the hint encoder's 32-channel level at 512 x 512)
+    for (n, H, Cc, N) in [(8, 64, 320, 320), (8, 32, 640, 640), (8, 16, 1280, 1280), (8, 8, 1280, 1280), (8, 512, 32, 32)]:
         x = torch.randn(n, H, H, Cc, device="cuda").to(torch.bfloat16)
         w = (torch.randn(N, 9 * Cc, device="cuda") / (9 * Cc) ** 0.5).to(torch.bfloat16)
         out = torch.empty(n, H, H, N, device="cuda", dtype=torch.bfloat16)
