@@ -7,8 +7,9 @@ from .models import (ControlLoRA, ControlLoRACrossAttnProcessor, ControlLoRACros
                      LoRACrossAttnProcessor, LoRALinearLayer)
 from .unet_module import UNet2DConditionModel
 from .vae import AutoencoderKL
+from .clip import CLIPTextModel
 
 __all__ = [
     "ControlLoRA", "ControlLoRAOutput", "ControlLoRACrossAttnProcessor", "ControlLoRACrossAttnProcessorV2",
-    "LoRACrossAttnProcessor", "LoRALinearLayer", "UNet2DConditionModel", "AutoencoderKL",
+    "LoRACrossAttnProcessor", "LoRALinearLayer", "UNet2DConditionModel", "AutoencoderKL", "CLIPTextModel",
 ]

@@ -435,6 +435,100 @@ __global__ void channel_affine_nchw_kernel(const float* __restrict__ x, float* _
         y[i] = fmaf(mul, x[i], shift[c]);
     }
 }
+
+// ---------------------------------------------------------------------------------------------- CLIP text encoder helpers
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+// (transformers CLIPTextModel behind train_text_to_image_control_lora.py:768 `text_encoder(batch["input_ids"])[0]`)
+// x[b, t, :] = token_embedding[ids[b, t]] + position_embedding[t]     (bf16 tables, 16 bytes per thread)
+__global__ void __launch_bounds__(256)
+clip_embed_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ tok, const __nv_bfloat16* __restrict__ pos,
+                  __nv_bfloat16* __restrict__ out, int T, int C, int vocab, long long total_chunks) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int chunks = C / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / chunks;
+        const int ch = (int)(i - row * chunks);
+        long long id = ids[row];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        const int t = (int)(row % T);
+        float a[8], b[8];
+        load8(tok + id * C + ch * 8, a);
+        load8(pos + (long long)t * C + ch * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += b[j];
+        store8(out + row * C + ch * 8, a);
+    }
+}
+
+// y = x * sigmoid(1.702 x) in place (CLIP's `quick_gelu`), 8 bf16 per thread
+__global__ void __launch_bounds__(256)
+quick_gelu_kernel(__nv_bfloat16* __restrict__ x, long long total_chunks) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks; i += (long long)gridDim.x * blockDim.x) {
+        float a[8];
+        load8(x + i * 8, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = a[j] / (1.f + __expf(-1.702f * a[j]));
+        store8(x + i * 8, a);
+    }
+}
+
+// causal softmax(q k^T * scale) v for short sequences (T <= 128, d <= 64): one CTA per (batch, head), K and V of the head in
+// shared memory as fp32, one thread per query row with an online softmax over keys 0..row (fp32 throughout).
+// qkv [B*T, 3*C] bf16 (q | k | v, head h at columns h*d), out [B*T, C] bf16.
+__global__ void __launch_bounds__(128)
+causal_attention_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int C, int d, float scale) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float sm_kv[];            // [T][d] K | [T][d] V
+    float* sk = sm_kv;
+    float* sv = sm_kv + T * d;
+    const int b = blockIdx.x, h = blockIdx.y;
+    const long long ld = 3LL * C;
+    const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * d;
+    for (int i = threadIdx.x; i < T * d; i += blockDim.x) {
+        const int t = i / d, c = i - t * d;
+        sk[i] = __bfloat162float(base[t * ld + C + c]);
+        sv[i] = __bfloat162float(base[t * ld + 2 * C + c]);
+    }
+    __syncthreads();
+    const int row = threadIdx.x;
+    if (row >= T) return;
+    float q[64], o[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) { q[c] = (c < d) ? __bfloat162float(base[row * ld + c]) * scale : 0.f; o[c] = 0.f; }
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j <= row; ++j) {
+        float sdot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+            if (c < d) sdot = fmaf(q[c], sk[j * d + c], sdot);
+        const float mn = fmaxf(m, sdot);
+        const float corr = __expf(m - mn), pj = __expf(sdot - mn);
+        l = l * corr + pj;
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+            if (c < d) o[c] = fmaf(pj, sv[j * d + c], o[c] * corr);
+        m = mn;
+    }
+    const float inv = 1.f / l;
+    __nv_bfloat16* op = out + ((long long)b * T + row) * C + h * d;
+#pragma unroll
+    for (int c = 0; c < 64; ++c)
+        if (c < d) op[c] = __float2bfloat16(o[c] * inv);
+}
 }  // namespace clb
 
 extern "C" int cl_softmax_rows(const float* s, void* p, int rows, int cols, float scale, void* stream_) {
@@ -455,5 +549,35 @@ extern "C" int cl_channel_affine_nchw(const float* x, float* y, const float* shi
     if (!x || !y || !shift || n <= 0 || C <= 0 || hw <= 0) return set_error(CL_ERR_INVALID, "cl_channel_affine_nchw: bad args");
     const long long total = (long long)n * C * hw;
     launch_k(clb::channel_affine_nchw_kernel, ew_blocks(total), 256, 0, stream, x, y, shift, mul, C, (long long)hw, total);
+    DONE();
+}
+
+extern "C" int cl_clip_embed(const int64_t* ids, const void* tok, const void* pos, void* out, int rows, int T, int C, int vocab, void* stream_) {
+    STREAM;
+    if (!ids || !tok || !pos || !out || rows <= 0 || T <= 0 || C % 8 != 0 || vocab <= 0) return set_error(CL_ERR_INVALID, "cl_clip_embed: bad args");
+    const long long total = (long long)rows * (C / 8);
+    launch_k(clb::clip_embed_kernel, ew_blocks(total), 256, 0, stream, reinterpret_cast<const long long*>(ids), BF(tok), BF(pos), BFW(out), T, C,
+             vocab, total);
+    DONE();
+}
+
+extern "C" int cl_quick_gelu(void* x, int64_t n, void* stream_) {
+    STREAM;
+    if (!x || n <= 0 || n % 8 != 0) return set_error(CL_ERR_INVALID, "cl_quick_gelu: n must be a positive multiple of 8");
+    launch_k(clb::quick_gelu_kernel, ew_blocks(n / 8), 256, 0, stream, BFW(x), (long long)(n / 8));
+    DONE();
+}
+
+extern "C" int cl_causal_attention_small(const void* qkv, void* out, int B, int T, int heads, int d, float scale, void* stream_) {
+    STREAM;
+    if (!qkv || !out || B <= 0 || heads <= 0 || T <= 0 || T > 128 || d <= 0 || d > 64)
+        return set_error(CL_ERR_INVALID, "cl_causal_attention_small: T <= 128, head dim <= 64");
+    const size_t smem = (size_t)2 * T * d * sizeof(float);
+    static bool done = false;
+    if (!done) {
+        CL_CUDA_CHECK(cudaFuncSetAttribute(clb::causal_attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 64 * 4));
+        done = true;
+    }
+    launch_k(clb::causal_attention_small_kernel, dim3(B, heads), 128, smem, stream, BF(qkv), BFW(out), T, heads * d, d, scale);
     DONE();
 }

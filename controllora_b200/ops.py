@@ -656,6 +656,36 @@ def softmax_rows(s, scale: float):
     return p
 
 
+def clip_embed(ids, tok, pos):
+    """x[b, t] = tok[ids[b, t]] + pos[t] (bf16); ids int64 [B, T]."""
+    _req(tok, BF16, "tok")
+    _req(pos, BF16, "pos")
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.dim() == 2
+    B, T = ids.shape
+    Cc = tok.shape[1]
+    out = torch.empty(B, T, Cc, device=tok.device, dtype=BF16)
+    _call("cl_clip_embed", _p(ids), _p(tok), _p(pos), _p(out), B * T, T, Cc, tok.shape[0])
+    return out
+
+
+def quick_gelu_(x):
+    """in place: x * sigmoid(1.702 x) (bf16, numel % 8 == 0)."""
+    _req(x, BF16, "x")
+    assert x.is_contiguous()
+    _call("cl_quick_gelu", _p(x), C.c_int64(x.numel()))
+    return x
+
+
+def causal_attention_small(qkv, B: int, T: int, heads: int, scale: float):
+    """causal softmax(q k^T * scale) v of a short sequence; qkv [B*T, 3*C] bf16 (q | k | v) -> [B*T, C] bf16."""
+    _req(qkv, BF16, "qkv")
+    assert qkv.is_contiguous() and qkv.shape[0] == B * T and qkv.shape[1] % (3 * heads) == 0
+    Cc = qkv.shape[1] // 3
+    out = torch.empty(B * T, Cc, device=qkv.device, dtype=BF16)
+    _call("cl_causal_attention_small", _p(qkv), _p(out), B, T, heads, Cc // heads, C.c_float(scale))
+    return out
+
+
 def channel_affine_nchw(x, mul: float, shift):
     """y[n, c] = mul * x[n, c] + shift[c] on NCHW fp32."""
     _req(x, torch.float32, "x")

@@ -193,6 +193,13 @@ int cl_add_noise(const float* x0, const float* sqrt_ac, const float* sqrt_1mac, 
  * (p = softmax(scale * s) per row, fp32 in, bf16 out, cols % 4 == 0, <= 12288) and the post_quant_conv bias as a per-channel
  * shift of NCHW fp32 latents (y = mul * x + shift[c]). */
 int cl_softmax_rows(const float* s, void* p, int rows, int cols, float scale, void* stream);
+/* CLIP text encoder (transformers CLIPTextModel, train_text_to_image_control_lora.py:768 `text_encoder(batch["input_ids"])[0]`):
+ * token + position embedding gather (bf16 tables, ids int64 [rows], row r is position r % T), the in-place quick_gelu
+ * x * sigmoid(1.702 x) of CLIPMLP, and the causal self-attention of the 77-token sequence (T <= 128, head dim <= 64; fp32
+ * online softmax, one CTA per (batch, head)); qkv [B*T, 3*heads*d] bf16 = q | k | v, out [B*T, heads*d] bf16. */
+int cl_clip_embed(const int64_t* ids, const void* tok, const void* pos, void* out, int rows, int T, int C, int vocab, void* stream);
+int cl_quick_gelu(void* x, int64_t n, void* stream);
+int cl_causal_attention_small(const void* qkv, void* out, int B, int T, int heads, int d, float scale, void* stream);
 int cl_channel_affine_nchw(const float* x, float* y, const float* shift, float mul, int n, int C, int64_t hw, void* stream);
 /* strided weight-space helpers of the dense (concat_hidden, models.py:208-214) control MLP: bf16 view / transpose of an fp32
  * master (dst[i*ld + j] = bf16(alpha * src[i*s_i + j*s_j])) and strided fp32 accumulation (dst[i*ld + j] += alpha * src[i*J + j]) */

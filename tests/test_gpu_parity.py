@@ -342,6 +342,17 @@ def test_graphed_sampler_matches_eager_loop(scheduler, variant):
     assert gs._graph is not None
 
 
+# ------------------------------------------------------------------------------------------------ CLIP text encoder in front of the step
+@pytest.mark.parametrize("which", ["tiny", "full"])
+def test_clip_text_encoder_matches_oracle(which):
+    """`text_encoder(input_ids)[0]` (train_...:768) against the fp32 oracle restatement of transformers' CLIPTextModel (pinned
+    to transformers itself in tests/test_oracle.py): a 2-layer config and the SD-1.5 text tower (12 x 768, 12 heads, 77 tokens)
+    at batch 8; <= 3e-2 relative and no worse than 1.25x the same math in eager bf16 PyTorch."""
+    from tests import check_clip
+
+    assert check_clip.run(which)
+
+
 # ------------------------------------------------------------------------------------------------ VAE either side of the step
 @pytest.mark.parametrize("which", ["tiny", "full"])
 def test_vae_encode_decode_matches_oracle(which):

@@ -242,3 +242,35 @@ def test_vae_oracle_matches_sd15_anchors():
         assert z.shape == (1, 4, 16, 16) and t.decode(z).shape == (1, 3, 32, 32)
         mean, logvar = t.encode_moments(torch.zeros(1, 3, 32, 32))
         assert float(logvar.max()) <= 20.0 and float(logvar.min()) >= -30.0
+
+
+def test_clip_oracle_matches_transformers():
+    """oracle/clip_ref.clip_text_forward is pinned to the reference's own dependency: transformers.CLIPTextModel (the class
+    train_text_to_image_control_lora.py:401-403 instantiates) with the same synthetic weights, CPU fp32; plus the parameter
+    count of the SD-1.5 text encoder (123 060 480)."""
+    import pytest
+    import torch
+    from oracle import clip_ref as CR
+
+    tr = pytest.importorskip("transformers")
+    cfg = dict(CR.SD15_TEXT_CONFIG)
+    cfg.update(num_hidden_layers=2, vocab_size=1000)
+    sd = CR.synthetic_state_dict(cfg, seed=0)
+    hc = tr.CLIPTextConfig(vocab_size=cfg["vocab_size"], hidden_size=cfg["hidden_size"], intermediate_size=cfg["intermediate_size"],
+                           num_hidden_layers=cfg["num_hidden_layers"], num_attention_heads=cfg["num_attention_heads"],
+                           max_position_embeddings=cfg["max_position_embeddings"], hidden_act="quick_gelu", layer_norm_eps=1e-5)
+    m = tr.CLIPTextModel(hc).eval()
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    ids = torch.randint(0, cfg["vocab_size"], (2, 77), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        want = m(ids)[0]
+    got = CR.clip_text_forward(sd, ids, cfg)
+    assert float((got - want).abs().max()) < 1e-4
+    short = CR.clip_text_forward(sd, ids[:, :9], cfg)
+    with torch.no_grad():
+        assert float((short - m(ids[:, :9])[0]).abs().max()) < 1e-4
+    full = CR.SD15_TEXT_CONFIG
+    Cw, Fi, L = full["hidden_size"], full["intermediate_size"], full["num_hidden_layers"]
+    n = (full["vocab_size"] + full["max_position_embeddings"]) * Cw + L * (4 * (Cw * Cw + Cw) + 2 * Cw * Fi + Fi + Cw + 4 * Cw) + 2 * Cw
+    assert n == 123060480
