@@ -454,6 +454,13 @@ def run_ours(a):
     ms_step = float(tmax) / a.steps
     value = world * B / (ms_step / 1e3)
     final_loss = float(loss)
+    # data-parallel sanity: every rank trained on its own batch, so the replicas are in sync only if the gradient exchange works
+    replicas_in_sync = None
+    if world > 1:
+        chk = torch.stack([tr.flat_p.double().sum(), (tr.flat_p.double() ** 2).sum()])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        replicas_in_sync = bool(all(torch.equal(allc[0], c) for c in allc[1:]))
 
     trace("end-to-end region")
     # ---------------- end-to-end: host (pinned) buffers in, loss out, every step
@@ -582,7 +589,7 @@ def run_ours(a):
             "data": "synthetic",
             "config": {"workload": f"{a.config} ControlLoRA train step on the SD-1.5 UNet, 512x512 (64x64 latents, 77x768 text states), "
                                    f"batch {B}/GPU, hint encoder + UNet fwd/bwd + clip + AdamW" + (" + NCCL all-reduce of the flat grad arena" if world > 1 else ""),
-                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "global_batch": world * B, "parallelism": f"dp{world}", "replicas_in_sync": replicas_in_sync,
                        "cuda_graph": graph_used,
                        "l2_policy": "no explicit flush: each step streams 1.7 GB of frozen weights plus >5 GB of activations, far beyond the 126 MB L2",
                        "weights": "random-init (seeded), SD-1.5 / ControlLoRA shapes", "final_loss": final_loss},
@@ -600,7 +607,17 @@ def run_ours(a):
             out["cpu_baseline"] = cpu
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # orderly teardown, then a hard exit: a rank must never linger in NCCL / CUDA-graph destructors after the line is out
+        trace("teardown")
+        try:
+            tr._graph = None
+        except NameError:
+            pass
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -127,8 +127,9 @@ class HintEncoderEngine:
         return h
 
     # ------------------------------------------------------------------------------------------------ forward
-    def forward(self, ctx: Ctx, guide: torch.Tensor) -> List[Var]:
-        """guide: NCHW fp32 [B, 3, H, W] -> control states, one NHWC bf16 Var per level."""
+    def forward(self, ctx: Ctx, guide: torch.Tensor, on_level=None) -> List[Var]:
+        """guide: NCHW fp32 [B, 3, H, W] -> control states, one NHWC bf16 Var per level.  on_level(i) is called before level
+        i's ops are recorded (a tape entry recorded there runs AFTER level i's backward: the Trainer's gradient buckets)."""
         m = self.model
         ci = m.conv_in
         ops.conv_weight_prep(ci.weight, self.conv_in_w, None)
@@ -151,7 +152,9 @@ class HintEncoderEngine:
 
             ctx.tape.record(bwd_in)
         states = []
-        for lvl_ops, pre_ops in self.levels:
+        for i, (lvl_ops, pre_ops) in enumerate(self.levels):
+            if on_level is not None:
+                on_level(i)
             h = self._run_ops(ctx, h, lvl_ops)
             states.append(self._run_ops(ctx, h, pre_ops) if pre_ops else h)
         return states

@@ -552,6 +552,16 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, gnorm_sq=None, max_norm=0
           C.c_float(eps), C.c_float(wd), int(step), _p(gnorm_sq), C.c_float(max_norm), C.c_float(grad_scale), int(zero_grad))
 
 
+def step_begin(gnorm_sq, step_dev):
+    _call("cl_step_begin", _p(gnorm_sq), _p(step_dev))
+
+
+def adamw_dev(p, g, m, v, lr, beta1, beta2, eps, wd, step_dev, gnorm_sq=None, max_norm=0.0, grad_scale=1.0, zero_grad=True):
+    """AdamW whose bias corrections come from the device-side step counter `step_dev` (int64 [1], advanced by step_begin)."""
+    _call("cl_adamw_dev", _p(p), _p(g), _p(m), _p(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(beta1), C.c_float(beta2),
+          C.c_float(eps), C.c_float(wd), _p(step_dev), _p(gnorm_sq), C.c_float(max_norm), C.c_float(grad_scale), int(zero_grad))
+
+
 def hilo_combine(src, nb: int):
     M = src.shape[0]
     dst = torch.empty(M, 8 * nb, device=src.device, dtype=torch.float32)

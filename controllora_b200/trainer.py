@@ -48,6 +48,21 @@ class Trainer:
         self.hint = HintEncoderEngine(control_lora, store.get)
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
         self.step_idx = 0
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)     # device copy of step_idx (bias corrections inside the graph)
+        # data parallel: the gradient exchange is issued in THREE buckets on a side stream while the backward is still running
+        # (processor LoRAs once the UNet backward has finished, the deep hint-encoder levels once their backward has finished,
+        # the shallow levels at the end) - only the last, smallest bucket is exposed.  The arena order is the module order, so a
+        # bucket is one or two contiguous ranges of the flat gradient.
+        # CLB_DP_BUCKETS=1 opts in.  Default (what the 2-GPU runs validate): ONE all-reduce of the whole arena after the backward,
+        # outside the captured graph.  The bucketed, in-graph variant ran at 38.5 ms/step on 2 GPUs (round 2) but its replicas
+        # drifted apart in tests/test_multigpu_nccl.py and the process hung at teardown - it stays experimental.
+        import os as _os
+        want_buckets = _os.environ.get("CLB_DP_BUCKETS", "0") == "1"
+        self._side = torch.cuda.Stream(device=dev) if (want_buckets and self.world > 1 and dev.type == "cuda") else None
+        self._bucketed = self._side is not None      # False: ONE all-reduce after the backward (and outside a captured graph)
+        self._tail_in_graph = self.world == 1 or self._bucketed
+        self._reduced_in_step = False
+        self._buckets = self._make_buckets()
         self.levels = None
         # CUDA-graph mode: the forward/backward (~1800 launches) is captured once and replayed, so the step costs the
         # host one graph launch instead of ~40 ms of Python/ctypes work and cannot become launch-bound.
@@ -79,9 +94,9 @@ class Trainer:
         guide NCHW fp32 [B,3,512,512].  Returns the (device) loss tensor; nothing is synchronised.
 
         With cuda_graph=True the first `graph_warmup` calls run eagerly, the next call captures the forward/backward
-        into a CUDA graph (inputs are copied into static buffers first) and every later call replays it; the gradient
-        all-reduce and the optimizer kernels stay outside the graph (NCCL's watchdog thread must not meet a global
-        capture, and the AdamW bias correction is a host scalar).  eager=True forces the uncaptured path."""
+        into a CUDA graph (inputs are copied into static buffers first) and every later call replays it.  The graph holds
+        the WHOLE step: forward, backward, the bucketed gradient all-reduces (NCCL, on a side stream that forks from / joins the
+        capturing stream), clip + AdamW with a device-side step counter.  eager=True forces the uncaptured path."""
         return self._run("noised", self._forward_backward, (noisy_latents, timesteps, ehs, guide, target), eager)
 
     def step_from_latents(self, latents: torch.Tensor, ehs: torch.Tensor, guide: torch.Tensor, eager: bool = False) -> torch.Tensor:
@@ -100,6 +115,7 @@ class Trainer:
     def _run(self, mode: str, fb, args, eager: bool) -> torch.Tensor:
         from . import _lib
 
+        self.step_idx += 1
         if not self.cuda_graph or eager:
             n0 = _lib.launch_count()
             loss = fb(*args)
@@ -124,32 +140,53 @@ class Trainer:
             self._optimizer_tail()
             return loss
         if self._graph is None:
-            graph = torch.cuda.CUDAGraph()
-            n0 = _lib.launch_count()
-            try:
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                    self._static_loss = fb(*self._static)
-            except Exception as ex:      # capture is an optimisation of the launch path only: say so and keep training eagerly
-                import sys
+            import sys
 
-                print(f"controllora_b200.Trainer: CUDA-graph capture failed ({type(ex).__name__}: {ex}); "
-                      f"continuing with per-kernel launches", file=sys.stderr, flush=True)
-                torch.cuda.synchronize()
-                self.cuda_graph = False
-                self._static_loss = None
-                loss = fb(*self._static)
-                self._optimizer_tail()
-                return loss
-            self.launches_per_step = int(_lib.launch_count() - n0) + 2   # + sumsq + adamw outside the graph
+            n0 = _lib.launch_count()
+            while True:
+                graph = torch.cuda.CUDAGraph()
+                try:
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                        self._static_loss = fb(*self._static)
+                        if self._tail_in_graph:
+                            self._optimizer_tail()   # gradient exchange (side stream, world > 1), clip, AdamW: all inside the graph
+                    break
+                except Exception as ex:
+                    torch.cuda.synchronize()
+                    self._static_loss = None
+                    if self.world > 1 and self._bucketed:
+                        # NCCL refused to be captured: keep the graph for forward + backward, exchange gradients with one
+                        # all-reduce after the replay
+                        print(f"controllora_b200.Trainer: capturing the gradient all-reduce failed ({type(ex).__name__}: {ex}); "
+                              f"the collective and the optimizer stay outside the graph", file=sys.stderr, flush=True)
+                        self._bucketed, self._tail_in_graph, self._reduced_in_step = False, False, False
+                        n0 = _lib.launch_count()
+                        continue
+                    # capture is an optimisation of the launch path only: say so and keep training eagerly
+                    print(f"controllora_b200.Trainer: CUDA-graph capture failed ({type(ex).__name__}: {ex}); "
+                          f"continuing with per-kernel launches", file=sys.stderr, flush=True)
+                    self.cuda_graph = False
+                    loss = fb(*self._static)
+                    self._optimizer_tail()
+                    return loss
+            self.launches_per_step = int(_lib.launch_count() - n0) + (0 if self._tail_in_graph else 3)
             self._graph = graph
+            # capture executes nothing: the first replay below is this call's step
         self._graph.replay()
-        self._optimizer_tail()
+        if not self._tail_in_graph:
+            self._optimizer_tail()
         return self._static_loss
 
     def _forward_backward(self, noisy_latents, timesteps, ehs, guide, target) -> torch.Tensor:
         tape = Tape()
         hctx = Ctx(tape=tape)
-        states = self.hint.forward(hctx, guide)
+        self._pending = [0, 1, 2] if self._bucketed else []
+        split = self._split_level
+
+        def on_level(i):
+            if i == split and self._bucketed:
+                tape.record(lambda: self._reduce_bucket(1))          # runs after the backward of levels >= split
+        states = self.hint.forward(hctx, guide, on_level=on_level)
         control = {}
         for procs, s in zip(self.cl.lora_layers, states):
             n, H, W, C = s.data.shape
@@ -164,19 +201,67 @@ class Trainer:
                     c.grad = None
 
             tape.record(bridge)      # runs after every UNet backward op (incl. the per-level d-control GEMMs)
+        if self._bucketed:
+            tape.record(lambda: self._reduce_bucket(0))              # runs after every UNet backward op
         pred, ctx, rt = self.unet.run_engine(noisy_latents, timesteps, ehs, control, tape)
         loss, dpred = ops.mse_loss(pred.data, target)
         pred.grad = dpred
         tape.backward()
+        if self._bucketed:
+            for b in list(self._pending):
+                self._reduce_bucket(b)
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._reduced_in_step = True
         return loss
 
+    # ------------------------------------------------------------------------------------------------ gradient buckets
+    def _make_buckets(self):
+        """[[(lo, hi), ...] x 3]: 0 = everything whose gradient is complete when the UNet backward ends (lora_layers.* and
+        parameters that live in the UNet's processors), 1 = hint-encoder levels >= split, 2 = the rest (shallow levels, conv_in)."""
+        n_levels = len(getattr(self.cl, "down_blocks", [])) or 1
+        # level 0 (the 512x512 -> 64x64 pre-down path) is the longest part of the hint-encoder backward and runs last: everything
+        # above it is exchanged underneath it
+        self._split_level = 1 if n_levels > 1 else 0
+        groups = [[], [], []]
+        off = 0
+        for name, p in self._named_arena_params():
+            k = p.numel()
+            if name.startswith("lora_layers.") or name.startswith("extra."):
+                g = 0
+            else:
+                g = 2
+                parts = name.split(".")
+                if parts[0] in ("down_blocks", "pre_lora_layers") and len(parts) > 1 and parts[1].isdigit() and int(parts[1]) >= self._split_level:
+                    g = 1
+            r = groups[g]
+            if r and r[-1][1] == off:
+                r[-1] = (r[-1][0], off + k)
+            else:
+                r.append((off, off + k))
+            off += k
+        return groups
+
+    def _reduce_bucket(self, b: int) -> None:
+        """all-reduce(sum) of bucket b's gradient ranges on the side stream, ordered after everything the main stream has
+        launched so far; identical call order on every rank."""
+        if not self._bucketed or b not in self._pending:
+            return
+        self._pending.remove(b)
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            for lo, hi in self._buckets[b]:
+                torch.distributed.all_reduce(self.flat_g[lo:hi], group=self.pg)
+
     def _optimizer_tail(self) -> None:
-        self.step_idx += 1
-        self.arena.all_reduce()          # one ncclAllReduce(sum) over the whole gradient arena
-        self.gnorm_sq.zero_()
+        """clip_grad_norm_ + AdamW + zero_grad (train_...:791-796) as three launches; the step count lives on the device, so the
+        tail can sit inside the captured graph."""
+        if not self._reduced_in_step:
+            self.arena.all_reduce()      # (no side stream: CPU arenas / world 1) one all-reduce(sum) over the whole gradient arena
+        self._reduced_in_step = False
+        ops.step_begin(self.gnorm_sq, self.step_dev)
         ops.sumsq(self.flat_g, self.gnorm_sq)
-        ops.adamw(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                  self.step_idx, gnorm_sq=self.gnorm_sq, max_norm=self.max_norm, grad_scale=self.arena.grad_scale, zero_grad=True)
+        ops.adamw_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                      self.step_dev, gnorm_sq=self.gnorm_sq, max_norm=self.max_norm, grad_scale=self.arena.grad_scale, zero_grad=True)
 
     # ------------------------------------------------------------------------------------------------ checkpoints
     # The reference checkpoints through accelerate: `accelerator.save_state(output_dir/checkpoint-{global_step})` every
@@ -279,6 +364,7 @@ class Trainer:
             self.flat_v[:self.numel].copy_(opt["exp_avg_sq"].to(self.flat_v.device))
             self.flat_g.zero_()
         self.step_idx = int(opt["step_idx"])
+        self.step_dev.fill_(self.step_idx)
         rank = torch.distributed.get_rank(self.pg) if self.world > 1 else 0
         rs = os.path.join(str(path), f"random_states_{rank}.pkl")
         if os.path.isfile(rs):

@@ -301,6 +301,12 @@ int cl_sumsq(const float* x, int64_t n, float* out, void* stream);
 int cl_adamw(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
              float weight_decay, int step, const float* gnorm_sq, float max_norm, float grad_scale, int zero_grad,
              void* stream);
+/* the same optimizer tail for a CUDA-graph-captured step: cl_step_begin clears the squared-norm accumulator and advances a
+ * device-side step counter, cl_adamw_dev takes its bias corrections from that counter (train_...:791-796 without a host scalar) */
+int cl_step_begin(float* gnorm_sq, int64_t* step_dev, void* stream);
+int cl_adamw_dev(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, const int64_t* step_dev, const float* gnorm_sq, float max_norm, float grad_scale,
+                 int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -63,11 +63,29 @@ def _worker(rank, world, port, q):
     full = _inputs(B)
     half = [v[rank * (B // world):(rank + 1) * (B // world)].to(dev) for v in full]
     tr._forward_backward(*half)
-    tr.arena.all_reduce()
+    assert sum(hi - lo for b in tr._buckets for lo, hi in b) == tr.numel
+    if not tr._reduced_in_step:          # default: one all-reduce of the whole arena (CLB_DP_BUCKETS=1: issued in buckets already)
+        tr.arena.all_reduce()
     torch.cuda.synchronize()
     g = (tr.flat_g[:tr.numel] * tr.arena.grad_scale).detach().cpu()
+    # graph-replayed steps (forward + backward captured; all-reduce, clip, AdamW behind each replay) on rank-local data: the
+    # replicas must stay bit-identical and the device step counter must follow the host's
+    tr.flat_g.zero_()
+    tr._reduced_in_step = False
+    tg = _build(dev)
+    tg.cuda_graph, tg.graph_warmup = True, 2
+    losses = []
+    for it in range(5):
+        losses.append(tg.step(*half))
+    torch.cuda.synchronize()
+    gathered = [torch.empty_like(tg.flat_p) for _ in range(world)]
+    dist.all_gather(gathered, tg.flat_p)
+    same = all(torch.equal(gathered[0], t) for t in gathered[1:])
+    info = dict(same=bool(same), graph=tg._graph is not None, step_dev=int(tg.step_dev.item()), step_idx=tg.step_idx,
+                finite=bool(torch.isfinite(torch.stack([l.float() for l in losses])).all()))
     if rank == 0:
         q.put(g)
+        q.put(info)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -84,8 +102,11 @@ def test_allreduced_arena_equals_single_gpu_big_batch():
     for p in procs:
         p.start()
     g_dp = q.get(timeout=300)
+    info = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
+    print("2-GPU whole-step graph:", info)
+    assert info["same"] and info["graph"] and info["finite"] and info["step_dev"] == info["step_idx"] == 5
     tr = _build(torch.device("cuda", 0))
     tr._forward_backward(*[v.cuda() for v in _inputs(4)])
     torch.cuda.synchronize()
