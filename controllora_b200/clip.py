@@ -53,8 +53,9 @@ class CLIPTextModel(nn.Module):
             raise NotImplementedError("CLIPTextModel: only the quick_gelu MLP of SD-1.5's text encoder is implemented")
         self.config = SimpleNamespace(**cfg)
         dev = torch.device(device)
-        if dev.type != "cuda":
-            raise RuntimeError("controllora_b200.CLIPTextModel runs only on CUDA (sm_100a); there is no CPU path")
+        from ._lib import require_cuda
+
+        require_cuda(dev, "CLIPTextModel")
         self.device_ = dev
         pre = "text_model." if any(k.startswith("text_model.") for k in sd) else ""
         self.tok = sd[pre + "embeddings.token_embedding.weight"].detach().to(dev, BF16).contiguous()
@@ -105,7 +106,7 @@ class CLIPTextModel(nn.Module):
     def forward(self, input_ids: torch.Tensor, attention_mask=None, return_dict: bool = True):
         if attention_mask is not None:
             raise NotImplementedError("CLIPTextModel: the reference never passes an attention_mask (padded prompts attend causally)")
-        if not input_ids.is_cuda:
+        if input_ids.device != self.device_:
             input_ids = input_ids.to(self.device_)
         ids = input_ids.to(torch.int64).contiguous()
         B, T = ids.shape

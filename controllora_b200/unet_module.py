@@ -201,9 +201,9 @@ class UNet2DConditionModel(nn.Module):
     @staticmethod
     def _prep_inputs(sample, timestep, encoder_hidden_states):
         dev = sample.device
-        import os
-        if not sample.is_cuda and not os.environ.get("CLB_DRYRUN"):
-            raise RuntimeError("controllora_b200.UNet2DConditionModel runs only on CUDA (sm_100a); there is no CPU path")
+        from ._lib import require_cuda
+
+        require_cuda(sample.device, "UNet2DConditionModel")
         x = sample.detach()
         if x.dtype != torch.float32:
             x = x.float()

@@ -188,8 +188,9 @@ class AutoencoderKL(nn.Module):
     @torch.no_grad()
     def encode(self, x: torch.Tensor, return_dict: bool = True):
         """x [n, 3, H, W] in [-1, 1] (any float dtype) -> object with `.latent_dist` (DiagonalGaussianDistribution, fp32 NCHW)."""
-        if not x.is_cuda:
-            raise RuntimeError("controllora_b200.AutoencoderKL runs only on CUDA (sm_100a); there is no CPU path")
+        from ._lib import require_cuda
+
+        require_cuda(x.device, "AutoencoderKL")
         ctx = Ctx(tape=None)
         cin = self.enc_conv_in_w.shape[-1]
         h = Var(ops.conv_in(x.detach().float().contiguous(), self.enc_conv_in_w.view(self.enc_conv_in_w.shape[0], 3, 3, cin),
@@ -212,8 +213,9 @@ class AutoencoderKL(nn.Module):
     @torch.no_grad()
     def decode(self, z: torch.Tensor, return_dict: bool = True):
         """z [n, 4, h, w] (already divided by scaling_factor, like the reference's call) -> `.sample` [n, 3, 8h, 8w] fp32."""
-        if not z.is_cuda:
-            raise RuntimeError("controllora_b200.AutoencoderKL runs only on CUDA (sm_100a); there is no CPU path")
+        from ._lib import require_cuda
+
+        require_cuda(z.device, "AutoencoderKL")
         ctx = Ctx(tape=None)
         zs = ops.channel_affine_nchw(z.detach().float().contiguous(), 1.0, self.dec_shift)
         c0 = self.dec_conv_in_w.shape[0]

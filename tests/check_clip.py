@@ -8,6 +8,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+from tests._device import DEV  # noqa: E402
 
 CAP = 3e-2          # relative L2 of last_hidden_state vs the fp32 oracle (12 bf16 transformer layers)
 MARGIN = 1.25       # ours <= MARGIN * eager-bf16 error (both are bf16 pipelines with different rounding points)
@@ -39,21 +40,21 @@ def run(which="tiny"):
     t0 = time.time()
     ref = CR.clip_text_forward(sd, ids, cfg)
     t_or = time.time() - t0
-    model = cb.CLIPTextModel.from_state_dict(sd, "cuda", cfg)
-    out = model(ids.cuda())
+    model = cb.CLIPTextModel.from_state_dict(sd, DEV, cfg)
+    out = model(ids.to(DEV))
     y = out[0]
     assert y.shape == (B, T, cfg["hidden_size"]) and y.dtype == torch.bfloat16 and out.last_hidden_state is y
     # short prompt (T < 77) goes through the same kernels
-    y_short = model(ids[:, :16].cuda())[0]
+    y_short = model(ids[:, :16].to(DEV))[0]
     ref_short = CR.clip_text_forward(sd, ids[:, :16], cfg)
     # the reference's own precision: the same math in eager PyTorch, bf16 weights + activations on the GPU
-    sd16 = {k: v.cuda().to(torch.bfloat16) for k, v in sd.items()}
+    sd16 = {k: v.to(DEV).to(torch.bfloat16) for k, v in sd.items()}
 
     import torch.nn.functional as F
-    x = sd16["text_model.embeddings.token_embedding.weight"][ids.cuda()] + sd16["text_model.embeddings.position_embedding.weight"][:T]
+    x = sd16["text_model.embeddings.token_embedding.weight"][ids.to(DEV)] + sd16["text_model.embeddings.position_embedding.weight"][:T]
     Cw, heads = cfg["hidden_size"], cfg["num_attention_heads"]
     d = Cw // heads
-    causal = torch.full((T, T), float("-inf"), device="cuda", dtype=torch.bfloat16).triu(1)
+    causal = torch.full((T, T), float("-inf"), device=DEV, dtype=torch.bfloat16).triu(1)
     for i in range(cfg["num_hidden_layers"]):
         p = f"text_model.encoder.layers.{i}."
         w = lambda k: sd16[p + k]

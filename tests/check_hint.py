@@ -8,18 +8,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-DEV = "cpu" if os.environ.get("CLB_DRYRUN") else "cuda"
-if DEV == "cpu":
-    from controllora_b200 import _lib, ops
-
-    class _Dummy:
-        def __getattr__(self, name):
-            return lambda *a, **k: 0
-
-    _lib.lib = lambda: _Dummy()
-    ops._req = lambda *a, **k: None
-    ops._stream = lambda: None
-
+from tests._device import DEV  # noqa: E402
 from tests.check_unet import TINY, TINY_LORA, rel  # noqa: E402
 
 

@@ -9,19 +9,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-import os
-DEV = "cpu" if os.environ.get("CLB_DRYRUN") else "cuda"
-if DEV == "cpu":
-    # plumbing dry-run without a GPU: kernels are replaced by no-ops (outputs are uninitialised memory)
-    from controllora_b200 import _lib, ops
-
-    class _Dummy:
-        def __getattr__(self, name):
-            return lambda *a, **k: 0
-
-    _lib.lib = lambda: _Dummy()
-    ops._req = lambda *a, **k: None
-    ops._stream = lambda: None
+from tests._device import DEV  # noqa: E402  ("cuda", or "cpu" in the emulated host-logic mode)
 
 TINY = dict(block_out_channels=(64, 128, 128, 128), layers_per_block=1, cross_attention_dim=64, attention_head_dim=8)
 TINY_LORA = dict(

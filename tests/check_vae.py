@@ -7,6 +7,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+from tests._device import DEV, sync  # noqa: E402
 
 
 def rel(a, b):
@@ -31,7 +32,7 @@ def run(which="tiny"):
     with torch.no_grad():
         for p in ovae.parameters():
             p.copy_(p.to(torch.bfloat16).float())          # the reference runs the frozen VAE in weight_dtype = bf16
-    mvae = cb.AutoencoderKL.from_state_dict({k: v.detach().clone() for k, v in ovae.state_dict().items()}, "cuda", cfg)
+    mvae = cb.AutoencoderKL.from_state_dict({k: v.detach().clone() for k, v in ovae.state_dict().items()}, DEV, cfg)
     g = torch.Generator().manual_seed(1)
     x = (torch.rand(n, 3, size, size, generator=g) * 2 - 1).to(torch.bfloat16).float()
     lat_hw = size // (2 ** (len(ovae.config["block_out_channels"]) - 1))
@@ -42,10 +43,10 @@ def run(which="tiny"):
         z_o = (mean_o + torch.exp(0.5 * logvar_o) * eps) * ovae.config["scaling_factor"]
         img_o = ovae.decode(z_o)
     t_or = time.time() - t0
-    dist = mvae.encode(x.cuda()).latent_dist
-    z_m = (dist.mean + dist.std * eps.cuda()) * mvae.config.scaling_factor
-    img_m = mvae.decode(z_o.cuda() / mvae.config.scaling_factor).sample       # decode the ORACLE's latents: isolates the decoder
-    torch.cuda.synchronize()
+    dist = mvae.encode(x.to(DEV)).latent_dist
+    z_m = (dist.mean + dist.std * eps.to(DEV)) * mvae.config.scaling_factor
+    img_m = mvae.decode(z_o.to(DEV) / mvae.config.scaling_factor).sample       # decode the ORACLE's latents: isolates the decoder
+    sync()
     e = {"mean": rel(dist.mean, mean_o), "logvar": rel(dist.logvar, logvar_o), "latents": rel(z_m, z_o), "decode": rel(img_m, img_o)}
     print(f"[vae {which}] n={n} {size}x{size}: oracle {t_or:.1f}s  " + "  ".join(f"{k} rel={v:.3e}" for k, v in e.items()))
     ok = e["mean"] < 2e-2 and e["logvar"] < 2e-2 and e["latents"] < 2e-2 and e["decode"] < 2e-2

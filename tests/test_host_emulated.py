@@ -1,0 +1,47 @@
+"""CPU suite: the product's HOST logic (everything above the C ABI) against the fp32 oracle, with the CUDA kernels replaced by
+their torch restatements (tests/emu_ops.py).  The same checkers run against the real kernels in the `-m gpu` suite; here they
+prove that the tape engine, the LoRA slot packing, the v1 / V2 / post_add / concat_hidden control algebra, the hint-encoder
+program and the Trainer issue the right operations - on a box without a GPU.  One subprocess runs all cases (the emulation mode
+is a per-process switch, tests/_device.py)."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+CASES = ["unet_none", "unet_plain", "unet_v1", "unet_v2", "unet_v1_stacked", "unet_v1_post_add", "unet_v1_concat",
+         "unet_v1_stacked@0.5", "unet_v2@0.5", "hint_v1", "hint_v2", "train_v1", "train_v2", "vae_tiny", "clip_tiny"]
+try:
+    sys.path.insert(0, str(ROOT))
+    from tests.check_variants import CASE_NAMES as _EXTRA
+
+    CASES += list(_EXTRA)
+except ImportError:
+    pass
+
+
+@pytest.fixture(scope="module")
+def emulated_results():
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "run_emulated.py"), *CASES], capture_output=True, text=True, timeout=1500,
+                       cwd=str(ROOT))
+    res = {}
+    for line in r.stdout.splitlines():
+        if line.startswith("RESULT "):
+            _, name, verdict, _ = line.split()
+            res[name] = verdict == "OK"
+    return res, r.stdout[-6000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_host_logic_matches_oracle(emulated_results, case):
+    res, log = emulated_results
+    assert case in res, f"{case} did not run:\n{log}"
+    assert res[case], f"{case} deviates from the oracle:\n{log}"
+
+
+def test_emulation_is_test_only():
+    """The torch restatements are test infrastructure: nothing that ships may import them."""
+    for p in [*ROOT.glob("controllora_b200/*.py"), ROOT / "bench.py"]:
+        src = p.read_text()
+        assert "emu_ops" not in src and "run_emulated" not in src, p
