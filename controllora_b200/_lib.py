@@ -40,7 +40,7 @@ def lib() -> C.CDLL:
 
 def require_cuda(device, what: str) -> None:
     """Every public entry of the package calls this: the product has no CPU path.  The one exception is the test suite's
-    host-logic mode (CLB_DRYRUN=1, set by tests/emu_ops.py / tests/check_*.py), where the kernel wrappers have been replaced by
+    host-logic mode (CLB_DRYRUN=1, set by the checkers under tests/), where the kernel wrappers have been replaced by
     test doubles and only the Python program above the C ABI is being exercised."""
     dev_type = device if isinstance(device, str) else getattr(device, "type", str(device))
     if dev_type != "cuda" and not os.environ.get("CLB_DRYRUN"):
