@@ -41,6 +41,18 @@ def gemm(a, b, *, out=None, bias=None, row_bias=None, rows_per_group=0, residual
          lora_scale=1.0, t_add=None, t_out=None, out_fp32=False, conv_stride=0, pad_lo=1, block_n=0):
     assert a.dtype == BF16 and b.dtype == BF16
     N, K = b.shape
+    # the argument checks of cl_gemm (csrc/gemm.cu): a host program the kernel would reject must fail here too
+    assert N % 4 == 0 and K % 8 == 0 and b.stride(0) % 8 == 0 and b.stride(1) == 1, "cl_gemm: N % 4, K % 8, ldb % 8"
+    assert (ext is None) == (lora_up is None) and (lora_up is not None or (t_add is None and t_out is None))
+    if lora_up is not None:
+        assert lora_up.shape[1] in (4, 8) and ext.stride(0) % 8 == 0 and not conv_stride
+    if not conv_stride:
+        assert a.stride(1) == 1 and a.stride(0) % 8 == 0, "cl_gemm: lda % 8"
+    else:
+        assert a.is_contiguous() and a.shape[-1] % 32 == 0 and a.shape[1] % conv_stride == 0 and a.shape[2] % conv_stride == 0
+    for t_, nm in ((out, "ldd"), (residual, "ldr")):
+        if t_ is not None and not t_.is_contiguous():
+            assert t_.dim() == 2 and t_.stride(1) == 1 and t_.stride(0) % 4 == 0, f"cl_gemm: {nm} % 4"
     if conv_stride:
         n, H, W, C = a.shape
         assert K == 9 * C
@@ -311,7 +323,10 @@ def _pack_run(self):
 
 def skinny_atb(a, r, b, out, so_j, so_c, alpha):
     b2 = b.reshape(-1, b.shape[-1]) if b.is_contiguous() else b
-    assert b2.shape[0] == a.shape[0]
+    assert b2.shape[0] == a.shape[0] and a.dtype == torch.float32 and b2.dtype == BF16 and out.dtype == torch.float32
+    Cc = b2.shape[1]
+    assert 1 <= r <= 8 and Cc % 8 == 0 and Cc // 8 <= 512 and b2.stride(1) == 1 and b2.stride(0) % 8 == 0, "cl_skinny_atb: bad descriptor"
+    assert max(1, 512 // (Cc // 8)) * r * Cc * 4 <= 200 * 1024, "cl_skinny_atb_batch: shared memory"
     o = _sv(out, (r, b2.shape[1]), (so_j, so_c))
     o += float(alpha) * (a[:, :r].float().t() @ b2.float())
 
@@ -326,11 +341,14 @@ def _skinny_flush(self):
 
 def rowdot(a, u):
     a2 = a.reshape(-1, a.shape[-1]) if a.is_contiguous() else a
+    assert a2.dtype == BF16 and u.dtype == torch.float32 and u.is_contiguous() and u.shape[1] in (4, 8)
+    assert a2.shape[1] % 8 == 0 and a2.stride(0) % 8 == 0 and a2.shape[1] * u.shape[1] * 4 <= 48 * 1024, "cl_rowdot: bad args"
     return a2.float() @ u
 
 
 def rowmat(a, w, sw_i, sw_j, I, J, alpha, out, ldo, out_mode=0, col_off=0, lo_off=0, accumulate=False):
     M = a.shape[0]
+    assert 1 <= I <= 8 and 1 <= J <= 8 and a.dtype == torch.float32, "cl_rowmat: bad args"
     Wm = _sv(w, (I, J), (sw_i, sw_j)).float()
     s = float(alpha) * (a[:, :J].float() @ Wm.t())                       # [M, I]
     if out_mode == 0:
@@ -343,6 +361,7 @@ def rowmat(a, w, sw_i, sw_j, I, J, alpha, out, ldo, out_mode=0, col_off=0, lo_of
 
 
 def skinny_small(a, I, b, J, out, alpha):
+    assert I <= 8 and J <= 8, "cl_skinny_small: bad args"
     out.view(-1)[: I * J].view(I, J).add_(float(alpha) * (a[:, :I].float().t() @ b[:, :J].float()))
 
 
@@ -361,6 +380,8 @@ def hilo_combine(src, nb):
 def rank_update(x, t, tab, alpha, out=None):
     C = x.shape[-1]
     rp = tab.shape[1]
+    assert x.dtype == BF16 and x.is_contiguous() and tab.is_contiguous() and tab.shape[0] == C and t.dtype == torch.float32
+    assert C % 8 == 0 and rp in (4, 8) and C * rp * 4 <= 48 * 1024 and t.shape[1] >= rp, "cl_rank_update: bad args"
     y = _bf(x.float().reshape(-1, C) + float(alpha) * (t[:, :rp] @ tab.t())).reshape(x.shape)
     if out is None:
         return y
@@ -370,6 +391,7 @@ def rank_update(x, t, tab, alpha, out=None):
 
 def v2_inject_fwd(x, th16, uc, rc, tab, alpha):
     C = x.shape[-1]
+    assert C % 8 == 0 and 1 <= rc <= 4 and C * 16 <= 48 * 1024 and tab.shape == (C, 4), "cl_v2_inject_fwd: bad args"
     t = (th16[:, :8] + th16[:, 8:]).clone()
     if uc is not None:
         t[:, :rc] += uc[:, :rc]
@@ -379,6 +401,7 @@ def v2_inject_fwd(x, th16, uc, rc, tab, alpha):
 
 def v2_inject_bwd(dy, up_tab, down_tab, alpha, need_dh):
     C = dy.shape[-1]
+    assert C % 8 == 0 and C <= 1280 and up_tab.shape == (C, 4) and (not need_dh or down_tab.shape == (C, 4)), "cl_v2_inject_bwd: bad args"
     d2 = dy.float().reshape(-1, C)
     dt = d2 @ up_tab
     dh = _bf(d2 + float(alpha) * (dt @ down_tab.t())).reshape(dy.shape) if need_dh else None
@@ -387,6 +410,7 @@ def v2_inject_bwd(dy, up_tab, down_tab, alpha, need_dh):
 
 def rank4_project_update(x, proj_tab, upd_tab, uc, rc, alpha):
     C = x.shape[-1]
+    assert C % 8 == 0 and C <= 1280 and 0 <= rc <= 4 and proj_tab.shape == (C, 4) and upd_tab.shape == (C, 4), "cl_rank4_project_update"
     x2 = x.float().reshape(-1, C)
     t = x2 @ proj_tab
     if uc is not None:
