@@ -90,6 +90,34 @@ class LoraRuntime:
             sig.append(tuple((id(a), a.key_states_skipped, a.value_states_skipped, a.output_states_skipped) for a in chain))
         return tuple(sig)
 
+    @staticmethod
+    def _needs_generic(p, chain, post_add, cat) -> Optional[str]:
+        """None when the fused one-launch path covers this layer's adapter chain, else the reason it does not."""
+        if os.environ.get("CLB_GENERIC_CHAIN", "0") == "1":      # tests: run EVERY layer through lora_generic
+            return "CLB_GENERIC_CHAIN=1"
+        if any(post_add) and (len(chain) > 1 or _is_v2(p)):
+            return "post_add inside a stacked chain"
+        if any(a is not p and (_is_v1(a) or _is_v2(a)) for a in chain):
+            return "a ControlLoRA processor stacked as pre / post LoRA"
+        if cat and (len(chain) > 1 or any(post_add) or p.to_q_lora.down.weight.shape[0] > 4):
+            return "concat_hidden control combined with stacked adapters / post_add / q rank > 4"
+        if not cat and (_is_v1(p) or _is_v2(p)):
+            ctrl = [p.to_control] + ([p.to_control_out] if _is_v2(p) else [])
+            if any(c.down.weight.shape[0] > 4 for c in ctrl):
+                return "control rank > 4"
+
+        def total(name, skip):
+            return sum(getattr(a, name).down.weight.shape[0] for a in chain if not skip(a))
+
+        ranks = [total("to_q_lora", lambda a: False), total("to_k_lora", lambda a: a.key_states_skipped),
+                 total("to_v_lora", lambda a: a.value_states_skipped),
+                 total("to_out_lora", lambda a: a is not p and a.output_states_skipped)]
+        if max(ranks) > 8:
+            return "adapter ranks on one projection sum to more than 8"
+        if any(post_add) and max(ranks) > 4:
+            return "post_add adapter of rank > 4"
+        return None
+
     def _adapter(self, slot: LoraSlot, layer, unscaled: bool = False) -> E.Adapter:
         a = slot.add(layer.down.weight, layer.up.weight, unscaled=unscaled)
         a.down_grad = self.grad_of(layer.down.weight)
@@ -108,20 +136,16 @@ class LoraRuntime:
             chain = [*getattr(p, "pre_loras", []), p, *getattr(p, "post_loras", [])]
             lp.chain = chain
             post_add = [bool(getattr(a, "post_add", False)) for a in chain]
-            if any(post_add) and (len(chain) > 1 or _is_v2(p)):
-                raise NotImplementedError("lora_post_add=True is supported for single (unstacked) LoRA / v1 ControlLoRA processors only")
-            for a in chain:
-                if a is not p and (_is_v1(a) or _is_v2(a)):
-                    raise NotImplementedError("stacking a second *Control*LoRA processor as pre/post LoRA is not supported")
             cat = _is_v1(p) and getattr(p, "concat_hidden", False)
-            if cat and (len(chain) > 1 or any(post_add) or p.to_q_lora.down.weight.shape[0] > 4):
-                raise NotImplementedError("lora_concat_hidden=True is supported for single (unstacked, non-post_add, rank <= 4) processors only")
             lp.kind = "v1cat" if cat else ("v1" if _is_v1(p) else ("v2" if _is_v2(p) else "plain"))
-            if lp.kind in ("v1", "v2"):
-                ctrl = [p.to_control] + ([p.to_control_out] if lp.kind == "v2" else [])
-                if any(c.down.weight.shape[0] > 4 for c in ctrl):
-                    raise NotImplementedError("control rank > 4 is supported only with lora_concat_hidden=True on v1 processors "
-                                              "(dense control MLP path); the rank-4 control tables hold 4 rows per processor")
+            why = self._needs_generic(p, chain, post_add, cat)
+            if why is not None:
+                # a wiring the one-launch path cannot express (see lora_generic.py): this layer runs adapter by adapter
+                from .lora_generic import GenericLayer
+
+                lp.kind, lp.generic_reason = "generic", why
+                lp.generic = GenericLayer(self, L, p, chain)
+                continue
             C = L.to_q.w.shape[0]
             kv_in = L.to_k.w.shape[1]
             lp.post_add = any(post_add)
@@ -180,6 +204,7 @@ class LoraRuntime:
         if getattr(self, "_level_key", None) != key:
             self._build_levels(groups, control_vars)
             self._level_key = key
+        ctx.stash["control_vars"] = control_vars          # generic layers look their processors' control states up themselves
         s = ctx.scale
         if self.plan._unscaled:
             if s == 0.0:
@@ -422,6 +447,8 @@ class LoraRuntime:
     # ------------------------------------------------------------------------------------------------ attention layer
     def attn_fn(self, ctx: Ctx, L, hs: Var, ehs: Optional[Var], residual: Var) -> Var:
         lp = self.layers[L.name]
+        if lp.kind == "generic":
+            return lp.generic.run(ctx, hs, ehs, residual)
         if lp.kind == "v2":
             hs = self._v2_inject(ctx, lp, hs, 0)
         kv_in = hs if ehs is None else ehs

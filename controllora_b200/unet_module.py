@@ -190,12 +190,14 @@ class UNet2DConditionModel(nn.Module):
         control: Dict[int, Var] = {}
         tensors: List[torch.Tensor] = []
         for p in self._procs.values():
-            cs = getattr(p, "control_states", None)
-            if cs is None or not torch.is_tensor(cs):
-                continue
-            if cs.data_ptr() not in control:
-                control[cs.data_ptr()] = _control_to_var(cs.detach(), rg=need_grad and cs.requires_grad)
-                tensors.append(cs)
+            # stacked ControlLoRA processors (pre / post LoRAs, models.py:234-236, 366-372) carry their own control states
+            for m in [*getattr(p, "pre_loras", []), p, *getattr(p, "post_loras", [])]:
+                cs = getattr(m, "control_states", None)
+                if cs is None or not torch.is_tensor(cs):
+                    continue
+                if cs.data_ptr() not in control:
+                    control[cs.data_ptr()] = _control_to_var(cs.detach(), rg=need_grad and cs.requires_grad)
+                    tensors.append(cs)
         return control, tensors
 
     @staticmethod

@@ -1,0 +1,19 @@
+"""B200: the general adapter-chain path (controllora_b200/lora_generic.py) on the real kernels against the fp32 oracle - the
+wirings of /root/reference/models.py:118-431 beyond the fused one-launch path (post_add inside stacked chains, ranks > 8, control
+ranks > 4, stacked ControlLoRA processors, concat_hidden + stacking), and the standard wirings forced through the same path.
+The same cases run in host-logic mode on the CPU (tests/test_host_emulated.py)."""
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from tests import check_variants  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", check_variants.CASE_NAMES)
+def test_general_chain_matches_oracle(case):
+    assert check_variants.CASES[case]()
