@@ -9,9 +9,11 @@ reference's configs/*.json and the wiring code of train_text_to_image_control_lo
     control_lora(guide)                                        # injects control states into the processors
     noise_pred = unet(noisy_latents, timesteps, encoder_hidden_states).sample
 
-The processors here are *parameter containers + wiring*: the arithmetic of a processor call (models.py:118-152,
-222-287, 357-431) is executed by the UNet as fused kernel launches (controllora_b200/lora_runtime.py) — there is no
-PyTorch/CPU implementation of it in this package.
+The processors here are *parameter containers + wiring*: inside this package's UNet the arithmetic of a processor call
+(models.py:118-152, 222-287, 357-431) is part of the whole-network program (controllora_b200/lora_runtime.py).  Installed on
+a real diffusers UNet they are called per attention module like the reference's (`processor(attn, hidden_states, ...)`), which
+runs the same kernels for that one layer through an autograd bridge (controllora_b200/eager_attn.py).  There is no
+PyTorch/CPU implementation of the arithmetic in this package.
 """
 from __future__ import annotations
 
@@ -23,9 +25,6 @@ from typing import List, Optional, Tuple
 
 import torch
 import torch.nn as nn
-
-_NO_EAGER = ("controllora_b200 processors are executed by controllora_b200.UNet2DConditionModel as fused CUDA kernels; "
-             "calling one directly on tensors is not supported (there is no PyTorch fallback path).")
 
 
 class LoRALinearLayer(nn.Module):
@@ -41,7 +40,10 @@ class LoRALinearLayer(nn.Module):
         nn.init.zeros_(self.up.weight)
 
     def forward(self, x):
-        raise NotImplementedError(_NO_EAGER)
+        """up(down(x)) on the CUDA kernels (fp32 rank space), differentiable w.r.t. x, down and up."""
+        from .eager_attn import lora_linear_forward
+
+        return lora_linear_forward(self, x)
 
 
 class LoRACrossAttnProcessor(nn.Module):
@@ -82,7 +84,12 @@ class LoRACrossAttnProcessor(nn.Module):
         self.output_states_skipped = is_skipped
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, scale=1.0):
-        raise NotImplementedError(_NO_EAGER)
+        """The call diffusers' CrossAttention.forward makes (models.py:118-152 / 222-287 / 357-431 for the three processor classes;
+        which algebra runs is decided by the class and its pre / post chain): one attention layer on the CUDA kernels, inside
+        torch autograd."""
+        from .eager_attn import call_processor
+
+        return call_processor(self, attn, hidden_states, encoder_hidden_states, attention_mask, scale)
 
 
 class ControlLoRACrossAttnProcessor(LoRACrossAttnProcessor):

@@ -27,12 +27,10 @@ def _cases():
         c[k] = check_hint.CASES[k]
     c["vae_tiny"] = lambda: check_vae.run("tiny")
     c["clip_tiny"] = lambda: check_clip.run("tiny")
-    try:
-        from tests import check_variants
+    from tests import check_eager, check_variants
 
-        c.update(check_variants.CASES)
-    except ImportError:
-        pass
+    c.update(check_variants.CASES)
+    c.update(check_eager.CASES)
     return c
 
 

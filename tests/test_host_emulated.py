@@ -12,13 +12,13 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 CASES = ["unet_none", "unet_plain", "unet_v1", "unet_v2", "unet_v1_stacked", "unet_v1_post_add", "unet_v1_concat",
          "unet_v1_stacked@0.5", "unet_v2@0.5", "hint_v1", "hint_v2", "train_v1", "train_v2", "vae_tiny", "clip_tiny"]
-try:
-    sys.path.insert(0, str(ROOT))
-    from tests.check_variants import CASE_NAMES as _EXTRA
-
-    CASES += list(_EXTRA)
-except ImportError:
-    pass
+# general adapter chains (tests/check_variants.py) and the diffusers-style per-module processor call (tests/check_eager.py); listed
+# by name so that collecting this file never imports a checker (the device mode is fixed at their import, tests/_device.py)
+CASES += ["variant_" + k for k in ("v1_pre_post_add", "v1_post_add_main_stacked", "v2_post_post_add", "v1_rank16", "v1_rank8_stacked8",
+                                   "v1_control_rank12", "v2_control_rank8", "post_add_rank8", "v1_on_v1", "v2_on_v2",
+                                   "v1_concat_stacked", "v1_concat_post_add", "v1_concat_rank8")]
+CASES += ["generic_" + v for v in ("plain", "v1", "v2", "v1_stacked@0.5", "v1_post_add", "v1_concat")]
+CASES += ["eager_" + k for k in ("plain_self", "plain_cross", "v1_self", "v1_cross_stacked", "v2_self", "v2_cross", "lora_linear")]
 
 
 @pytest.fixture(scope="module")

@@ -9,7 +9,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from tests import check_variants  # noqa: E402
+from tests import check_eager, check_variants  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -17,3 +17,10 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("case", check_variants.CASE_NAMES)
 def test_general_chain_matches_oracle(case):
     assert check_variants.CASES[case]()
+
+
+@pytest.mark.parametrize("case", check_eager.CASE_NAMES)
+def test_processor_called_like_diffusers_matches_oracle(case):
+    """`processor(attn, hidden_states, encoder_hidden_states, None, scale)` on a stand-alone attention module (models.py:118-152,
+    222-287, 357-431 as diffusers' CrossAttention.forward invokes them) and LoRALinearLayer.forward."""
+    assert check_eager.CASES[case]()
