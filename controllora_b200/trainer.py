@@ -281,13 +281,67 @@ class Trainer:
                 k += 1
         return out
 
+    def _param_slices(self):
+        """(name, parameter, arena offset) in arena order."""
+        out, off = [], 0
+        for n, p in self._named_arena_params():
+            out.append((n, p, off))
+            off += p.numel()
+        return out
+
+    def optimizer_state_dict(self) -> dict:
+        """The AdamW state as `torch.optim.AdamW(control_lora.parameters(), ...).state_dict()` would hold it (what
+        `accelerator.save_state` pickles into optimizer.bin, train_text_to_image_control_lora.py:512-518, 805-809): per-parameter
+        `step` / `exp_avg` / `exp_avg_sq` in parameter order + one param group.  `torch.optim.AdamW.load_state_dict` accepts it."""
+        sl = self._param_slices()
+        proto = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))], lr=self.lr, betas=tuple(self.betas), eps=self.eps,
+                                  weight_decay=self.wd).state_dict()["param_groups"][0]
+        group = dict(proto)
+        group["params"] = list(range(len(sl)))
+        state = {}
+        if self.step_idx > 0:
+            m, v = self.flat_m.detach().cpu(), self.flat_v.detach().cpu()
+            for i, (_, p, off) in enumerate(sl):
+                k = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_idx)), "exp_avg": m[off:off + k].view(p.shape).clone(),
+                            "exp_avg_sq": v[off:off + k].view(p.shape).clone()}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        """Inverse of optimizer_state_dict(); also reads an optimizer.bin written by accelerate for the reference's AdamW."""
+        sl = self._param_slices()
+        g = sd["param_groups"][0]
+        if len(sd["param_groups"]) != 1 or len(g["params"]) != len(sl):
+            raise ValueError("optimizer state does not match this Trainer's parameter list")
+        steps = set()
+        with torch.no_grad():
+            self.flat_m.zero_()
+            self.flat_v.zero_()
+            for i, (n, p, off) in zip(g["params"], sl):
+                st = sd["state"].get(i)
+                if st is None:
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state of parameter {i} ({n}) has shape {tuple(st['exp_avg'].shape)}, expected {tuple(p.shape)}")
+                k = p.numel()
+                self.flat_m[off:off + k].copy_(st["exp_avg"].reshape(-1).to(self.flat_m.device, torch.float32))
+                self.flat_v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1).to(self.flat_v.device, torch.float32))
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter AdamW step counts differ ({sorted(steps)}): the fused optimizer keeps one step counter")
+        self.step_idx = steps.pop() if steps else 0
+        self.step_dev.fill_(self.step_idx)
+        self.lr, self.betas, self.eps, self.wd = float(g["lr"]), tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"])
+
     def save_checkpoint(self, output_dir, global_step: Optional[int] = None) -> str:
-        """`checkpoint-N/` = what `accelerator.save_state` keeps (train_text_to_image_control_lora.py:805-809: model, optimizer,
-        LR scheduler, RNG), in this framework's own file layout (NOT interchangeable with accelerate's pickles):
-          config.json + diffusion_pytorch_model.safetensors   the ControlLoRA in the reference's save_pretrained format (:927-929)
-          optimizer.bin    flat AdamW moments + hyper-parameters + the ordered parameter-name list + arena-only parameters
-          scheduler.bin    LR schedule state (the reference's default `constant` schedule: base lr and last_epoch)
-          random_states_<rank>.pkl   device Philox (seed, step counter) of the noise / timestep draws + torch / numpy / python RNG"""
+        """`checkpoint-N/` with the files `accelerator.save_state` writes (train_text_to_image_control_lora.py:805-809) - so the
+        reference's `accelerator.load_state` can resume from it, and `load_checkpoint` reads one written by the reference:
+          pytorch_model.bin          control_lora.state_dict()                                  (accelerate's model file)
+          optimizer.bin              torch.optim.AdamW state_dict layout (optimizer_state_dict()) + a private `controllora_b200` entry
+                                     (arena parameter names, clip norm, parameters that live outside control_lora)
+          scheduler.bin              LambdaLR state_dict keys of the reference's default `constant` schedule
+          random_states_<rank>.pkl   accelerate's keys (python / numpy / torch / CUDA RNG) + the device Philox (seed, step counter)
+        plus the ControlLoRA in the reference's save_pretrained format (config.json + diffusion_pytorch_model.safetensors, :927-929)."""
         import os
         import pickle
         import random
@@ -300,22 +354,25 @@ class Trainer:
         if rank == 0:
             self.cl.save_config(path)
             self.cl.save_pretrained(path, safe_serialization=True)
-            torch.save({"step_idx": self.step_idx, "global_step": step, "numel": self.numel, "lr": self.lr, "betas": self.betas,
-                        "weight_decay": self.wd, "eps": self.eps, "max_grad_norm": self.max_norm,
-                        "exp_avg": self.flat_m[:self.numel].detach().cpu(), "exp_avg_sq": self.flat_v[:self.numel].detach().cpu(),
-                        "param_names": [n for n, _ in named], "param_numels": [p.numel() for _, p in named],
-                        "extra_params": {n: p.detach().cpu() for n, p in named if n.startswith("extra.")}},
-                       os.path.join(path, "optimizer.bin"))
-            torch.save({"schedule": "constant", "base_lr": self.lr, "last_epoch": self.step_idx}, os.path.join(path, "scheduler.bin"))
+            torch.save({k: v.detach().cpu().clone() for k, v in self.cl.state_dict().items()}, os.path.join(path, "pytorch_model.bin"))
+            opt = self.optimizer_state_dict()
+            opt["controllora_b200"] = {"step_idx": self.step_idx, "global_step": step, "numel": self.numel, "max_grad_norm": self.max_norm,
+                                       "param_names": [n for n, _ in named], "param_numels": [p.numel() for _, p in named],
+                                       "extra_params": {n: p.detach().cpu().clone() for n, p in named if n.startswith("extra.")}}
+            torch.save(opt, os.path.join(path, "optimizer.bin"))
+            torch.save({"base_lrs": [self.lr], "last_epoch": self.step_idx, "_step_count": self.step_idx + 1, "verbose": False,
+                        "_get_lr_called_within_step": False, "_last_lr": [self.lr], "lr_lambdas": [None], "schedule": "constant"},
+                       os.path.join(path, "scheduler.bin"))
         try:
             import numpy as np
             np_state = np.random.get_state()
         except Exception:
             np_state = None
+        cuda_all = torch.cuda.get_rng_state_all() if self.flat_p.is_cuda else None
         with open(os.path.join(path, f"random_states_{rank}.pkl"), "wb") as f:
-            pickle.dump({"noise_seed": self.noise_seed, "rank_seed": self._rank_seed, "rng_counter": int(self.rng_counter.item()),
-                         "torch_cpu": torch.get_rng_state(), "torch_cuda": torch.cuda.get_rng_state(self.flat_p.device)
-                         if self.flat_p.is_cuda else None, "numpy": np_state, "python": random.getstate()}, f)
+            pickle.dump({"step": step, "random_state": random.getstate(), "numpy_random_seed": np_state,
+                         "torch_manual_seed": torch.get_rng_state(), "torch_cuda_manual_seed": cuda_all,
+                         "noise_seed": self.noise_seed, "rank_seed": self._rank_seed, "rng_counter": int(self.rng_counter.item())}, f)
         return path
 
     @staticmethod
@@ -332,27 +389,35 @@ class Trainer:
         return None if best is None else os.path.join(str(output_dir), best)
 
     def load_checkpoint(self, path) -> int:
-        """Restore parameters (into the flat arena the kernels read), AdamW moments, the step count and the RNG state;
-        returns the stored global step.  A captured CUDA graph stays valid: it reads the same arena / counter addresses."""
+        """Restore parameters (into the flat arena the kernels read), AdamW moments, the step count and the RNG state from a
+        `checkpoint-N` directory written by save_checkpoint() OR by the reference's `accelerator.save_state` (pytorch_model.bin /
+        model.safetensors, torch-format optimizer.bin, scheduler.bin, random_states_<rank>.pkl); returns the global step.  A captured
+        CUDA graph stays valid: it reads the same arena / counter addresses."""
         import os
         import pickle
         import random
 
-        st = os.path.join(str(path), "diffusion_pytorch_model.safetensors")
-        if os.path.isfile(st):
-            from safetensors.torch import load_file
+        path = str(path)
+        sd = None
+        for fn in ("diffusion_pytorch_model.safetensors", "model.safetensors", "pytorch_model.bin", "diffusion_pytorch_model.bin"):
+            f = os.path.join(path, fn)
+            if os.path.isfile(f):
+                if fn.endswith(".safetensors"):
+                    from safetensors.torch import load_file
 
-            sd = load_file(st)
-        else:
-            sd = torch.load(os.path.join(str(path), "diffusion_pytorch_model.bin"), map_location="cpu")
-        opt = torch.load(os.path.join(str(path), "optimizer.bin"), map_location="cpu", weights_only=False)
+                    sd = load_file(f)
+                else:
+                    sd = torch.load(f, map_location="cpu")
+                break
+        if sd is None:
+            raise FileNotFoundError(f"{path}: no model file (pytorch_model.bin / model.safetensors / diffusion_pytorch_model.*)")
+        opt = torch.load(os.path.join(path, "optimizer.bin"), map_location="cpu", weights_only=False)
         named = self._named_arena_params()
-        if int(opt["numel"]) != self.numel:
-            raise ValueError("optimizer state does not match this Trainer's parameter count")
-        if "param_names" in opt and (list(opt["param_names"]) != [n for n, _ in named]
-                                     or list(opt.get("param_numels", [p.numel() for _, p in named])) != [p.numel() for _, p in named]):
+        priv = opt.get("controllora_b200", {})
+        if "param_names" in priv and (list(priv["param_names"]) != [n for n, _ in named]
+                                      or list(priv["param_numels"]) != [p.numel() for _, p in named]):
             raise ValueError("checkpoint parameter order / names do not match this Trainer's arena (different wiring or config)")
-        extra = opt.get("extra_params", {})
+        extra = priv.get("extra_params", {})
         missing = [n for n, _ in named if (n not in sd and n not in extra)]
         if missing:
             raise KeyError(f"checkpoint {path} lacks parameters: {missing[:4]}...")
@@ -360,23 +425,47 @@ class Trainer:
             for n, p in named:
                 src = sd[n] if n in sd else extra[n]
                 p.data.copy_(src.to(p.data.device, p.data.dtype))      # p.data is a view into flat_p
-            self.flat_m[:self.numel].copy_(opt["exp_avg"].to(self.flat_m.device))
-            self.flat_v[:self.numel].copy_(opt["exp_avg_sq"].to(self.flat_v.device))
             self.flat_g.zero_()
-        self.step_idx = int(opt["step_idx"])
-        self.step_dev.fill_(self.step_idx)
+        if "state" in opt:
+            self.load_optimizer_state_dict(opt)
+        else:                                                          # round-1/2 layout of this framework: flat moments
+            if int(opt["numel"]) != self.numel:
+                raise ValueError("optimizer state does not match this Trainer's parameter count")
+            with torch.no_grad():
+                self.flat_m[:self.numel].copy_(opt["exp_avg"].to(self.flat_m.device))
+                self.flat_v[:self.numel].copy_(opt["exp_avg_sq"].to(self.flat_v.device))
+            self.step_idx = int(opt["step_idx"])
+            self.step_dev.fill_(self.step_idx)
+            priv = opt
+        if "max_grad_norm" in priv:
+            self.max_norm = float(priv["max_grad_norm"])
         rank = torch.distributed.get_rank(self.pg) if self.world > 1 else 0
-        rs = os.path.join(str(path), f"random_states_{rank}.pkl")
+        rs = os.path.join(path, f"random_states_{rank}.pkl")
         if os.path.isfile(rs):
             with open(rs, "rb") as f:
                 r = pickle.load(f)
-            self.noise_seed, self._rank_seed = int(r["noise_seed"]), int(r["rank_seed"])
-            self.rng_counter.fill_(int(r["rng_counter"]))
-            torch.set_rng_state(r["torch_cpu"])
-            if r.get("torch_cuda") is not None and self.flat_p.is_cuda:
-                torch.cuda.set_rng_state(r["torch_cuda"], self.flat_p.device)
-            if r.get("numpy") is not None:
+            if "noise_seed" in r:                                       # absent in a checkpoint written by accelerate
+                self.noise_seed, self._rank_seed = int(r["noise_seed"]), int(r["rank_seed"])
+                self.rng_counter.fill_(int(r["rng_counter"]))
+            cpu_state = r.get("torch_manual_seed", r.get("torch_cpu"))
+            if cpu_state is not None:
+                torch.set_rng_state(cpu_state)
+            cuda_state = r.get("torch_cuda_manual_seed", r.get("torch_cuda"))
+            if cuda_state is not None and self.flat_p.is_cuda:
+                if isinstance(cuda_state, (list, tuple)):
+                    if len(cuda_state) == torch.cuda.device_count():
+                        torch.cuda.set_rng_state_all(cuda_state)
+                else:
+                    torch.cuda.set_rng_state(cuda_state, self.flat_p.device)
+            np_state = r.get("numpy_random_seed", r.get("numpy"))
+            if np_state is not None:
                 import numpy as np
-                np.random.set_state(r["numpy"])
-            random.setstate(r["python"])
-        return int(opt.get("global_step", self.step_idx))
+                np.random.set_state(np_state)
+            py_state = r.get("random_state", r.get("python"))
+            if py_state is not None:
+                random.setstate(py_state)
+        gs = priv.get("global_step")
+        if gs is None:
+            tail = os.path.basename(os.path.normpath(path))
+            gs = int(tail.split("-")[1]) if tail.startswith("checkpoint-") and tail.split("-")[1].isdigit() else self.step_idx
+        return int(gs)

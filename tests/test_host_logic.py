@@ -290,3 +290,111 @@ def test_trainer_checkpoint_keeps_arena_only_parameters_and_checks_names(tmp_pat
     tr3, _ = make(False)
     with pytest.raises(ValueError):
         tr3.load_checkpoint(path)
+
+
+def _tiny_trainer(seed):
+    from controllora_b200.trainer import Trainer
+
+    torch.manual_seed(seed)
+    mu = _tiny_unet()
+    mcl = cb.ControlLoRA(**TINY_LORA)
+    wire_processors(mu, mcl)
+    return Trainer(mu, mcl, lr=3e-4, betas=(0.9, 0.99), weight_decay=2e-2, eps=1e-7), mcl
+
+
+def test_checkpoint_is_loadable_by_the_reference_stack(tmp_path):
+    """`accelerator.load_state(checkpoint-N)` (train_text_to_image_control_lora.py:733) does, for the reference's objects:
+    control_lora.load_state_dict(torch.load(pytorch_model.bin)), optimizer.load_state_dict(torch.load(optimizer.bin)),
+    lr_scheduler.load_state_dict(torch.load(scheduler.bin)) and restores random_states_0.pkl.  The files save_checkpoint() writes
+    must go through exactly those calls with the reference's classes (oracle restatement of ControlLoRA, torch.optim.AdamW,
+    LambdaLR) and reproduce the arena's state."""
+    import pickle
+
+    tr, cl = _tiny_trainer(0)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        tr.flat_p[:tr.numel].copy_(torch.randn(tr.numel, generator=g))
+        tr.flat_m[:tr.numel].copy_(torch.randn(tr.numel, generator=g))
+        tr.flat_v[:tr.numel].copy_(torch.rand(tr.numel, generator=g))
+    tr.step_idx = 11
+    path = tr.save_checkpoint(tmp_path)
+    ref = MR.ControlLoRA(**TINY_LORA)
+    ref.load_state_dict(torch.load(f"{path}/pytorch_model.bin"))                       # strict: same keys, same shapes
+    for (n1, a), (n2, b) in zip(ref.named_parameters(), cl.named_parameters()):
+        assert n1 == n2 and torch.equal(a, b)
+    opt = torch.optim.AdamW(ref.parameters(), lr=1.0)                                   # train_...:512-518
+    opt.load_state_dict(torch.load(f"{path}/optimizer.bin", weights_only=False))
+    grp = opt.param_groups[0]
+    assert grp["lr"] == 3e-4 and tuple(grp["betas"]) == (0.9, 0.99) and grp["weight_decay"] == 2e-2 and grp["eps"] == 1e-7
+    off = 0
+    for p in ref.parameters():
+        st = opt.state[p]
+        k = p.numel()
+        assert float(st["step"]) == 11
+        assert torch.equal(st["exp_avg"].flatten(), tr.flat_m[off:off + k]) and torch.equal(st["exp_avg_sq"].flatten(), tr.flat_v[off:off + k])
+        off += k
+    assert off == tr.numel
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda _: 1.0)                       # diffusers get_scheduler("constant")
+    sched.load_state_dict(torch.load(f"{path}/scheduler.bin", weights_only=False))
+    assert sched.last_epoch == 11 and sched.get_last_lr() == [3e-4]
+    with open(f"{path}/random_states_0.pkl", "rb") as f:
+        rs = pickle.load(f)
+    assert {"random_state", "numpy_random_seed", "torch_manual_seed", "torch_cuda_manual_seed"} <= set(rs)      # accelerate's keys
+    # and one optimizer step of the reference stack from this state is what the arena formulas give
+    grads = [torch.randn(p.shape, generator=g) for p in ref.parameters()]
+    for p, gr in zip(ref.parameters(), grads):
+        p.grad = gr.clone()
+    before = torch.cat([p.detach().flatten() for p in ref.parameters()])
+    opt.step()
+    after = torch.cat([p.detach().flatten() for p in ref.parameters()])
+    gflat = torch.cat([x.flatten() for x in grads])
+    m = 0.9 * tr.flat_m[:tr.numel] + 0.1 * gflat
+    v = 0.99 * tr.flat_v[:tr.numel] + 0.01 * gflat * gflat
+    want = before * (1 - 3e-4 * 2e-2) - (3e-4 / (1 - 0.9 ** 12)) * m / (v.sqrt() / (1 - 0.99 ** 12) ** 0.5 + 1e-7)
+    assert torch.allclose(after, want, rtol=1e-5, atol=1e-7)
+
+
+def test_checkpoint_written_by_the_reference_stack_resumes_here(tmp_path):
+    """The reverse direction: a `checkpoint-N` as `accelerator.save_state` leaves it (model / optimizer / scheduler pickles of the
+    reference's objects + accelerate's random_states file) restores the arena, the moments and the step counter."""
+    import pickle
+    import random
+
+    import numpy as np
+
+    ref = MR.ControlLoRA(**TINY_LORA)
+    opt = torch.optim.AdamW(ref.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda _: 1.0)
+    g = torch.Generator().manual_seed(4)
+    for _ in range(3):
+        for p in ref.parameters():
+            p.grad = torch.randn(p.shape, generator=g)
+        opt.step()
+        sched.step()
+    d = tmp_path / "checkpoint-3"
+    d.mkdir()
+    torch.save(ref.state_dict(), d / "pytorch_model.bin")
+    torch.save(opt.state_dict(), d / "optimizer.bin")
+    torch.save(sched.state_dict(), d / "scheduler.bin")
+    with open(d / "random_states_0.pkl", "wb") as f:
+        pickle.dump({"random_state": random.getstate(), "numpy_random_seed": np.random.get_state(),
+                     "torch_manual_seed": torch.get_rng_state(), "torch_cuda_manual_seed": None}, f)
+    expected_next = torch.rand(2)
+    tr, cl = _tiny_trainer(9)
+    seed_before = tr.noise_seed
+    assert tr.load_checkpoint(str(d)) == 3 and tr.step_idx == 3 and int(tr.step_dev) == 3
+    assert torch.equal(torch.rand(2), expected_next) and tr.noise_seed == seed_before
+    assert tr.lr == 2e-4 and tr.wd == 1e-2
+    off = 0
+    for (n1, a), (n2, b) in zip(ref.named_parameters(), cl.named_parameters()):
+        k = a.numel()
+        assert n1 == n2 and torch.equal(a.detach(), b.detach())
+        assert torch.equal(opt.state[a]["exp_avg"].flatten(), tr.flat_m[off:off + k])
+        assert torch.equal(opt.state[a]["exp_avg_sq"].flatten(), tr.flat_v[off:off + k])
+        off += k
+    # a mismatched wiring is refused, not silently mis-assigned
+    opt2 = opt.state_dict()
+    opt2["param_groups"][0]["params"] = opt2["param_groups"][0]["params"][:-1]
+    torch.save(opt2, d / "optimizer.bin")
+    with pytest.raises(ValueError):
+        tr.load_checkpoint(str(d))
