@@ -76,10 +76,20 @@ def test_processor_flags_and_skip_helpers():
     assert v1.pre_loras == [lo] and "pre_loras" not in dict(v1.named_modules())   # plain lists, not sub-modules
 
 
-def test_processors_have_no_eager_fallback():
+def test_processors_have_no_cpu_fallback(monkeypatch):
+    """A processor is callable the way diffusers calls it (controllora_b200/eager_attn.py) - on CUDA.  CPU tensors are refused:
+    there is no PyTorch implementation of the arithmetic in the package."""
+    from oracle import unet_ref as UR
+
+    monkeypatch.delenv("CLB_DRYRUN", raising=False)
     p = cb.LoRACrossAttnProcessor(64)
+    attn = UR.CrossAttention(64, None, 8, 8)
+    with pytest.raises(RuntimeError, match="runs only on CUDA"):
+        p(attn, torch.zeros(1, 4, 64))
+    with pytest.raises(RuntimeError, match="runs only on CUDA"):
+        cb.LoRALinearLayer(64, 64, 4)(torch.zeros(2, 64))
     with pytest.raises(NotImplementedError):
-        p(None, torch.zeros(1, 4, 64))
+        p(attn, torch.zeros(1, 4, 64), attention_mask=torch.zeros(1, 4, 4))
 
 
 def test_unet_wrapper_refuses_cpu_inputs(monkeypatch):
@@ -132,26 +142,35 @@ def test_synthetic_state_dict_has_diffusers_keys_and_sd15_size():
         assert tuple(sd[k].shape) == tuple(v.shape), k
 
 
-def test_unsupported_variants_fail_loudly():
+def test_wirings_beyond_the_fused_path_select_the_general_chain_path():
+    """The one-launch path covers the shipped configs; every other wiring models.py:118-431 allows is routed, per attention
+    layer, to the general chain path (lora_generic.py) instead of being refused (numerics: tests/check_variants.py)."""
     from controllora_b200.lora_runtime import LoraRuntime
     from controllora_b200.unet_module import GradStore
+
+    def kinds(rt):
+        return {lp.kind for lp in rt.layers.values() if lp.proc is not None}
 
     mu = _tiny_unet()
     mcl = cb.ControlLoRA(lora_concat_hidden=True, **TINY_LORA)          # configs/danbooru-sketch.json flavour ...
     procs = wire_processors(mu, mcl)
-    LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)       # ... builds on its own,
-    for p in procs.values():                                            # but not with another adapter stacked on it
+    assert kinds(LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)) == {"v1cat"}      # ... fused on its own,
+    for p in procs.values():                                            # general path with another adapter stacked on it
         p.inject_pre_lora(cb.LoRACrossAttnProcessor(p.hidden_size, p.cross_attention_dim, rank=4))
-    with pytest.raises(NotImplementedError):
-        LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)
-    # post_add stacked with a pre-LoRA is outside the supported set as well
+    rt = LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)
+    assert kinds(rt) == {"generic"} and all("concat_hidden" in lp.generic_reason for lp in rt.layers.values() if lp.proc is not None)
     mu = _tiny_unet()
     mcl = cb.ControlLoRA(lora_post_add=True, **TINY_LORA)
     procs = wire_processors(mu, mcl)
     for p in procs.values():
         p.inject_pre_lora(cb.LoRACrossAttnProcessor(p.hidden_size, p.cross_attention_dim, rank=4))
-    with pytest.raises(NotImplementedError):
-        LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)
+    assert kinds(LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)) == {"generic"}
+    # the standard stacked wiring (mix_lora_and_control_lora.py: one rank-4 pre-LoRA) stays on the fused path
+    mu = _tiny_unet()
+    procs = wire_processors(mu, cb.ControlLoRA(**TINY_LORA))
+    for p in procs.values():
+        p.inject_pre_lora(cb.LoRACrossAttnProcessor(p.hidden_size, p.cross_attention_dim, rank=4))
+    assert kinds(LoraRuntime(mu.weights, torch.device("cpu"), GradStore().get)) == {"v1"}
 
 
 def test_post_add_config_builds_a_runtime_plan():
