@@ -18,8 +18,12 @@ act silu, scaling_factor 0.18215.  Restated pieces (diffusers `models/vae.py`, `
            on all but the last) -> GroupNorm -> SiLU -> conv_out 3x3 (-> 3)
   AttentionBlock: h = GroupNorm(x); q,k,v = Linear(h) (with bias); softmax(q k^T / sqrt(C)) v; proj_attn; + x  (rescale factor 1)
 
-PARITY STATUS: **parity unpinned** — diffusers is not installable here and no SD-1.5 VAE weights are on disk; anchors: the
-parameter count of the SD-1.5 VAE (83 653 863) and its state-dict key names (tests/test_oracle.py).
+PARITY STATUS: Encoder and Decoder are **pinned** to an independent published implementation of the same network - the CompVis
+latent-diffusion / taming `Encoder` / `Decoder` (the code SD-1.5's VAE comes from; `transformers` ships it as JanusVQVAEEncoder /
+JanusVQVAEDecoder): same weights -> same outputs to 1e-4 (tests/test_oracle.py).  diffusers itself is not installable here and no
+SD-1.5 VAE weights are on disk, so the thin AutoencoderKL wrapper around them (quant_conv / post_quant_conv 1x1 convs, the
+DiagonalGaussianDistribution clamp + sample, scaling_factor) is anchored by the parameter count of the SD-1.5 VAE (83 653 863) and
+its state-dict key names only.
 """
 from __future__ import annotations
 

@@ -274,3 +274,80 @@ def test_clip_oracle_matches_transformers():
     Cw, Fi, L = full["hidden_size"], full["intermediate_size"], full["num_hidden_layers"]
     n = (full["vocab_size"] + full["max_position_embeddings"]) * Cw + L * (4 * (Cw * Cw + Cw) + 2 * Cw * Fi + Fi + Cw + 4 * Cw) + 2 * Cw
     assert n == 123060480
+
+
+def test_vae_oracle_encoder_decoder_match_the_ldm_implementation_in_transformers():
+    """oracle/vae_ref.py's Encoder / Decoder are pinned to an independent published implementation of the same network: the
+    CompVis latent-diffusion / taming `Encoder` and `Decoder` (the code SD-1.5's VAE was trained with and diffusers' AutoencoderKL
+    re-implements), which `transformers` ships as JanusVQVAEEncoder / JanusVQVAEDecoder.  Same synthetic weights (key names mapped
+    diffusers -> LDM: down_blocks.i.resnets.j -> down.i.block.j, conv_shortcut -> nin_shortcut, mid_block.resnets.0/1 -> mid.block_1/2,
+    attention Linear [C, C] -> 1x1 conv), CPU fp32.  Janus adds attention blocks at the lowest resolution level, which SD's config
+    (attn_resolutions = []) does not have: their output projection is zeroed, which makes them the identity (x + 0)."""
+    import pytest
+    import torch
+    from oracle import vae_ref as VR
+
+    pytest.importorskip("transformers")
+    from transformers.models.janus.configuration_janus import JanusVQVAEConfig
+    from transformers.models.janus.modeling_janus import JanusVQVAEDecoder, JanusVQVAEEncoder
+
+    chans, layers = (32, 64, 64), 1
+    cfg = JanusVQVAEConfig(base_channels=32, channel_multiplier=[c // 32 for c in chans], num_res_blocks=layers, in_channels=3,
+                           out_channels=3, latent_channels=4, double_latent=True, dropout=0.0)
+    torch.manual_seed(0)
+    enc, dec = JanusVQVAEEncoder(cfg).eval(), JanusVQVAEDecoder(cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for m in (enc, dec):
+            for n, p in m.named_parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * (0.3 if p.dim() == 1 else 0.08) + (1.0 if ("norm" in n and n.endswith("weight")) else 0.0))
+        for blk in (enc.down[-1], dec.up[0]):                      # level attention blocks -> identity
+            for a in blk.attn:
+                a.proj_out.weight.zero_()
+                a.proj_out.bias.zero_()
+    ovae = VR.AutoencoderKL(block_out_channels=chans, layers_per_block=layers)
+
+    def res(dst, src):
+        out = {f"{dst}.{k}.{w}": f"{src}.{k}.{w}" for k in ("norm1", "conv1", "norm2", "conv2") for w in ("weight", "bias")}
+        out.update({f"{dst}.conv_shortcut.{w}": f"{src}.nin_shortcut.{w}" for w in ("weight", "bias")})
+        return out
+
+    def mid(dst, src):
+        out = {**res(f"{dst}.resnets.0", f"{src}.block_1"), **res(f"{dst}.resnets.1", f"{src}.block_2")}
+        for a, b in (("group_norm", "norm"), ("query", "q"), ("key", "k"), ("value", "v"), ("proj_attn", "proj_out")):
+            out.update({f"{dst}.attentions.0.{a}.{w}": f"{src}.attn_1.{b}.{w}" for w in ("weight", "bias")})
+        return out
+
+    def load(omod, jmod, mapping):
+        jsd, used = jmod.state_dict(), set()
+        with torch.no_grad():
+            for k, p in omod.state_dict().items():
+                src = jsd[mapping[k]]
+                used.add(mapping[k])
+                p.copy_(src.reshape(p.shape))                      # [C, C, 1, 1] conv <-> [C, C] Linear
+        rest = [k for k in jsd if k not in used]
+        assert all(".attn." in k for k in rest), rest              # only the (identity) level attention blocks are unmapped
+
+    emap = {f"conv_in.{w}": f"conv_in.{w}" for w in ("weight", "bias")}
+    emap.update({f"conv_norm_out.{w}": f"norm_out.{w}" for w in ("weight", "bias")})
+    emap.update({f"conv_out.{w}": f"conv_out.{w}" for w in ("weight", "bias")})
+    dmap = dict(emap)
+    for i in range(len(chans)):
+        for j in range(layers):
+            emap.update(res(f"down_blocks.{i}.resnets.{j}", f"down.{i}.block.{j}"))
+        emap.update({f"down_blocks.{i}.downsamplers.0.conv.{w}": f"down.{i}.downsample.conv.{w}" for w in ("weight", "bias")})
+        for j in range(layers + 1):
+            dmap.update(res(f"up_blocks.{i}.resnets.{j}", f"up.{i}.block.{j}"))
+        dmap.update({f"up_blocks.{i}.upsamplers.0.conv.{w}": f"up.{i}.upsample.conv.{w}" for w in ("weight", "bias")})
+    emap.update(mid("mid_block", "mid"))
+    dmap.update(mid("mid_block", "mid"))
+    load(ovae.encoder, enc, emap)
+    load(ovae.decoder, dec, dmap)
+    x = torch.randn(2, 3, 32, 32, generator=g)
+    z = torch.randn(2, 4, 8, 8, generator=g)
+    with torch.no_grad():
+        e_want, e_got = enc(x.clone()), ovae.encoder(x)
+        d_want, d_got = dec(z.clone()), ovae.decoder(z)
+    assert e_got.shape == e_want.shape == (2, 8, 8, 8) and d_got.shape == d_want.shape == (2, 3, 32, 32)
+    assert float((e_got - e_want).abs().max()) < 1e-4 * float(e_want.abs().max())
+    assert float((d_got - d_want).abs().max()) < 1e-4 * float(d_want.abs().max())
