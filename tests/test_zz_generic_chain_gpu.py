@@ -9,7 +9,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from tests import check_eager, check_variants  # noqa: E402
+from tests import check_eager, check_reference_golden, check_variants  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -24,3 +24,10 @@ def test_processor_called_like_diffusers_matches_oracle(case):
     """`processor(attn, hidden_states, encoder_hidden_states, None, scale)` on a stand-alone attention module (models.py:118-152,
     222-287, 357-431 as diffusers' CrossAttention.forward invokes them) and LoRALinearLayer.forward."""
     assert check_eager.CASES[case]()
+
+
+@pytest.mark.parametrize("case", check_reference_golden.CASE_NAMES)
+def test_cuda_path_matches_golden_vectors_computed_by_the_reference_code(case):
+    """Expected values come from /root/reference/models.py itself (imported unmodified when the fixture was generated,
+    tests/golden/make_reference_golden.py), not from the oracle restatement."""
+    assert check_reference_golden.CASES[case]()
