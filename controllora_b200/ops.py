@@ -380,9 +380,11 @@ def small_linear(x, w, bias, silu_in=False, silu_out=False):
     return out
 
 
-def mse_loss(pred, target, gscale: float = 1.0, need_grad=True):
+def mse_loss(pred, target, gscale: float = 1.0, need_grad=True, out=None):
+    """loss = mean((pred - target)^2);  dpred = gscale * 2 (pred - target) / n  (written into `out` when given)."""
+    assert pred.is_contiguous() and target.is_contiguous() and (out is None or out.is_contiguous())
     loss = torch.empty(1, device=pred.device, dtype=torch.float32)
-    dpred = torch.empty_like(pred) if need_grad else None
+    dpred = out if out is not None else (torch.empty_like(pred) if need_grad else None)
     _call("cl_mse_loss", _p(pred), _p(target), _p(loss), _p(dpred), C.c_int64(pred.numel()), C.c_float(gscale))
     return loss, dpred
 

@@ -23,12 +23,17 @@ BF16 = torch.bfloat16
 class Trainer:
     def __init__(self, unet, control_lora, lr: float = 1e-4, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,
                  max_grad_norm: float = 1.0, process_group=None, cuda_graph: bool = False, graph_warmup: int = 2,
-                 noise_seed: int = 0, prediction_type: str = "epsilon", num_train_timesteps: int = 1000):
+                 noise_seed: int = 0, prediction_type: str = "epsilon", num_train_timesteps: int = 1000,
+                 prior_loss_weight: Optional[float] = None):
+        """control_lora=None trains the adapters installed on the UNet alone (plain `LoRACrossAttnProcessor`s on every attention
+        layer): the step of train_dreambooth_lora.py:880-918.  prior_loss_weight (DreamBooth's prior preservation, :898-910): the
+        batch is [instance images | class images] and loss = mse(first half) + prior_loss_weight * mse(second half)."""
         self.unet, self.cl = unet, control_lora
+        self.prior_loss_weight = None if prior_loss_weight is None else float(prior_loss_weight)
         self.lr, self.betas, self.wd, self.eps, self.max_norm = lr, betas, weight_decay, eps, max_grad_norm
         self.pg = process_group
         dev = unet.device_
-        params: List[torch.nn.Parameter] = [p for p in control_lora.parameters() if p.requires_grad]
+        params: List[torch.nn.Parameter] = [] if control_lora is None else [p for p in control_lora.parameters() if p.requires_grad]
         seen = {id(p) for p in params}
         for p in unet.trainable_parameters():          # e.g. stacked pre_loras that are not part of control_lora
             if id(p) not in seen and p.requires_grad:
@@ -45,7 +50,9 @@ class Trainer:
             store.bufs[id(p)] = self.arena.grad_of(p)
             store.params[id(p)] = p
         unet._runtime = None                          # rebuild the LoRA runtime against the arena views
-        self.hint = HintEncoderEngine(control_lora, store.get)
+        self.hint = None if control_lora is None else HintEncoderEngine(control_lora, store.get)
+        if not params:
+            raise ValueError("Trainer: nothing to train (no ControlLoRA and no adapter processors installed on the UNet)")
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
         self.step_idx = 0
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)     # device copy of step_idx (bias corrections inside the graph)
@@ -127,9 +134,11 @@ class Trainer:
         elif self._mode != mode:
             raise ValueError("Trainer(cuda_graph=True): step() and step_from_latents() cannot be mixed on one Trainer")
         if self._static is None:
-            self._static = [torch.empty_like(a_).copy_(a_) for a_ in args]
+            self._static = [None if a_ is None else torch.empty_like(a_).copy_(a_) for a_ in args]
         else:
             for st, a_ in zip(self._static, args):
+                if st is None and a_ is None:
+                    continue
                 if st.shape != a_.shape or st.dtype != a_.dtype:
                     raise ValueError("Trainer(cuda_graph=True): input shapes/dtypes must not change between steps")
                 if st.data_ptr() != a_.data_ptr():
@@ -186,9 +195,9 @@ class Trainer:
         def on_level(i):
             if i == split and self._bucketed:
                 tape.record(lambda: self._reduce_bucket(1))          # runs after the backward of levels >= split
-        states = self.hint.forward(hctx, guide, on_level=on_level)
+        states = [] if self.cl is None else self.hint.forward(hctx, guide, on_level=on_level)
         control = {}
-        for procs, s in zip(self.cl.lora_layers, states):
+        for procs, s in zip([] if self.cl is None else self.cl.lora_layers, states):
             n, H, W, C = s.data.shape
             c = Var(s.data.view(n, H * W, C), rg=True)       # token-matrix view of the same memory for the UNet side
             for proc in procs:
@@ -204,7 +213,7 @@ class Trainer:
         if self._bucketed:
             tape.record(lambda: self._reduce_bucket(0))              # runs after every UNet backward op
         pred, ctx, rt = self.unet.run_engine(noisy_latents, timesteps, ehs, control, tape)
-        loss, dpred = ops.mse_loss(pred.data, target)
+        loss, dpred = self._loss(pred.data, target)
         pred.grad = dpred
         tape.backward()
         if self._bucketed:
@@ -213,6 +222,21 @@ class Trainer:
             torch.cuda.current_stream().wait_stream(self._side)
             self._reduced_in_step = True
         return loss
+
+    def _loss(self, pred: torch.Tensor, target: torch.Tensor):
+        """MSE (train_text_to_image_control_lora.py:783), or DreamBooth's prior-preservation sum (train_dreambooth_lora.py:898-910):
+        mse(instance half) + w * mse(class half) - two launches of the fused loss + gradient kernel on the two halves."""
+        if self.prior_loss_weight is None:
+            return ops.mse_loss(pred, target)
+        B = pred.shape[0]
+        if B % 2:
+            raise ValueError("prior preservation needs an even batch: [instance images | class images]")
+        h = B // 2
+        dpred = torch.empty_like(pred)
+        loss, _ = ops.mse_loss(pred[:h], target[:h], out=dpred[:h])
+        prior, _ = ops.mse_loss(pred[h:], target[h:], gscale=self.prior_loss_weight, out=dpred[h:])
+        ops.axpy_matrix(prior.view(1, 1), loss.view(1, 1), self.prior_loss_weight)
+        return loss, dpred
 
     # ------------------------------------------------------------------------------------------------ gradient buckets
     def _make_buckets(self):
@@ -271,7 +295,12 @@ class Trainer:
     def _named_arena_params(self):
         """(name, parameter) of every tensor in the arena: ControlLoRA parameters under their state-dict names, parameters
         that live outside control_lora (e.g. stacked pre_loras from unet.trainable_parameters()) as `extra.<index>`."""
-        names = {id(p): n for n, p in self.cl.named_parameters()}
+        if self.cl is None:
+            # diffusers' AttnProcsLayers naming (train_dreambooth_lora.py:723): "<attn_processors key>.<parameter name>"
+            names = {id(p): f"{k}.{n}" for k, proc in self.unet.attn_processors.items() if isinstance(proc, torch.nn.Module)
+                     for n, p in proc.named_parameters()}
+        else:
+            names = {id(p): n for n, p in self.cl.named_parameters()}
         out, k = [], 0
         for p in self.params:
             if id(p) in names:
@@ -352,9 +381,12 @@ class Trainer:
         rank = torch.distributed.get_rank(self.pg) if self.world > 1 else 0
         named = self._named_arena_params()
         if rank == 0:
-            self.cl.save_config(path)
-            self.cl.save_pretrained(path, safe_serialization=True)
-            torch.save({k: v.detach().cpu().clone() for k, v in self.cl.state_dict().items()}, os.path.join(path, "pytorch_model.bin"))
+            if self.cl is None:      # the model accelerate would have saved is AttnProcsLayers(unet.attn_processors)
+                torch.save({n: p.detach().cpu().clone() for n, p in named if not n.startswith("extra.")}, os.path.join(path, "pytorch_model.bin"))
+            else:
+                self.cl.save_config(path)
+                self.cl.save_pretrained(path, safe_serialization=True)
+                torch.save({k: v.detach().cpu().clone() for k, v in self.cl.state_dict().items()}, os.path.join(path, "pytorch_model.bin"))
             opt = self.optimizer_state_dict()
             opt["controllora_b200"] = {"step_idx": self.step_idx, "global_step": step, "numel": self.numel, "max_grad_norm": self.max_norm,
                                        "param_names": [n for n, _ in named], "param_numels": [p.numel() for _, p in named],

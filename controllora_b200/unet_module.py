@@ -136,6 +136,54 @@ class UNet2DConditionModel(nn.Module):
                 del self._proc_modules[key]
         self._runtime = None
 
+    # diffusers' UNet2DConditionLoadersMixin surface used by train_dreambooth_lora.py:944 (`unet.save_attn_procs(output_dir)`) and
+    # test_dreambooth_lora.py / apps (`pipe.unet.load_attn_procs(path)`): one state dict "<attn_processors key>.<parameter name>"
+    def attn_procs_state_dict(self) -> Dict[str, torch.Tensor]:
+        return {f"{k}.{n}": p.detach() for k, proc in self._procs.items() if isinstance(proc, nn.Module) for n, p in proc.named_parameters()}
+
+    def save_attn_procs(self, save_directory, weight_name: str = "pytorch_lora_weights.bin") -> str:
+        import os
+
+        os.makedirs(str(save_directory), exist_ok=True)
+        path = os.path.join(str(save_directory), weight_name)
+        torch.save({k: v.cpu().clone() for k, v in self.attn_procs_state_dict().items()}, path)
+        return path
+
+    def load_attn_procs(self, pretrained_model_name_or_path_or_dict, weight_name: str = "pytorch_lora_weights.bin", **unused) -> None:
+        """Builds a `LoRACrossAttnProcessor` per attention layer from the file's shapes (rank, cross-attention width) and installs
+        them - diffusers' behaviour for a LoRA attention-processor file."""
+        import os
+        from .models import LoRACrossAttnProcessor
+
+        sd = pretrained_model_name_or_path_or_dict
+        if not isinstance(sd, dict):
+            f = str(sd) if os.path.isfile(str(sd)) else os.path.join(str(sd), weight_name)
+            if f.endswith(".safetensors"):
+                from safetensors.torch import load_file
+
+                sd = load_file(f)
+            else:
+                sd = torch.load(f, map_location="cpu")
+        groups: Dict[str, Dict[str, torch.Tensor]] = {}
+        for k, v in sd.items():
+            key, sub = ".".join(k.split(".")[:-3]), ".".join(k.split(".")[-3:])        # "...attn1.processor" + "to_q_lora.down.weight"
+            groups.setdefault(key, {})[sub] = v
+        names = list(self.weights.attn_layers.keys())
+        if set(groups) != set(names):
+            raise ValueError(f"load_attn_procs: file covers {len(groups)} attention processors, this UNet has {len(names)}")
+        procs = {}
+        for n in names:
+            g = groups[n]
+            rank, hidden = g["to_q_lora.down.weight"].shape
+            has_k = "to_k_lora.down.weight" in g
+            xd = g["to_k_lora.down.weight"].shape[1] if has_k else None
+            p = LoRACrossAttnProcessor(hidden, None if (xd is None or n.endswith("attn1.processor")) else xd, rank=rank,
+                                       key_states_skipped=not has_k, value_states_skipped="to_v_lora.down.weight" not in g,
+                                       output_states_skipped="to_out_lora.down.weight" not in g)
+            p.load_state_dict(g)
+            procs[n] = p.to(self.device_)
+        self.set_attn_processor(procs)
+
     def _get_runtime(self) -> LoraRuntime:
         sig = LoraRuntime.make_signature(self.weights)
         if self._runtime is None or self._runtime.signature != sig:

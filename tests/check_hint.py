@@ -189,6 +189,86 @@ def train_case(v2: bool, B=2, HW=16):
     return ok
 
 
+def train_lora_only_case(B=4, HW=16, prior_w=0.7):
+    """The DreamBooth-LoRA step (train_dreambooth_lora.py:880-918): plain LoRACrossAttnProcessor on every attention layer, no
+    ControlLoRA, loss = mse(instance half) + prior_loss_weight * mse(class half), clip + AdamW - Trainer(control_lora=None) against
+    the oracle driven by torch autograd + torch.optim.AdamW.  Also the attention-processor file round trip (`save_attn_procs`)."""
+    import tempfile
+
+    import torch
+    from oracle import models_ref as MR
+    from oracle import unet_ref as UR
+    import controllora_b200 as cb
+    from controllora_b200.trainer import Trainer
+
+    torch.manual_seed(0)
+    ounet = UR.UNet2DConditionModel(**TINY)
+    UR.init_synthetic_(ounet, seed=1)
+    with torch.no_grad():
+        for p in ounet.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+    ounet.requires_grad_(False)
+    munet = cb.UNet2DConditionModel.from_state_dict({k: v.clone() for k, v in ounet.state_dict().items()}, DEV, TINY)
+    g = torch.Generator().manual_seed(7)
+    oprocs, mprocs = {}, {}
+    for name in ounet.attn_processors.keys():
+        C = dict(ounet._attn_modules())[name].to_q.weight.shape[0]
+        xd = None if name.endswith("attn1.processor") else TINY["cross_attention_dim"]
+        op = MR.LoRACrossAttnProcessor(C, xd, rank=4)
+        with torch.no_grad():
+            for n_, p_ in op.named_parameters():
+                if n_.endswith("up.weight"):
+                    p_.copy_(0.05 * torch.randn(p_.shape, generator=g))
+        mp = cb.LoRACrossAttnProcessor(C, xd, rank=4)
+        mp.load_state_dict(op.state_dict())
+        oprocs[name], mprocs[name] = op, mp.to(DEV)
+    ounet.set_attn_processor(oprocs)
+    munet.set_attn_processor(mprocs)
+    oparams = [p for op in oprocs.values() for p in op.parameters()]
+    opt = torch.optim.AdamW(oparams, lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    tr = Trainer(munet, None, lr=1e-4, prior_loss_weight=prior_w)
+    assert tr.numel == sum(p.numel() for p in oparams)
+    worst_grad, worst_loss = 0.0, 0.0
+    for step in range(2):
+        x = torch.randn(B, 4, HW, HW, generator=g).to(torch.bfloat16).float()
+        t = torch.randint(0, 1000, (B,), generator=g)
+        e = torch.randn(B, 77, TINY["cross_attention_dim"], generator=g).to(torch.bfloat16).float()
+        tgt = torch.randn(B, 4, HW, HW, generator=g)
+        pred = ounet(x, t, e).sample
+        h = B // 2
+        lo = torch.nn.functional.mse_loss(pred[:h], tgt[:h]) + prior_w * torch.nn.functional.mse_loss(pred[h:], tgt[h:])
+        lo.backward()
+        go = torch.cat([p.grad.flatten() for p in oparams])
+        torch.nn.utils.clip_grad_norm_(oparams, 1.0)
+        opt.step()
+        opt.zero_grad()
+        lm = tr._forward_backward(x.to(DEV), t.to(DEV).float(), e.to(DEV).to(torch.bfloat16), None, tgt.to(DEV))
+        gm = tr.flat_g[:tr.numel].detach().cpu().clone()
+        tr.step_idx += 1
+        tr._optimizer_tail()
+        if DEV == "cuda":
+            torch.cuda.synchronize()
+        worst_grad = max(worst_grad, rel(gm, go))
+        worst_loss = max(worst_loss, abs(float(lm) - float(lo)) / abs(float(lo)))
+        print(f"  step {step}: loss oracle={float(lo):.6f} ours={float(lm):.6f}  all-adapter gradient rel={rel(gm, go):.3e}")
+    po = torch.cat([p.detach().flatten() for p in oparams])
+    pm = tr.flat_p[:tr.numel].detach().cpu()
+    with tempfile.TemporaryDirectory() as d:
+        f = munet.save_attn_procs(d)
+        sd = torch.load(f)
+        okeys = [f"{k}.{n}" for k, op in oprocs.items() for n, _ in op.named_parameters()]
+        keys_ok = list(sd.keys()) == okeys
+        m2 = cb.UNet2DConditionModel.from_state_dict({k: v.clone() for k, v in ounet.state_dict().items() if ".processor." not in k}, DEV, TINY)
+        m2.load_attn_procs(d)
+        rt_ok = all(torch.equal(a.detach().cpu(), b.detach().cpu()) for a, b in zip(m2.attn_procs_state_dict().values(), munet.attn_procs_state_dict().values()))
+    e_upd = rel(pm, po)      # parameters after two steps (Adam's +-lr steps on an O(0.05..0.25) scale: dominated by the unchanged part)
+    print(f"  gradient rel (worst step) = {worst_grad:.3e}; loss rel = {worst_loss:.2e}; parameters after 2 steps rel = {e_upd:.3e}; "
+          f"attn-procs file keys ok={keys_ok}, round trip ok={rt_ok}")
+    ok = worst_grad < 5e-2 and worst_loss < 2e-3 and e_upd < 1e-3 and keys_ok and rt_ok
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
 def graph_case(v2: bool = True, B=2, HW=16, steps=5):
     """Trainer(cuda_graph=True) (2 eager warm-up steps, capture, replays) against the eager Trainer on the same
     per-step inputs: the same kernels run in the same order, so losses and parameters must agree to fp32 atomics noise."""
@@ -247,6 +327,7 @@ CASES = {
     "hint_v2": lambda: hint_case(True),
     "train_v1": lambda: train_case(False),
     "train_v2": lambda: train_case(True),
+    "train_lora_only": train_lora_only_case,
 }
 
 

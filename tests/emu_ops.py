@@ -298,10 +298,14 @@ def small_linear(x, w, bias, silu_in=False, silu_out=False):
     return F.silu(y) if silu_out else y
 
 
-def mse_loss(pred, target, gscale=1.0, need_grad=True):
+def mse_loss(pred, target, gscale=1.0, need_grad=True, out=None):
     d = pred - target
     loss = (d * d).mean().reshape(1)
-    return loss, ((2.0 * gscale / pred.numel()) * d if need_grad else None)
+    g = (2.0 * gscale / pred.numel()) * d
+    if out is not None:
+        out.copy_(g)
+        return loss, out
+    return loss, (g if need_grad else None)
 
 
 # ------------------------------------------------------------------------------------------------------------ LoRA side path

@@ -9,7 +9,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from tests import check_eager, check_reference_golden, check_variants  # noqa: E402
+from tests import check_eager, check_hint, check_reference_golden, check_variants  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -31,3 +31,8 @@ def test_cuda_path_matches_golden_vectors_computed_by_the_reference_code(case):
     """Expected values come from /root/reference/models.py itself (imported unmodified when the fixture was generated,
     tests/golden/make_reference_golden.py), not from the oracle restatement."""
     assert check_reference_golden.CASES[case]()
+
+
+def test_lora_only_train_step_with_prior_preservation_matches_oracle():
+    """Trainer(control_lora=None, prior_loss_weight=w): the DreamBooth-LoRA step (train_dreambooth_lora.py:880-918)."""
+    assert check_hint.CASES["train_lora_only"]()
