@@ -561,7 +561,7 @@ def run_ours(a):
     trace("aux")
     aux = {}
     graph_used = bool(tr.cuda_graph and tr._graph is not None)
-    if rank == 0 and not a.no_aux:
+    if rank == 0 and world == 1 and not a.no_aux:      # single-GPU numbers: a scaling run must not keep N-1 ranks waiting on them
         del tr
         torch.cuda.empty_cache()
         for key, fn in (("denoise_c3", lambda: aux_denoise(torch, cb, unet, "c3")), ("denoise_c5", lambda: aux_denoise(torch, cb, unet, "c5")),
