@@ -1,0 +1,92 @@
+"""Denoise loops and the device-side step glue against the oracle (tiny SD-style UNet):
+  ddim / dpmpp    `ddim_sample` / `dpmpp_sample` (CFG, UNet batch 2B, control injected once; train_...:824-843, mix_lora_and_control_lora.py:
+                  153-164) vs the oracle UNet driven by the restated schedulers (oracle/sampler_ref.py)
+  step_glue       `Trainer.step_from_latents` (train_...:757-796): the draw of step k equals the Philox restatement for counter k, the
+                  loss equals the oracle's on the same noisy latents / target, fresh draws every step
+usage: python tests/check_sampler.py [ddim|dpmpp|step_glue]        (CLB_EMU=1: host-logic mode on the CPU)"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from tests._device import DEV, sync  # noqa: E402
+from tests import check_unet  # noqa: E402
+
+
+def loop_case(which):
+    import torch
+    from controllora_b200.sampler import ddim_sample, dpmpp_sample
+    from oracle import sampler_ref as SR
+
+    ounet, munet, ocl, mcl = check_unet.build_pair("v1" if which == "ddim" else "v2")
+    g = torch.Generator().manual_seed(9 if which == "ddim" else 11)
+    B, HW = 2, 16
+    guide = (torch.rand(B, 3, HW * 8, HW * 8, generator=g) * 2 - 1).to(torch.bfloat16).float()
+    cond = torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).float()
+    unc = torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).float()
+    lat0 = torch.randn(B, 4, HW, HW, generator=g)
+    steps = 3 if which == "ddim" else 4
+    with torch.no_grad():
+        ocl(torch.cat([guide, guide], 0))
+        x = lat0.clone()
+        if which == "ddim":
+            for t in SR.timesteps(steps):
+                eps = ounet(torch.cat([x, x], 0), torch.full((2 * B,), int(t)), torch.cat([unc, cond], 0)).sample
+                x = SR.cfg_ddim_step(eps[:B], eps[B:], x, t, steps, 7.5)
+        else:
+            sched = SR.DPMSolverPP2M(steps)
+            for t in sched.timesteps:
+                eps = ounet(torch.cat([x, x], 0), torch.full((2 * B,), int(t)), torch.cat([unc, cond], 0)).sample
+                x = sched.step(SR.cfg_combine(eps[:B], eps[B:], 7.5), t, x)
+    fn = ddim_sample if which == "ddim" else dpmpp_sample
+    out = fn(munet, mcl, guide.to(DEV), cond.to(DEV).to(torch.bfloat16), unc.to(DEV).to(torch.bfloat16), num_inference_steps=steps,
+             guidance_scale=7.5, latents=lat0.to(DEV))
+    sync()
+    err = float((out.cpu() - x).norm() / x.norm())
+    print(f"[sampler {which}] {steps}-step latent rel err {err:.3e}")
+    ok = err < (6e-2 if which == "ddim" else 8e-2)
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
+def step_glue_case():
+    import numpy as np
+    import torch
+    from controllora_b200.trainer import Trainer
+    from oracle import sampler_ref as SR
+
+    ounet, munet, ocl, mcl = check_unet.build_pair("v2")
+    B, HW = 2, 16
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(B, 4, HW, HW, generator=g)
+    ehs = torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).float()
+    guide = (torch.rand(B, 3, HW * 8, HW * 8, generator=g) * 2 - 1).to(torch.bfloat16).float()
+    tr = Trainer(munet, mcl, lr=0.0, noise_seed=1234)      # lr 0: the step runs, the adapters stay where the oracle's are
+    ok, prev = True, None
+    for k in range(3):
+        loss = tr.step_from_latents(lat.to(DEV), ehs.to(DEV).to(torch.bfloat16), guide.to(DEV))
+        sync()
+        noisy, target, ts = [t.detach().cpu() for t in tr.last_noise_draw]
+        n_ref, t_ref = SR.device_noise(tr._rank_seed, k, B, 4 * HW * HW)
+        n_ref, t_t = torch.from_numpy(n_ref).view(B, 4, HW, HW), torch.from_numpy(t_ref)
+        same_draw = np.array_equal(ts.numpy().astype(np.int64), t_ref) and torch.allclose(noisy, SR.add_noise(lat, n_ref, t_t), atol=2e-5, rtol=1e-5) \
+            and torch.allclose(target, n_ref, atol=2e-5, rtol=1e-5)
+        fresh = prev is None or not torch.equal(prev, noisy)
+        prev = noisy
+        with torch.no_grad():
+            ocl(guide)
+            lo = torch.nn.functional.mse_loss(ounet(noisy, ts.long(), ehs).sample, target)
+        e = abs(float(loss) - float(lo)) / abs(float(lo))
+        print(f"[step_glue] step {k}: timesteps {ts.tolist()} draw==restatement {same_draw} fresh {fresh} loss ours={float(loss):.6f} oracle={float(lo):.6f} rel={e:.2e}")
+        ok = ok and same_draw and fresh and e < 2e-3 and int(tr.rng_counter) == k + 1
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
+CASES = {"sampler_ddim": lambda: loop_case("ddim"), "sampler_dpmpp": lambda: loop_case("dpmpp"), "step_glue": step_glue_case}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    bad = [n for n in names if not CASES[n if n in CASES else "sampler_" + n]()]
+    print("SUMMARY", "all ok" if not bad else f"FAILED {bad}")
+    sys.exit(1 if bad else 0)

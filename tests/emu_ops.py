@@ -308,6 +308,28 @@ def mse_loss(pred, target, gscale=1.0, need_grad=True, out=None):
     return loss, (g if need_grad else None)
 
 
+def add_noise(x0, sqrt_ac, sqrt_1mac, step_counter, seed, v_prediction=False, out=None):
+    """cl_add_noise through the numpy Philox restatement of its counter layout (oracle/sampler_ref.device_noise)."""
+    from oracle import sampler_ref as SR
+
+    B = x0.shape[0]
+    per = x0.numel() // B
+    noise, ts = SR.device_noise(int(seed) & (2**64 - 1), int(step_counter), B, per, sqrt_ac.numel())
+    noise = torch.from_numpy(noise).view(x0.shape)
+    ts = torch.from_numpy(ts)
+    a = sqrt_ac[ts].view(B, *([1] * (x0.dim() - 1)))
+    b = sqrt_1mac[ts].view(B, *([1] * (x0.dim() - 1)))
+    noisy = a * x0 + b * noise
+    target = a * noise - b * x0 if v_prediction else noise
+    step_counter += 1
+    res = (noisy, target, ts.float())
+    if out is not None:
+        for o, r in zip(out, res):
+            o.copy_(r)
+        return out
+    return res
+
+
 # ------------------------------------------------------------------------------------------------------------ LoRA side path
 def _pack_run(self):
     for d, (src, dst) in zip(self.descs, self._keep):
@@ -580,7 +602,7 @@ def channel_affine_nchw(x, mul, shift):
 _FUNCS = [
     "gemm", "attention_fwd", "attention_bwd", "groupnorm_fwd", "groupnorm_bwd", "layernorm_fwd", "layernorm_bwd", "geglu_fwd",
     "geglu_bwd", "add", "upsample2x_fwd", "upsample2x_bwd", "zero_insert2x", "concat_channels", "slice_channels", "nchw_to_nhwc",
-    "nhwc_to_nchw_f32", "f32_to_bf16", "conv_in", "conv_out", "conv_out_bwd", "timestep_embedding", "small_linear", "mse_loss",
+    "nhwc_to_nchw_f32", "f32_to_bf16", "conv_in", "conv_out", "conv_out_bwd", "timestep_embedding", "small_linear", "mse_loss", "add_noise",
     "skinny_atb", "rowdot", "rowmat", "skinny_small", "small_matmul", "hilo_combine", "rank_update", "v2_inject_fwd",
     "v2_inject_bwd", "rank4_project_update", "cast_matrix", "axpy_matrix", "conv_wgrad", "conv_weight_prep", "colsum",
     "conv_in_wgrad", "sumsq", "adamw", "step_begin", "adamw_dev", "cfg_ddim_step", "cfg_dpmpp_step", "sampler_prep",

@@ -27,11 +27,12 @@ def _cases():
         c[k] = check_hint.CASES[k]
     c["vae_tiny"] = lambda: check_vae.run("tiny")
     c["clip_tiny"] = lambda: check_clip.run("tiny")
-    from tests import check_eager, check_reference_golden, check_variants
+    from tests import check_eager, check_reference_golden, check_sampler, check_variants
 
     c.update(check_variants.CASES)
     c.update(check_eager.CASES)
     c.update(check_reference_golden.CASES)
+    c.update(check_sampler.CASES)
     return c
 
 

@@ -19,6 +19,7 @@ CASES += ["variant_" + k for k in ("v1_pre_post_add", "v1_post_add_main_stacked"
                                    "v1_concat_stacked", "v1_concat_post_add", "v1_concat_rank8")]
 CASES += ["generic_" + v for v in ("plain", "v1", "v2", "v1_stacked@0.5", "v1_post_add", "v1_concat")]
 CASES += ["refgold_" + k for k in ("v1_stacked", "v2", "post_add", "concat")]      # vs vectors computed by the reference's own models.py
+CASES += ["sampler_ddim", "sampler_dpmpp", "step_glue"]                              # tests/check_sampler.py
 CASES += ["eager_" + k for k in ("plain_self", "plain_cross", "v1_self", "v1_cross_stacked", "v2_self", "v2_cross", "lora_linear")]
 
 
