@@ -61,12 +61,15 @@ class Trainer:
         # the shallow levels at the end) - only the last, smallest bucket is exposed.  The arena order is the module order, so a
         # bucket is one or two contiguous ranges of the flat gradient.
         # CLB_DP_BUCKETS=1 opts in.  Default (what the 2-GPU runs validate): ONE all-reduce of the whole arena after the backward,
-        # outside the captured graph.  The bucketed, in-graph variant ran at 38.5 ms/step on 2 GPUs (round 2) but its replicas
-        # drifted apart in tests/test_multigpu_nccl.py and the process hung at teardown - it stays experimental.
+        # outside the captured graph.  Round 2: the bucketed variant ran at 38.5 ms/step on 2 GPUs but its replicas drifted apart -
+        # bucket 0 was reduced while up to 15 LoRA dA / dB reductions were still sitting in the batched skinny queue (ops.SKINNY), so
+        # those gradients reached the arena AFTER the exchange.  _reduce_bucket now flushes the queue first; the world-2 gloo test
+        # (tests/test_dp_gloo.py, host-logic mode) checks bucketed == unbucketed == single-process big batch.  It stays opt-in until it
+        # has been re-measured on GPUs (the process also hung at teardown with NCCL inside the captured graph).
         import os as _os
         want_buckets = _os.environ.get("CLB_DP_BUCKETS", "0") == "1"
-        self._side = torch.cuda.Stream(device=dev) if (want_buckets and self.world > 1 and dev.type == "cuda") else None
-        self._bucketed = self._side is not None      # False: ONE all-reduce after the backward (and outside a captured graph)
+        self._bucketed = bool(want_buckets and self.world > 1)   # False: ONE all-reduce after the backward (and outside a captured graph)
+        self._side = torch.cuda.Stream(device=dev) if (self._bucketed and dev.type == "cuda") else None
         self._tail_in_graph = self.world == 1 or self._bucketed
         self._reduced_in_step = False
         self._buckets = self._make_buckets()
@@ -219,7 +222,8 @@ class Trainer:
         if self._bucketed:
             for b in list(self._pending):
                 self._reduce_bucket(b)
-            torch.cuda.current_stream().wait_stream(self._side)
+            if self._side is not None:
+                torch.cuda.current_stream().wait_stream(self._side)
             self._reduced_in_step = True
         return loss
 
@@ -271,6 +275,11 @@ class Trainer:
         if not self._bucketed or b not in self._pending:
             return
         self._pending.remove(b)
+        ops.SKINNY.flush()       # queued rank-r reductions (LoRA dA / dB) must be IN the arena before it is exchanged
+        if self._side is None:   # no side stream (host-logic tests on the CPU): same order, no overlap
+            for lo, hi in self._buckets[b]:
+                torch.distributed.all_reduce(self.flat_g[lo:hi], group=self.pg)
+            return
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
             for lo, hi in self._buckets[b]:

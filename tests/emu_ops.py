@@ -358,11 +358,18 @@ def skinny_atb(a, r, b, out, so_j, so_c, alpha):
 
 
 def _skinny_add(self, a, r, b, out, so_j, so_c, alpha):
-    skinny_atb(a, r, b, out, so_j, so_c, alpha)
+    """Like the real queue (ops.SkinnyQueue): reductions are only COLLECTED here and run in batches of CL_SKINNY_MAX or at flush()
+    - code that reads a gradient before flushing must see it missing here too."""
+    self.keep.append((a, r, b, out, so_j, so_c, alpha))
+    self.descs.append(None)
+    if len(self.keep) >= self._max:
+        _skinny_flush(self)
 
 
 def _skinny_flush(self):
-    return None
+    for args in self.keep:
+        skinny_atb(*args)
+    self.descs, self.keep = [], []
 
 
 def rowdot(a, u):
@@ -630,7 +637,7 @@ def install() -> None:
     _INSTALLED["SkinnyQueue.flush"] = ops.SkinnyQueue.flush
     ops.PackPlan.run = ng(_pack_run)
     ops.SkinnyQueue.add = ng(_skinny_add)
-    ops.SkinnyQueue.flush = _skinny_flush
+    ops.SkinnyQueue.flush = ng(_skinny_flush)
 
 
 def uninstall() -> None:
