@@ -59,6 +59,7 @@ class LayerPlan:
         self.level: Optional[_LevelCtx] = None
         self.col = 0           # first column of this processor's block inside level.u
         self.ctrl_adapter = None        # engine.Adapter of the processor's own to_q_lora (v1)
+        self.v_chain = None             # [(is the processor's own adapter, GAdapter)] when the value projection carries unscaled adapters
         # V2 helper tables (fp32): Bc [C, rp] etc. are read directly from the parameters
 
 
@@ -173,6 +174,14 @@ class LoraRuntime:
                     self._adapter(lp.v, a.to_v_lora, unscaled=a is not p)
                 if a is p or not a.output_states_skipped:
                     self._adapter(lp.out, a.to_out_lora)
+            # value projections with unscaled (stacked) adapters keep an adapter-by-adapter form as well: begin() selects it for a
+            # forward whose `scale` differs from the one the shared tables are packed for while another forward is still in flight
+            lp.v_chain = None
+            if any(ad.unscaled for ad in lp.v.adapters):
+                from .lora_generic import GAdapter
+
+                lp.v_chain = [(a is p, GAdapter(a.to_v_lora.down.weight, a.to_v_lora.up.weight, self.plan, self.grad_of, dev))
+                              for a in chain if not a.value_states_skipped]
             lp.q.finalize(self.plan, need_dx=True)
             lp.k.finalize(self.plan, need_dx=lp.post_add or not L.is_cross)     # post_add: down_tab = A^T feeds dy0 = dy + s dt A
             lp.v.finalize(self.plan, need_dx=lp.post_add or not L.is_cross)
@@ -207,9 +216,20 @@ class LoraRuntime:
         ctx.stash["control_vars"] = control_vars          # generic layers look their processors' control states up themselves
         s = ctx.scale
         if self.plan._unscaled:
-            if s == 0.0:
-                raise NotImplementedError("scale == 0 with stacked value adapters (their deltas are unscaled in the reference)")
-            self.plan.set_unscaled_mul(1.0 / s)
+            # The fused epilogue has ONE scale per projection, so the unscaled stacked value deltas (models.py:260,265,397,402) are
+            # packed with 1/scale into tables that every forward of this runtime shares.  They may only be re-packed for another
+            # scale when no earlier forward still needs them for its backward (two UNet calls with different `scale` before one
+            # backward): such a forward - and scale == 0, where 1/scale does not exist - takes the adapter-by-adapter value
+            # projection instead, which applies each adapter's own factor.
+            inflight = getattr(self, "_inflight", 0)
+            packed = 1.0 / self.plan._unscaled_mul
+            if s == 0.0 or (inflight > 0 and abs(packed - s) > 1e-12 * max(1.0, abs(s))):
+                ctx.stash["v_chain"] = True
+            else:
+                self.plan.set_unscaled_mul(1.0 / s)
+            if ctx.tape is not None:
+                self._inflight = inflight + 1
+                ctx.stash["counts_inflight"] = True
         self.plan.run()
         self.v2_plan.run()
         self.level_plan.run()
@@ -482,7 +502,12 @@ class LoraRuntime:
                 kvc[L.name] = (k, v)
         else:
             k = E.linear(ctx, kv_in, L.to_k, slot=lp.k)
-            v = E.linear(ctx, kv_in, L.to_v, slot=lp.v)
+            if lp.v_chain is not None and ctx.stash.get("v_chain"):
+                from .lora_generic import Entry, chain_linear
+
+                v = chain_linear(ctx, kv_in, L.to_v, [Entry(ad, False, ctx.scale if own else 1.0) for own, ad in lp.v_chain])
+            else:
+                v = E.linear(ctx, kv_in, L.to_v, slot=lp.v)
             if kvc is not None:
                 kvc[L.name] = (k, v)
         o = E.attention(ctx, q, k, v, L.heads)
@@ -492,6 +517,8 @@ class LoraRuntime:
 
     def finish_backward(self, ctx: Ctx):
         """After the tape ran: one GEMM per level turns the collected du blocks into d(control state)."""
+        if ctx.stash.pop("counts_inflight", False):
+            self._inflight = max(0, getattr(self, "_inflight", 0) - 1)
         for lv in getattr(self, "level_list", []):
             st = self._fs(ctx, lv)
             if st.du is None or st.c is None or not st.c.rg:

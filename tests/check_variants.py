@@ -194,6 +194,65 @@ CASES.update({"generic_" + v: (lambda v=v: run_forced(v)) for v in FORCED})
 CASE_NAMES = list(CASES)
 
 
+SCALES = (1.0, 0.6)
+
+
+def run_two_forwards(variant="v1_stacked"):
+    """Two UNet forwards (different inputs, the second one with a different `scale`) BEFORE one backward - gradient accumulation /
+    several UNet calls per loss (train_text_to_image_control_lora.py:751 `accelerator.accumulate`): the per-forward LoRA products must
+    live with their forward, not on the shared runtime."""
+    import torch
+    from tests import check_unet
+
+    ounet, munet, ocl, mcl = check_unet.build_pair(variant)
+    g = torch.Generator().manual_seed(21)
+    B, HW = 2, 16
+    cc = [256] * 4 if variant in ("v2", "v1_concat") else list(check_unet.TINY["block_out_channels"])
+    ctrl = []
+    for lvl in range(4):
+        c = (0.5 * torch.randn(B, cc[lvl], HW >> lvl, HW >> lvl, generator=g)).to(torch.bfloat16).float()
+        co, cm = c.clone().requires_grad_(True), c.clone().to(DEV).requires_grad_(True)
+        ctrl.append((co, cm))
+        for p in ocl.lora_layers[lvl]:
+            p.inject_control_states(co)
+        for p in mcl.lora_layers[lvl]:
+            p.inject_control_states(cm)
+    lo = lm = 0.0
+    preds = []
+    for k, scale in enumerate(SCALES):
+        x = torch.randn(B, 4, HW, HW, generator=g).to(torch.bfloat16).float()
+        t = torch.randint(0, 1000, (B,), generator=g)
+        e = torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).float()
+        tgt = torch.randn(B, 4, HW, HW, generator=g)
+        cak = {"scale": scale}
+        po = ounet(x, t, e, cross_attention_kwargs=cak).sample
+        pm = munet(x.to(DEV), t.to(DEV), e.to(DEV).to(torch.bfloat16), cross_attention_kwargs=cak).sample
+        lo = lo + torch.nn.functional.mse_loss(po, tgt)
+        lm = lm + torch.nn.functional.mse_loss(pm, tgt.to(DEV))
+        preds.append(rel(pm, po))
+    lo.backward()
+    lm.backward()
+    sync()
+    go, gm = [], []
+    for n in ounet.attn_processors:
+        for o_, m_ in [(ounet.attn_processors[n], munet.attn_processors[n])]:
+            for (n1, p1), (n2, p2) in zip(o_.named_parameters(), m_.named_parameters()):
+                if p1.grad is not None:
+                    go.append(p1.grad.flatten())
+                    gm.append(p2.grad.flatten().cpu())
+    e_all = rel(torch.cat(gm), torch.cat(go))
+    e_ctrl = max(rel(cm.grad, co.grad) for co, cm in ctrl)
+    print(f"[two forwards {variant}] preds rel={preds[0]:.3e} / {preds[1]:.3e}; all adapter grads rel={e_all:.3e}; worst d control rel={e_ctrl:.3e}")
+    ok = max(preds) < 2e-2 and e_all < 5e-2 and e_ctrl < 8e-2
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
+CASES["two_forwards_v1_stacked"] = lambda: run_two_forwards("v1_stacked")
+CASES["two_forwards_v2"] = lambda: run_two_forwards("v2")
+CASE_NAMES = list(CASES)
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)
     bad = [n for n in names if not CASES[n if n in CASES else "variant_" + n]()]
