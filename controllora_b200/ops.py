@@ -586,6 +586,7 @@ def v2_inject_fwd(x, th16, uc, rc: int, tab, alpha: float):
     Cc = x.shape[-1]
     M = x.numel() // Cc
     assert x.is_contiguous() and th16.is_contiguous() and th16.shape == (M, 16) and tab.shape == (Cc, 4)
+    assert uc is None or uc.shape[0] == M, "control product rows != hidden-state rows"
     out = torch.empty_like(x)
     t = torch.empty(M, 8, device=x.device, dtype=torch.float32)
     ldu = 0 if uc is None else uc.stride(0)
@@ -609,6 +610,9 @@ def rank4_project_update(x, proj_tab, upd_tab, uc, rc: int, alpha: float):
     Cc = x.shape[-1]
     M = x.numel() // Cc
     assert x.is_contiguous()
+    if uc is not None and uc.shape[0] != M:
+        raise ValueError(f"control states cover {uc.shape[0]} tokens but the hidden states have {M}: inject control states with the UNet's "
+                         f"batch size (e.g. control_lora(torch.cat([guide] * 2)) under classifier-free guidance)")
     t = torch.empty(M, 4, device=x.device, dtype=torch.float32)
     y = torch.empty_like(x)
     ldu = 0 if uc is None else uc.stride(0)

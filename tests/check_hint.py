@@ -269,6 +269,54 @@ def train_lora_only_case(B=4, HW=16, prior_w=0.7):
     return ok
 
 
+def resume_case(B=2, HW=16):
+    """Resume equivalence (train_text_to_image_control_lora.py:713-735 / 805-809): 3 steps in one run == 2 steps, save_checkpoint, a
+    NEW Trainer on freshly initialised models, load_checkpoint, 1 more step - bit for bit (parameters, AdamW moments, device step
+    counter, and the device Philox counter: step 3 draws the same noise / timesteps in both runs)."""
+    import tempfile
+
+    import torch
+    import controllora_b200 as cb
+    from controllora_b200.trainer import Trainer
+    from oracle import models_ref as MR
+
+    def make(seed):
+        torch.manual_seed(seed)
+        munet = cb.UNet2DConditionModel.synthetic(DEV, TINY, seed=1)
+        mcl = cb.ControlLoRA(**dict(TINY_LORA, lora_control_version=2, lora_pre_conv_skipped=True)).to(DEV)
+        if seed == 0:
+            MR.randomize_lora_up_(mcl, seed=3, std=0.05)
+        MR.wire_processors(munet, mcl)
+        return Trainer(munet, mcl, lr=1e-3, noise_seed=77), mcl
+
+    g = torch.Generator().manual_seed(8)
+    batches = [((0.2 * torch.randn(B, 4, HW, HW, generator=g)).to(DEV), torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).to(DEV),
+                (torch.rand(B, 3, HW * 8, HW * 8, generator=g) * 2 - 1).to(DEV)) for _ in range(3)]
+    a, _ = make(0)
+    for b in batches:
+        loss_a = a.step_from_latents(*b)
+    draw_a = [t.detach().cpu().clone() for t in a.last_noise_draw]
+    b1, _ = make(0)
+    for b in batches[:2]:
+        b1.step_from_latents(*b)
+    with tempfile.TemporaryDirectory() as d:
+        path = b1.save_checkpoint(d)
+        b2, _ = make(5)                                   # different initial weights: everything must come from the checkpoint
+        gs = b2.load_checkpoint(path)
+    loss_b = b2.step_from_latents(*batches[2])
+    if DEV == "cuda":
+        torch.cuda.synchronize()
+    draw_b = [t.detach().cpu().clone() for t in b2.last_noise_draw]
+    same = {"global_step": gs == 2, "params": torch.equal(a.flat_p, b2.flat_p), "exp_avg": torch.equal(a.flat_m, b2.flat_m),
+            "exp_avg_sq": torch.equal(a.flat_v, b2.flat_v), "step": a.step_idx == b2.step_idx == int(b2.step_dev) == 3,
+            "rng_counter": int(a.rng_counter) == int(b2.rng_counter) == 3, "loss": float(loss_a) == float(loss_b),
+            "noise_draw": all(torch.equal(x, y) for x, y in zip(draw_a, draw_b))}
+    print("  resume equivalence:", same)
+    ok = all(same.values())
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
 def graph_case(v2: bool = True, B=2, HW=16, steps=5):
     """Trainer(cuda_graph=True) (2 eager warm-up steps, capture, replays) against the eager Trainer on the same
     per-step inputs: the same kernels run in the same order, so losses and parameters must agree to fp32 atomics noise."""
@@ -328,6 +376,7 @@ CASES = {
     "train_v1": lambda: train_case(False),
     "train_v2": lambda: train_case(True),
     "train_lora_only": train_lora_only_case,
+    "resume": resume_case,
 }
 
 

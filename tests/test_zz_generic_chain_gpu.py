@@ -36,3 +36,9 @@ def test_cuda_path_matches_golden_vectors_computed_by_the_reference_code(case):
 def test_lora_only_train_step_with_prior_preservation_matches_oracle():
     """Trainer(control_lora=None, prior_loss_weight=w): the DreamBooth-LoRA step (train_dreambooth_lora.py:880-918)."""
     assert check_hint.CASES["train_lora_only"]()
+
+
+def test_checkpoint_resume_equivalence_on_gpu():
+    """3 steps == 2 steps + save_checkpoint + fresh Trainer + load_checkpoint + 1 step, bit for bit, incl. the device Philox counter
+    (train_text_to_image_control_lora.py:713-735, 805-809)."""
+    assert check_hint.CASES["resume"]()
