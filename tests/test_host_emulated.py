@@ -48,3 +48,14 @@ def test_emulation_is_test_only():
     for p in [*ROOT.glob("controllora_b200/*.py"), ROOT / "bench.py"]:
         src = p.read_text()
         assert "emu_ops" not in src and "run_emulated" not in src, p
+
+
+def test_fullsize_sd15_shapes_pass_the_real_launchers_argument_validation():
+    """One train step at the BASELINE shapes per path: canny-v2 on the fused path (the bench configuration) and v1 + a stacked
+    pre-LoRA forced through the general chain path - every launch's arguments are checked by the real C launchers
+    (tests/run_fullsize_emulated.py)."""
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "run_fullsize_emulated.py"), "diffusiondb-canny-v2", "0", "0",
+                        "diffusiondb-canny", "1", "1"], capture_output=True, text=True, timeout=1500, cwd=str(ROOT))
+    lines = [l for l in r.stdout.splitlines() if l.startswith("FULLSIZE")]
+    assert r.returncode == 0 and len(lines) == 2 and all(l.endswith("OK") for l in lines), r.stdout[-3000:] + r.stderr[-3000:]
+    assert "'v2': 32" in lines[0] and "'generic': 32" in lines[1]
