@@ -72,3 +72,19 @@ def test_ops_fail_loudly_without_cuda():
         pytest.skip("CPU-only check")
     with pytest.raises(_lib.CLError):
         ops.gemm(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(64, 64, dtype=torch.bfloat16))
+
+
+def test_every_entry_point_is_listed_in_the_integration_table():
+    """INTEGRATION.md's C-ABI table (entry point -> reference call site it replaces) stays in step with the header."""
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    words = set(re.findall(r"cl_[a-z0-9_]+", doc))
+    expanded = set(words)
+    for w in words:                                   # `cl_attn_fwd`, `cl_groupnorm_fwd/bwd`, `cl_conv_out(_bwd)`, `cl_upsample2x_*`
+        for m in re.finditer(re.escape(w) + r"/([a-z0-9_]+)", doc):
+            expanded.add(w.rsplit("_", 1)[0] + "_" + m.group(1))
+        for m in re.finditer(re.escape(w) + r"\((_[a-z0-9_]+)\)", doc):
+            expanded.add(w + m.group(1))
+    utility = {"cl_last_error", "cl_version", "cl_launch_count", "cl_gemm_split_hint", "cl_bf16_to_f32", "cl_f32_to_bf16", "cl_nchw_to_nhwc",
+               "cl_nhwc_to_nchw_f32"}                  # housekeeping + the "layout casts" of the elementwise row
+    missing = [n for n in declared_functions() if n not in expanded and n not in utility and not any(n.startswith(w[:-1]) for w in words if w.endswith("_"))]
+    assert not missing, f"declared in the header but absent from INTEGRATION.md's table: {missing}"
