@@ -43,3 +43,28 @@ def test_checkpoint_resume_equivalence_on_gpu():
     the run-to-run tolerance of the atomically reduced weight gradients), incl. the device Philox counter
     (train_text_to_image_control_lora.py:713-735, 805-809)."""
     assert check_hint.CASES["resume"]()
+
+
+@pytest.mark.parametrize("rp", [4, 8])
+def test_rank_update_and_rowdot_kernels(rp):
+    """The two per-row rank-r kernels the general chain path leans on, at both template widths, against torch:
+    out = x + alpha * t[:, :rp] tab^T (t a strided view, in place and out of place) and e = a u."""
+    import torch
+    from controllora_b200 import ops
+
+    g = torch.Generator().manual_seed(rp)
+    M, C = 1000, 1280
+    x = torch.randn(M, C, generator=g).to(torch.bfloat16).cuda()
+    t_full = torch.randn(M, 16, generator=g).cuda()
+    tab = (0.1 * torch.randn(C, rp, generator=g)).cuda()
+    t = t_full[:, 8:] if rp == 8 else t_full[:, 4:]           # a view with row stride 16 and a non-zero column offset (block b of t)
+    want = (x.float() + 0.7 * (t[:, :rp] @ tab.t())).to(torch.bfloat16)
+    got = ops.rank_update(x, t, tab, 0.7)
+    buf = x.clone()
+    ops.rank_update(buf, t, tab, 0.7, out=buf)
+    u = (0.1 * torch.randn(C, rp, generator=g)).cuda()
+    e = ops.rowdot(x, u)
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
+    assert rel(got, want) < 4e-3 and torch.equal(got, buf)
+    assert rel(e, x.float() @ u) < 1e-5
