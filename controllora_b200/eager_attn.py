@@ -108,6 +108,9 @@ def _run(bind: _Binding, hs, ehs, scale, ctensors, tape, hs_rg=False, c_rg=()):
     control = {}
     for i, cs in enumerate(ctensors):
         control[cs.data_ptr()] = _control_to_var(cs.detach(), rg=bool(tape is not None and i < len(c_rg) and c_rg[i]))
+    from .unet_module import UNet2DConditionModel
+
+    UNet2DConditionModel._match_control_batch(control, hs.shape[0], tape is not None)      # CFG pipelines: control batch 1, UNet batch 2
     rt.begin(ctx, control)
     if tape is not None:
         tape.record(lambda: rt.finish_backward(ctx))

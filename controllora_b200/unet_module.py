@@ -249,6 +249,24 @@ class UNet2DConditionModel(nn.Module):
         return control, tensors
 
     @staticmethod
+    def _match_control_batch(control: Dict[int, Var], batch: int, need_grad: bool) -> None:
+        """Control states injected with a smaller batch than the UNet call (the pipelines run classifier-free guidance with UNet batch
+        2 while `control_lora(guide)` saw batch 1: apps/gradio_*2image.py:75-89, mix_lora_and_control_lora.py:163-164).  The reference
+        broadcasts them (v1, models.py:236-238: only defined for control batch 1) or repeats each sample b2 // b1 times in place
+        (concat_hidden / V2, models.py:209-212, 344-347); both are `repeat_interleave` along the batch, done here once per call as a copy
+        at the boundary (inference only - a training step always injects the UNet's own batch)."""
+        for key, v in control.items():
+            b1 = v.data.shape[0]
+            if b1 == batch:
+                continue
+            if batch % b1 != 0:
+                raise ValueError(f"control states with batch {b1} cannot be matched to a UNet batch of {batch}")
+            if need_grad and v.rg:
+                raise NotImplementedError("differentiating through control states that are repeated along the batch is not supported: "
+                                          "inject control states with the UNet's batch size (control_lora(guide) on the same batch)")
+            control[key] = Var(v.data.repeat_interleave(batch // b1, dim=0).contiguous(), rg=False)
+
+    @staticmethod
     def _prep_inputs(sample, timestep, encoder_hidden_states):
         dev = sample.device
         from ._lib import require_cuda
@@ -276,6 +294,7 @@ class UNet2DConditionModel(nn.Module):
         params = [p for p in self.trainable_parameters() if p.requires_grad]
         need_grad = torch.is_grad_enabled() and (len(params) > 0)
         control, ctensors = self.collect_control(need_grad)
+        self._match_control_batch(control, x.shape[0], need_grad)
         if not need_grad:
             pred, _, _ = self.run_engine(x, t, e, control, tape=None, scale=scale)
             out = pred.data

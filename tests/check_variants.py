@@ -253,6 +253,42 @@ CASES["two_forwards_v2"] = lambda: run_two_forwards("v2")
 CASE_NAMES = list(CASES)
 
 
+def run_cfg_broadcast(variant):
+    """Classifier-free guidance the way the reference's pipelines run it: `control_lora(guide)` on batch 1, UNet batch 2
+    (apps/gradio_*2image.py:75-89, mix_lora_and_control_lora.py:163-164) - the injected control states are broadcast / repeated
+    along the batch (models.py:209-212, 236-238, 344-347)."""
+    import torch
+    from tests import check_unet
+
+    ounet, munet, ocl, mcl = check_unet.build_pair(variant)
+    g = torch.Generator().manual_seed(31)
+    HW = 16
+    cc = [256] * 4 if variant in ("v2", "v1_concat") else list(check_unet.TINY["block_out_channels"])
+    for lvl in range(4):
+        c = (0.5 * torch.randn(1, cc[lvl], HW >> lvl, HW >> lvl, generator=g)).to(torch.bfloat16).float()
+        for p in ocl.lora_layers[lvl]:
+            p.inject_control_states(c.clone())
+        for p in mcl.lora_layers[lvl]:
+            p.inject_control_states(c.clone().to(DEV))
+    x = torch.randn(1, 4, HW, HW, generator=g).to(torch.bfloat16).float().repeat(2, 1, 1, 1)
+    t = torch.tensor([400, 400])
+    e = torch.randn(2, 77, 64, generator=g).to(torch.bfloat16).float()
+    with torch.no_grad():
+        po = ounet(x, t, e).sample
+        pm = munet(x.to(DEV), t.to(DEV), e.to(DEV).to(torch.bfloat16)).sample
+    sync()
+    err = rel(pm, po)
+    print(f"[cfg broadcast {variant}] control batch 1, UNet batch 2: noise-pred rel={err:.3e}")
+    ok = err < 2e-2
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
+CASES["cfg_broadcast_v1"] = lambda: run_cfg_broadcast("v1")
+CASES["cfg_broadcast_v2"] = lambda: run_cfg_broadcast("v2")
+CASE_NAMES = list(CASES)
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)
     bad = [n for n in names if not CASES[n if n in CASES else "variant_" + n]()]

@@ -17,6 +17,7 @@ CASES = ["unet_none", "unet_plain", "unet_v1", "unet_v2", "unet_v1_stacked", "un
 CASES += ["variant_" + k for k in ("v1_pre_post_add", "v1_post_add_main_stacked", "v2_post_post_add", "v1_rank16", "v1_rank8_stacked8",
                                    "v1_control_rank12", "v2_control_rank8", "post_add_rank8", "v1_on_v1", "v2_on_v2",
                                    "v1_concat_stacked", "v1_concat_post_add", "v1_concat_rank8")]
+CASES += ["cfg_broadcast_v1", "cfg_broadcast_v2"]                                      # control batch 1 under a CFG UNet batch of 2
 CASES += ["two_forwards_v1_stacked", "two_forwards_v2", "unet_v1_stacked@0.0"]      # two UNet calls (different scale) before one backward; scale 0
 CASES += ["generic_" + v for v in ("plain", "v1", "v2", "v1_stacked@0.5", "v1_post_add", "v1_concat")]
 CASES += ["refgold_" + k for k in ("v1_stacked", "v2", "post_add", "concat")]      # vs vectors computed by the reference's own models.py
