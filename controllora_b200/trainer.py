@@ -97,6 +97,7 @@ class Trainer:
         self.rng_counter = torch.zeros(1, device=dev, dtype=torch.int64)
         self._rank_seed = (self.noise_seed + 0x9E3779B97F4A7C15 * rank) & (2**64 - 1)
         self._mode = None                # "noised" (step) or "latents" (step_from_latents): one captured graph per Trainer
+        self._micro = 0                  # micro-batches accumulated since the last optimizer step (accumulate())
 
     def step(self, noisy_latents: torch.Tensor, timesteps: torch.Tensor, ehs: torch.Tensor, guide: torch.Tensor,
              target: torch.Tensor, eager: bool = False) -> torch.Tensor:
@@ -294,7 +295,22 @@ class Trainer:
         ops.step_begin(self.gnorm_sq, self.step_dev)
         ops.sumsq(self.flat_g, self.gnorm_sq)
         ops.adamw_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                      self.step_dev, gnorm_sq=self.gnorm_sq, max_norm=self.max_norm, grad_scale=self.arena.grad_scale, zero_grad=True)
+                      self.step_dev, gnorm_sq=self.gnorm_sq, max_norm=self.max_norm,
+                      grad_scale=self.arena.grad_scale / (1 + self._micro), zero_grad=True)
+        self._micro = 0
+
+    def accumulate(self, noisy_latents, timesteps, ehs, guide, target) -> torch.Tensor:
+        """A micro-batch WITHOUT an optimizer step (`with accelerator.accumulate(control_lora)`, train_...:751, when
+        `--gradient_accumulation_steps` > 1): forward + backward only, gradients add up in the arena (every gradient kernel
+        accumulates; AdamW zeroes them).  The next step() closes the window: its clip + AdamW see the MEAN over the micro-batches,
+        like accelerate's 1/N loss scaling.  Not available on a Trainer that replays a captured step graph."""
+        if self.cuda_graph:
+            raise NotImplementedError("Trainer(cuda_graph=True) replays one captured whole step: gradient accumulation needs cuda_graph=False")
+        if self.world > 1 and self._bucketed:
+            raise NotImplementedError("gradient accumulation with the bucketed exchange (the buckets would be reduced once per micro-batch)")
+        loss = self._forward_backward(noisy_latents, timesteps, ehs, guide, target)
+        self._micro += 1
+        return loss
 
     # ------------------------------------------------------------------------------------------------ checkpoints
     # The reference checkpoints through accelerate: `accelerator.save_state(output_dir/checkpoint-{global_step})` every

@@ -269,6 +269,76 @@ def train_lora_only_case(B=4, HW=16, prior_w=0.7):
     return ok
 
 
+def accumulate_case(B=2, HW=16, micro=3):
+    """`--gradient_accumulation_steps 3` (train_text_to_image_control_lora.py:751 `accelerator.accumulate`, 1/N loss scaling, clip + AdamW
+    once per window): Trainer.accumulate() x2 + step() against the oracle + torch.optim.AdamW doing the same."""
+    import copy
+
+    import torch
+    from oracle import models_ref as MR
+    from oracle import unet_ref as UR
+    import controllora_b200 as cb
+    from controllora_b200.trainer import Trainer
+
+    torch.manual_seed(0)
+    ounet = UR.UNet2DConditionModel(**TINY)
+    UR.init_synthetic_(ounet, seed=1)
+    with torch.no_grad():
+        for p in ounet.parameters():
+            p.copy_(p.to(torch.bfloat16).float())
+    ounet.requires_grad_(False)
+    munet = cb.UNet2DConditionModel.from_state_dict({k: v.clone() for k, v in ounet.state_dict().items()}, DEV, TINY)
+    kw = dict(TINY_LORA, lora_control_version=2, lora_pre_conv_skipped=True)
+    ocl = MR.ControlLoRA(**kw)
+    MR.randomize_lora_up_(ocl, seed=3, std=0.05)
+    mcl = cb.ControlLoRA(**kw)
+    mcl.load_state_dict(ocl.state_dict())
+    mcl.to(DEV)
+    hcl = copy.deepcopy(ocl)                      # host twin that receives OUR accumulated gradient
+    MR.wire_processors(ounet, ocl)
+    MR.wire_processors(munet, mcl)
+    tr = Trainer(munet, mcl, lr=1e-4)
+    g = torch.Generator().manual_seed(5)
+    zero_b = _zero_grad_biases(ocl)
+    for k in range(micro):
+        x = torch.randn(B, 4, HW, HW, generator=g).to(torch.bfloat16).float()
+        t = torch.randint(0, 1000, (B,), generator=g)
+        e = torch.randn(B, 77, TINY["cross_attention_dim"], generator=g).to(torch.bfloat16).float()
+        guide = (torch.rand(B, 3, HW * 8, HW * 8, generator=g) * 2 - 1).to(torch.bfloat16).float()
+        tgt = torch.randn(B, 4, HW, HW, generator=g)
+        ocl(guide)
+        (torch.nn.functional.mse_loss(ounet(x, t, e).sample, tgt) / micro).backward()
+        args = (x.to(DEV), t.to(DEV).float(), e.to(DEV).to(torch.bfloat16), guide.to(DEV), tgt.to(DEV))
+        if k < micro - 1:
+            tr.accumulate(*args)
+        else:
+            tr.step_idx += 1
+            tr._forward_backward(*args)
+            gm = {n: (tr.arena.grad_of(p) / micro).detach().cpu().clone() for n, p in mcl.named_parameters()}
+            tr._optimizer_tail()
+    if DEV == "cuda":
+        torch.cuda.synchronize()
+    names = [n for n, _ in ocl.named_parameters() if n not in zero_b]
+    go = {n: p.grad.detach().clone() for n, p in ocl.named_parameters()}
+    e_grad = rel(torch.cat([gm[n].flatten() for n in names]), torch.cat([go[n].flatten() for n in names]))
+    # clip + AdamW on OUR accumulated mean gradient must be what the fused tail did
+    with torch.no_grad():
+        for n, p in hcl.named_parameters():
+            p.grad = gm[n].clone()
+    hopt = torch.optim.AdamW(hcl.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    torch.nn.utils.clip_grad_norm_(hcl.parameters(), 1.0)
+    p0 = {n: p.detach().clone() for n, p in ocl.named_parameters()}
+    hopt.step()
+    num = sum(float(((pm.detach().cpu() - p0[n]) - (ph.detach() - p0[n])).pow(2).sum()) for (n, ph), (_, pm) in zip(hcl.named_parameters(), mcl.named_parameters()))
+    den = sum(float((ph.detach() - p0[n]).pow(2).sum()) for n, ph in hcl.named_parameters())
+    e_opt = (num / den) ** 0.5
+    print(f"  accumulated over {micro} micro-batches: mean-gradient rel vs oracle = {e_grad:.3e}; clip + AdamW on it rel = {e_opt:.3e}; "
+          f"arena zeroed = {float(tr.flat_g.abs().sum()) == 0.0}; micro counter reset = {tr._micro == 0}")
+    ok = e_grad < 5e-2 and e_opt < 2e-3 and float(tr.flat_g.abs().sum()) == 0.0 and tr._micro == 0
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
 def resume_case(B=2, HW=16):
     """Resume equivalence (train_text_to_image_control_lora.py:713-735 / 805-809): 3 steps in one run == 2 steps, save_checkpoint, a
     NEW Trainer on freshly initialised models, load_checkpoint, 1 more step - bit for bit (parameters, AdamW moments, device step
@@ -386,6 +456,7 @@ CASES = {
     "train_v2": lambda: train_case(True),
     "train_lora_only": train_lora_only_case,
     "resume": resume_case,
+    "accumulate": accumulate_case,
 }
 
 

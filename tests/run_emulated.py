@@ -23,7 +23,7 @@ def _cases():
     c = {}
     for v in ("none", "plain", "v1", "v2", "v1_stacked", "v1_post_add", "v1_concat", "v1_stacked@0.5", "v2@0.5", "v1_stacked@0.0"):
         c["unet_" + v] = lambda v=v: check_unet.run(v)
-    for k in ("hint_v1", "hint_v2", "train_v1", "train_v2", "train_lora_only", "resume"):
+    for k in ("hint_v1", "hint_v2", "train_v1", "train_v2", "train_lora_only", "resume", "accumulate"):
         c[k] = check_hint.CASES[k]
     c["vae_tiny"] = lambda: check_vae.run("tiny")
     c["clip_tiny"] = lambda: check_clip.run("tiny")

@@ -11,7 +11,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 CASES = ["unet_none", "unet_plain", "unet_v1", "unet_v2", "unet_v1_stacked", "unet_v1_post_add", "unet_v1_concat",
-         "unet_v1_stacked@0.5", "unet_v2@0.5", "hint_v1", "hint_v2", "train_v1", "train_v2", "train_lora_only", "resume", "vae_tiny", "clip_tiny"]
+         "unet_v1_stacked@0.5", "unet_v2@0.5", "hint_v1", "hint_v2", "train_v1", "train_v2", "train_lora_only", "resume", "accumulate", "vae_tiny", "clip_tiny"]
 # general adapter chains (tests/check_variants.py) and the diffusers-style per-module processor call (tests/check_eager.py); listed
 # by name so that collecting this file never imports a checker (the device mode is fixed at their import, tests/_device.py)
 CASES += ["variant_" + k for k in ("v1_pre_post_add", "v1_post_add_main_stacked", "v2_post_post_add", "v1_rank16", "v1_rank8_stacked8",

@@ -68,3 +68,8 @@ def test_rank_update_and_rowdot_kernels(rp):
     rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
     assert rel(got, want) < 4e-3 and torch.equal(got, buf)
     assert rel(e, x.float() @ u) < 1e-5
+
+
+def test_gradient_accumulation_window_matches_oracle():
+    """Trainer.accumulate() x2 + step(): `--gradient_accumulation_steps 3` (train_text_to_image_control_lora.py:751)."""
+    assert check_hint.CASES["accumulate"]()
