@@ -129,21 +129,6 @@ class Entry:
     on_bwd: Optional[Callable[[torch.Tensor], None]] = None    # receives dt (unscaled dy B) of this adapter
 
 
-def add_vars(ctx: Ctx, a: Var, b: Var) -> Var:
-    out = Var(ops.add(a.data, b.data.view(a.data.shape)), rg=a.rg or b.rg)
-    if ctx.tape is not None and out.rg:
-        def bwd():
-            g = out.grad
-            out.grad = None
-            if g is None:
-                return
-            E.give_tensor(a, g)
-            E.give_tensor(b, g.view(b.data.shape))
-
-        ctx.tape.record(bwd)
-    return out
-
-
 def chain_linear(ctx: Ctx, x: Var, lw: E.LinearW, entries: List[Entry], residual: Optional[Var] = None) -> Var:
     """y = x W^T + b, then for every entry in order  y <- y + alpha * up(down(in)),  in = (y if post_add else x) (+ extra)
     (models.py:231-243, 248-265, 275-282), finally + residual."""
