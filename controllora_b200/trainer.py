@@ -117,6 +117,22 @@ class Trainer:
         VAE latents [B,4,h,w] fp32."""
         return self._run("latents", self._forward_backward_latents, (latents, ehs, guide), eager)
 
+    def step_from_pixels(self, vae, text_encoder, pixel_values: torch.Tensor, input_ids: torch.Tensor, guide: torch.Tensor,
+                         latent_noise: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None,
+                         eager: bool = False) -> torch.Tensor:
+        """The COMPLETE loop body of train_text_to_image_control_lora.py:751-796 from the batch as the dataloader hands it over:
+        `vae.encode(pixel_values).latent_dist.sample() * scaling_factor` (:753-754) and `text_encoder(input_ids)[0]` (:768) on the frozen
+        `controllora_b200.AutoencoderKL` / `CLIPTextModel`, then step_from_latents (noise, timesteps, add_noise, control injection,
+        UNet, loss, backward, clip, AdamW).  The two frozen encoders run in front of the (captured) step; `latent_noise` replaces the
+        standard-normal draw of `latent_dist.sample()` (tests)."""
+        with torch.no_grad():
+            dist = vae.encode(pixel_values).latent_dist
+            lat = dist.sample(generator) if latent_noise is None else dist.mean + dist.std * latent_noise.to(dist.mean.device, dist.mean.dtype)
+            lat = (lat * float(vae.config.scaling_factor)).contiguous()
+            ehs = text_encoder(input_ids)[0]
+        self.last_latents = lat
+        return self.step_from_latents(lat, ehs, guide, eager=eager)
+
     def _forward_backward_latents(self, latents, ehs, guide) -> torch.Tensor:
         noisy, target, ts = ops.add_noise(latents, self.sqrt_ac, self.sqrt_1mac, self.rng_counter, self._rank_seed,
                                           v_prediction=self.prediction_type == "v_prediction")

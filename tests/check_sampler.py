@@ -83,7 +83,53 @@ def step_glue_case():
     return ok
 
 
-CASES = {"sampler_ddim": lambda: loop_case("ddim"), "sampler_dpmpp": lambda: loop_case("dpmpp"), "step_glue": step_glue_case}
+def pixels_case():
+    """Trainer.step_from_pixels: the whole loop body train_text_to_image_control_lora.py:751-796 from pixels / token ids / guide - VAE
+    encode + latent sample, CLIP text tower, device noise + timesteps + add_noise, control injection, UNet, MSE - against the oracle
+    chain (vae_ref -> clip_ref -> sampler_ref.add_noise -> models_ref + unet_ref) on the same weights, the same latent-sampling noise
+    and the noise / timesteps the device drew."""
+    import torch
+    import controllora_b200 as cb
+    from controllora_b200.trainer import Trainer
+    from oracle import clip_ref as CR
+    from oracle import sampler_ref as SR
+    from oracle import vae_ref as VR
+
+    ounet, munet, ocl, mcl = check_unet.build_pair("v2")
+    vcfg = dict(block_out_channels=(32, 64, 64), layers_per_block=1)             # 3 levels: 64x64 pixels -> 16x16 latents
+    ovae = VR.AutoencoderKL(**vcfg)
+    VR.init_synthetic_(ovae, seed=4)
+    mvae = cb.AutoencoderKL.from_state_dict({k: v.detach().clone() for k, v in ovae.state_dict().items()}, DEV, vcfg)
+    ccfg = dict(CR.SD15_TEXT_CONFIG)
+    ccfg.update(num_hidden_layers=2, vocab_size=1000, hidden_size=64, intermediate_size=256, num_attention_heads=4)
+    csd = CR.synthetic_state_dict(ccfg, seed=0)
+    mclip = cb.CLIPTextModel.from_state_dict(csd, DEV, ccfg)
+    B = 2
+    g = torch.Generator().manual_seed(13)
+    pix = (torch.rand(B, 3, 64, 64, generator=g) * 2 - 1)
+    ids = torch.randint(0, ccfg["vocab_size"], (B, 77), generator=g)
+    guide = (torch.rand(B, 3, 128, 128, generator=g) * 2 - 1).to(torch.bfloat16).float()
+    eps = torch.randn(B, 4, 16, 16, generator=g)
+    tr = Trainer(munet, mcl, lr=0.0, noise_seed=99)
+    loss = tr.step_from_pixels(mvae, mclip, pix.to(DEV), ids.to(DEV), guide.to(DEV), latent_noise=eps)
+    sync()
+    noisy_m, target, ts = [t.detach().cpu() for t in tr.last_noise_draw]
+    with torch.no_grad():
+        lat_o = ovae.encode_sample(pix, eps)
+        ehs_o = CR.clip_text_forward(csd, ids, ccfg)
+        noisy_o = SR.add_noise(lat_o, target, ts.long())
+        ocl(guide)
+        lo = torch.nn.functional.mse_loss(ounet(noisy_o, ts.long(), ehs_o).sample, target)
+    e_lat = float((tr.last_latents.cpu() - lat_o).norm() / lat_o.norm())
+    e_noisy = float((noisy_m - noisy_o).norm() / noisy_o.norm())
+    e_loss = abs(float(loss) - float(lo)) / abs(float(lo))
+    print(f"[pixels] latents rel={e_lat:.3e} noisy latents rel={e_noisy:.3e} loss ours={float(loss):.6f} oracle={float(lo):.6f} rel={e_loss:.2e} timesteps {ts.tolist()}")
+    ok = e_lat < 2e-2 and e_noisy < 2e-2 and e_loss < 1e-2
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
+CASES = {"step_from_pixels": pixels_case, "sampler_ddim": lambda: loop_case("ddim"), "sampler_dpmpp": lambda: loop_case("dpmpp"), "step_glue": step_glue_case}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

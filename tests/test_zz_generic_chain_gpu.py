@@ -9,7 +9,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from tests import check_eager, check_hint, check_reference_golden, check_variants  # noqa: E402
+from tests import check_eager, check_hint, check_reference_golden, check_sampler, check_variants  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -73,3 +73,8 @@ def test_rank_update_and_rowdot_kernels(rp):
 def test_gradient_accumulation_window_matches_oracle():
     """Trainer.accumulate() x2 + step(): `--gradient_accumulation_steps 3` (train_text_to_image_control_lora.py:751)."""
     assert check_hint.CASES["accumulate"]()
+
+
+def test_whole_loop_body_from_pixels_matches_oracle_chain():
+    """Trainer.step_from_pixels: VAE encode + sample, CLIP text tower, device noise glue, hint encoder, UNet, loss (train_...:751-796)."""
+    assert check_sampler.CASES["step_from_pixels"]()
