@@ -245,3 +245,26 @@ class GraphedSampler:
             if getattr(st_old, "c", None) is not None and getattr(st_new, "c", None) is not None:
                 if st_old.c.data.data_ptr() != st_new.c.data.data_ptr():
                     st_old.c.data.copy_(st_new.c.data)
+
+
+@torch.no_grad()
+def generate(unet, control_lora, vae, text_encoder, guide: torch.Tensor, input_ids: torch.Tensor, uncond_input_ids: torch.Tensor,
+             num_inference_steps: int = 50, guidance_scale: float = 7.5, scheduler: str = "ddim", latents: Optional[torch.Tensor] = None,
+             seed: int = 0, sampler: Optional["GraphedSampler"] = None) -> torch.Tensor:
+    """What the reference's validation loop and apps ask of `StableDiffusionPipeline` after `control_lora(guide)`
+    (train_text_to_image_control_lora.py:824-843, apps/gradio_*2image.py:75-89, mix_lora_and_control_lora.py:153-164), on this
+    package's frozen encoders: prompt / negative-prompt token ids -> text states (`text_encoder(ids)[0]`), the CFG denoise loop
+    (`scheduler` = "ddim" or "dpmpp"; pass a `GraphedSampler` to replay the captured step instead of launching from Python), then
+    `vae.decode(latents / scaling_factor).sample` mapped from [-1, 1] to [0, 1] like the pipeline's `(image / 2 + 0.5).clamp(0, 1)`.
+    guide [B,3,H,W] in [-1,1]; ids [B,77] (tokenisation stays with the caller: the tokenizer is data-pipeline code).  Returns images
+    [B,3,H,W] fp32 in [0,1]."""
+    cond = text_encoder(input_ids)[0]
+    uncond = text_encoder(uncond_input_ids)[0]
+    if sampler is not None:
+        lat = sampler(guide, cond, uncond, latents=latents, seed=seed).clone()
+    else:
+        fn = {"ddim": ddim_sample, "dpmpp": dpmpp_sample}[scheduler]
+        lat = fn(unet, control_lora, guide, cond, uncond, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
+                 latents=latents, seed=seed)
+    img = vae.decode(lat / float(vae.config.scaling_factor)).sample
+    return ops.channel_affine_nchw(img.contiguous(), 0.5, torch.full((img.shape[1],), 0.5, device=img.device, dtype=torch.float32)).clamp_(0.0, 1.0)

@@ -129,7 +129,51 @@ def pixels_case():
     return ok
 
 
-CASES = {"step_from_pixels": pixels_case, "sampler_ddim": lambda: loop_case("ddim"), "sampler_dpmpp": lambda: loop_case("dpmpp"), "step_glue": step_glue_case}
+def generate_case():
+    """sampler.generate: prompt ids -> CLIP text states -> 3 CFG + DDIM steps -> VAE decode -> [0, 1] images, against the oracle chain
+    (clip_ref -> models_ref + unet_ref driven by sampler_ref -> vae_ref.decode)."""
+    import torch
+    import controllora_b200 as cb
+    from controllora_b200.sampler import generate
+    from oracle import clip_ref as CR
+    from oracle import sampler_ref as SR
+    from oracle import vae_ref as VR
+
+    ounet, munet, ocl, mcl = check_unet.build_pair("v1")
+    vcfg = dict(block_out_channels=(32, 64, 64, 64), layers_per_block=1)          # 4 levels: 16x16 latents -> 128x128 pixels
+    ovae = VR.AutoencoderKL(**vcfg)
+    VR.init_synthetic_(ovae, seed=4)
+    mvae = cb.AutoencoderKL.from_state_dict({k: v.detach().clone() for k, v in ovae.state_dict().items()}, DEV, vcfg)
+    ccfg = dict(CR.SD15_TEXT_CONFIG)
+    ccfg.update(num_hidden_layers=2, vocab_size=1000, hidden_size=64, intermediate_size=256, num_attention_heads=4)
+    csd = CR.synthetic_state_dict(ccfg, seed=0)
+    mclip = cb.CLIPTextModel.from_state_dict(csd, DEV, ccfg)
+    B, HW, steps = 2, 16, 3
+    g = torch.Generator().manual_seed(17)
+    guide = (torch.rand(B, 3, HW * 8, HW * 8, generator=g) * 2 - 1).to(torch.bfloat16).float()
+    ids = torch.randint(0, ccfg["vocab_size"], (B, 77), generator=g)
+    neg = torch.randint(0, ccfg["vocab_size"], (B, 77), generator=g)
+    lat0 = torch.randn(B, 4, HW, HW, generator=g)
+    with torch.no_grad():
+        cond, unc = CR.clip_text_forward(csd, ids, ccfg), CR.clip_text_forward(csd, neg, ccfg)
+        ocl(torch.cat([guide, guide], 0))
+        x = lat0.clone()
+        for t in SR.timesteps(steps):
+            eps = ounet(torch.cat([x, x], 0), torch.full((2 * B,), int(t)), torch.cat([unc, cond], 0)).sample
+            x = SR.cfg_ddim_step(eps[:B], eps[B:], x, t, steps, 7.5)
+        want = (ovae.decode(x) / 2 + 0.5).clamp(0, 1)
+    got = generate(munet, mcl, mvae, mclip, guide.to(DEV), ids.to(DEV), neg.to(DEV), num_inference_steps=steps, guidance_scale=7.5,
+                   scheduler="ddim", latents=lat0.to(DEV))
+    sync()
+    err = float((got.cpu() - want).norm() / want.norm())
+    rng_ok = float(got.min()) >= 0.0 and float(got.max()) <= 1.0 and tuple(got.shape) == (B, 3, HW * 8, HW * 8)
+    print(f"[generate] {steps}-step DDIM + decode: image rel err {err:.3e}, range/shape ok {rng_ok}")
+    ok = err < 5e-2 and rng_ok
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
+CASES = {"generate": generate_case, "step_from_pixels": pixels_case, "sampler_ddim": lambda: loop_case("ddim"), "sampler_dpmpp": lambda: loop_case("dpmpp"), "step_glue": step_glue_case}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

@@ -78,3 +78,8 @@ def test_gradient_accumulation_window_matches_oracle():
 def test_whole_loop_body_from_pixels_matches_oracle_chain():
     """Trainer.step_from_pixels: VAE encode + sample, CLIP text tower, device noise glue, hint encoder, UNet, loss (train_...:751-796)."""
     assert check_sampler.CASES["step_from_pixels"]()
+
+
+def test_generate_pipeline_matches_oracle_chain():
+    """sampler.generate: token ids -> text states -> CFG + DDIM loop -> VAE decode -> [0, 1] images (train_...:824-843, apps/*)."""
+    assert check_sampler.CASES["generate"]()
