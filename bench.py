@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary numbers (denoise C3/C5, drop-in path, per-shape GEMM table)")
+    ap.add_argument("--aux-only", default=None, choices=["train_from_pixels"],
+                    help="run ONE auxiliary measurement in this process and print its JSON (bench.py runs it as an isolated child process)")
     return ap.parse_args()
 
 
@@ -322,6 +324,76 @@ def aux_dropin(torch, cb, unet, config_name, B, steps=4):
                                                 "per-kernel launches from Python (no fused Trainer, no CUDA graph)"}
 
 
+def aux_from_pixels(torch, cb, unet, config_name, B, steps=6):
+    """The whole loop body train_text_to_image_control_lora.py:751-796 from what the dataloader delivers: pixel_values [B,3,512,512],
+    input_ids [B,77], guide [B,3,512,512] -> VAE encode + latent sample (:753-754), CLIP text tower (:768), then the fused step
+    (device noise / timesteps / add_noise, hint encoder, UNet fwd / bwd, clip, AdamW; captured CUDA graph).  Frozen SD-1.5-shape VAE
+    and text encoder with seeded synthetic weights.  This is the images/s a training run sees once data loading is excluded."""
+    from controllora_b200.configs import NAMED, wire_processors
+    from controllora_b200.trainer import Trainer
+
+    dev = unet.device_
+    cl = cb.ControlLoRA.from_config(NAMED[config_name]).to(dev)
+    _randomize_up(torch, cl, dev, 3)
+    wire_processors(unet, cl)
+    tr = Trainer(unet, cl, lr=1e-4, cuda_graph=True)
+    vae = cb.AutoencoderKL.synthetic(dev)
+    clip = cb.CLIPTextModel.synthetic(dev)
+    g = torch.Generator().manual_seed(7)
+    pix = (torch.rand(B, 3, 512, 512, generator=g) * 2 - 1).to(dev)
+    ids = torch.randint(0, 49408, (B, 77), generator=g).to(dev)
+    guide = (torch.rand(B, 3, 512, 512, generator=g) * 2 - 1).to(dev)
+    for _ in range(4):                                   # 2 eager warm-ups, capture, first replay
+        loss = tr.step_from_pixels(vae, clip, pix, ids, guide)
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(steps):
+        loss = tr.step_from_pixels(vae, clip, pix, ids, guide)
+    e1.record()
+    with torch.no_grad():
+        for _ in range(steps):
+            vae.encode(pix).latent_dist.sample()
+            clip(ids)
+    e2.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "vae_encode_plus_clip_ms": e1.elapsed_time(e2) / steps, "steps": steps,
+            "graph": tr._graph is not None, "final_loss": float(loss),
+            "what": "pixels + token ids + guide -> VAE encode + sample, CLIP text tower, fused train step (train_...:751-796 complete); "
+                    "synthetic SD-1.5-shape VAE / text-encoder weights"}
+
+
+def aux_in_child(which, a, timeout_s=420):
+    """An auxiliary measurement whose shapes the headline never touches (the 512x512 batch-8 VAE encode) runs in its OWN process: its
+    CUDA context, allocator and any failure stay away from the process that has to print the bench line."""
+    import subprocess
+
+    cmd = [sys.executable, os.path.abspath(__file__), "--aux-only", which, "--config", a.config, "--batch", str(a.batch)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return {"value": None, "what": f"child process timed out after {timeout_s} s"}
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    return {"value": None, "what": f"child process failed (rc {r.returncode}): {(r.stderr or r.stdout)[-300:]}"}
+
+
+def run_aux_only(a):
+    try:
+        import torch
+
+        import controllora_b200 as cb
+
+        torch.cuda.set_device(0)
+        unet = cb.UNet2DConditionModel.synthetic(torch.device("cuda", 0), seed=0)
+        out = {"train_from_pixels": lambda: aux_from_pixels(torch, cb, unet, a.config, a.batch)}[a.aux_only]()
+    except Exception as ex:
+        out = {"value": None, "what": f"failed: {type(ex).__name__}: {ex}"}
+    print(json.dumps(out), flush=True)
+
+
 def aux_gemm_table(torch, ops):
     """Per-shape throughput of the tcgen05 GEMM family at the SD-1.5 shapes (SURVEY 8a census), each timed ALONE with CUDA
     events over operand sets that rotate through > 126 MB (so L2 does not hold them), against the burst bf16 peak of
@@ -566,6 +638,7 @@ def run_ours(a):
         torch.cuda.empty_cache()
         for key, fn in (("denoise_c3", lambda: aux_denoise(torch, cb, unet, "c3")), ("denoise_c5", lambda: aux_denoise(torch, cb, unet, "c5")),
                         ("dropin_train_step", lambda: aux_dropin(torch, cb, unet, a.config, B)),
+                        ("train_from_pixels", lambda: aux_in_child("train_from_pixels", a)),
                         ("gemm_per_shape", lambda: aux_gemm_table(torch, ops))):
             try:
                 aux[key] = fn()
@@ -622,6 +695,9 @@ def run_ours(a):
 
 def main():
     a = parse()
+    if a.aux_only:
+        run_aux_only(a)
+        return
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -72,6 +72,29 @@ class CLIPTextModel(nn.Module):
         return cls(sd, device, config)
 
     @classmethod
+    def synthetic(cls, device="cuda", config: Optional[dict] = None, seed: int = 0):
+        """Seeded random weights with transformers' key names (123 060 480 parameters for the SD-1.5 text tower): benchmarks / smoke
+        runs on machines without the published checkpoint."""
+        cfg = dict(SD15_TEXT_CONFIG)
+        cfg.update(config or {})
+        g = torch.Generator().manual_seed(seed)
+        Cw, Fi = cfg["hidden_size"], cfg["intermediate_size"]
+        sd = {"text_model.embeddings.token_embedding.weight": 0.02 * torch.randn(cfg["vocab_size"], Cw, generator=g),
+              "text_model.embeddings.position_embedding.weight": 0.01 * torch.randn(cfg["max_position_embeddings"], Cw, generator=g)}
+        for i in range(cfg["num_hidden_layers"]):
+            p = f"text_model.encoder.layers.{i}."
+            for name, (o, n) in {"self_attn.q_proj": (Cw, Cw), "self_attn.k_proj": (Cw, Cw), "self_attn.v_proj": (Cw, Cw),
+                                 "self_attn.out_proj": (Cw, Cw), "mlp.fc1": (Fi, Cw), "mlp.fc2": (Cw, Fi)}.items():
+                sd[p + name + ".weight"] = torch.randn(o, n, generator=g) / math.sqrt(n)
+                sd[p + name + ".bias"] = 0.02 * torch.randn(o, generator=g)
+            for ln in ("layer_norm1", "layer_norm2"):
+                sd[p + ln + ".weight"] = 1.0 + 0.1 * torch.randn(Cw, generator=g)
+                sd[p + ln + ".bias"] = 0.1 * torch.randn(Cw, generator=g)
+        sd["text_model.final_layer_norm.weight"] = 1.0 + 0.1 * torch.randn(Cw, generator=g)
+        sd["text_model.final_layer_norm.bias"] = 0.1 * torch.randn(Cw, generator=g)
+        return cls(sd, device, cfg)
+
+    @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None, device="cuda", **unused):
         """Local transformers-format directory (`<root>[/subfolder]/config.json` + `model.safetensors | pytorch_model.bin`), the
         layout `CLIPTextModel.from_pretrained(..., subfolder="text_encoder")` reads at train_text_to_image_control_lora.py:401-403."""

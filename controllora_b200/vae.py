@@ -29,6 +29,66 @@ SD15_VAE_CONFIG = dict(in_channels=3, out_channels=3, latent_channels=4, block_o
                        layers_per_block=2, norm_num_groups=32, scaling_factor=0.18215)
 
 
+def synthetic_vae_state_dict(config: Optional[dict] = None, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """State dict of a diffusers-0.13 AutoencoderKL with this config (exact key names and shapes of the published SD-1.5 `vae/`
+    checkpoint for the default config: 83 653 863 parameters), filled with seeded random values."""
+    cfg = dict(SD15_VAE_CONFIG)
+    cfg.update(config or {})
+    ch, L, lat = list(cfg["block_out_channels"]), cfg["layers_per_block"], cfg["latent_channels"]
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, cout, cin, k):
+        sd[name + ".weight"] = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+        sd[name + ".bias"] = 0.02 * torch.randn(cout, generator=g)
+
+    def lin(name, cout, cin):
+        sd[name + ".weight"] = torch.randn(cout, cin, generator=g) / math.sqrt(cin)
+        sd[name + ".bias"] = 0.02 * torch.randn(cout, generator=g)
+
+    def norm(name, c):
+        sd[name + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
+        sd[name + ".bias"] = 0.1 * torch.randn(c, generator=g)
+
+    def resnet(p, cin, cout):
+        norm(p + "norm1", cin); conv(p + "conv1", cout, cin, 3); norm(p + "norm2", cout); conv(p + "conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + "conv_shortcut", cout, cin, 1)
+
+    def mid(p, c):
+        norm(p + "attentions.0.group_norm", c)
+        for k in ("query", "key", "value", "proj_attn"):
+            lin(p + "attentions.0." + k, c, c)
+        resnet(p + "resnets.0.", c, c); resnet(p + "resnets.1.", c, c)
+
+    conv("encoder.conv_in", ch[0], cfg["in_channels"], 3)
+    cin = ch[0]
+    for i, c in enumerate(ch):
+        for j in range(L):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}.", cin, c)
+            cin = c
+        if i != len(ch) - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", c, c, 3)
+    mid("encoder.mid_block.", ch[-1])
+    norm("encoder.conv_norm_out", ch[-1]); conv("encoder.conv_out", 2 * lat, ch[-1], 3)
+    conv("decoder.conv_in", ch[-1], lat, 3)
+    mid("decoder.mid_block.", ch[-1])
+    rev = ch[::-1]
+    cin = rev[0]
+    for i, c in enumerate(rev):
+        for j in range(L + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}.", cin, c)
+            cin = c
+        if i != len(rev) - 1:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", c, c, 3)
+    norm("decoder.conv_norm_out", rev[-1]); conv("decoder.conv_out", cfg["out_channels"], rev[-1], 3)
+    conv("quant_conv", 2 * lat, 2 * lat, 1); conv("post_quant_conv", lat, lat, 1)
+    # near-identity 1x1 quant convs keep the latent statistics of the encoder (and post_quant_conv well conditioned: it is inverted)
+    sd["quant_conv.weight"] = torch.eye(2 * lat).view(2 * lat, 2 * lat, 1, 1) + 0.05 * sd["quant_conv.weight"]
+    sd["post_quant_conv.weight"] = torch.eye(lat).view(lat, lat, 1, 1) + 0.05 * sd["post_quant_conv.weight"]
+    return sd
+
+
 class DiagonalGaussianDistribution:
     """diffusers' DiagonalGaussianDistribution over NCHW fp32 moments (logvar clamped to [-30, 20])."""
 
@@ -132,6 +192,12 @@ class AutoencoderKL(nn.Module):
     @classmethod
     def from_state_dict(cls, sd, device="cuda", config: Optional[dict] = None):
         return cls(sd, device, config)
+
+    @classmethod
+    def synthetic(cls, device="cuda", config: Optional[dict] = None, seed: int = 0):
+        """Seeded random weights of the architecture (diffusers key names; W ~ N(0, 1/fan_in), norm gamma ~ 1): benchmarks and smoke runs
+        on machines without the published checkpoint."""
+        return cls(synthetic_vae_state_dict(config, seed), device, config)
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None, device="cuda", **unused):
