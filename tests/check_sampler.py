@@ -173,7 +173,35 @@ def generate_case():
     return ok
 
 
-CASES = {"generate": generate_case, "step_from_pixels": pixels_case, "sampler_ddim": lambda: loop_case("ddim"), "sampler_dpmpp": lambda: loop_case("dpmpp"), "step_glue": step_glue_case}
+def graphed_program_case():
+    """GraphedSampler's per-step program (timestep-invariant products prepared once, text k / v cache, timestep and solver
+    coefficients read from device tables through a device step counter) run WITHOUT capturing it, against the plain Python loops: the
+    same latents, bit for bit on the CPU (host-logic mode), to rounding on the GPU.  Capture + replay itself is a GPU test
+    (tests/test_gpu_parity.py::test_graphed_sampler_matches_eager_loop)."""
+    import torch
+    from controllora_b200.sampler import GraphedSampler, ddim_sample, dpmpp_sample
+
+    ok = True
+    for sched, variant, fn in (("ddim", "v1", ddim_sample), ("dpmpp", "v2", dpmpp_sample)):
+        _, munet, _, mcl = check_unet.build_pair(variant)
+        g = torch.Generator().manual_seed(9)
+        B, HW = 2, 16
+        guide = (torch.rand(B, 3, HW * 8, HW * 8, generator=g) * 2 - 1).to(torch.bfloat16).float().to(DEV)
+        cond = torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).to(DEV)
+        unc = torch.randn(B, 77, 64, generator=g).to(torch.bfloat16).to(DEV)
+        lat0 = torch.randn(B, 4, HW, HW, generator=g).to(DEV)
+        gs = GraphedSampler(munet, mcl, B, HW * 8, HW * 8, scheduler=sched, num_inference_steps=4, guidance_scale=7.5)
+        a = gs(guide, cond, unc, latents=lat0, use_graph=False).clone()
+        b = fn(munet, mcl, guide, cond, unc, num_inference_steps=4, guidance_scale=7.5, latents=lat0)
+        sync()
+        err = float((a - b).norm() / b.norm())
+        print(f"[graphed program {sched}] prepared-context step program vs plain loop: rel {err:.3e}")
+        ok = ok and err <= (0.0 if DEV == "cpu" else 2e-2)
+    print("CASE_OK" if ok else "CASE_FAIL")
+    return ok
+
+
+CASES = {"graphed_program": graphed_program_case, "generate": generate_case, "step_from_pixels": pixels_case, "sampler_ddim": lambda: loop_case("ddim"), "sampler_dpmpp": lambda: loop_case("dpmpp"), "step_glue": step_glue_case}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

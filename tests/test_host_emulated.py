@@ -21,7 +21,7 @@ CASES += ["cfg_broadcast_v1", "cfg_broadcast_v2"]                               
 CASES += ["two_forwards_v1_stacked", "two_forwards_v2", "unet_v1_stacked@0.0"]      # two UNet calls (different scale) before one backward; scale 0
 CASES += ["generic_" + v for v in ("plain", "v1", "v2", "v1_stacked@0.5", "v1_post_add", "v1_concat")]
 CASES += ["refgold_" + k for k in ("v1_stacked", "v2", "post_add", "concat")]      # vs vectors computed by the reference's own models.py
-CASES += ["sampler_ddim", "sampler_dpmpp", "step_glue", "step_from_pixels", "generate"]                              # tests/check_sampler.py
+CASES += ["sampler_ddim", "sampler_dpmpp", "step_glue", "step_from_pixels", "generate", "graphed_program"]                              # tests/check_sampler.py
 CASES += ["eager_" + k for k in ("plain_self", "plain_cross", "v1_self", "v1_cross_stacked", "v2_self", "v2_cross", "lora_linear")]
 
 
