@@ -20,16 +20,52 @@ from .hint_encoder import HintEncoderEngine
 BF16 = torch.bfloat16
 
 
+def lr_lambda_for(name: str, warmup: int = 0, total: Optional[int] = None):
+    """The multiplier schedules of diffusers.optimization.get_scheduler (the six names `--lr_scheduler` accepts, train_...:221-228) as
+    functions of the number of completed optimizer steps; None for "constant"."""
+    import math
+
+    if name == "constant":
+        return None
+    if name == "constant_with_warmup":
+        return lambda s: min(1.0, s / max(1.0, warmup))
+    if total is None:
+        raise ValueError(f"lr_scheduler={name!r} needs max_train_steps")
+    ramp = lambda s: s / max(1, warmup)
+    if name == "linear":
+        return lambda s: ramp(s) if s < warmup else max(0.0, (total - s) / max(1, total - warmup))
+    if name == "cosine":
+        return lambda s: ramp(s) if s < warmup else max(0.0, 0.5 * (1.0 + math.cos(math.pi * 0.5 * 2.0 * (s - warmup) / max(1, total - warmup))))
+    if name == "cosine_with_restarts":          # num_cycles = 1 (get_scheduler's default)
+        def f(s):
+            if s < warmup:
+                return ramp(s)
+            pr = (s - warmup) / max(1, total - warmup)
+            return 0.0 if pr >= 1.0 else max(0.0, 0.5 * (1.0 + math.cos(math.pi * ((1.0 * pr) % 1.0))))
+        return f
+    if name == "polynomial":                    # power 1.0, lr_end 1e-7: needs the base lr, resolved by the caller as a ratio
+        raise NotImplementedError("polynomial decays to an absolute lr_end (1e-7): not expressible as a pure multiplier here")
+    raise ValueError(f"unknown lr_scheduler {name!r}")
+
+
 class Trainer:
     def __init__(self, unet, control_lora, lr: float = 1e-4, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,
                  max_grad_norm: float = 1.0, process_group=None, cuda_graph: bool = False, graph_warmup: int = 2,
                  noise_seed: int = 0, prediction_type: str = "epsilon", num_train_timesteps: int = 1000,
-                 prior_loss_weight: Optional[float] = None):
+                 prior_loss_weight: Optional[float] = None, lr_scheduler: str = "constant", lr_warmup_steps: int = 0,
+                 max_train_steps: Optional[int] = None):
         """control_lora=None trains the adapters installed on the UNet alone (plain `LoRACrossAttnProcessor`s on every attention
         layer): the step of train_dreambooth_lora.py:880-918.  prior_loss_weight (DreamBooth's prior preservation, :898-910): the
         batch is [instance images | class images] and loss = mse(first half) + prior_loss_weight * mse(second half)."""
         self.unet, self.cl = unet, control_lora
         self.prior_loss_weight = None if prior_loss_weight is None else float(prior_loss_weight)
+        # `get_scheduler(args.lr_scheduler, num_warmup_steps, num_training_steps)` (train_...:675-681).  "constant" (the reference's
+        # default) is the only schedule a captured step graph can hold - the learning rate is a launch scalar - the others apply to
+        # per-kernel (cuda_graph=False) stepping.
+        self.lr_lambda = lr_lambda_for(lr_scheduler, lr_warmup_steps, max_train_steps)
+        self.lr_scheduler_name = lr_scheduler
+        if self.lr_lambda is not None and cuda_graph:
+            raise NotImplementedError(f"lr_scheduler={lr_scheduler!r} needs cuda_graph=False: a captured step graph holds one constant learning rate")
         self.lr, self.betas, self.wd, self.eps, self.max_norm = lr, betas, weight_decay, eps, max_grad_norm
         self.pg = process_group
         dev = unet.device_
@@ -310,7 +346,10 @@ class Trainer:
         self._reduced_in_step = False
         ops.step_begin(self.gnorm_sq, self.step_dev)
         ops.sumsq(self.flat_g, self.gnorm_sq)
-        ops.adamw_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+        # LambdaLR semantics: the k-th optimizer step (k = 1, 2, ...) runs with base_lr * lambda(k - 1)
+        lr = self.lr if self.lr_lambda is None else self.lr * self.lr_lambda(max(self.step_idx - 1, 0))
+        self.last_lr = lr
+        ops.adamw_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, self.betas[0], self.betas[1], self.eps, self.wd,
                       self.step_dev, gnorm_sq=self.gnorm_sq, max_norm=self.max_norm,
                       grad_scale=self.arena.grad_scale / (1 + self._micro), zero_grad=True)
         self._micro = 0
@@ -433,8 +472,9 @@ class Trainer:
                                        "param_names": [n for n, _ in named], "param_numels": [p.numel() for _, p in named],
                                        "extra_params": {n: p.detach().cpu().clone() for n, p in named if n.startswith("extra.")}}
             torch.save(opt, os.path.join(path, "optimizer.bin"))
+            cur = self.lr if self.lr_lambda is None else self.lr * self.lr_lambda(self.step_idx)
             torch.save({"base_lrs": [self.lr], "last_epoch": self.step_idx, "_step_count": self.step_idx + 1, "verbose": False,
-                        "_get_lr_called_within_step": False, "_last_lr": [self.lr], "lr_lambdas": [None], "schedule": "constant"},
+                        "_get_lr_called_within_step": False, "_last_lr": [cur], "lr_lambdas": [None], "schedule": self.lr_scheduler_name},
                        os.path.join(path, "scheduler.bin"))
         try:
             import numpy as np

@@ -417,3 +417,26 @@ def test_checkpoint_written_by_the_reference_stack_resumes_here(tmp_path):
     torch.save(opt2, d / "optimizer.bin")
     with pytest.raises(ValueError):
         tr.load_checkpoint(str(d))
+
+
+@pytest.mark.parametrize("name", ["constant", "constant_with_warmup", "linear", "cosine", "cosine_with_restarts"])
+def test_lr_schedules_equal_transformers_get_scheduler(name):
+    """`get_scheduler(args.lr_scheduler, optimizer, num_warmup_steps, num_training_steps)` (train_...:675-681; diffusers' optimization.py is
+    the transformers file): the multiplier the Trainer applies to its k-th optimizer step equals the learning rate LambdaLR holds there."""
+    tr_mod = pytest.importorskip("transformers")
+    from controllora_b200.trainer import lr_lambda_for
+
+    warm, total, base = 7, 50, 3e-4
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=base)
+    sched = tr_mod.get_scheduler(name, opt, num_warmup_steps=warm, num_training_steps=total)
+    lam = lr_lambda_for(name, warm, total)
+    for k in range(1, 61):                       # k-th optimizer step
+        ours = base if lam is None else base * lam(k - 1)
+        assert abs(ours - opt.param_groups[0]["lr"]) <= 1e-12 * base + 1e-18, (name, k)
+        opt.step()
+        sched.step()
+    from controllora_b200.trainer import Trainer
+    with pytest.raises(NotImplementedError):
+        tr, _ = _tiny_trainer(0)
+        Trainer(tr.unet, tr.cl, cuda_graph=True, lr_scheduler="cosine", max_train_steps=10)
