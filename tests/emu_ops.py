@@ -207,6 +207,7 @@ def layernorm_bwd(x, dy, gamma, stats, dx=None, accumulate=False):
 
 # ------------------------------------------------------------------------------------------------------------ elementwise
 def geglu_fwd(p):
+    assert p.dtype == BF16 and p.is_contiguous()
     a, g = p.float().chunk(2, -1)
     return _bf(a * F.gelu(g))
 
@@ -220,7 +221,9 @@ def geglu_bwd(p, dout):
 
 
 def add(a, b, out=None):
-    r = _bf(a.float() + b.float()) if a.dtype == BF16 else a + b
+    assert a.dtype == BF16 and b.dtype == BF16 and (out is None or out.dtype == BF16), "cl_add is a bf16 kernel"
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape and a.numel() % 8 == 0
+    r = _bf(a.float() + b.float())
     if out is None:
         return r
     out.copy_(r)
@@ -248,10 +251,12 @@ def zero_insert2x(x, off):
 
 
 def concat_channels(a, b):
+    assert a.dtype == b.dtype == BF16 and a.shape[-1] % 8 == 0 and b.shape[-1] % 8 == 0
     return torch.cat([a, b], -1).contiguous()
 
 
 def slice_channels(src, c_off, Cd, dst=None, accumulate=False):
+    assert src.dtype == BF16 and (dst is None or dst.dtype == BF16)
     s = src[..., c_off:c_off + Cd]
     if dst is None:
         return s.contiguous()
@@ -310,6 +315,7 @@ def small_linear(x, w, bias, silu_in=False, silu_out=False):
 
 
 def mse_loss(pred, target, gscale=1.0, need_grad=True, out=None):
+    assert pred.dtype == target.dtype == torch.float32 and (out is None or out.dtype == torch.float32)
     d = pred - target
     loss = (d * d).mean().reshape(1)
     g = (2.0 * gscale / pred.numel()) * d
@@ -406,16 +412,19 @@ def rowmat(a, w, sw_i, sw_j, I, J, alpha, out, ldo, out_mode=0, col_off=0, lo_of
 
 def skinny_small(a, I, b, J, out, alpha):
     assert I <= 8 and J <= 8, "cl_skinny_small: bad args"
+    assert a.dtype == b.dtype == out.dtype == torch.float32 and a.shape[0] == b.shape[0]
     out.view(-1)[: I * J].view(I, J).add_(float(alpha) * (a[:, :I].float().t() @ b[:, :J].float()))
 
 
 def small_matmul(a, sa_i, sa_j, b, sb_j, sb_k, out, so_i, so_k, I, J, K, alpha=1.0, accumulate=False):
+    assert a.dtype == b.dtype == out.dtype == torch.float32
     r = float(alpha) * (_sv(a, (I, J), (sa_i, sa_j)).float() @ _sv(b, (J, K), (sb_j, sb_k)).float())
     o = _sv(out, (I, K), (so_i, so_k))
     o.copy_(o + r if accumulate else r)
 
 
 def hilo_combine(src, nb):
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.shape[1] == 16 * nb
     M = src.shape[0]
     s = src.view(M, nb, 16)
     return (s[..., :8] + s[..., 8:]).reshape(M, 8 * nb).contiguous()
@@ -505,6 +514,7 @@ def conv_weight_prep(w, wf, wd=None):
 
 
 def colsum(x, out, alpha=1.0):
+    assert x.dtype == BF16 and out.dtype == torch.float32
     C = x.shape[-1]
     out += float(alpha) * x.float().reshape(-1, C).sum(0)
 
