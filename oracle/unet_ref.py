@@ -16,8 +16,12 @@ its published algorithm is restated here from the diffusers-0.13 sources' behavi
   * topology: 3x CrossAttnDownBlock2D + DownBlock2D, mid (res, attn, res), UpBlock2D + 3x CrossAttnUpBlock2D,
     GN -> SiLU -> conv_out.  Module / parameter names equal diffusers' state-dict keys.
 
-PARITY STATUS: **parity unpinned** — the reference ships no tests / golden vectors and diffusers cannot
-be imported here, so this restatement could not be checked against the reference's own outputs.  It is anchored by
+PARITY STATUS: **parity unpinned as a whole** — the reference ships no tests / golden vectors and diffusers cannot
+be imported here, so the assembled network could not be checked against diffusers' own outputs.  Its building blocks ARE pinned to
+independent implementations of the same published blocks (tests/test_oracle.py): BasicTransformerBlock == torch.nn.TransformerDecoderLayer
+(norm_first, GEGLU activation), ResnetBlock2D (time projection zeroed) / Upsample2D / Downsample2D(padding=0) == the CompVis LDM blocks
+shipped in transformers, the timestep embedding == its closed form.  Unpinned: the block wiring (skip connections, resolution schedule),
+the time-embedding injection, the Transformer2DModel wrapper.  The whole is anchored by
 (a) the parameter-count sanity anchors of SURVEY.md §8c (859.08 M weights in conv/linear kernels), (b) the reference's
 call sites, and (c) self-consistency tests in tests/test_oracle.py.
 """

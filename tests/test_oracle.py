@@ -351,3 +351,80 @@ def test_vae_oracle_encoder_decoder_match_the_ldm_implementation_in_transformers
     assert e_got.shape == e_want.shape == (2, 8, 8, 8) and d_got.shape == d_want.shape == (2, 3, 32, 32)
     assert float((e_got - e_want).abs().max()) < 1e-4 * float(e_want.abs().max())
     assert float((d_got - d_want).abs().max()) < 1e-4 * float(d_want.abs().max())
+
+
+def test_unet_oracle_blocks_match_independent_implementations():
+    """diffusers itself cannot run here, so the WHOLE-UNet restatement (oracle/unet_ref.py) stays unpinned; its building blocks are
+    pinned to independent implementations of the same published blocks:
+      BasicTransformerBlock (LN -> self-attn -> +, LN -> cross-attn -> +, LN -> GEGLU FF -> +)   == torch.nn.TransformerDecoderLayer(norm_first)
+      ResnetBlock2D (time-embedding projection zeroed), Upsample2D, Downsample2D(padding=0)       == the LDM blocks shipped in transformers
+      sinusoidal timestep embedding (flip_sin_to_cos, freq_shift 0)                                == the closed form, evaluated in float64."""
+    import math
+
+    import pytest
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from oracle import unet_ref as UR
+
+    torch.manual_seed(0)
+    # ---- transformer block
+    dim, heads, T, S, B = 64, 4, 24, 9, 2
+    blk = UR.BasicTransformerBlock(dim, heads, dim // heads, dim)          # cross_attention_dim == dim: nn.MultiheadAttention's memory width
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape) * (0.2 if p.dim() > 1 else 0.1) + (1.0 if p.dim() == 1 and p.numel() == dim and p is not blk.ff.net[2].bias else 0.0))
+    Fd = blk.ff.net[2].in_features
+
+    def geglu_padded(p):                                                     # GEGLU as an `activation`: output padded back to 2F for linear2
+        a, g = p.chunk(2, dim=-1)
+        return torch.cat([a * F.gelu(g), torch.zeros_like(a)], -1)
+
+    ref = nn.TransformerDecoderLayer(dim, heads, dim_feedforward=2 * Fd, dropout=0.0, activation=geglu_padded, batch_first=True, norm_first=True)
+    with torch.no_grad():
+        for mha, att in ((ref.self_attn, blk.attn1), (ref.multihead_attn, blk.attn2)):
+            mha.in_proj_weight.copy_(torch.cat([att.to_q.weight, att.to_k.weight, att.to_v.weight], 0))
+            mha.in_proj_bias.zero_()
+            mha.out_proj.weight.copy_(att.to_out[0].weight)
+            mha.out_proj.bias.copy_(att.to_out[0].bias)
+        for a, b in ((ref.norm1, blk.norm1), (ref.norm2, blk.norm2), (ref.norm3, blk.norm3)):
+            a.weight.copy_(b.weight); a.bias.copy_(b.bias)
+        ref.linear1.weight.copy_(blk.ff.net[0].proj.weight); ref.linear1.bias.copy_(blk.ff.net[0].proj.bias)
+        ref.linear2.weight.zero_()
+        ref.linear2.weight[:, :Fd].copy_(blk.ff.net[2].weight); ref.linear2.bias.copy_(blk.ff.net[2].bias)
+    x, mem = torch.randn(B, T, dim), torch.randn(B, S, dim)
+    with torch.no_grad():
+        want = ref.eval()(x, mem)
+        got = blk(x, encoder_hidden_states=mem)
+    assert float((got - want).abs().max()) < 2e-5 * float(want.abs().max())
+    # ---- conv blocks (LDM implementation in transformers)
+    pytest.importorskip("transformers")
+    from transformers.models.janus.configuration_janus import JanusVQVAEConfig
+    from transformers.models.janus.modeling_janus import JanusVQVAEConvDownsample, JanusVQVAEConvUpsample, JanusVQVAEResnetBlock
+
+    cfg = JanusVQVAEConfig(dropout=0.0)
+    for cin, cout in ((32, 64), (64, 64)):
+        r = UR.ResnetBlock2D(cin, cout, temb_channels=16, groups=32, eps=1e-6)
+        j = JanusVQVAEResnetBlock(cfg, cin, cout).eval()
+        with torch.no_grad():
+            for p in r.parameters():
+                p.copy_(torch.randn(p.shape) * 0.1)
+            r.time_emb_proj.weight.zero_(); r.time_emb_proj.bias.zero_()
+            for a, b in (("norm1", "norm1"), ("conv1", "conv1"), ("norm2", "norm2"), ("conv2", "conv2")):
+                getattr(j, b).weight.copy_(getattr(r, a).weight); getattr(j, b).bias.copy_(getattr(r, a).bias)
+            if cin != cout:
+                j.nin_shortcut.weight.copy_(r.conv_shortcut.weight); j.nin_shortcut.bias.copy_(r.conv_shortcut.bias)
+            xi = torch.randn(2, cin, 12, 12)
+            assert float((r(xi, torch.randn(2, 16)) - j(xi.clone())).abs().max()) < 1e-4
+    up, jup = UR.Upsample2D(32), JanusVQVAEConvUpsample(32)
+    dn, jdn = UR.Downsample2D(32, padding=0), JanusVQVAEConvDownsample(32)
+    with torch.no_grad():
+        jup.conv.load_state_dict(up.conv.state_dict()); jdn.conv.load_state_dict(dn.conv.state_dict())
+        xi = torch.randn(2, 32, 10, 10)
+        assert torch.allclose(up(xi), jup(xi), atol=1e-6) and torch.allclose(dn(xi), jdn(xi), atol=1e-6)
+    # ---- timestep embedding: [cos | sin](t * 10000^(-i / half))
+    t = torch.tensor([0.0, 1.0, 17.0, 999.0])
+    emb = UR.sinusoidal_embedding(t, 320)
+    i = torch.arange(160, dtype=torch.float64)
+    ang = t.double()[:, None] * torch.exp(-math.log(10000.0) * i / 160)[None]
+    assert torch.allclose(emb.double(), torch.cat([ang.cos(), ang.sin()], -1), atol=2e-4)       # fp32 argument reduction at t = 999
