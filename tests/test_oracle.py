@@ -428,3 +428,43 @@ def test_unet_oracle_blocks_match_independent_implementations():
     i = torch.arange(160, dtype=torch.float64)
     ang = t.double()[:, None] * torch.exp(-math.log(10000.0) * i / 160)[None]
     assert torch.allclose(emb.double(), torch.cat([ang.cos(), ang.sin()], -1), atol=2e-4)       # fp32 argument reduction at t = 999
+
+
+def test_scheduler_restatements_are_exact_on_the_point_mass_ode():
+    """Property pin of oracle/sampler_ref.py (diffusers' DDIMScheduler / DPMSolverMultistepScheduler cannot be imported): for data
+    concentrated on one point x* the optimal denoiser is eps(x, t) = (x - alpha_t x*) / sigma_t, the probability-flow ODE has the closed
+    form x_t = alpha_t x* + (sigma_t / sigma_T)(x_T - alpha_T x*), and both deterministic DDIM and DPM-Solver++(2M) are EXACT on it for
+    any number of steps (constant x0 prediction, constant noise direction).  A wrong first-order coefficient, timestep table, final-step rule or
+    multistep history in the restatement breaks the identity (the second-order correction of 2M multiplies the CHANGE of the x0 prediction,
+    which is zero here: its coefficient is covered by the committed golden trajectories only)."""
+    import torch
+    from oracle import sampler_ref as SR
+
+    g = torch.Generator().manual_seed(0)
+    xs, xT = torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64), torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64)
+    ac = SR.alphas_cumprod()
+    al, sg = ac.sqrt(), (1 - ac).sqrt()
+    eps_star = lambda x, t: (x - al[t] * xs) / sg[t]
+    for steps in (5, 20, 50):
+        ts = [int(t) for t in SR.timesteps(steps)]
+        x = xT.clone()
+        for t in ts:
+            e = eps_star(x, t)
+            x = SR.cfg_ddim_step(e, e, x, t, steps, 7.5)                      # uncond == cond: the guidance term vanishes
+        t_end = max(ts[-1] - 1000 // steps, 0)
+        want = al[t_end] * xs + (sg[t_end] / sg[ts[0]]) * (xT - al[ts[0]] * xs)
+        assert float((x - want).abs().max()) < 1e-9, ("ddim", steps)
+    for steps in (4, 12, 30):                                                  # < 15: the last step is first order (lower_order_final)
+        s = SR.DPMSolverPP2M(steps)
+        x = xT.clone()
+        for t in s.timesteps:
+            x = s.step(eps_star(x, t), t, x)
+        T = s.timesteps[0]
+        want = al[0] * xs + (sg[0] / sg[T]) * (xT - al[T] * xs)
+        assert float((x - want).abs().max()) < 1e-9, ("dpmpp", steps)
+    # add_noise / get_velocity are the closed forms of the forward process (DDPMScheduler.add_noise / get_velocity)
+    t = torch.tensor([3, 700])
+    n = torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64)
+    a, b = al[t].view(2, 1, 1, 1), sg[t].view(2, 1, 1, 1)
+    assert torch.allclose(SR.add_noise(xs, n, t).double(), a * xs + b * n, atol=1e-6)
+    assert torch.allclose(SR.get_velocity(xs, n, t).double(), a * n - b * xs, atol=1e-6)
