@@ -18,7 +18,6 @@ import sys
 import types
 from pathlib import Path
 
-import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
