@@ -364,7 +364,7 @@ def aux_from_pixels(torch, cb, unet, config_name, B, steps=6):
                     "synthetic SD-1.5-shape VAE / text-encoder weights"}
 
 
-def aux_in_child(which, a, timeout_s=420):
+def aux_in_child(which, a, timeout_s=240):
     """An auxiliary measurement whose shapes the headline never touches (the 512x512 batch-8 VAE encode) runs in its OWN process: its
     CUDA context, allocator and any failure stay away from the process that has to print the bench line."""
     import subprocess
